@@ -1,0 +1,465 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json: views/sec fwd+bwd @1080p, N Gaussians x feat_dim).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-cuda] [--workload cfg3|cfg2]
+
+Workloads (synthetic, seeded -- SURVEY.md §8d):
+  cfg3 (default, BASELINE.json configs[2], the one the north-star target is quoted on):
+        2M Gaussians, F=16, 1920x1080; one step per rank = render() of one view + 32768 sampled pixels +
+        ProtoNCE contrastive loss + backward to the raw seg-feature parameter + (N>1) NCCL all-reduce of
+        dL/d_seg_feature + fused Adam step.   Views shard over ranks (weak scaling: one view per rank per step).
+  cfg2 (BASELINE.json configs[1]): 500k Gaussians, F=0, 1080p, RGB+depth+normal forward + backward of ALL
+        gradients with seeded random cotangents.
+One JSON line on stdout (rank 0).  See the task contract for the keys.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg3": dict(P=2_000_000, F=16, W=1920, H=1080, seed=1003, n_views=200, samples=32768, labels=64,
+                 desc="cfg3: 2M Gaussians x 16-dim features @1920x1080, render + ProtoNCE(32768 px) + backward + Adam"),
+    "cfg2": dict(P=500_000, F=0, W=1920, H=1080, seed=1002, n_views=200, samples=0, labels=0,
+                 desc="cfg2: 500k Gaussians @1920x1080, RGB+depth+normal forward + backward of all gradients"),
+}
+KERNELS_PER_STEP = {"cfg3": 17, "cfg2": 9}  # our own kernels per step (see DESIGN.md "launch list")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks/throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.samples, self._stop, self._t = gpu_index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                    str(self.gpu)], capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.samples.append([x.strip() for x in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[1])); mx.append(float(s[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def build_workload(name: str, n_views_needed: int):
+    from instascene_b200 import synth
+    w = WORKLOADS[name]
+    scene = synth.synth_scene(w["P"], F=w["F"], seed=w["seed"])
+    cams = synth.ring_cameras(w["n_views"], w["W"], w["H"])
+    return w, scene, cams
+
+
+class _Pipe:
+    compute_cov3D_python, convert_SHs_python, depth_ratio = False, False, 1.0
+
+
+def _make_pc(scene, dev):
+    import torch
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    class PC:
+        active_sh_degree, max_sh_degree = 3, 3
+
+        def __init__(self):
+            self.get_xyz = t(scene.xyz)
+            self.get_opacity = t(scene.opacities()).reshape(-1, 1)
+            self.get_scaling = t(scene.scales())
+            self.get_rotation = t(scene.rotations())
+            self.get_features = t(scene.shs())
+            self._seg_feature = t(scene.seg_feature_raw).requires_grad_(True) if scene.seg_feature_raw is not None else None
+
+        @property
+        def get_seg_feature(self):  # scene/gaussian_model.py:121-125
+            if self._seg_feature is None:
+                return None
+            return self._seg_feature / (torch.norm(self._seg_feature, p=2, dim=1, keepdim=True) + 1e-6)
+
+    return PC()
+
+
+class _Cam:
+    znear, zfar = 0.01, 100.0
+
+    def __init__(self, cam, wvt, fpt, center):
+        self.FoVx, self.FoVy, self.image_width, self.image_height = cam.FoVx, cam.FoVy, cam.image_width, cam.image_height
+        self.world_view_transform, self.full_proj_transform, self.camera_center = wvt, fpt, center
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import instascene_b200 as isr
+    from instascene_b200 import dist as idist, synth
+    rank, local_rank, world = idist.init()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    wl, scene, cams = build_workload(args.workload, args.steps + args.warmup)
+    P, F, W, H = wl["P"], wl["F"], wl["W"], wl["H"]
+    pc = _make_pc(scene, dev)
+    bg = torch.zeros(3, device=dev)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    total_steps = args.steps + args.warmup
+    my_views = [idist.step_views(s, len(cams), rank, world) for s in range(total_steps)]
+
+    # ---- per-view host data (pinned) and its device copies ------------------------------------------------------
+    host, devdata = {}, {}
+    for v in sorted(set(my_views)):
+        c = cams[v]
+        h = dict(wvt=torch.from_numpy(c.world_view_transform).pin_memory(),
+                 fpt=torch.from_numpy(c.full_proj_transform).pin_memory(),
+                 center=torch.from_numpy(c.camera_center).pin_memory())
+        if args.workload == "cfg3":
+            lab = synth.label_map(W, H, wl["seed"] + 2 + v)
+            valid = np.flatnonzero(lab.reshape(-1) > 0).astype(np.int32)
+            h["labels"] = torch.from_numpy(lab.reshape(-1).astype(np.int16)).pin_memory()
+            h["valid"] = torch.from_numpy(valid).pin_memory()
+        else:
+            rng = np.random.default_rng(wl["seed"] + 1 + v)
+            h["dcolor"] = torch.from_numpy(rng.standard_normal((3, H, W)).astype(np.float32)).pin_memory()
+            h["dothers"] = torch.from_numpy(rng.standard_normal((7, H, W)).astype(np.float32)).pin_memory()
+        host[v] = h
+        devdata[v] = {k: x.to(dev) for k, x in h.items()}
+    torch.cuda.synchronize()
+
+    opt = None
+    if args.workload == "cfg3":
+        opt = torch.optim.Adam([pc._seg_feature], lr=0.025, eps=1e-15, fused=True)  # scene/gaussian_model.py:217-249
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    geo_params = []
+    if args.workload == "cfg2":
+        for name in ("get_xyz", "get_scaling", "get_rotation", "get_opacity", "get_features"):
+            p = getattr(pc, name).detach().clone().requires_grad_(True)
+            setattr(pc, name, p)
+            geo_params.append(p)
+
+    def step(v, data):
+        cam = _Cam(cams[v], data["wvt"], data["fpt"], data["center"])
+        if args.workload == "cfg3":
+            pkg = isr.render(cam, pc, _Pipe, bg)
+            n_valid = int(data["valid"].numel())
+            sel = torch.randint(0, n_valid, (wl["samples"],), device=dev, generator=gen)
+            pix = data["valid"][sel].long()
+            labels = data["labels"][pix]
+            feats = isr.sample_pixels(pkg["seg_feature"], pix)
+            loss = isr.contrastive_loss(feats, labels, num_labels=wl["labels"]) * (1e-6 * 0.5)
+            loss.backward()
+            idist.allreduce_grads([pc._seg_feature.grad], world)
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return loss
+        else:
+            pkg = isr.render(cam, pc, _Pipe, bg)
+            # cotangent pattern of train.py:76-104 replaced by seeded random cotangents on the three maps it uses
+            loss = (pkg["render"] * data["dcolor"]).sum() + (pkg["rend_normal"] * data["dothers"][2:5]).sum() \
+                + (pkg["rend_dist"] * data["dothers"][6:7]).sum() + (pkg["surf_depth"] * data["dothers"][0:1]).sum() \
+                + (pkg["rend_alpha"] * data["dothers"][1:2]).sum()
+            loss.backward()
+            idist.allreduce_grads([p.grad for p in geo_params], world)
+            for p in geo_params:
+                p.grad = None
+            return loss
+
+    def timed(n_steps, first, e2e):
+        idist.barrier(world)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h2d = d2h = 0
+        e0.record()
+        last = None
+        for s in range(first, first + n_steps):
+            v = my_views[s]
+            if e2e:
+                data = {k: x.to(dev, non_blocking=True) for k, x in host[v].items()}
+                if s == first:
+                    h2d = sum(x.numel() * x.element_size() for x in host[v].values())
+            else:
+                data = devdata[v]
+            loss = step(v, data)
+            if e2e:
+                last = float(loss.detach().to("cpu", non_blocking=False))  # device -> host read of the step's result
+                d2h = 4
+        e1.record()
+        torch.cuda.synchronize()
+        idist.barrier(world)
+        ms = idist.max_over_ranks(e0.elapsed_time(e1), world, dev)
+        return ms, h2d, d2h, last
+
+    timed(args.warmup, 0, False)  # warm-up (untimed)
+    with ClockSampler(local_rank) as cs:
+        ms, _, _, _ = timed(args.steps, args.warmup, False)
+    clocks = cs.summary()
+    ms_e2e, h2d, d2h, _ = timed(args.steps, args.warmup, True)
+    views = args.steps * world
+    value = views / (ms / 1e3)
+    e2e_value = views / (ms_e2e / 1e3)
+
+    line = {"metric": "views/sec fwd+bwd @1080p", "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "gaussians": P, "feat_dim": F, "image": [W, H],
+                       "views_per_step_per_gpu": 1, "parallelism": f"dp{world} (views sharded, grad all-reduce)",
+                       "l2": "inputs larger than L2 (Gaussian state %.0f MB >> 126 MB), distinct view every step" % (P * (232 + 4 * F) / 1e6),
+                       "optimizer": "adam(fused) on _seg_feature" if args.workload == "cfg3" else "none"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": KERNELS_PER_STEP[args.workload] * args.steps}
+
+    if rank == 0:
+        line["roofline"] = measure_roofline(args, wl, pc, cams, devdata, my_views, dev)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.workload, budget_s=20.0)
+        if world == 1 and not args.no_ref_cuda:
+            rc = ref_cuda_leg(args, wl, pc, cams, devdata, my_views, dev)
+            if rc is not None:
+                line["ref_cuda"] = rc
+        print(json.dumps(line), flush=True)
+    idist.barrier(world)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def measure_roofline(args, wl, pc, cams, devdata, my_views, dev):
+    """Dominant kernel = blend_fwd_kernel.  Re-launches ONLY that kernel (ISR_FLAG_SKIP_BINNING) on an already
+    binned view and times it with CUDA events on the launching (= torch current) stream."""
+    import ctypes as C
+    import torch
+    from instascene_b200 import _lib
+    from instascene_b200.rasterizer import c_rasterize_gaussians
+    P, F, W, H = wl["P"], wl["F"], wl["W"], wl["H"]
+    v = my_views[-1]
+    d = devdata[v]
+    e = torch.empty(0, device=dev)
+    with torch.no_grad():
+        seg = e
+        if F:
+            seg = pc.get_seg_feature
+            seg = (seg / (seg.norm(dim=-1, keepdim=True) + 1e-9)).contiguous()
+        cam = cams[v]
+        res = c_rasterize_gaussians(torch.zeros(3, device=dev), pc.get_xyz.detach(), e, pc.get_opacity.detach(),
+                                    pc.get_scaling.detach(), pc.get_rotation.detach(), 1.0, e, seg, F, d["wvt"], d["fpt"],
+                                    cam.tanfovx, cam.tanfovy, H, W, pc.get_features.detach(), 3, d["center"], False, False,
+                                    want_pairs=True, return_args=True)
+    (R, color, others, radii, extra, geom, binning, img, pairs, pidx, a) = res
+    G = int(pidx.item()) + 1
+    V = int((radii > 0).sum().item())
+    L = _lib.lib()
+    a.flags = a.flags | _lib.FLAG_SKIP_BINNING
+    stream = torch.cuda.current_stream().cuda_stream
+    times = []
+    for i in range(8):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(L.isr_forward_render(C.byref(a), R, stream), "isr_forward_render(blend only)")
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            times.append(e0.elapsed_time(e1))
+    ms = float(np.mean(times))
+    HW = W * H
+    # sorted id (4) + instance record gather (64 + 12 + 4F) per instance, outputs 4*(3+7+F) and
+    # saved per-pixel state (20) per pixel, 8 bytes per emitted pair
+    alg = R * (4 + 64 + 12 + 4 * F) + HW * 4 * (3 + 7 + F) + HW * 20 + 8 * G
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg / (ms / 1e3) / 1e9
+    return {"bound": "hbm", "kernel": "blend_fwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "peak_source": "measured" if peaks else "fallback", "traffic": None,
+            "kernel_ms": ms, "algorithmic_bytes": alg, "R": R, "V": V, "pairs": G,
+            "note": "blend is fp32-ALU bound by construction (every pixel x every tile-list Gaussian); see DESIGN.md"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_baseline(workload: str, budget_s: float = 20.0, steps: int = 1, warmup: int = 0):
+    """The reference has no CPU rasterizer; its algorithm restated in C (oracle/, OpenMP, all host cores) is timed on a
+    bounded sample: one view, ALL Gaussians preprocessed + binned, blend forward + dense backward on every S-th tile,
+    extrapolated to the full view."""
+    from instascene_b200 import synth
+    from oracle import oracle as orc
+    wl = WORKLOADS[workload]
+    P, F, W, H = wl["P"], wl["F"], wl["W"], wl["H"]
+    scene = synth.synth_scene(P, F=F, seed=wl["seed"])
+    cam = synth.ring_cameras(wl["n_views"], W, H)[0]
+    cores = orc.num_threads()
+    kw = dict(scales=scene.scales(), rotations=scene.rotations(), shs=scene.shs(), sh_degree=3,
+              extra_attrs=scene.seg_features())
+    base = (scene.xyz, scene.opacities(), cam.world_view_transform, cam.full_proj_transform, cam.camera_center, W, H,
+            np.zeros(3, np.float32))
+    rng = np.random.default_rng(1)
+    dcolor = rng.standard_normal((3, H, W)).astype(np.float32)
+    dothers = rng.standard_normal((7, H, W)).astype(np.float32)
+    dextra = rng.standard_normal((F, H, W)).astype(np.float32) if F else None
+    # calibration with a coarse sample
+    stride = 64
+    t0 = time.time()
+    fwd = orc.forward(*base, **kw, want_pairs=False, blend=False)
+    t_pre = time.time() - t0
+    t0 = time.time()
+    fwd = orc.forward(*base, **kw, want_pairs=False, tile_stride=stride)
+    t_cal = max(time.time() - t0 - t_pre, 1e-3)
+    est_full_fwd = t_cal * stride
+    per_step = budget_s / max(steps + warmup, 1)
+    stride = int(min(256, max(1, math.ceil(est_full_fwd * 3.0 / max(per_step - t_pre, 1.0)))))
+    results = []
+    for s in range(steps + warmup):
+        t0 = time.time()
+        fwd = orc.forward(*base, **kw, want_pairs=False, tile_stride=stride)
+        t_f = time.time() - t0
+        t1 = time.time()
+        orc.backward(fwd, scene.xyz, cam.world_view_transform, cam.full_proj_transform, cam.camera_center, W, H,
+                     np.zeros(3, np.float32), cam.tanfovx, cam.tanfovy, dcolor, dothers, dextra, **kw, tile_stride=stride)
+        t_b = time.time() - t1
+        # preprocessing/binning/K8 run on all Gaussians; only the per-tile blends are sampled
+        t_view = t_pre + (t_f - t_pre) * stride + t_b * stride
+        if s >= warmup:
+            results.append(t_view)
+    t_view = float(np.mean(results))
+    return {"value": 1.0 / t_view, "unit": "views/s", "cores": cores, "kind": "port",
+            "sample": f"1 view of {wl['desc'].split(':')[0]}: all {P} Gaussians projected+sorted, blend fwd + dense bwd on "
+                      f"every {stride}-th of {((W + 15) // 16) * ((H + 15) // 16)} tiles, extrapolated x{stride}",
+            "seconds_per_view_extrapolated": t_view}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's algorithm on the host cores (oracle port; the reference ships no CPU path)."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    t0 = time.time()
+    cb = cpu_baseline(args.workload, budget_s=150.0, steps=args.steps, warmup=args.warmup)
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    line = {"impl": "reference", "metric": "views/sec fwd+bwd @1080p", "value": cb["value"], "unit": "views/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * cb["seconds_per_view_extrapolated"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "gaussians": wl["P"], "feat_dim": wl["F"], "image": [wl["W"], wl["H"]]},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.time() - t0, "world_size_env": world}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def ref_cuda_leg(args, wl, pc, cams, devdata, my_views, dev, n=4):
+    """Extra baseline: the UNMODIFIED reference CUDA rasterizer (baseline/_ref) driven through the reference's own
+    render() / contrastive_loss on the same inputs, timed in the same run with CUDA events."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    try:
+        import ref_loader
+        if not ref_loader.available():
+            return None
+        rrender, rloss, _ = ref_loader.load()
+    except Exception as ex:  # noqa: BLE001
+        return {"unavailable": repr(ex)[:200]}
+    F, W, H = wl["F"], wl["W"], wl["H"]
+    bg = torch.zeros(3, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99)
+
+    def step(v):
+        d = devdata[v]
+        cam = _Cam(cams[v], d["wvt"], d["fpt"], d["center"])
+        pkg = rrender(cam, pc, _Pipe, bg)
+        if args.workload == "cfg3":
+            segmap = d["labels"].reshape(H, W)
+            mask = segmap > 0                                     # train_semantic.py:118-129
+            valid_feat = pkg["seg_feature"][:, mask]
+            valid_lab = segmap[mask]
+            idx = torch.randint(0, len(valid_lab), size=(wl["samples"],), device=dev, generator=gen)
+            loss = rloss(valid_feat[:, idx].T, valid_lab[idx].long()) * (1e-6 * 0.5)
+            loss.backward()
+            pc._seg_feature.grad = None
+        else:
+            loss = (pkg["render"] * d["dcolor"]).sum() + (pkg["rend_normal"] * d["dothers"][2:5]).sum() \
+                + (pkg["rend_dist"] * d["dothers"][6:7]).sum() + (pkg["surf_depth"] * d["dothers"][0:1]).sum() \
+                + (pkg["rend_alpha"] * d["dothers"][1:2]).sum()
+            loss.backward()
+            for name in ("get_xyz", "get_scaling", "get_rotation", "get_opacity", "get_features"):
+                getattr(pc, name).grad = None
+
+    views = [my_views[i % len(my_views)] for i in range(n + 2)]
+    for v in views[:2]:
+        step(v)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for v in views[2:]:
+        step(v)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"value": 1e3 / ms, "unit": "views/s", "ms_per_step": ms, "steps": n,
+            "what": "unmodified reference CUDA (diff_surfel_rasterization built for sm_100a) via its own render()/contrastive_loss, no optimizer step"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

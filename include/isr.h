@@ -1,0 +1,213 @@
+/*
+ * isr.h -- C ABI of libisr.so, the B200 (sm_100a) surfel rasterizer for InstaScene.
+ *
+ * Drop-in boundary for the reference's native op  diff_surfel_rasterization._C  (DSR/ =
+ * submodules/diff-surfel-rasterization) plus simple_knn._C.distCUDA2 and the sampled-pixel contrastive
+ * loss.  Plain pointers and sizes only: no torch / glm / CUDA types in any signature.  All pointers are
+ * DEVICE pointers unless the name ends in _host.  `stream` is a cudaStream_t passed as void*.
+ * Every function returns 0 (ISR_OK) or a negative IsrStatus; nothing ever synchronises the device except
+ * where stated.  The library owns no memory: outputs, gradients and workspaces are allocated by the
+ * caller (DSR/rasterize_points.cu:88-109 does the same with torch tensors).
+ *
+ * Reference interface each entry point replaces (file:line relative to /root/reference):
+ *   isr_forward_geometry + isr_forward_render  <- CudaRasterizer::Rasterizer::forward
+ *                                                 DSR/cuda_rasterizer/rasterizer.h:31-58,
+ *                                                 DSR/cuda_rasterizer/rasterizer_impl.cu:198-351,
+ *                                                 bound as _C.rasterize_gaussians (DSR/ext.cpp:16,
+ *                                                 DSR/rasterize_points.cu:39-151)
+ *   isr_backward                               <- Rasterizer::backward  rasterizer.h:60-93,
+ *                                                 rasterizer_impl.cu:355-463, bound as
+ *                                                 _C.rasterize_gaussians_backward (DSR/ext.cpp:17,
+ *                                                 DSR/rasterize_points.cu:153-262)
+ *   isr_backward_extra_sparse                  <- same, restricted to dL/d(extra_attrs) for a list of
+ *                                                 sampled pixels (the only non-zero cotangents in
+ *                                                 train_semantic.py:118-141)
+ *   isr_mark_visible                           <- Rasterizer::markVisible rasterizer.h:24-29,
+ *                                                 rasterizer_impl.cu:141-153 (_C.mark_visible, ext.cpp:18)
+ *   isr_geom_bytes / isr_image_bytes / isr_binning_bytes
+ *                                              <- required<GeometryState|ImageState|BinningState>()
+ *                                                 DSR/cuda_rasterizer/rasterizer_impl.h:29-72
+ *   isr_contrastive_forward / _backward        <- utils/contrastive_utils.py:18-73 (contrastive_loss)
+ *   isr_gather_pixels                          <- train_semantic.py:124-129 (boolean-mask gather + index)
+ *   isr_knn_mean_dist2                         <- SimpleKNN::knn submodules/simple-knn/simple_knn.cu:186-222
+ *                                                 (distCUDA2, submodules/simple-knn/spatial.cu:15-25)
+ */
+#ifndef ISR_H_INCLUDED
+#define ISR_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISR_VERSION 100
+
+typedef enum IsrStatus {
+    ISR_OK = 0,
+    ISR_ERR_INVALID_ARG = -1,   /* null pointer / negative size / inconsistent optional inputs          */
+    ISR_ERR_UNSUPPORTED = -2,   /* e.g. extra dims F > ISR_MAX_EXTRA_DIMS                                */
+    ISR_ERR_WORKSPACE = -3,     /* a workspace is smaller than isr_*_bytes() says                        */
+    ISR_ERR_CUDA = -4,          /* a CUDA call failed; isr_last_cuda_error() has the code                */
+    ISR_ERR_NO_DEVICE = -5      /* no sm_100 device / kernels not loadable                                */
+} IsrStatus;
+
+#define ISR_MAX_EXTRA_DIMS 32   /* reference: MAX_EXTRA_DIMS 24 (DSR/cuda_rasterizer/auxiliary.h:20)      */
+#define ISR_TILE 16             /* BLOCK_X = BLOCK_Y = 16 (DSR/cuda_rasterizer/config.h:16-17)            */
+
+/* flags */
+#define ISR_FLAG_BWD_WH_QUIRK 1u  /* backward uses W,H = int(focal*tan*2) like backward.cu:633-634 (Q5)   */
+#define ISR_FLAG_NO_PAIRS     2u  /* do not emit the gau_related_pixels list                              */
+#define ISR_FLAG_SKIP_BINNING 4u  /* isr_forward_render: reuse the binning already in the workspaces and run
+                                     only the blend kernel (profiling / roofline measurement)              */
+
+/* gradient request mask for isr_backward (needs_input_grad gating; all = reference behaviour) */
+#define ISR_GRAD_GEOMETRY 1u   /* means3D, means2D, scales, rotations, transMat, normal                  */
+#define ISR_GRAD_COLOR    2u   /* colors_precomp / SH                                                    */
+#define ISR_GRAD_OPACITY  4u
+#define ISR_GRAD_EXTRA    8u
+#define ISR_GRAD_ALL      15u
+
+int isr_version(void);
+const char* isr_status_string(int status);
+int isr_last_cuda_error(void);              /* cudaError_t of the last failing CUDA call on this thread    */
+int isr_device_sm_count(void);              /* SM count of the current device, or a negative IsrStatus    */
+
+/* ---- workspace sizes --------------------------------------------------------------------------------- */
+size_t isr_geom_bytes(int P);               /* per-Gaussian state saved for backward                       */
+size_t isr_image_bytes(int W, int H);       /* per-pixel state saved for backward + per-tile ranges        */
+size_t isr_binning_bytes(int P, int64_t R, int W, int H);  /* sorted instance list + sort scratch          */
+
+/* Offsets (in bytes) of the fields inside the geometry / image / binning workspaces, so that tests and
+ * tools can compare intermediates with the oracle.  Field ids: */
+enum IsrField {
+    ISR_GEOM_SPLAT = 0,      /* float[P][16]: Tu[3] Tv[3] Tw[3] mean2D[2] normal[3] opacity, alpha-cut power  */
+    ISR_GEOM_RGB = 1,        /* float[P][4]:  rgb, unused                                                 */
+    ISR_GEOM_DEPTH = 2,      /* float[P]                                                                  */
+    ISR_GEOM_TILES = 3,      /* uint32[P] tiles_touched                                                   */
+    ISR_GEOM_CLAMPED = 4,    /* uint8[P]  bit c set <=> SH colour channel c was clamped                    */
+    ISR_GEOM_DEPTH_ORDER = 5,/* uint32[P] Gaussian ids in ascending (depth bits, id) order                */
+    ISR_GEOM_OFFSETS = 6,    /* uint32[P] exclusive scan of tiles_touched in depth order                  */
+    ISR_IMG_FINAL_T = 16,    /* float[3][H*W]: T, M1, M2                                                  */
+    ISR_IMG_NCONTRIB = 17,   /* uint32[2][H*W]: last contributor, median contributor                      */
+    ISR_IMG_RANGES = 18,     /* uint32[tiles][2]                                                          */
+    ISR_BIN_POINT_LIST = 32  /* uint32[R] Gaussian ids sorted by (tile, depth bits, id)                    */
+};
+int64_t isr_field_offset(int field, int P, int64_t R, int W, int H);   /* <0: unknown field               */
+
+/* ---- forward ----------------------------------------------------------------------------------------- */
+typedef struct IsrForwardArgs {
+    /* sizes */
+    int P;                 /* number of Gaussians                                                         */
+    int sh_degree;         /* active SH degree D (0..3)                                                   */
+    int sh_coeffs;         /* M: coefficients per Gaussian in `shs` (0 if shs == NULL)                     */
+    int F;                 /* extra (semantic feature) dims, 0..ISR_MAX_EXTRA_DIMS                        */
+    int W, H;
+    unsigned flags;
+    /* camera */
+    float tan_fovx, tan_fovy;
+    float scale_modifier;
+    const float* background;    /* [3]                                                                    */
+    const float* viewmatrix;    /* [16] world_view_transform, m[4*col+row]                                */
+    const float* projmatrix;    /* [16] full_proj_transform                                               */
+    const float* campos;        /* [3]                                                                    */
+    /* Gaussians (row-major fp32); exactly one of shs/colors_precomp and of (scales,rotations)/transMat_precomp */
+    const float* means3D;       /* [P,3]                                                                  */
+    const float* opacities;     /* [P]                                                                    */
+    const float* scales;        /* [P,2] or NULL                                                          */
+    const float* rotations;     /* [P,4] (w,x,y,z) or NULL                                                */
+    const float* transMat_precomp; /* [P,9] or NULL                                                       */
+    const float* shs;           /* [P,M,3] or NULL                                                        */
+    const float* colors_precomp;/* [P,3] or NULL                                                          */
+    const float* extra_attrs;   /* [P,F] or NULL when F == 0                                              */
+    /* workspaces */
+    void* geom;  size_t geom_bytes;
+    void* image; size_t image_bytes;
+    void* binning; size_t binning_bytes;      /* only needed by isr_forward_render                        */
+    /* outputs */
+    int* radii;                 /* [P] int32                                                              */
+    float* out_color;           /* [3,H,W]                                                                */
+    float* out_others;          /* [7,H,W]: depth, alpha, normal xyz, median depth, distortion            */
+    float* out_extra;           /* [F,H,W] or NULL                                                        */
+    int* pairs;                 /* [pair_capacity,2] (gaussian id, pixel id) or NULL                      */
+    int64_t pair_capacity;      /* 9*H*W always suffices (sum of weights <= 1, each weight > 0.1)         */
+    int* pair_count;            /* device int32: number of pairs written (NOT count-1 as in the reference)*/
+    int64_t* num_rendered_host; /* pinned HOST int64 written asynchronously by isr_forward_geometry       */
+} IsrForwardArgs;
+
+/* Phase A: K1 preprocess + depth ordering + offsets.  Enqueues an async copy of R (= num_rendered) into
+ * *num_rendered_host; the caller synchronises `stream`, sizes the binning workspace with
+ * isr_binning_bytes(P, R, W, H) and calls phase B.  (The reference blocks on a cudaMemcpy at the same
+ * point, rasterizer_impl.cu:287.) */
+int isr_forward_geometry(const IsrForwardArgs* args, void* stream);
+/* Phase B: instance emission, stable tile sort, tile ranges, front-to-back blend. */
+int isr_forward_render(const IsrForwardArgs* args, int64_t num_rendered, void* stream);
+
+/* ---- backward ---------------------------------------------------------------------------------------- */
+typedef struct IsrBackwardArgs {
+    int P, sh_degree, sh_coeffs, F, W, H;
+    unsigned flags;
+    unsigned grad_mask;         /* ISR_GRAD_*                                                             */
+    int64_t num_rendered;
+    float tan_fovx, tan_fovy, scale_modifier;
+    const float* background; const float* viewmatrix; const float* projmatrix; const float* campos;
+    const float* means3D; const float* scales; const float* rotations; const float* transMat_precomp;
+    const float* shs; const float* colors_precomp; const float* extra_attrs;
+    const int* radii;
+    const void* geom; const void* image; const void* binning;   /* as filled by the forward               */
+    /* cotangents (CHW); NULL == all zeros */
+    const float* dL_dcolor;     /* [3,H,W]                                                                */
+    const float* dL_dothers;    /* [7,H,W]                                                                */
+    const float* dL_dextra_pix; /* [F,H,W]                                                                */
+    /* gradients; every requested buffer must be ZERO-FILLED by the caller (the reference binding does the
+     * same with torch::zeros, rasterize_points.cu:207-220); NULL where not requested by grad_mask */
+    float* dL_dmeans2D;   /* [P,3] */
+    float* dL_dnormal;    /* [P,3] */
+    float* dL_dopacity;   /* [P]   */
+    float* dL_dcolors;    /* [P,3] */
+    float* dL_dmeans3D;   /* [P,3] */
+    float* dL_dtransMat;  /* [P,9] */
+    float* dL_dsh;        /* [P,M,3] */
+    float* dL_dscales;    /* [P,2] */
+    float* dL_drotations; /* [P,4] */
+    float* dL_dextra;     /* [P,F] */
+} IsrBackwardArgs;
+
+int isr_backward(const IsrBackwardArgs* args, void* stream);
+
+/* dL/d(extra_attrs) only, for `n` sampled pixels: pix_ids[n] (= W*y+x, duplicates allowed) with cotangent
+ * rows dL_dextra_samples[n,F].  Exactly equal (up to fp32 summation order) to isr_backward with a dense
+ * [F,H,W] cotangent that is zero everywhere else.  dL_dextra [P,F] must be zero-filled by the caller. */
+int isr_backward_extra_sparse(int P, int F, int W, int H, const float* extra_attrs, const void* geom,
+                              const void* image, const void* binning, int64_t num_rendered, int n,
+                              const int* pix_ids, const float* dL_dextra_samples, float* dL_dextra,
+                              void* stream);
+
+int isr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream);
+
+/* ---- sampled-pixel gather + ProtoNCE contrastive loss -------------------------------------------------- */
+/* out[n,F] = feature_map[:, pix_ids[n]] for a CHW map [F, HW] */
+int isr_gather_pixels(int F, int64_t HW, const float* feature_map, int n, const int* pix_ids, float* out,
+                      void* stream);
+
+size_t isr_contrastive_workspace_bytes(int N, int F, int K);
+/* features [N,F], labels [N] int32 already shifted so that valid labels are 0..K-1 and invalid ones < 0;
+ * predef_u [K,F] or NULL (cluster means).  Writes *loss (device float) and saves what backward needs in ws. */
+int isr_contrastive_forward(int N, int F, int K, const float* features, const int* labels,
+                            const float* predef_u, float temp_lambda, void* ws, size_t ws_bytes,
+                            float* loss, void* stream);
+/* dL_dfeatures[N,F] = grad_scale * d loss / d features */
+int isr_contrastive_backward(int N, int F, int K, const float* features, const int* labels,
+                             const float* predef_u, const void* ws, const float* grad_scale,
+                             float* dL_dfeatures, void* stream);
+
+/* ---- simple-knn ------------------------------------------------------------------------------------- */
+size_t isr_knn_workspace_bytes(int P);
+int isr_knn_mean_dist2(int P, const float* points, float* mean_dist2, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISR_H_INCLUDED */

@@ -1,0 +1,218 @@
+// isr_api.cu -- the extern "C" boundary declared in include/isr.h.
+#include <cstdio>
+
+#include "isr_common.cuh"
+
+namespace isr {
+static thread_local cudaError_t g_last_cuda_error = cudaSuccess;
+void set_last_cuda_error(cudaError_t e) { g_last_cuda_error = e; }
+
+int launch_preprocess_fwd(const IsrForwardArgs& a, cudaStream_t stream);
+int launch_depth_order_and_offsets(const IsrForwardArgs& a, cudaStream_t stream);
+int launch_binning(const IsrForwardArgs& a, int64_t R, cudaStream_t stream);
+int launch_blend_fwd(const IsrForwardArgs& a, cudaStream_t stream);
+int launch_blend_bwd(const IsrBackwardArgs& a, cudaStream_t stream);
+int launch_preprocess_bwd(const IsrBackwardArgs& a, cudaStream_t stream);
+int launch_extra_sparse_bwd(int P, int F, int W, int H, const void* geom, const void* image, const void* binning, int n,
+                            const int* pix_ids, const float* dLdE, float* dL_dextra, cudaStream_t stream);
+int launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, uint8_t* present,
+                        cudaStream_t stream);
+size_t contrastive_ws_bytes(int N, int F, int K);
+int launch_gather_pixels(int F, int64_t HW, const float* map, int n, const int* pix_ids, float* out, cudaStream_t stream);
+int launch_contrastive_fwd(int N, int F, int K, const float* features, const int* labels, const float* predef_u,
+                           float temp_lambda, void* ws, float* loss, cudaStream_t stream);
+int launch_contrastive_bwd(int N, int F, int K, const int* labels, const float* predef_u, const void* ws,
+                           const float* grad_scale, float* dfeat, cudaStream_t stream);
+size_t knn_ws_bytes(int P);
+int launch_knn(int P, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
+}  // namespace isr
+
+using namespace isr;
+
+extern "C" {
+
+int isr_version(void) { return ISR_VERSION; }
+
+const char* isr_status_string(int status) {
+    switch (status) {
+        case ISR_OK: return "ok";
+        case ISR_ERR_INVALID_ARG: return "invalid argument";
+        case ISR_ERR_UNSUPPORTED: return "unsupported configuration";
+        case ISR_ERR_WORKSPACE: return "workspace too small";
+        case ISR_ERR_CUDA: return "CUDA error";
+        case ISR_ERR_NO_DEVICE: return "no usable CUDA device";
+        default: return "unknown status";
+    }
+}
+
+int isr_last_cuda_error(void) { return (int)g_last_cuda_error; }
+
+int isr_device_sm_count(void) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return ISR_ERR_NO_DEVICE;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return ISR_ERR_NO_DEVICE;
+    return n;
+}
+
+size_t isr_geom_bytes(int P) { return GeomLayout(P).total + 256; }
+size_t isr_image_bytes(int W, int H) { return ImageLayout(W, H).total + 256; }
+size_t isr_binning_bytes(int P, int64_t R, int W, int H) { return BinLayout(P, R, W, H).total + 256; }
+
+int64_t isr_field_offset(int field, int P, int64_t R, int W, int H) {
+    switch (field) {
+        case ISR_GEOM_SPLAT: return (int64_t)GeomLayout(P).splat;
+        case ISR_GEOM_RGB: return (int64_t)GeomLayout(P).rgb;
+        case ISR_GEOM_DEPTH: return (int64_t)GeomLayout(P).depth;
+        case ISR_GEOM_TILES: return (int64_t)GeomLayout(P).tiles;
+        case ISR_GEOM_CLAMPED: return (int64_t)GeomLayout(P).clamped;
+        case ISR_GEOM_DEPTH_ORDER: return (int64_t)GeomLayout(P).order;
+        case ISR_GEOM_OFFSETS: return (int64_t)GeomLayout(P).offsets;
+        case ISR_IMG_FINAL_T: return (int64_t)ImageLayout(W, H).final_T;
+        case ISR_IMG_NCONTRIB: return (int64_t)ImageLayout(W, H).n_contrib;
+        case ISR_IMG_RANGES: return (int64_t)ImageLayout(W, H).ranges;
+        case ISR_BIN_POINT_LIST: return (int64_t)BinLayout(P, R, W, H).point_list;
+        default: return -1;
+    }
+}
+
+static int check_forward_args(const IsrForwardArgs* a) {
+    if (!a) return ISR_ERR_INVALID_ARG;
+    if (a->P < 0 || a->W <= 0 || a->H <= 0 || a->F < 0) return ISR_ERR_INVALID_ARG;
+    if (a->F > ISR_MAX_EXTRA_DIMS) return ISR_ERR_UNSUPPORTED;
+    if (a->P == 0) return ISR_OK;
+    if (!a->means3D || !a->opacities || !a->viewmatrix || !a->projmatrix || !a->background) return ISR_ERR_INVALID_ARG;
+    // exactly one of SH / precomputed colours, exactly one of (scales, rotations) / transMat_precomp
+    if ((a->shs == nullptr) == (a->colors_precomp == nullptr)) return ISR_ERR_INVALID_ARG;
+    const bool has_sr = a->scales != nullptr && a->rotations != nullptr;
+    if (has_sr == (a->transMat_precomp != nullptr)) return ISR_ERR_INVALID_ARG;
+    if (!has_sr && (a->scales != nullptr || a->rotations != nullptr)) return ISR_ERR_INVALID_ARG;
+    if (a->shs && (!a->campos || a->sh_coeffs < (a->sh_degree + 1) * (a->sh_degree + 1) || a->sh_degree < 0 || a->sh_degree > 3))
+        return ISR_ERR_INVALID_ARG;
+    if (a->F > 0 && (!a->extra_attrs || !a->out_extra)) return ISR_ERR_INVALID_ARG;
+    if (!a->geom || !a->image || !a->radii || !a->out_color || !a->out_others) return ISR_ERR_INVALID_ARG;
+    if (a->geom_bytes < GeomLayout(a->P).total || a->image_bytes < ImageLayout(a->W, a->H).total) return ISR_ERR_WORKSPACE;
+    return ISR_OK;
+}
+
+int isr_forward_geometry(const IsrForwardArgs* a, void* stream_) {
+    int st = check_forward_args(a);
+    if (st != ISR_OK) return st;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (a->P == 0) {
+        if (a->num_rendered_host) *a->num_rendered_host = 0;
+        return ISR_OK;
+    }
+    st = launch_preprocess_fwd(*a, stream);
+    if (st != ISR_OK) return st;
+    return launch_depth_order_and_offsets(*a, stream);
+}
+
+int isr_forward_render(const IsrForwardArgs* a, int64_t R, void* stream_) {
+    int st = check_forward_args(a);
+    if (st != ISR_OK) return st;
+    if (R < 0 || R > 0x7fffffffLL) return ISR_ERR_INVALID_ARG;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (a->pair_count) ISR_CUDA_TRY(cudaMemsetAsync(a->pair_count, 0, sizeof(int), stream));
+    if (a->P > 0 && R > 0) {
+        if (!a->binning || a->binning_bytes < BinLayout(a->P, R, a->W, a->H).total) return ISR_ERR_WORKSPACE;
+    }
+    if (!(a->flags & ISR_FLAG_SKIP_BINNING)) {
+        st = launch_binning(*a, a->P > 0 ? R : 0, stream);
+        if (st != ISR_OK) return st;
+    }
+    // With no instances every tile range is (0,0): the blend kernel still runs to write background / zeros.
+    return launch_blend_fwd(*a, stream);
+}
+
+int isr_backward(const IsrBackwardArgs* a, void* stream_) {
+    if (!a) return ISR_ERR_INVALID_ARG;
+    if (a->P < 0 || a->W <= 0 || a->H <= 0 || a->F < 0) return ISR_ERR_INVALID_ARG;
+    if (a->F > ISR_MAX_EXTRA_DIMS) return ISR_ERR_UNSUPPORTED;
+    if (a->P == 0) return ISR_OK;
+    if (!a->geom || !a->image || !a->radii || !a->means3D || !a->viewmatrix || !a->projmatrix || !a->background)
+        return ISR_ERR_INVALID_ARG;
+    if (a->num_rendered > 0 && !a->binning) return ISR_ERR_INVALID_ARG;
+    const unsigned m = a->grad_mask;
+    if ((m & ISR_GRAD_GEOMETRY) && (!a->dL_dmeans2D || !a->dL_dnormal || !a->dL_dtransMat || !a->dL_dmeans3D))
+        return ISR_ERR_INVALID_ARG;
+    if ((m & ISR_GRAD_GEOMETRY) && a->scales && (!a->dL_dscales || !a->dL_drotations)) return ISR_ERR_INVALID_ARG;
+    if ((m & ISR_GRAD_COLOR) && !a->dL_dcolors) return ISR_ERR_INVALID_ARG;
+    if ((m & ISR_GRAD_OPACITY) && !a->dL_dopacity) return ISR_ERR_INVALID_ARG;
+    if ((m & ISR_GRAD_EXTRA) && a->F > 0 && !a->dL_dextra) return ISR_ERR_INVALID_ARG;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int st = launch_blend_bwd(*a, stream);
+    if (st != ISR_OK) return st;
+    // K8 needs the geometry-gradient buffers (it also produces the SH gradient from dL_dcolors)
+    if ((m & ISR_GRAD_GEOMETRY) && (m & ISR_GRAD_COLOR)) return launch_preprocess_bwd(*a, stream);
+    if (m & (ISR_GRAD_GEOMETRY | ISR_GRAD_COLOR)) {
+        // partial requests: run K8 only when everything it touches is present
+        if (a->dL_dmeans2D && a->dL_dnormal && a->dL_dtransMat && a->dL_dmeans3D && a->dL_dcolors)
+            return launch_preprocess_bwd(*a, stream);
+    }
+    return ISR_OK;
+}
+
+int isr_backward_extra_sparse(int P, int F, int W, int H, const float* extra_attrs, const void* geom, const void* image,
+                              const void* binning, int64_t num_rendered, int n, const int* pix_ids,
+                              const float* dL_dextra_samples, float* dL_dextra, void* stream_) {
+    (void)extra_attrs;
+    if (P < 0 || F < 0 || W <= 0 || H <= 0 || n < 0) return ISR_ERR_INVALID_ARG;
+    if (F > ISR_MAX_EXTRA_DIMS) return ISR_ERR_UNSUPPORTED;
+    if (P == 0 || n == 0 || F == 0 || num_rendered <= 0) return ISR_OK;
+    if (!geom || !image || !binning || !pix_ids || !dL_dextra_samples || !dL_dextra) return ISR_ERR_INVALID_ARG;
+    return launch_extra_sparse_bwd(P, F, W, H, geom, image, binning, n, pix_ids, dL_dextra_samples, dL_dextra,
+                                   static_cast<cudaStream_t>(stream_));
+}
+
+int isr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
+                     void* stream_) {
+    if (P < 0) return ISR_ERR_INVALID_ARG;
+    if (P == 0) return ISR_OK;
+    if (!means3D || !viewmatrix || !present) return ISR_ERR_INVALID_ARG;
+    return launch_mark_visible(P, means3D, viewmatrix, projmatrix, present, static_cast<cudaStream_t>(stream_));
+}
+
+int isr_gather_pixels(int F, int64_t HW, const float* feature_map, int n, const int* pix_ids, float* out, void* stream_) {
+    if (F < 0 || n < 0 || HW < 0) return ISR_ERR_INVALID_ARG;
+    if (F == 0 || n == 0) return ISR_OK;
+    if (!feature_map || !pix_ids || !out) return ISR_ERR_INVALID_ARG;
+    return launch_gather_pixels(F, HW, feature_map, n, pix_ids, out, static_cast<cudaStream_t>(stream_));
+}
+
+size_t isr_contrastive_workspace_bytes(int N, int F, int K) {
+    if (N < 0 || F < 0 || K < 0) return 0;
+    return contrastive_ws_bytes(N, F, K) + 256;
+}
+
+int isr_contrastive_forward(int N, int F, int K, const float* features, const int* labels, const float* predef_u,
+                            float temp_lambda, void* ws, size_t ws_bytes, float* loss, void* stream_) {
+    if (N < 0 || F <= 0 || K < 0 || !loss) return ISR_ERR_INVALID_ARG;
+    if (F > ISR_MAX_EXTRA_DIMS) return ISR_ERR_UNSUPPORTED;
+    if (N > 0 && (!features || !labels || !ws)) return ISR_ERR_INVALID_ARG;
+    if (ws_bytes < contrastive_ws_bytes(N, F, K)) return ISR_ERR_WORKSPACE;
+    if ((size_t)K * (F + 1) * sizeof(float) > 200 * 1024) return ISR_ERR_UNSUPPORTED;
+    return launch_contrastive_fwd(N, F, K, features, labels, predef_u, temp_lambda, ws, loss,
+                                  static_cast<cudaStream_t>(stream_));
+}
+
+int isr_contrastive_backward(int N, int F, int K, const float* features, const int* labels, const float* predef_u,
+                             const void* ws, const float* grad_scale, float* dL_dfeatures, void* stream_) {
+    (void)features;
+    if (N < 0 || F <= 0 || K < 0) return ISR_ERR_INVALID_ARG;
+    if (F > ISR_MAX_EXTRA_DIMS) return ISR_ERR_UNSUPPORTED;
+    if (N > 0 && (!labels || !ws || !dL_dfeatures)) return ISR_ERR_INVALID_ARG;
+    return launch_contrastive_bwd(N, F, K, labels, predef_u, ws, grad_scale, dL_dfeatures,
+                                  static_cast<cudaStream_t>(stream_));
+}
+
+size_t isr_knn_workspace_bytes(int P) { return P < 0 ? 0 : knn_ws_bytes(P) + 256; }
+
+int isr_knn_mean_dist2(int P, const float* points, float* mean_dist2, void* ws, size_t ws_bytes, void* stream_) {
+    if (P < 0) return ISR_ERR_INVALID_ARG;
+    if (P == 0) return ISR_OK;
+    if (!points || !mean_dist2 || !ws) return ISR_ERR_INVALID_ARG;
+    if (ws_bytes < knn_ws_bytes(P)) return ISR_ERR_WORKSPACE;
+    return launch_knn(P, points, mean_dist2, ws, ws_bytes, static_cast<cudaStream_t>(stream_));
+}
+
+}  // extern "C"

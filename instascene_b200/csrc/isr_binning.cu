@@ -1,0 +1,166 @@
+// isr_binning.cu -- tile binning and per-tile depth ordering.
+//
+// Reference (DSR/cuda_rasterizer/rasterizer_impl.cu:283-324): scan tiles_touched in Gaussian-id order, emit
+// one 64-bit key (tile<<32 | depth bits) per (Gaussian, tile) instance, ONE stable radix sort of R 12-byte
+// pairs over 32+log2(tiles) bits (6 onesweep passes at 1080p), then identifyTileRanges.
+//
+// Here (same resulting order, bit for bit):
+//   1. stable sort of the P Gaussians by depth bits (culled ones carry key 0xFFFFFFFF and sink to the end)
+//   2. exclusive scan of tiles_touched in that depth order -> instance offsets, R
+//   3. emission of (tile id, Gaussian id) in depth order
+//   4. stable sort of the R instances by tile id ONLY (13 bits at 1080p = 2 onesweep passes of 8-byte pairs)
+//   5. tile ranges from the sorted tile ids
+// Because both sorts are stable, instances of a tile end up ordered by (depth bits, Gaussian id) -- exactly
+// the reference's (tile, depth, id) order (ties: SURVEY.md Q2) -- while the R-sized traffic drops ~6x.
+// The radix-sort/scan primitives are CUB (CUDA toolkit), as in the reference.
+#include <cub/cub.cuh>
+
+#include "isr_common.cuh"
+
+namespace isr {
+
+struct TilesInDepthOrder {
+    const uint32_t* tiles;
+    const uint32_t* order;
+    __host__ __device__ uint32_t operator()(int i) const { return tiles[order[i]]; }
+};
+
+size_t sort_temp_bytes_gauss(int P) {
+    if (P <= 0) return 256;
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, P, 0, 32);
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr, P + 1);
+    return align_up((a > b ? a : b) + 256, 256);
+}
+
+size_t sort_temp_bytes_inst(int64_t R, int num_tiles) {
+    if (R <= 0) return 256;
+    size_t a = 0;
+    int bits = 1;
+    while ((1 << bits) < num_tiles) bits++;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)R, 0, bits);
+    return align_up(a + 256, 256);
+}
+
+__global__ void iota_kernel(int n, uint32_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)i;
+}
+
+// gathered[i] = tiles[order[i]] for i < P, gathered[P] = 0  (so that an exclusive scan over P+1 items leaves
+// R in offsets[P])
+__global__ void gather_tiles_kernel(int P, const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ order,
+                                    uint32_t* __restrict__ gathered) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) gathered[i] = tiles[order[i]];
+    else if (i == P) gathered[i] = 0;
+}
+
+__global__ void copy_count_kernel(const uint32_t* __restrict__ offsets, int P, int64_t* __restrict__ out) {
+    *out = (int64_t)offsets[P];
+}
+
+// One thread per Gaussian in depth order (DSR duplicateWithKeys, rasterizer_impl.cu:70-111).
+__global__ void __launch_bounds__(256)
+emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
+                      const int* __restrict__ radii, const Splat* __restrict__ splats, int gx, int gy,
+                      uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ gauss_ids) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const uint32_t g = order[i];
+    const int r = radii[g];
+    if (r <= 0) return;
+    uint32_t off = offsets[i];
+    int mnx, mny, mxx, mxy;
+    get_rect(splats[g].mx, splats[g].my, r, gx, gy, mnx, mny, mxx, mxy);
+    for (int y = mny; y < mxy; y++)
+        for (int x = mnx; x < mxx; x++) {
+            tile_keys[off] = (uint32_t)(y * gx + x);
+            gauss_ids[off] = g;
+            off++;
+        }
+}
+
+// DSR identifyTileRanges (rasterizer_impl.cu:116-138) on 32-bit tile keys.
+__global__ void tile_ranges_kernel(int64_t R, const uint32_t* __restrict__ keys, uint2* __restrict__ ranges) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const uint32_t cur = keys[i];
+    if (i == 0) ranges[cur].x = 0;
+    else {
+        const uint32_t prev = keys[i - 1];
+        if (cur != prev) {
+            ranges[prev].y = (uint32_t)i;
+            ranges[cur].x = (uint32_t)i;
+        }
+    }
+    if (i == R - 1) ranges[cur].y = (uint32_t)R;
+}
+
+// Phase A tail: depth order + offsets + R -> pinned host.
+int launch_depth_order_and_offsets(const IsrForwardArgs& a, cudaStream_t stream) {
+    const int P = a.P;
+    GeomLayout gl(P);
+    char* g = static_cast<char*>(a.geom);
+    uint32_t* order = reinterpret_cast<uint32_t*>(g + gl.order);
+    uint32_t* order_alt = reinterpret_cast<uint32_t*>(g + gl.order_alt);
+    uint32_t* keys = reinterpret_cast<uint32_t*>(g + gl.depth_key);
+    uint32_t* keys_alt = reinterpret_cast<uint32_t*>(g + gl.keys_alt);
+    uint32_t* tiles = reinterpret_cast<uint32_t*>(g + gl.tiles);
+    uint32_t* offsets = reinterpret_cast<uint32_t*>(g + gl.offsets);
+    void* temp = g + gl.sort_temp;
+    size_t temp_bytes = gl.sort_temp_bytes;
+    iota_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, order_alt);
+    ISR_CUDA_TRY(cudaGetLastError());
+    // stable: equal depth bits keep ascending Gaussian id
+    ISR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_alt, order_alt, order, P, 0, 32, stream));
+    // keys_alt now holds sorted keys (unused afterwards) -> reuse it for the gathered tile counts
+    gather_tiles_kernel<<<(P + 1 + 255) / 256, 256, 0, stream>>>(P, tiles, order, keys_alt);
+    ISR_CUDA_TRY(cudaGetLastError());
+    temp_bytes = gl.sort_temp_bytes;
+    ISR_CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, keys_alt, offsets, P + 1, stream));
+    if (a.num_rendered_host != nullptr) {
+        // offsets[P] (uint32) -> int64 on the host; widen on the device into the scratch first
+        int64_t* wide = reinterpret_cast<int64_t*>(temp);
+        copy_count_kernel<<<1, 1, 0, stream>>>(offsets, P, wide);
+        ISR_CUDA_TRY(cudaGetLastError());
+        ISR_CUDA_TRY(cudaMemcpyAsync(a.num_rendered_host, wide, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    }
+    return ISR_OK;
+}
+
+// Phase B head: emission, tile sort, ranges.
+int launch_binning(const IsrForwardArgs& a, int64_t R, cudaStream_t stream) {
+    const int P = a.P;
+    const int gx = (a.W + TILE - 1) / TILE, gy = (a.H + TILE - 1) / TILE;
+    const int num_tiles = gx * gy;
+    GeomLayout gl(P);
+    ImageLayout il(a.W, a.H);
+    BinLayout bl(P, R, a.W, a.H);
+    char* g = static_cast<char*>(a.geom);
+    char* im = static_cast<char*>(a.image);
+    char* b = static_cast<char*>(a.binning);
+    uint2* ranges = reinterpret_cast<uint2*>(im + il.ranges);
+    ISR_CUDA_TRY(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, stream));
+    if (R <= 0 || P <= 0) return ISR_OK;
+    uint32_t* point_list = reinterpret_cast<uint32_t*>(b + bl.point_list);
+    uint32_t* point_list_alt = reinterpret_cast<uint32_t*>(b + bl.point_list_alt);
+    uint32_t* tile_keys = reinterpret_cast<uint32_t*>(b + bl.tile_keys);
+    uint32_t* tile_keys_alt = reinterpret_cast<uint32_t*>(b + bl.tile_keys_alt);
+    emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
+        P, reinterpret_cast<const uint32_t*>(g + gl.order), reinterpret_cast<const uint32_t*>(g + gl.offsets), a.radii,
+        reinterpret_cast<const Splat*>(g + gl.splat), gx, gy, tile_keys_alt, point_list_alt);
+    ISR_CUDA_TRY(cudaGetLastError());
+    int bits = 1;
+    while ((1 << bits) < num_tiles) bits++;
+    size_t temp_bytes = bl.temp_bytes;
+    ISR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(b + bl.temp, temp_bytes, tile_keys_alt, tile_keys, point_list_alt,
+                                                 point_list, (int)R, 0, bits, stream));
+    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, tile_keys, ranges);
+    ISR_CUDA_TRY(cudaGetLastError());
+    return ISR_OK;
+}
+
+}  // namespace isr

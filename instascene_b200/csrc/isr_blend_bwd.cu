@@ -1,0 +1,395 @@
+// isr_blend_bwd.cu -- K7: backward of the per-tile blend.  Reference: DSR/cuda_rasterizer/backward.cu:143-466.
+//
+// Dense kernel (all gradients, dense CHW cotangents): one CTA per 16x16 tile, one thread per pixel, a warp per
+// 8x4 pixel block, list replayed back-to-front from the per-pixel state saved by the forward.  Where the
+// reference issues 21+F global float atomics per contributing (pixel, Gaussian) pair -- 32 lanes hitting the
+// same address -- this kernel first reduces the 18+F per-Gaussian partial gradients across the warp with a
+// transposing butterfly (31 shuffles for 32 values: after the last step lane L owns the total of value L) and
+// then issues ONE red.global per value per (warp, Gaussian), skipping Gaussians no lane of the warp touched.
+//
+// Sparse kernel (isr_backward_extra_sparse): when only the semantic feature is trainable (train_semantic.py)
+// the only non-zero cotangent is dL/d(extra map) at <= 32768 sampled pixels, and
+//   dL/d extra[g][ch] = sum_pixels w(g,pix) * dL/dE[ch](pix)            (backward.cu:401)
+// needs just the forward weights w = alpha*T, so one warp per sampled pixel walks that pixel's tile list
+// front-to-back with the lanes spread over 32 consecutive Gaussians and a warp-shuffle product scan for T.
+#include "isr_common.cuh"
+
+namespace isr {
+
+constexpr int kBatchB = 128;
+
+template <int N, int OFF>
+struct Butterfly {
+    __device__ __forceinline__ static void run(float* v, int lane) {
+        if constexpr (N > 1) {
+            constexpr int h = N / 2;
+            const bool up = (lane & OFF) != 0;
+#pragma unroll
+            for (int i = 0; i < h; i++) {
+                const float send = up ? v[i] : v[i + h];
+                const float keep = up ? v[i + h] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+            }
+            if constexpr (OFF > 1) Butterfly<h, OFF / 2>::run(v, lane);
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], OFF);
+            if constexpr (OFF > 1) Butterfly<1, OFF / 2>::run(v, lane);
+        }
+    }
+};
+// After warp_transpose_reduce<N>(v): v[0] on lane L is the warp-wide sum of value index (L >> log2(32/N)).
+template <int N>
+__device__ __forceinline__ float warp_transpose_reduce(float* v, int lane) {
+    Butterfly<N, 16>::run(v, lane);
+    return v[0];
+}
+
+template <int FP>
+__global__ void __launch_bounds__(256)
+blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int F,
+                 const float* __restrict__ bg, const float4* __restrict__ splats, const float4* __restrict__ rgb4,
+                 const float* __restrict__ extras, const float* __restrict__ final_Ts,
+                 const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
+                 const float* __restrict__ dL_dothers, const float* __restrict__ dL_dpix_extra,
+                 float* __restrict__ dL_dtransMat, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dnormal3D,
+                 float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolors, float* __restrict__ dL_dextras) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* s_splat = reinterpret_cast<float4*>(smem_raw);           // [kBatchB][4]
+    float4* s_rgb = s_splat + kBatchB * 4;                           // [kBatchB]
+    float4* s_feat = s_rgb + kBatchB;                                // [kBatchB][FP/4]
+    int* s_id = reinterpret_cast<int*>(s_feat + kBatchB * (FP / 4)); // [kBatchB]
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int tiles_x = (W + TILE - 1) / TILE;
+    const int tile_id = blockIdx.y * tiles_x + blockIdx.x;
+    const int wx0 = blockIdx.x * TILE + (warp & 1) * 8;
+    const int wy0 = blockIdx.y * TILE + (warp >> 1) * 4;
+    const int pxi = wx0 + (lane & 7), pyi = wy0 + (lane >> 3);
+    const bool inside = pxi < W && pyi < H;
+    const size_t HW = (size_t)H * W;
+    const size_t pix_id = (size_t)W * pyi + pxi;
+    const float pixx = (float)pxi, pixy = (float)pyi;
+
+    const uint2 range = ranges[tile_id];
+    const int n_total = (int)(range.y - range.x);
+    const float c1 = __fdiv_rn(kFar, __fsub_rn(kFar, kNear));
+    const float c3 = __fdiv_rn(__fmul_rn(kFar, kNear), __fsub_rn(kFar, kNear));
+
+    const float T_final = inside ? final_Ts[pix_id] : 0.0f;
+    float T = T_final;
+    const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0u;
+    const uint32_t median_contributor = inside ? n_contrib[pix_id + HW] : 0u;
+    float dLdC0 = 0, dLdC1 = 0, dLdC2 = 0, dL_ddepth = 0, dL_daccum = 0, dL_dreg = 0, dL_dmedian = 0;
+    float dLdN0 = 0, dLdN1 = 0, dLdN2 = 0;
+    float dLdE[FP > 0 ? FP : 1];
+#pragma unroll
+    for (int ch = 0; ch < FP; ch++) dLdE[ch] = 0.0f;
+    if (inside) {
+        if (dL_dpixels) { dLdC0 = dL_dpixels[pix_id]; dLdC1 = dL_dpixels[pix_id + HW]; dLdC2 = dL_dpixels[pix_id + 2 * HW]; }
+        if (dL_dothers) {
+            dL_ddepth = dL_dothers[pix_id];
+            dL_daccum = dL_dothers[pix_id + HW];
+            dLdN0 = dL_dothers[pix_id + 2 * HW]; dLdN1 = dL_dothers[pix_id + 3 * HW]; dLdN2 = dL_dothers[pix_id + 4 * HW];
+            dL_dmedian = dL_dothers[pix_id + 5 * HW];
+            dL_dreg = dL_dothers[pix_id + 6 * HW];
+        }
+        if (FP > 0 && dL_dpix_extra) {
+#pragma unroll
+            for (int ch = 0; ch < FP; ch++) if (ch < F) dLdE[ch] = dL_dpix_extra[(size_t)ch * HW + pix_id];
+        }
+    }
+    const float final_D = inside ? final_Ts[pix_id + HW] : 0.0f;
+    const float final_D2 = inside ? final_Ts[pix_id + 2 * HW] : 0.0f;
+    const float final_A = 1.0f - T_final;
+    const float bg_dot = fma_(__ldg(bg + 2), dLdC2, fma_(__ldg(bg + 1), dLdC1, mul(__ldg(bg + 0), dLdC0)));
+
+    float acc_c0 = 0, acc_c1 = 0, acc_c2 = 0, last_c0 = 0, last_c1 = 0, last_c2 = 0;
+    float acc_depth = 0, last_depth = 0, acc_alpha = 0;
+    float acc_n0 = 0, acc_n1 = 0, acc_n2 = 0, last_n0 = 0, last_n1 = 0, last_n2 = 0;
+    float acc_e[FP > 0 ? FP : 1], last_e[FP > 0 ? FP : 1];
+#pragma unroll
+    for (int ch = 0; ch < FP; ch++) { acc_e[ch] = 0.0f; last_e[ch] = 0.0f; }
+    float last_dL_dT = 0, last_alpha = 0;
+
+    // the highest list index any pixel of this CTA needs
+    __shared__ int s_max_contrib;
+    if (tid == 0) s_max_contrib = 0;
+    __syncthreads();
+    if (last_contributor > 0) atomicMax(&s_max_contrib, (int)last_contributor);
+    __syncthreads();
+    const int n_need = min(n_total, s_max_contrib);
+
+    // batches walk the list from index n_need-1 down to 0
+    for (int top = n_need; top > 0; top -= kBatchB) {
+        const int n_batch = min(kBatchB, top);
+        __syncthreads();
+        if (tid < n_batch) {
+            const int g = (int)point_list[range.x + top - 1 - tid];  // slot t <-> list index top-1-t
+            s_id[tid] = g;
+            const float4* sp = splats + (size_t)g * 4;
+            s_splat[tid * 4 + 0] = __ldg(sp + 0);
+            s_splat[tid * 4 + 1] = __ldg(sp + 1);
+            s_splat[tid * 4 + 2] = __ldg(sp + 2);
+            s_splat[tid * 4 + 3] = __ldg(sp + 3);
+            s_rgb[tid] = __ldg(rgb4 + g);
+            if (FP > 0) {
+                if ((F & 3) == 0) {
+                    const float4* fp = reinterpret_cast<const float4*>(extras + (size_t)g * F);
+#pragma unroll
+                    for (int v = 0; v < FP / 4; v++)
+                        s_feat[tid * (FP / 4) + v] = (v * 4 < F) ? __ldg(fp + v) : make_float4(0, 0, 0, 0);
+                } else {
+                    float* dstf = reinterpret_cast<float*>(s_feat + tid * (FP / 4));
+#pragma unroll
+                    for (int ch = 0; ch < FP; ch++) dstf[ch] = (ch < F) ? __ldg(extras + (size_t)g * F + ch) : 0.0f;
+                }
+            }
+        }
+        __syncthreads();
+
+        for (int t = 0; t < n_batch; t++) {
+            const uint32_t contributor = (uint32_t)(top - 1 - t);  // 0-based list index
+            const bool active = contributor < last_contributor;
+            if (!__any_sync(0xffffffffu, active)) continue;
+            const float* s = reinterpret_cast<const float*>(s_splat + t * 4);
+            PairEval e;
+            const bool hit = active && eval_pair<true>(pixx, pixy, s, e);
+            if (!__any_sync(0xffffffffu, hit)) continue;
+
+            // per-lane partial gradients (0 when this lane does not contribute)
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = 0.0f;
+            float ve[FP > 0 ? FP : 1];
+#pragma unroll
+            for (int ch = 0; ch < FP; ch++) ve[ch] = 0.0f;
+            if (hit) {
+                const float alpha = e.alpha, G = e.G, c_d = e.depth;
+                const float ra = rcp(sub(1.0f, alpha));
+                T = mul(T, ra);
+                const float w = mul(alpha, T);
+                float dL_dalpha = 0.0f;
+                const float one_m_la = sub(1.0f, last_alpha);
+                const float4 col = s_rgb[t];
+                acc_c0 = fma_(last_alpha, last_c0, mul(one_m_la, acc_c0)); last_c0 = col.x;
+                dL_dalpha = fma_(sub(col.x, acc_c0), dLdC0, dL_dalpha);
+                acc_c1 = fma_(last_alpha, last_c1, mul(one_m_la, acc_c1)); last_c1 = col.y;
+                dL_dalpha = fma_(sub(col.y, acc_c1), dLdC1, dL_dalpha);
+                acc_c2 = fma_(last_alpha, last_c2, mul(one_m_la, acc_c2)); last_c2 = col.z;
+                dL_dalpha = fma_(sub(col.z, acc_c2), dLdC2, dL_dalpha);
+                v[0] = mul(w, dLdC0); v[1] = mul(w, dLdC1); v[2] = mul(w, dLdC2);
+
+                float dL_dz = 0.0f;
+                const float rcd = rcp(c_d);
+                const float m_d = mul(c1, sub(1.0f, mul(kNear, rcd)));
+                const float dmd_dd = mul(mul(c3, rcd), rcd);
+                if (contributor == median_contributor - 1u) dL_dz = add(dL_dz, dL_dmedian);
+                const float mm = mul(m_d, m_d);
+                const float dL_dweight = mul(fma_(-add(m_d, m_d), final_D, fma_(mm, final_A, final_D2)), dL_dreg);
+                dL_dalpha = add(dL_dalpha, sub(dL_dweight, last_dL_dT));
+                last_dL_dT = fma_(dL_dweight, alpha, mul(sub(1.0f, alpha), last_dL_dT));
+                const float dL_dmd = mul(mul(add(w, w), fma_(m_d, final_A, -final_D)), dL_dreg);
+                dL_dz = fma_(dL_dmd, dmd_dd, dL_dz);
+                acc_depth = fma_(last_alpha, last_depth, mul(one_m_la, acc_depth));
+                last_depth = c_d;
+                dL_dalpha = fma_(sub(c_d, acc_depth), dL_ddepth, dL_dalpha);
+                acc_alpha = add(last_alpha, mul(one_m_la, acc_alpha));
+                dL_dalpha = fma_(sub(1.0f, acc_alpha), dL_daccum, dL_dalpha);
+                acc_n0 = fma_(last_alpha, last_n0, mul(one_m_la, acc_n0)); last_n0 = s[11];
+                dL_dalpha = fma_(sub(s[11], acc_n0), dLdN0, dL_dalpha);
+                acc_n1 = fma_(last_alpha, last_n1, mul(one_m_la, acc_n1)); last_n1 = s[12];
+                dL_dalpha = fma_(sub(s[12], acc_n1), dLdN1, dL_dalpha);
+                acc_n2 = fma_(last_alpha, last_n2, mul(one_m_la, acc_n2)); last_n2 = s[13];
+                dL_dalpha = fma_(sub(s[13], acc_n2), dLdN2, dL_dalpha);
+                v[3] = mul(w, dLdN0); v[4] = mul(w, dLdN1); v[5] = mul(w, dLdN2);
+                if (FP > 0) {
+                    const float* f = reinterpret_cast<const float*>(s_feat + t * (FP / 4));
+#pragma unroll
+                    for (int ch = 0; ch < FP; ch++) {
+                        const float ex = f[ch];
+                        acc_e[ch] = fma_(last_alpha, last_e[ch], mul(one_m_la, acc_e[ch]));
+                        last_e[ch] = ex;
+                        dL_dalpha = fma_(sub(ex, acc_e[ch]), dLdE[ch], dL_dalpha);
+                        ve[ch] = mul(w, dLdE[ch]);
+                    }
+                }
+                dL_dalpha = mul(dL_dalpha, T);
+                last_alpha = alpha;
+                dL_dalpha = fma_(mul(-T_final, ra), bg_dot, dL_dalpha);
+                const float dL_dG = mul(s[14], dL_dalpha);
+                dL_dz = fma_(w, dL_ddepth, dL_dz);
+                if (e.use3d) {
+                    const float nGd = mul(dL_dG, -G);
+                    const float dsx = fma_(nGd, e.sx, mul(dL_dz, s[6]));
+                    const float dsy = fma_(nGd, e.sy, mul(dL_dz, s[7]));
+                    const float dpx = mul(dsx, e.rpz), dpy = mul(dsy, e.rpz);
+                    const float dpz = -fma_(dpx, e.sx, mul(dpy, e.sy));
+                    const float dkx = fma_(e.ly, dpz, -mul(e.lz, dpy));
+                    const float dky = fma_(e.lz, dpx, -mul(e.lx, dpz));
+                    const float dkz = fma_(e.lx, dpy, -mul(e.ly, dpx));
+                    const float dlx = fma_(dpy, e.kz, -mul(dpz, e.ky));
+                    const float dly = fma_(dpz, e.kx, -mul(dpx, e.kz));
+                    const float dlz = fma_(dpx, e.ky, -mul(dpy, e.kx));
+                    v[6] = -dkx; v[7] = -dky; v[8] = -dkz;
+                    v[9] = -dlx; v[10] = -dly; v[11] = -dlz;
+                    v[12] = fma_(dL_dz, e.sx, fma_(pixx, dkx, mul(pixy, dlx)));
+                    v[13] = fma_(dL_dz, e.sy, fma_(pixx, dky, mul(pixy, dly)));
+                    v[14] = add(fma_(pixx, dkz, mul(pixy, dlz)), dL_dz);
+                } else {
+                    const float nG2 = mul(-G, kFilterInvSquare);
+                    v[15] = mul(dL_dG, mul(nG2, e.ddx));
+                    v[16] = mul(dL_dG, mul(nG2, e.ddy));
+                    v[14] = dL_dz;
+                }
+                v[17] = mul(G, dL_dalpha);
+            }
+            const int g = s_id[t];
+            const float tot = warp_transpose_reduce<32>(v, lane);
+            if (lane < 18 && tot != 0.0f) {
+                float* dst;
+                if (lane < 3) dst = dL_dcolors ? dL_dcolors + (size_t)g * 3 + lane : nullptr;
+                else if (lane < 6) dst = dL_dnormal3D ? dL_dnormal3D + (size_t)g * 3 + (lane - 3) : nullptr;
+                else if (lane < 15) dst = dL_dtransMat ? dL_dtransMat + (size_t)g * 9 + (lane - 6) : nullptr;
+                else if (lane < 17) dst = dL_dmean2D ? dL_dmean2D + (size_t)g * 3 + (lane - 15) : nullptr;
+                else dst = dL_dopacity ? dL_dopacity + g : nullptr;
+                if (dst) atomicAdd(dst, tot);
+            }
+            if (FP > 0) {
+                constexpr int NE = FP <= 8 ? 8 : (FP <= 16 ? 16 : 32);
+                float vp[NE];
+#pragma unroll
+                for (int i = 0; i < NE; i++) vp[i] = (i < FP) ? ve[i] : 0.0f;
+                const float tote = warp_transpose_reduce<NE>(vp, lane);
+                constexpr int shift = NE == 32 ? 0 : (NE == 16 ? 1 : 2);
+                const int ch = lane >> shift;
+                if ((lane & ((1 << shift) - 1)) == 0 && ch < F && tote != 0.0f && dL_dextras)
+                    atomicAdd(dL_dextras + (size_t)g * F + ch, tote);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Sparse feature-only backward: one warp per sampled pixel.
+// ---------------------------------------------------------------------------------------------------------
+template <int FP>
+__global__ void __launch_bounds__(256)
+extra_sparse_bwd_kernel(int n, const int* __restrict__ pix_ids, const float* __restrict__ dLdE_samples, int W, int H,
+                        int F, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                        const float4* __restrict__ splats, const uint32_t* __restrict__ n_contrib,
+                        float* __restrict__ dL_dextras) {
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp_global >= n) return;
+    const int pix = pix_ids[warp_global];
+    if (pix < 0 || pix >= W * H) return;
+    const int pxi = pix % W, pyi = pix / W;
+    const int tiles_x = (W + TILE - 1) / TILE;
+    const uint2 range = ranges[(pyi / TILE) * tiles_x + (pxi / TILE)];
+    const int last = (int)n_contrib[pix];  // number of list entries up to and including the last contributor
+    const float pixx = (float)pxi, pixy = (float)pyi;
+    float dE[FP];
+#pragma unroll
+    for (int ch = 0; ch < FP; ch++) dE[ch] = (ch < F) ? dLdE_samples[(size_t)warp_global * F + ch] : 0.0f;
+    float T = 1.0f;  // transmittance in front of the current group of 32 (warp-uniform)
+    for (int base = 0; base < last; base += 32) {
+        const int i = base + lane;
+        float alpha = 0.0f;
+        int g = -1;
+        if (i < last) {
+            g = (int)point_list[range.x + i];
+            float s[16];
+            const float4* sp = splats + (size_t)g * 4;
+            *reinterpret_cast<float4*>(s + 0) = __ldg(sp + 0);
+            *reinterpret_cast<float4*>(s + 4) = __ldg(sp + 1);
+            *reinterpret_cast<float4*>(s + 8) = __ldg(sp + 2);
+            *reinterpret_cast<float4*>(s + 12) = __ldg(sp + 3);
+            PairEval e;
+            if (eval_pair<false>(pixx, pixy, s, e)) alpha = e.alpha;
+        }
+        // sequential-exact transmittance: T_i = T_{i-1} * (1 - alpha_{i-1}) in list order, same roundings as
+        // the forward (a left-to-right product), obtained by passing the running value lane to lane.
+        float Tin = T;
+#pragma unroll
+        for (int l = 0; l < 32; l++) {
+            const float a_l = __shfl_sync(0xffffffffu, alpha, l);
+            if (lane == l) Tin = T;
+            if (a_l != 0.0f) T = mul(T, sub(1.0f, a_l));
+        }
+        if (alpha != 0.0f && g >= 0) {
+            const float w = mul(alpha, Tin);
+#pragma unroll
+            for (int ch = 0; ch < FP; ch++)
+                if (ch < F) {
+                    const float val = mul(w, dE[ch]);
+                    if (val != 0.0f) atomicAdd(dL_dextras + (size_t)g * F + ch, val);
+                }
+        }
+    }
+}
+
+template <int FP>
+static int launch_bwd_one(const IsrBackwardArgs& a, cudaStream_t stream) {
+    GeomLayout gl(a.P);
+    ImageLayout il(a.W, a.H);
+    const char* g = static_cast<const char*>(a.geom);
+    const char* im = static_cast<const char*>(a.image);
+    const char* b = static_cast<const char*>(a.binning);
+    const dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE);
+    const size_t smem = (size_t)kBatchB * (64 + 16 + 4 * FP + 4);
+    auto kern = blend_bwd_kernel<FP>;
+    ISR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned m = a.grad_mask;
+    kern<<<grid, 256, smem, stream>>>(
+        reinterpret_cast<const uint2*>(im + il.ranges), reinterpret_cast<const uint32_t*>(b), a.W, a.H, a.F, a.background,
+        reinterpret_cast<const float4*>(g + gl.splat), reinterpret_cast<const float4*>(g + gl.rgb), a.extra_attrs,
+        reinterpret_cast<const float*>(im + il.final_T), reinterpret_cast<const uint32_t*>(im + il.n_contrib), a.dL_dcolor,
+        a.dL_dothers, a.dL_dextra_pix, (m & ISR_GRAD_GEOMETRY) ? a.dL_dtransMat : nullptr,
+        (m & ISR_GRAD_GEOMETRY) ? a.dL_dmeans2D : nullptr, (m & ISR_GRAD_GEOMETRY) ? a.dL_dnormal : nullptr,
+        (m & ISR_GRAD_OPACITY) ? a.dL_dopacity : nullptr, (m & ISR_GRAD_COLOR) ? a.dL_dcolors : nullptr,
+        (m & ISR_GRAD_EXTRA) ? a.dL_dextra : nullptr);
+    ISR_CUDA_TRY(cudaGetLastError());
+    return ISR_OK;
+}
+
+int launch_blend_bwd(const IsrBackwardArgs& a, cudaStream_t stream) {
+    if (a.num_rendered <= 0) return ISR_OK;
+    const int F = a.F;
+    if (F == 0) return launch_bwd_one<0>(a, stream);
+    if (F <= 4) return launch_bwd_one<4>(a, stream);
+    if (F <= 8) return launch_bwd_one<8>(a, stream);
+    if (F <= 16) return launch_bwd_one<16>(a, stream);
+    if (F <= 24) return launch_bwd_one<24>(a, stream);
+    if (F <= 32) return launch_bwd_one<32>(a, stream);
+    return ISR_ERR_UNSUPPORTED;
+}
+
+template <int FP>
+static int launch_sparse_one(int P, int F, int W, int H, const void* geom, const void* image, const void* binning, int n,
+                             const int* pix_ids, const float* dLdE, float* dL_dextra, cudaStream_t stream) {
+    GeomLayout gl(P);
+    ImageLayout il(W, H);
+    const char* g = static_cast<const char*>(geom);
+    const char* im = static_cast<const char*>(image);
+    const int warps_per_block = 8;
+    extra_sparse_bwd_kernel<FP><<<(n + warps_per_block - 1) / warps_per_block, 256, 0, stream>>>(
+        n, pix_ids, dLdE, W, H, F, reinterpret_cast<const uint2*>(im + il.ranges),
+        reinterpret_cast<const uint32_t*>(binning), reinterpret_cast<const float4*>(g + gl.splat),
+        reinterpret_cast<const uint32_t*>(im + il.n_contrib), dL_dextra);
+    ISR_CUDA_TRY(cudaGetLastError());
+    return ISR_OK;
+}
+
+int launch_extra_sparse_bwd(int P, int F, int W, int H, const void* geom, const void* image, const void* binning, int n,
+                            const int* pix_ids, const float* dLdE, float* dL_dextra, cudaStream_t stream) {
+    if (n <= 0 || F <= 0) return ISR_OK;
+    if (F <= 4) return launch_sparse_one<4>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, stream);
+    if (F <= 8) return launch_sparse_one<8>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, stream);
+    if (F <= 16) return launch_sparse_one<16>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, stream);
+    if (F <= 24) return launch_sparse_one<24>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, stream);
+    if (F <= 32) return launch_sparse_one<32>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, stream);
+    return ISR_ERR_UNSUPPORTED;
+}
+
+}  // namespace isr

@@ -1,0 +1,490 @@
+// isr_preprocess.cu -- per-Gaussian kernels: K1 forward projection (DSR/cuda_rasterizer/forward.cu:148-251),
+// K8 backward chain rule (backward.cu:469-656, 20-139) and markVisible (rasterizer_impl.cu:54-66).
+// One thread per Gaussian; HBM-streaming kernels (algorithmic bytes in DESIGN.md).
+#include "isr_common.cuh"
+
+namespace isr {
+
+// DSR/cuda_rasterizer/auxiliary.h:44-61
+__device__ constexpr float SH_C0 = 0.28209479177387814f;
+__device__ constexpr float SH_C1 = 0.4886025119029199f;
+__device__ constexpr float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                       -1.0925484305920792f, 0.5462742152960396f};
+__device__ constexpr float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                       0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                       -0.5900435899266435f};
+
+// Camera matrices stay in device memory (they are torch CUDA tensors in the reference API); every thread
+// reads the same 35 floats through the read-only path (uniform addresses -> one broadcast transaction).
+struct Camera {
+    const float* __restrict__ view;    // [16]
+    const float* __restrict__ proj;    // [16]
+    const float* __restrict__ campos;  // [3]
+};
+
+// quat (w,x,y,z) -> rotation columns (auxiliary.h:214-236), rsqrtf replaced by rcp(sqrt) per the spec
+__device__ __forceinline__ void quat_to_rot(const float4 q, float R0[3], float R1[3], float R2[3]) {
+    const float sum = fma_(q.z, q.z, fma_(q.y, q.y, fma_(q.x, q.x, mul(q.w, q.w))));
+    const float s = rcp(sqrt_(sum));
+    const float w = mul(q.x, s), x = mul(q.y, s), y = mul(q.z, s), z = mul(q.w, s);
+    const float yy = mul(y, y), zz = mul(z, z);
+    const float yy_zz = add(yy, zz), xx_zz = fma_(x, x, zz), xx_yy = fma_(x, x, yy);
+    const float xy_p = fma_(x, y, mul(w, z)), xy_m = fma_(x, y, -mul(w, z));
+    const float xz_p = fma_(x, z, mul(w, y)), xz_m = fma_(x, z, -mul(w, y));
+    const float yz_p = fma_(y, z, mul(w, x)), yz_m = fma_(y, z, -mul(w, x));
+    R0[0] = sub(1.0f, add(yy_zz, yy_zz)); R0[1] = add(xy_p, xy_p);             R0[2] = add(xz_m, xz_m);
+    R1[0] = add(xy_m, xy_m);             R1[1] = sub(1.0f, add(xx_zz, xx_zz)); R1[2] = add(yz_p, yz_p);
+    R2[0] = add(xz_p, xz_p);             R2[1] = add(yz_m, yz_m);             R2[2] = sub(1.0f, add(xx_yy, xx_yy));
+}
+
+__global__ void __launch_bounds__(256)
+preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const float2* __restrict__ scales,
+                      float scale_modifier, const float4* __restrict__ rotations,
+                      const float* __restrict__ opacities, const float* __restrict__ shs,
+                      const float* __restrict__ transMat_precomp, const float* __restrict__ colors_precomp,
+                      const Camera cam, int W, int H, int gx, int gy, int* __restrict__ radii,
+                      Splat* __restrict__ splats, float4* __restrict__ cull4, float4* __restrict__ rgb4,
+                      float* __restrict__ depths,
+                      uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ tiles_touched,
+                      uint8_t* __restrict__ clamped) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    int radius_i = 0;
+    uint32_t tiles = 0, dkey = 0xFFFFFFFFu;
+    uint8_t clamp_mask = 0;
+    do {
+        const float p0 = means3D[3 * (size_t)idx], p1 = means3D[3 * (size_t)idx + 1], p2 = means3D[3 * (size_t)idx + 2];
+        float view[16], proj[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) { view[i] = __ldg(cam.view + i); proj[i] = __ldg(cam.proj + i); }
+        const float pvx = add(dot3c(view[0], p0, view[4], p1, view[8], p2), view[12]);
+        const float pvy = add(dot3c(view[1], p0, view[5], p1, view[9], p2), view[13]);
+        const float pvz = add(dot3c(view[2], p0, view[6], p1, view[10], p2), view[14]);
+        if (pvz <= 0.2f) break;
+        float T[9], nrm[3];
+        if (transMat_precomp == nullptr) {
+            const float2 sc = scales[idx];
+            const float sx = mul(scale_modifier, sc.x), sy = mul(scale_modifier, sc.y);
+            float R0[3], R1[3], R2[3];
+            quat_to_rot(rotations[idx], R0, R1, R2);
+            const float L0[3] = {mul(R0[0], sx), mul(R0[1], sx), mul(R0[2], sx)};
+            const float L1[3] = {mul(R1[0], sy), mul(R1[1], sy), mul(R1[2], sy)};
+            float X[4][3];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                X[c][0] = dot3c(L0[0], proj[c], L0[1], proj[4 + c], L0[2], proj[8 + c]);
+                X[c][1] = dot3c(L1[0], proj[c], L1[1], proj[4 + c], L1[2], proj[8 + c]);
+                X[c][2] = add(dot3c(p0, proj[c], p1, proj[4 + c], p2, proj[8 + c]), proj[12 + c]);
+            }
+            const float hw = mul((float)W, 0.5f), hw1 = mul((float)(W - 1), 0.5f);
+            const float hh = mul((float)H, 0.5f), hh1 = mul((float)(H - 1), 0.5f);
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                T[0 + r] = fma_(X[3][r], hw1, mul(X[0][r], hw));
+                T[3 + r] = fma_(X[3][r], hh1, mul(X[1][r], hh));
+                T[6 + r] = X[3][r];
+            }
+            nrm[0] = dot3c(view[0], R2[0], view[4], R2[1], view[8], R2[2]);
+            nrm[1] = dot3c(view[1], R2[0], view[5], R2[1], view[9], R2[2]);
+            nrm[2] = dot3c(view[2], R2[0], view[6], R2[1], view[10], R2[2]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 9; i++) T[i] = transMat_precomp[9 * (size_t)idx + i];
+            nrm[0] = 0.0f; nrm[1] = 0.0f; nrm[2] = 1.0f;
+        }
+        const float cosv = -fma_(pvz, nrm[2], fma_(pvx, nrm[0], mul(pvy, nrm[1])));
+        if (cosv == 0.0f) break;
+        const float mult = cosv > 0.0f ? 1.0f : -1.0f;
+        nrm[0] = mul(nrm[0], mult); nrm[1] = mul(nrm[1], mult); nrm[2] = mul(nrm[2], mult);
+        // compute_aabb (forward.cu:119-145), cutoff 3
+        const float* Tu = T; const float* Tv = T + 3; const float* Tw = T + 6;
+        const float d = fma_(-Tw[2], Tw[2], fma_(mul(Tw[0], Tw[0]), 9.0f, mul(mul(Tw[1], Tw[1]), 9.0f)));
+        if (d == 0.0f) break;
+        const float inv_d = rcp(d);
+        const float f9 = mul(inv_d, 9.0f);
+        const float cx = fma_(mul(Tu[2], Tw[2]), -inv_d, fma_(f9, mul(Tu[1], Tw[1]), mul(f9, mul(Tu[0], Tw[0]))));
+        const float cy = fma_(mul(Tv[2], Tw[2]), -inv_d, fma_(f9, mul(Tv[1], Tw[1]), mul(f9, mul(Tv[0], Tw[0]))));
+        const float ngx = fma_(mul(Tu[2], Tu[2]), inv_d, -fma_(f9, mul(Tu[1], Tu[1]), mul(f9, mul(Tu[0], Tu[0]))));
+        const float ngy = fma_(mul(Tv[2], Tv[2]), inv_d, -fma_(f9, mul(Tv[1], Tv[1]), mul(f9, mul(Tv[0], Tv[0]))));
+        const float ex = sqrt_(fmaxf(1e-4f, fma_(cx, cx, ngx)));
+        const float ey = sqrt_(fmaxf(1e-4f, fma_(cy, cy, ngy)));
+        const float radius = ceilf(fmaxf(fmaxf(ex, ey), mul(3.0f, kFilterSize)));
+        const int ri = __float2int_rz(radius);
+        int mnx, mny, mxx, mxy;
+        get_rect(cx, cy, ri, gx, gy, mnx, mny, mxx, mxy);
+        const int ntiles = (mxx - mnx) * (mxy - mny);
+        if (ntiles == 0) break;
+
+        float rgb[3];
+        if (colors_precomp == nullptr) {
+            // computeColorFromSH (forward.cu:20-71)
+            const float4* sh4 = reinterpret_cast<const float4*>(shs + (size_t)idx * M * 3);
+            const float* sh = shs + (size_t)idx * M * 3;
+            (void)sh4;
+            const float dx = sub(p0, __ldg(cam.campos)), dy = sub(p1, __ldg(cam.campos + 1)), dz = sub(p2, __ldg(cam.campos + 2));
+            const float len = sqrt_(fma_(dz, dz, fma_(dx, dx, mul(dy, dy))));
+            const float x = __fdiv_rn(dx, len), y = __fdiv_rn(dy, len), z = __fdiv_rn(dz, len);
+            float res[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) res[c] = mul(SH_C0, sh[c]);
+            if (D > 0) {
+                const float a1 = mul(SH_C1, y), a2 = mul(SH_C1, z), a3 = mul(SH_C1, x);
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    float r = res[c];
+                    r = fma_(-a1, sh[3 + c], r);
+                    r = fma_(a2, sh[6 + c], r);
+                    r = fma_(-a3, sh[9 + c], r);
+                    res[c] = r;
+                }
+                if (D > 1) {
+                    const float xx = mul(x, x), yy = mul(y, y), zz = mul(z, z);
+                    const float xy = mul(x, y), yz = mul(y, z), xz = mul(x, z);
+                    const float b4 = mul(SH_C2[0], xy), b5 = mul(SH_C2[1], yz);
+                    const float b6 = mul(SH_C2[2], sub(sub(mul(2.0f, zz), xx), yy));
+                    const float b7 = mul(SH_C2[3], xz), b8 = mul(SH_C2[4], sub(xx, yy));
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        float r = res[c];
+                        r = fma_(b4, sh[12 + c], r);
+                        r = fma_(b5, sh[15 + c], r);
+                        r = fma_(b6, sh[18 + c], r);
+                        r = fma_(b7, sh[21 + c], r);
+                        r = fma_(b8, sh[24 + c], r);
+                        res[c] = r;
+                    }
+                    if (D > 2) {
+                        const float c9 = mul(mul(SH_C3[0], y), sub(mul(3.0f, xx), yy));
+                        const float c10 = mul(mul(SH_C3[1], xy), z);
+                        const float c11 = mul(mul(SH_C3[2], y), sub(sub(mul(4.0f, zz), xx), yy));
+                        const float c12 = mul(mul(SH_C3[3], z), sub(sub(mul(2.0f, zz), mul(3.0f, xx)), mul(3.0f, yy)));
+                        const float c13 = mul(mul(SH_C3[4], x), sub(sub(mul(4.0f, zz), xx), yy));
+                        const float c14 = mul(mul(SH_C3[5], z), sub(xx, yy));
+                        const float c15 = mul(mul(SH_C3[6], x), sub(xx, mul(3.0f, yy)));
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            float r = res[c];
+                            r = fma_(c9, sh[27 + c], r);
+                            r = fma_(c10, sh[30 + c], r);
+                            r = fma_(c11, sh[33 + c], r);
+                            r = fma_(c12, sh[36 + c], r);
+                            r = fma_(c13, sh[39 + c], r);
+                            r = fma_(c14, sh[42 + c], r);
+                            r = fma_(c15, sh[45 + c], r);
+                            res[c] = r;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float r = add(res[c], 0.5f);
+                if (r < 0.0f) clamp_mask |= (uint8_t)(1u << c);
+                rgb[c] = fmaxf(r, 0.0f);
+            }
+        } else {
+            rgb[0] = colors_precomp[3 * (size_t)idx];
+            rgb[1] = colors_precomp[3 * (size_t)idx + 1];
+            rgb[2] = colors_precomp[3 * (size_t)idx + 2];
+        }
+
+        const float opa = opacities[idx];
+        // conservative alpha cut: alpha = opa*exp(power) < 1/255  <=  power < -ln(255*opa) - margin
+        float power_cut = __int_as_float(0x7f800000);  // +inf: never contributes (opa <= 0)
+        if (opa > 0.0f) power_cut = -__logf(255.0f * opa) - 1e-3f;
+        Splat s;
+        s.Tu[0] = T[0]; s.Tu[1] = T[1]; s.Tu[2] = T[2];
+        s.Tv[0] = T[3]; s.Tv[1] = T[4]; s.Tv[2] = T[5];
+        s.Tw[0] = T[6]; s.Tw[1] = T[7]; s.Tw[2] = T[8];
+        s.mx = cx; s.my = cy;
+        s.nx = nrm[0]; s.ny = nrm[1]; s.nz = nrm[2];
+        s.opacity = opa;
+        s.power_cut = power_cut;
+        float4* dst = reinterpret_cast<float4*>(splats + idx);
+        const float4* src = reinterpret_cast<const float4*>(&s);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+        // Conservative screen-space rectangle outside of which this Gaussian cannot pass the alpha test:
+        // a pair survives only if min(rho3d, rho2d) <= rho_max = -2*power_cut.  rho3d <= rho_max is the
+        // projection of the disk u^2+v^2 <= rho_max (an ellipse when dd < 0, same algebra as compute_aabb);
+        // rho2d <= rho_max is a disk of radius sqrt(rho_max/2) around the AABB centre.  Margins absorb fp32
+        // rounding; non-elliptic projections disable the test.  Used only to SKIP work, never to change results.
+        float4 cr = make_float4(1e30f, 1e30f, -1e30f, -1e30f);  // empty
+        const float rho_max = -2.0f * power_cut;
+        if (rho_max > 0.0f) {
+            const float INF = __int_as_float(0x7f800000);
+            const float tw2 = Tw[2] * Tw[2];
+            const float dd = rho_max * (Tw[0] * Tw[0] + Tw[1] * Tw[1]) - tw2;
+            if (!(dd < -1e-3f * tw2)) {
+                cr = make_float4(-INF, -INF, INF, INF);
+            } else {
+                const float fa = rho_max / dd, fz = -1.0f / dd;
+                const float ccx = fa * (Tu[0] * Tw[0] + Tu[1] * Tw[1]) + fz * Tu[2] * Tw[2];
+                const float ccy = fa * (Tv[0] * Tw[0] + Tv[1] * Tw[1]) + fz * Tv[2] * Tw[2];
+                const float hx2 = ccx * ccx - (fa * (Tu[0] * Tu[0] + Tu[1] * Tu[1]) + fz * Tu[2] * Tu[2]);
+                const float hy2 = ccy * ccy - (fa * (Tv[0] * Tv[0] + Tv[1] * Tv[1]) + fz * Tv[2] * Tv[2]);
+                const float hx = sqrtf(fmaxf(hx2, 0.0f)), hy = sqrtf(fmaxf(hy2, 0.0f));
+                const float mgx = 0.5f + 1e-3f * (hx + fabsf(ccx)), mgy = 0.5f + 1e-3f * (hy + fabsf(ccy));
+                const float r2 = sqrtf(0.5f * rho_max) + 0.5f;
+                cr.x = fminf(ccx - hx - mgx, cx - r2);
+                cr.y = fminf(ccy - hy - mgy, cy - r2);
+                cr.z = fmaxf(ccx + hx + mgx, cx + r2);
+                cr.w = fmaxf(ccy + hy + mgy, cy + r2);
+                if (!(hx2 == hx2) || !(hy2 == hy2)) cr = make_float4(-INF, -INF, INF, INF);
+            }
+        }
+        cull4[idx] = cr;
+        rgb4[idx] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+        depths[idx] = pvz;
+        dkey = __float_as_uint(pvz);
+        radius_i = ri;
+        tiles = (uint32_t)ntiles;
+    } while (false);
+    radii[idx] = radius_i;
+    tiles_touched[idx] = tiles;
+    depth_keys[idx] = dkey;
+    clamped[idx] = clamp_mask;
+}
+
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const Camera cam,
+                                    uint8_t* __restrict__ present) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float p0 = means3D[3 * (size_t)idx], p1 = means3D[3 * (size_t)idx + 1], p2 = means3D[3 * (size_t)idx + 2];
+    const float pvz = add(dot3c(__ldg(cam.view + 2), p0, __ldg(cam.view + 6), p1, __ldg(cam.view + 10), p2), __ldg(cam.view + 14));
+    present[idx] = pvz > 0.2f;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K8: backward of the per-Gaussian projection (backward.cu:469-656) + SH backward (backward.cu:20-139).
+// Float-only results; written as plain expressions (tolerance-compared with the oracle / reference).
+// ---------------------------------------------------------------------------------------------------------
+__device__ void sh_backward(int idx, int deg, int M, const float* __restrict__ means, const float* campos,
+                            const float* __restrict__ shs, uint8_t clamp_mask, const float* __restrict__ dL_dcolor,
+                            float* __restrict__ dL_dmeans, float* __restrict__ dL_dshs) {
+    const float dox = means[3 * (size_t)idx] - campos[0], doy = means[3 * (size_t)idx + 1] - campos[1],
+                doz = means[3 * (size_t)idx + 2] - campos[2];
+    const float len = sqrtf(dox * dox + doy * doy + doz * doz);
+    const float x = dox / len, y = doy / len, z = doz / len;
+    const float* sh = shs + (size_t)idx * M * 3;
+    float dRGB[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) dRGB[c] = ((clamp_mask >> c) & 1) ? 0.0f : dL_dcolor[3 * (size_t)idx + c];
+    float dx[3] = {0, 0, 0}, dy[3] = {0, 0, 0}, dz[3] = {0, 0, 0};
+    float* dsh = dL_dshs + (size_t)idx * M * 3;
+#define SH(i, c) sh[3 * (i) + (c)]
+#define DSH(i, v)                                                   \
+    {                                                               \
+        const float _v = (v);                                       \
+        for (int c = 0; c < 3; c++) dsh[3 * (i) + c] = _v * dRGB[c]; \
+    }
+    DSH(0, SH_C0);
+    if (deg > 0) {
+        DSH(1, -SH_C1 * y); DSH(2, SH_C1 * z); DSH(3, -SH_C1 * x);
+        for (int c = 0; c < 3; c++) { dx[c] = -SH_C1 * SH(3, c); dy[c] = -SH_C1 * SH(1, c); dz[c] = SH_C1 * SH(2, c); }
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            DSH(4, SH_C2[0] * xy); DSH(5, SH_C2[1] * yz); DSH(6, SH_C2[2] * (2.f * zz - xx - yy));
+            DSH(7, SH_C2[3] * xz); DSH(8, SH_C2[4] * (xx - yy));
+            for (int c = 0; c < 3; c++) {
+                dx[c] += SH_C2[0] * y * SH(4, c) + SH_C2[2] * 2.f * -x * SH(6, c) + SH_C2[3] * z * SH(7, c) + SH_C2[4] * 2.f * x * SH(8, c);
+                dy[c] += SH_C2[0] * x * SH(4, c) + SH_C2[1] * z * SH(5, c) + SH_C2[2] * 2.f * -y * SH(6, c) + SH_C2[4] * 2.f * -y * SH(8, c);
+                dz[c] += SH_C2[1] * y * SH(5, c) + SH_C2[2] * 2.f * 2.f * z * SH(6, c) + SH_C2[3] * x * SH(7, c);
+            }
+            if (deg > 2) {
+                DSH(9, SH_C3[0] * y * (3.f * xx - yy)); DSH(10, SH_C3[1] * xy * z);
+                DSH(11, SH_C3[2] * y * (4.f * zz - xx - yy));
+                DSH(12, SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy));
+                DSH(13, SH_C3[4] * x * (4.f * zz - xx - yy)); DSH(14, SH_C3[5] * z * (xx - yy));
+                DSH(15, SH_C3[6] * x * (xx - 3.f * yy));
+                for (int c = 0; c < 3; c++) {
+                    dx[c] += (SH_C3[0] * SH(9, c) * 3.f * 2.f * xy + SH_C3[1] * SH(10, c) * yz +
+                              SH_C3[2] * SH(11, c) * -2.f * xy + SH_C3[3] * SH(12, c) * -3.f * 2.f * xz +
+                              SH_C3[4] * SH(13, c) * (-3.f * xx + 4.f * zz - yy) + SH_C3[5] * SH(14, c) * 2.f * xz +
+                              SH_C3[6] * SH(15, c) * 3.f * (xx - yy));
+                    dy[c] += (SH_C3[0] * SH(9, c) * 3.f * (xx - yy) + SH_C3[1] * SH(10, c) * xz +
+                              SH_C3[2] * SH(11, c) * (-3.f * yy + 4.f * zz - xx) + SH_C3[3] * SH(12, c) * -3.f * 2.f * yz +
+                              SH_C3[4] * SH(13, c) * -2.f * xy + SH_C3[5] * SH(14, c) * -2.f * yz +
+                              SH_C3[6] * SH(15, c) * -3.f * 2.f * xy);
+                    dz[c] += (SH_C3[1] * SH(10, c) * xy + SH_C3[2] * SH(11, c) * 4.f * 2.f * yz +
+                              SH_C3[3] * SH(12, c) * 3.f * (2.f * zz - xx - yy) + SH_C3[4] * SH(13, c) * 4.f * 2.f * xz +
+                              SH_C3[5] * SH(14, c) * (xx - yy));
+                }
+            }
+        }
+    }
+#undef SH
+#undef DSH
+    const float ddx = dx[0] * dRGB[0] + dx[1] * dRGB[1] + dx[2] * dRGB[2];
+    const float ddy = dy[0] * dRGB[0] + dy[1] * dRGB[1] + dy[2] * dRGB[2];
+    const float ddz = dz[0] * dRGB[0] + dz[1] * dRGB[1] + dz[2] * dRGB[2];
+    const float sum2 = dox * dox + doy * doy + doz * doz;
+    const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+    dL_dmeans[3 * (size_t)idx + 0] += ((+sum2 - dox * dox) * ddx - doy * dox * ddy - doz * dox * ddz) * invsum32;
+    dL_dmeans[3 * (size_t)idx + 1] += (-dox * doy * ddx + (sum2 - doy * doy) * ddy - doz * doy * ddz) * invsum32;
+    dL_dmeans[3 * (size_t)idx + 2] += (-dox * doz * ddx - doy * doz * ddy + (sum2 - doz * doz) * ddz) * invsum32;
+}
+
+__global__ void __launch_bounds__(256)
+preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii,
+                      const float* __restrict__ shs, const uint8_t* __restrict__ clamped,
+                      const float2* __restrict__ scales, const float4* __restrict__ rotations,
+                      const float* __restrict__ transMat_precomp, const Splat* __restrict__ splats,
+                      const Camera cam, int W, int H, float* __restrict__ dL_dmean2D,
+                      const float* __restrict__ dL_dnormal3D, float* __restrict__ dL_dtransMat,
+                      const float* __restrict__ dL_dcolors, float* __restrict__ dL_dsh,
+                      float* __restrict__ dL_dmean3D, float* __restrict__ dL_dscales, float* __restrict__ dL_drots) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P || !(radii[idx] > 0)) return;
+    const bool precomp = (scales == nullptr);
+    float view[16], proj[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { view[i] = __ldg(cam.view + i); proj[i] = __ldg(cam.proj + i); }
+    float T[3][3], Pm[3][4], R[3][3], normal[3] = {0, 0, 0};
+    float sx = 0, sy = 0;
+    float4 q = make_float4(1, 0, 0, 0);
+    const float p[3] = {means3D[3 * (size_t)idx], means3D[3 * (size_t)idx + 1], means3D[3 * (size_t)idx + 2]};
+    if (precomp) {
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) T[i][j] = transMat_precomp[9 * (size_t)idx + 3 * i + j];
+    } else {
+        q = rotations[idx];
+        quat_to_rot(q, R[0], R[1], R[2]);
+        const float2 sc = scales[idx];
+        sx = sc.x; sy = sc.y;  // Q6: scale_modifier ignored (backward.cu:507)
+        const float L0[3] = {R[0][0] * sx, R[0][1] * sx, R[0][2] * sx};
+        const float L1[3] = {R[1][0] * sy, R[1][1] * sy, R[1][2] * sy};
+        const float Mm[3][4] = {{L0[0], L0[1], L0[2], 0.0f}, {L1[0], L1[1], L1[2], 0.0f}, {p[0], p[1], p[2], 1.0f}};
+        const float n2p[3][4] = {{(float)W * 0.5f, 0, 0, (float)(W - 1) * 0.5f},
+                                 {0, (float)H * 0.5f, 0, (float)(H - 1) * 0.5f},
+                                 {0, 0, 0, 1.0f}};
+        for (int c = 0; c < 3; c++)
+            for (int r = 0; r < 4; r++) {
+                float s = 0;
+                for (int k = 0; k < 4; k++) s += proj[4 * r + k] * n2p[c][k];
+                Pm[c][r] = s;
+            }
+        for (int c = 0; c < 3; c++)
+            for (int i = 0; i < 3; i++) {
+                float s = 0;
+                for (int k = 0; k < 4; k++) s += Mm[i][k] * Pm[c][k];
+                T[c][i] = s;
+            }
+        normal[0] = view[0] * R[2][0] + view[4] * R[2][1] + view[8] * R[2][2];
+        normal[1] = view[1] * R[2][0] + view[5] * R[2][1] + view[9] * R[2][2];
+        normal[2] = view[2] * R[2][0] + view[6] * R[2][1] + view[10] * R[2][2];
+    }
+    float dT[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) dT[i][j] = dL_dtransMat[9 * (size_t)idx + 3 * i + j];
+    const float dT_u2 = dT[0][2], dT_v2 = dT[1][2];
+    const float dm2x = dL_dmean2D[3 * (size_t)idx], dm2y = dL_dmean2D[3 * (size_t)idx + 1];
+    bool wrote_back = false;
+    if (dm2x != 0 || dm2y != 0) {
+        const float tv[3] = {9.0f, 9.0f, -1.0f};
+        const float d = tv[0] * T[2][0] * T[2][0] + tv[1] * T[2][1] * T[2][1] + tv[2] * T[2][2] * T[2][2];
+        float fv[3], dT3[3], df[3];
+        for (int j = 0; j < 3; j++) fv[j] = tv[j] * (1.0f / d);
+        for (int j = 0; j < 3; j++) {
+            dT[0][j] += dm2x * fv[j] * T[2][j];
+            dT[1][j] += dm2y * fv[j] * T[2][j];
+            dT3[j] = dm2x * fv[j] * T[0][j] + dm2y * fv[j] * T[1][j];
+            df[j] = dm2x * T[0][j] * T[2][j] + dm2y * T[1][j] * T[2][j];
+        }
+        const float dL_dd = (df[0] * fv[0] + df[1] * fv[1] + df[2] * fv[2]) * (-1.0f / d);
+        for (int j = 0; j < 3; j++) dT[2][j] += dT3[j] + dL_dd * (tv[j] * T[2][j] * 2.0f);
+        if (precomp) {
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) dL_dtransMat[9 * (size_t)idx + 3 * i + j] = dT[i][j];
+            wrote_back = true;
+        }
+    }
+    if (!precomp) {
+        float dM[3][4];
+        for (int c = 0; c < 3; c++)
+            for (int r = 0; r < 4; r++) dM[c][r] = Pm[0][r] * dT[0][c] + Pm[1][r] * dT[1][c] + Pm[2][r] * dT[2][c];
+        const float* dn = dL_dnormal3D + 3 * (size_t)idx;
+        float dtn[3] = {view[0] * dn[0] + view[1] * dn[1] + view[2] * dn[2],
+                        view[4] * dn[0] + view[5] * dn[1] + view[6] * dn[2],
+                        view[8] * dn[0] + view[9] * dn[1] + view[10] * dn[2]};
+        const float pvx = view[0] * p[0] + view[4] * p[1] + view[8] * p[2] + view[12];
+        const float pvy = view[1] * p[0] + view[5] * p[1] + view[9] * p[2] + view[13];
+        const float pvz = view[2] * p[0] + view[6] * p[1] + view[10] * p[2] + view[14];
+        const float cosv = -(pvx * normal[0] + pvy * normal[1] + pvz * normal[2]);
+        const float mult = cosv > 0 ? 1.0f : -1.0f;
+        for (int j = 0; j < 3; j++) dtn[j] *= mult;
+        const float dRS[3][3] = {{dM[0][0], dM[0][1], dM[0][2]}, {dM[1][0], dM[1][1], dM[1][2]}, {dtn[0], dtn[1], dtn[2]}};
+        float vR[3][3];
+        for (int j = 0; j < 3; j++) { vR[0][j] = dRS[0][j] * sx; vR[1][j] = dRS[1][j] * sy; vR[2][j] = dRS[2][j]; }
+        const float s = 1.0f / sqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+        const float w = q.x * s, x = q.y * s, y = q.z * s, z = q.w * s;
+        float4 dq;
+        dq.x = 2.f * (x * (vR[1][2] - vR[2][1]) + y * (vR[2][0] - vR[0][2]) + z * (vR[0][1] - vR[1][0]));
+        dq.y = 2.f * (-2.f * x * (vR[1][1] + vR[2][2]) + y * (vR[0][1] + vR[1][0]) + z * (vR[0][2] + vR[2][0]) + w * (vR[1][2] - vR[2][1]));
+        dq.z = 2.f * (x * (vR[0][1] + vR[1][0]) - 2.f * y * (vR[0][0] + vR[2][2]) + z * (vR[1][2] + vR[2][1]) + w * (vR[2][0] - vR[0][2]));
+        dq.w = 2.f * (x * (vR[0][2] + vR[2][0]) + y * (vR[1][2] + vR[2][1]) - 2.f * z * (vR[0][0] + vR[1][1]) + w * (vR[0][1] - vR[1][0]));
+        reinterpret_cast<float4*>(dL_drots)[idx] = dq;
+        dL_dscales[2 * (size_t)idx + 0] = dRS[0][0] * R[0][0] + dRS[0][1] * R[0][1] + dRS[0][2] * R[0][2];
+        dL_dscales[2 * (size_t)idx + 1] = dRS[1][0] * R[1][0] + dRS[1][1] * R[1][1] + dRS[1][2] * R[1][2];
+        dL_dmean3D[3 * (size_t)idx + 0] = dM[2][0];
+        dL_dmean3D[3 * (size_t)idx + 1] = dM[2][1];
+        dL_dmean3D[3 * (size_t)idx + 2] = dM[2][2];
+    }
+    if (shs != nullptr && dL_dsh != nullptr)
+        sh_backward(idx, D, M, means3D, cam.campos, shs, clamped[idx], dL_dcolors, dL_dmean3D, dL_dsh);
+    // densification proxy (backward.cu:652-655): uses the dL_dtransMat values as stored in memory
+    const float depth = precomp ? transMat_precomp[9 * (size_t)idx + 8] : splats[idx].Tw[2];
+    const float g2 = wrote_back ? dT[0][2] : dT_u2, g5 = wrote_back ? dT[1][2] : dT_v2;
+    dL_dmean2D[3 * (size_t)idx + 0] = g2 * depth * 0.5f * (float)W;
+    dL_dmean2D[3 * (size_t)idx + 1] = g5 * depth * 0.5f * (float)H;
+}
+
+// ---- host launchers ---------------------------------------------------------------------------------------
+int launch_preprocess_fwd(const IsrForwardArgs& a, cudaStream_t stream) {
+    if (a.P == 0) return ISR_OK;
+    GeomLayout gl(a.P);
+    char* g = static_cast<char*>(a.geom);
+    const int gx = (a.W + TILE - 1) / TILE, gy = (a.H + TILE - 1) / TILE;
+    Camera cam{a.viewmatrix, a.projmatrix, a.campos};
+    preprocess_fwd_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(
+        a.P, a.sh_degree, a.sh_coeffs, a.means3D, reinterpret_cast<const float2*>(a.scales), a.scale_modifier,
+        reinterpret_cast<const float4*>(a.rotations), a.opacities, a.shs, a.transMat_precomp, a.colors_precomp, cam,
+        a.W, a.H, gx, gy, a.radii, reinterpret_cast<Splat*>(g + gl.splat), reinterpret_cast<float4*>(g + gl.cull),
+        reinterpret_cast<float4*>(g + gl.rgb),
+        reinterpret_cast<float*>(g + gl.depth), reinterpret_cast<uint32_t*>(g + gl.depth_key),
+        reinterpret_cast<uint32_t*>(g + gl.tiles), reinterpret_cast<uint8_t*>(g + gl.clamped));
+    ISR_CUDA_TRY(cudaGetLastError());
+    return ISR_OK;
+}
+
+int launch_preprocess_bwd(const IsrBackwardArgs& a, cudaStream_t stream) {
+    if (a.P == 0) return ISR_OK;
+    GeomLayout gl(a.P);
+    const char* g = static_cast<const char*>(a.geom);
+    int W = a.W, H = a.H;
+    if (a.flags & ISR_FLAG_BWD_WH_QUIRK) {
+        // backward.cu:633-634 with focal = W / (2 tan) from rasterizer_impl.cu:399-400, all in fp32
+        volatile float focal_y = (float)a.H / (2.0f * a.tan_fovy);
+        volatile float focal_x = (float)a.W / (2.0f * a.tan_fovx);
+        volatile float fw = focal_x * a.tan_fovx;
+        volatile float fh = focal_y * a.tan_fovy;
+        volatile float fw2 = fw * 2.0f, fh2 = fh * 2.0f;
+        W = (int)fw2;
+        H = (int)fh2;
+    }
+    Camera cam{a.viewmatrix, a.projmatrix, a.campos};
+    preprocess_bwd_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(
+        a.P, a.sh_degree, a.sh_coeffs, a.means3D, a.radii, a.shs, reinterpret_cast<const uint8_t*>(g + gl.clamped),
+        reinterpret_cast<const float2*>(a.scales), reinterpret_cast<const float4*>(a.rotations), a.transMat_precomp,
+        reinterpret_cast<const Splat*>(g + gl.splat), cam, W, H, a.dL_dmeans2D, a.dL_dnormal, a.dL_dtransMat,
+        a.dL_dcolors, a.dL_dsh, a.dL_dmeans3D, a.dL_dscales, a.dL_drotations);
+    ISR_CUDA_TRY(cudaGetLastError());
+    return ISR_OK;
+}
+
+int launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, uint8_t* present,
+                        cudaStream_t stream) {
+    if (P == 0) return ISR_OK;
+    Camera cam{view, proj, nullptr};
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, cam, present);
+    ISR_CUDA_TRY(cudaGetLastError());
+    return ISR_OK;
+}
+
+}  // namespace isr

@@ -1,0 +1,413 @@
+"""Drop-in mirror of the reference package ``diff_surfel_rasterization``
+(submodules/diff-surfel-rasterization/diff_surfel_rasterization/__init__.py), backed by libisr.so.
+
+Same public names, argument order, return tuples and error behaviour:
+  GaussianRasterizationSettings  (NamedTuple, 12 fields)            reference __init__.py:179-191
+  GaussianRasterizer(nn.Module).forward / .markVisible              reference __init__.py:194-248
+  rasterize_gaussians(...) / _RasterizeGaussians                     reference __init__.py:22-176
+  _C.rasterize_gaussians / rasterize_gaussians_backward / mark_visible   DSR/ext.cpp:15-19
+
+Differences that do not change results:
+  * kernels run on torch's CURRENT stream (the reference uses the legacy default stream);
+  * gau_related_pixels is allocated as [9*H*W, 2] and not pre-filled (reference: [100*H*W, 2] filled with -1,
+    then sliced to the same [:count] view);
+  * backward honours ctx.needs_input_grad and skips all-zero (None) cotangents -- exact, adds of 0;
+  * an additional hidden sparse-cotangent handle lets `sample_pixels` route the <=32768 sampled-pixel
+    gradients of train_semantic.py to a sparse backward kernel.
+There is no CPU / eager fallback: everything raises if libisr.so or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_pinned_cache = {}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _pinned_i64(device: torch.device) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    t = _pinned_cache.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int64).pin_memory()
+        _pinned_cache[key] = t
+    return t
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")  # CHECK_INPUT, DSR/rasterize_points.cu:27-28
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _require_cuda_lib():
+    L = _lib.lib()
+    if not torch.cuda.is_available():
+        raise _lib.IsrError("instascene_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return L
+
+
+# --------------------------------------------------------------------------------------------------------------
+# _C-level functions: same signatures / returns as the reference pybind module (DSR/rasterize_points.h:17-73)
+# --------------------------------------------------------------------------------------------------------------
+def c_rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, transMat_precomp,
+                          extra_attrs, attr_degree, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
+                          image_width, sh, degree, campos, prefiltered, debug, want_pairs: bool = True,
+                          return_args: bool = False):
+    """RasterizeGaussiansCUDA (DSR/rasterize_points.cu:39-151).  Returns the reference's 10-tuple
+    (num_rendered, out_color, out_others, radii, out_extra, geomBuffer, binningBuffer, imgBuffer,
+     gau_related_pixels [cap,2], gau_pixel_indices [1] = count-1)."""
+    L = _require_cuda_lib()
+    if means3D.dim() != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    dev = means3D.device
+    P, H, W, F = int(means3D.shape[0]), int(image_height), int(image_width), int(attr_degree)
+    f32 = dict(dtype=torch.float32, device=dev)
+    if P == 0:  # DSR/rasterize_points.cu:112: nothing runs, outputs stay at their fill values
+        out_color = torch.zeros((3, H, W), **f32)
+        out_others = torch.zeros((7, H, W), **f32)
+        out_extra = torch.zeros((F, H, W), **f32) if F > 0 else torch.empty(0, **f32)
+        empty_u8 = torch.empty(0, dtype=torch.uint8, device=dev)
+        return (0, out_color, out_others, torch.zeros(0, dtype=torch.int32, device=dev), out_extra, empty_u8,
+                empty_u8.clone(), empty_u8.clone(), torch.empty((0, 2), dtype=torch.int32, device=dev),
+                torch.full((1,), -1, dtype=torch.int32, device=dev))
+    background = _f32c(background, "background")
+    means3D = _f32c(means3D, "means3D")
+    opacity = _f32c(opacity, "opacity")
+    viewmatrix = _f32c(viewmatrix, "viewmatrix")
+    projmatrix = _f32c(projmatrix, "projmatrix")
+    campos = _f32c(campos, "campos")
+    colors = _f32c(colors, "colors") if colors.numel() else colors
+    scales = _f32c(scales, "scales") if scales.numel() else scales
+    rotations = _f32c(rotations, "rotations") if rotations.numel() else rotations
+    transMat_precomp = _f32c(transMat_precomp, "transMat_precomp") if transMat_precomp.numel() else transMat_precomp
+    sh = _f32c(sh, "sh") if sh.numel() else sh
+    if F > 0:
+        extra_attrs = _f32c(extra_attrs, "extra_attrs")
+    M = int(sh.shape[1]) if sh.numel() else 0
+
+    out_color = torch.empty((3, H, W), **f32)
+    out_others = torch.empty((7, H, W), **f32)
+    out_extra = torch.empty((F, H, W), **f32) if F > 0 else torch.empty(0, **f32)
+    radii = torch.empty(P, dtype=torch.int32, device=dev)
+    geom_bytes, img_bytes = L.isr_geom_bytes(P), L.isr_image_bytes(W, H)
+    geomBuffer = torch.empty(geom_bytes, dtype=torch.uint8, device=dev)
+    imgBuffer = torch.empty(img_bytes, dtype=torch.uint8, device=dev)
+    pair_cap = 9 * H * W if want_pairs else 0
+    pairs = torch.empty((pair_cap, 2), dtype=torch.int32, device=dev)
+    pair_count = torch.zeros(1, dtype=torch.int32, device=dev)
+    nr_host = _pinned_i64(dev)
+
+    a = _lib.IsrForwardArgs()
+    a.P, a.sh_degree, a.sh_coeffs, a.F, a.W, a.H = P, int(degree), M, F, W, H
+    a.flags = 0 if want_pairs else _lib.FLAG_NO_PAIRS
+    a.tan_fovx, a.tan_fovy, a.scale_modifier = float(tan_fovx), float(tan_fovy), float(scale_modifier)
+    a.background, a.viewmatrix, a.projmatrix, a.campos = _ptr(background), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos)
+    a.means3D, a.opacities = _ptr(means3D), _ptr(opacity)
+    a.scales, a.rotations, a.transMat_precomp = _ptr(scales), _ptr(rotations), _ptr(transMat_precomp)
+    a.shs, a.colors_precomp, a.extra_attrs = _ptr(sh), _ptr(colors), (_ptr(extra_attrs) if F > 0 else None)
+    a.geom, a.geom_bytes, a.image, a.image_bytes = geomBuffer.data_ptr(), geom_bytes, imgBuffer.data_ptr(), img_bytes
+    a.radii, a.out_color, a.out_others, a.out_extra = radii.data_ptr(), out_color.data_ptr(), out_others.data_ptr(), _ptr(out_extra)
+    a.pairs, a.pair_capacity, a.pair_count = _ptr(pairs), pair_cap, pair_count.data_ptr()
+    a.num_rendered_host = nr_host.data_ptr()
+
+    stream = _stream()
+    _lib.check(L.isr_forward_geometry(C.byref(a), stream), "isr_forward_geometry")
+    torch.cuda.current_stream().synchronize()  # the reference blocks on a cudaMemcpy here (rasterizer_impl.cu:287)
+    num_rendered = int(nr_host.item())
+    bin_bytes = L.isr_binning_bytes(P, num_rendered, W, H)
+    binningBuffer = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
+    a.binning, a.binning_bytes = binningBuffer.data_ptr(), bin_bytes
+    _lib.check(L.isr_forward_render(C.byref(a), num_rendered, stream), "isr_forward_render")
+    if debug:
+        torch.cuda.synchronize()
+    res = (num_rendered, out_color, out_others, radii, out_extra, geomBuffer, binningBuffer, imgBuffer, pairs,
+           pair_count - 1)
+    if return_args:  # profiling hook (bench.py roofline leg); keeps every tensor the struct points to alive
+        a._keepalive = (background, means3D, colors, opacity, scales, rotations, transMat_precomp, sh, extra_attrs,
+                        viewmatrix, projmatrix, campos, pair_count, nr_host) + res[1:9]
+        return res + (a,)
+    return res
+
+
+def c_rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, extra_attrs, scale_modifier,
+                                   transMat_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
+                                   dL_dout_others, dL_dout_extra, sh, degree, campos, geomBuffer, R, binningBuffer,
+                                   imageBuffer, debug, grad_mask: int = _lib.GRAD_ALL, image_size=None,
+                                   sparse_extra=None, flags: int = _lib.FLAG_BWD_WH_QUIRK):
+    """RasterizeGaussiansBackwardCUDA (DSR/rasterize_points.cu:153-262).  Returns the reference's 9-tuple
+    (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dscales, dL_drotations, dL_dextra).
+    Cotangents may be None (== zeros).  `sparse_extra` = (pix_ids int32 [n], rows float32 [n,F])."""
+    L = _require_cuda_lib()
+    dev = means3D.device
+    P = int(means3D.shape[0])
+    if image_size is None:
+        H, W = int(dL_dout_color.shape[1]), int(dL_dout_color.shape[2])
+    else:
+        H, W = image_size
+    F = int(extra_attrs.shape[1]) if extra_attrs.numel() else 0
+    M = int(sh.shape[1]) if sh.numel() else 0
+    z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+    geo, col, opa, ext = (bool(grad_mask & m) for m in (_lib.GRAD_GEOMETRY, _lib.GRAD_COLOR, _lib.GRAD_OPACITY, _lib.GRAD_EXTRA))
+    dL_dmeans3D, dL_dmeans2D = z(P, 3), z(P, 3)
+    dL_dcolors, dL_dnormal, dL_dopacity, dL_dtransMat = z(P, 3), z(P, 3), z(P, 1), z(P, 9)
+    dL_dsh, dL_dscales, dL_drotations = z(P, M, 3), z(P, 2), z(P, 4)
+    dL_dextra = z(P, F) if F > 0 else torch.empty(0, dtype=torch.float32, device=dev)
+    if P == 0:
+        return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dscales, dL_drotations, dL_dextra
+    means3D = _f32c(means3D, "means3D")
+    # Q17: the reference reads scales/rotations without .contiguous(); enforce contiguity explicitly
+    scales = scales.contiguous() if scales.numel() else scales
+    rotations = rotations.contiguous() if rotations.numel() else rotations
+    cot = [None if t is None else _f32c(t, "cotangent") for t in (dL_dout_color, dL_dout_others, dL_dout_extra)]
+    dense_needed = any(t is not None for t in cot)
+    stream = _stream()
+    if dense_needed and (geo or col or opa or ext):
+        a = _lib.IsrBackwardArgs()
+        a.P, a.sh_degree, a.sh_coeffs, a.F, a.W, a.H = P, int(degree), M, F, W, H
+        a.flags, a.grad_mask, a.num_rendered = flags, grad_mask, int(R)
+        a.tan_fovx, a.tan_fovy, a.scale_modifier = float(tan_fovx), float(tan_fovy), float(scale_modifier)
+        a.background, a.viewmatrix, a.projmatrix, a.campos = _ptr(background), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos)
+        a.means3D, a.scales, a.rotations, a.transMat_precomp = _ptr(means3D), _ptr(scales), _ptr(rotations), _ptr(transMat_precomp)
+        a.shs, a.colors_precomp, a.extra_attrs = _ptr(sh), _ptr(colors), _ptr(extra_attrs)
+        a.radii, a.geom, a.image, a.binning = _ptr(radii), _ptr(geomBuffer), _ptr(imageBuffer), _ptr(binningBuffer)
+        a.dL_dcolor, a.dL_dothers, a.dL_dextra_pix = _ptr(cot[0]), _ptr(cot[1]), (_ptr(cot[2]) if F > 0 else None)
+        a.dL_dmeans2D, a.dL_dnormal, a.dL_dopacity, a.dL_dcolors = _ptr(dL_dmeans2D), _ptr(dL_dnormal), _ptr(dL_dopacity), _ptr(dL_dcolors)
+        a.dL_dmeans3D, a.dL_dtransMat, a.dL_dsh = _ptr(dL_dmeans3D), _ptr(dL_dtransMat), _ptr(dL_dsh)
+        a.dL_dscales, a.dL_drotations, a.dL_dextra = _ptr(dL_dscales), _ptr(dL_drotations), _ptr(dL_dextra)
+        _lib.check(L.isr_backward(C.byref(a), stream), "isr_backward")
+    if sparse_extra is not None and ext and F > 0:
+        pix_ids, rows = sparse_extra
+        pix_ids = pix_ids.to(torch.int32).contiguous()
+        rows = _f32c(rows, "sparse cotangent rows")
+        _lib.check(L.isr_backward_extra_sparse(P, F, W, H, _ptr(extra_attrs), _ptr(geomBuffer), _ptr(imageBuffer),
+                                               _ptr(binningBuffer), int(R), int(pix_ids.numel()), _ptr(pix_ids),
+                                               _ptr(rows), _ptr(dL_dextra), stream), "isr_backward_extra_sparse")
+    if debug:
+        torch.cuda.synchronize()
+    return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dscales, dL_drotations, dL_dextra
+
+
+def c_mark_visible(means3D, viewmatrix, projmatrix):
+    """markVisible (DSR/rasterize_points.cu:264-283)."""
+    L = _require_cuda_lib()
+    P = int(means3D.shape[0])
+    present = torch.zeros(P, dtype=torch.bool, device=means3D.device)
+    if P:
+        means3D, viewmatrix, projmatrix = _f32c(means3D, "means3D"), _f32c(viewmatrix, "viewmatrix"), _f32c(projmatrix, "projmatrix")
+        _lib.check(L.isr_mark_visible(P, _ptr(means3D), _ptr(viewmatrix), _ptr(projmatrix), present.data_ptr(), _stream()),
+                   "isr_mark_visible")
+    return present
+
+
+class _CNamespace:
+    """Stand-in for the reference's pybind module `diff_surfel_rasterization._C`."""
+    rasterize_gaussians = staticmethod(c_rasterize_gaussians)
+    rasterize_gaussians_backward = staticmethod(c_rasterize_gaussians_backward)
+    mark_visible = staticmethod(c_mark_visible)
+
+
+_C = _CNamespace()
+
+
+def cpu_deep_copy_tuple(input_tuple):
+    copied_tensors = [item.cpu().clone() if isinstance(item, torch.Tensor) else item for item in input_tuple]
+    return tuple(copied_tensors)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        extra_attrs, raster_settings):
+    out = _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                    cov3Ds_precomp, extra_attrs, raster_settings)
+    color, radii, depth, extra, pairs, handle = out
+    if extra.numel():
+        extra._isr_handle = handle  # consumed by instascene_b200.sample_pixels
+    return color, radii, depth, extra, pairs
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                extra_attrs, raster_settings):
+        F = extra_attrs.shape[1] if extra_attrs.shape[0] != 0 else 0
+        args = (raster_settings.bg, means3D, colors_precomp, opacities, scales, rotations,
+                raster_settings.scale_modifier, cov3Ds_precomp, extra_attrs, F,
+                raster_settings.viewmatrix, raster_settings.projmatrix, raster_settings.tanfovx,
+                raster_settings.tanfovy, raster_settings.image_height, raster_settings.image_width, sh,
+                raster_settings.sh_degree, raster_settings.campos, raster_settings.prefiltered, raster_settings.debug)
+        want_pairs = getattr(raster_settings, "want_pairs", True)
+        if raster_settings.debug:
+            cpu_args = cpu_deep_copy_tuple(args)
+            try:
+                res = c_rasterize_gaussians(*args, want_pairs=want_pairs)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise ex
+        else:
+            res = c_rasterize_gaussians(*args, want_pairs=want_pairs)
+        (num_rendered, color, depth, radii, extra, geomBuffer, binningBuffer, imgBuffer, gau_related_pixels,
+         gau_pixel_indices) = res
+        if want_pairs:
+            gau_related_pixels = gau_related_pixels[:(int(gau_pixel_indices.item()) + 1)]
+        ctx.raster_settings = raster_settings
+        ctx.num_rendered = num_rendered
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, extra_attrs, sh,
+                              geomBuffer, binningBuffer, imgBuffer)
+        H, W = int(raster_settings.image_height), int(raster_settings.image_width)
+        # zero-stride [H*W, F] handle: only its (hybrid-sparse) gradient is ever used
+        handle = torch.zeros(1, dtype=torch.float32, device=means3D.device).expand(H * W, max(F, 1))
+        ctx.mark_non_differentiable(radii, gau_related_pixels)
+        return color, radii, depth, extra, gau_related_pixels, handle
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_radii, grad_depth, grad_out_extra, grad_pairs, grad_handle):
+        num_rendered = ctx.num_rendered
+        rs = ctx.raster_settings
+        (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, extra_attrs, sh, geomBuffer,
+         binningBuffer, imgBuffer) = ctx.saved_tensors
+        # input order: means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, extra_attrs
+        need = ctx.needs_input_grad
+        mask = 0
+        if need[0] or need[1] or need[5] or need[6] or need[7]:
+            mask |= _lib.GRAD_GEOMETRY | _lib.GRAD_COLOR  # SH backward also feeds dL_dmeans3D
+        if need[2] or need[3]:
+            mask |= _lib.GRAD_COLOR | (_lib.GRAD_GEOMETRY if need[2] else 0)
+        if need[4]:
+            mask |= _lib.GRAD_OPACITY
+        if need[8]:
+            mask |= _lib.GRAD_EXTRA
+        sparse = None
+        if grad_handle is not None:
+            if grad_handle.is_sparse:
+                sparse = (grad_handle._indices()[0], grad_handle._values())
+            else:  # someone densified it: fold into the dense cotangent
+                F = extra_attrs.shape[1]
+                dense = grad_handle[:, :F].t().reshape(F, rs.image_height, rs.image_width)
+                grad_out_extra = dense if grad_out_extra is None else grad_out_extra + dense
+        args = (rs.bg, means3D, radii, colors_precomp, scales, rotations, extra_attrs, rs.scale_modifier,
+                cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, grad_depth,
+                grad_out_extra, sh, rs.sh_degree, rs.campos, geomBuffer, num_rendered, binningBuffer, imgBuffer,
+                rs.debug)
+        kw = dict(grad_mask=mask, image_size=(int(rs.image_height), int(rs.image_width)), sparse_extra=sparse)
+        if rs.debug:
+            cpu_args = cpu_deep_copy_tuple(args)
+            try:
+                res = c_rasterize_gaussians_backward(*args, **kw)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise ex
+        else:
+            res = c_rasterize_gaussians_backward(*args, **kw)
+        (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales,
+         grad_rotations, grad_extra_attrs) = res
+        grads = (grad_means3D if need[0] else None, grad_means2D if need[1] else None, grad_sh if need[2] else None,
+                 grad_colors_precomp if need[3] else None, grad_opacities if need[4] else None,
+                 grad_scales if need[5] else None, grad_rotations if need[6] else None,
+                 grad_cov3Ds_precomp if need[7] else None, grad_extra_attrs if need[8] else None, None)
+        return grads
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            rs = self.raster_settings
+            return c_mark_visible(positions, rs.viewmatrix, rs.projmatrix)
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None, extra_attrs=None):
+        rs = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or (
+                (scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        dev = means3D.device
+        empty = lambda: torch.empty(0, dtype=torch.float32, device=dev)
+        if shs is None:
+            shs = empty()
+        if colors_precomp is None:
+            colors_precomp = empty()
+        if scales is None:
+            scales = empty()
+        if rotations is None:
+            rotations = empty()
+        if cov3D_precomp is None:
+            cov3D_precomp = empty()
+        if extra_attrs is None:
+            extra_attrs = empty()
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                   extra_attrs, rs)
+
+
+# --------------------------------------------------------------------------------------------------------------
+class _SamplePixels(torch.autograd.Function):
+    """features[n,F] = extra_map[:, pix_ids]; the gradient travels as a hybrid-sparse [H*W, F] tensor on the
+    rasterizer's hidden handle so that the backward touches only the sampled pixels."""
+
+    @staticmethod
+    def forward(ctx, handle, extra_map, pix_ids):
+        L = _require_cuda_lib()
+        F = int(extra_map.shape[0])
+        HW = int(extra_map.shape[1] * extra_map.shape[2])
+        ids32 = pix_ids.to(torch.int32).contiguous()
+        out = torch.empty((ids32.numel(), F), dtype=torch.float32, device=extra_map.device)
+        src = extra_map.detach().contiguous()
+        _lib.check(L.isr_gather_pixels(F, HW, src.data_ptr(), int(ids32.numel()), _ptr(ids32), _ptr(out), _stream()),
+                   "isr_gather_pixels")
+        ctx.save_for_backward(pix_ids)
+        ctx.shape = (HW, int(handle.shape[1]))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (pix_ids,) = ctx.saved_tensors
+        g = torch.sparse_coo_tensor(pix_ids.reshape(1, -1).to(torch.int64), grad_out.contiguous(), size=ctx.shape,
+                                    check_invariants=False)
+        return g, None, None
+
+
+def sample_pixels(extra_map: torch.Tensor, pix_ids: torch.Tensor) -> torch.Tensor:
+    """Gather rows [n, F] of a rendered [F,H,W] feature map at flat pixel ids (= W*y + x).
+    Equivalent to `extra_map.reshape(F, -1)[:, pix_ids].T` (train_semantic.py:124-129 after the mask gather)."""
+    handle = getattr(extra_map, "_isr_handle", None)
+    if handle is None or not handle.requires_grad:
+        return extra_map.reshape(extra_map.shape[0], -1)[:, pix_ids.long()].t()
+    return _SamplePixels.apply(handle, extra_map, pix_ids)

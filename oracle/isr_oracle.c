@@ -418,14 +418,17 @@ void orc_blend_forward(int W, int H, int F, const uint32_t* ranges, const uint32
                        const float* means2D, const float* colors, const float* transMats,
                        const float* extras, const float* normal_opacity, const float* bg,
                        float* final_T, uint32_t* n_contrib, float* out_color, float* out_others,
-                       float* out_extra, int32_t* pairs, int64_t pair_cap, int64_t* pair_count) {
+                       float* out_extra, int32_t* pairs, int64_t pair_cap, int64_t* pair_count,
+                       int tile_stride) {
     const int gx = (W + BLOCK_X - 1) / BLOCK_X, gy = (H + BLOCK_Y - 1) / BLOCK_Y;
     const size_t HW = (size_t)H * W;
     const float c1 = far_n / (far_n - near_n);
     int64_t npairs = 0;
+    if (tile_stride < 1) tile_stride = 1; /* >1: only every tile_stride-th tile (bounded CPU-baseline sample) */
 #pragma omp parallel for schedule(dynamic, 4) collapse(2)
     for (int ty = 0; ty < gy; ty++)
         for (int tx = 0; tx < gx; tx++) {
+            if ((ty * gx + tx) % tile_stride != 0) continue;
             const uint32_t r0 = ranges[2 * ((size_t)ty * gx + tx)], r1 = ranges[2 * ((size_t)ty * gx + tx) + 1];
             float* E = (float*)malloc(sizeof(float) * (size_t)(F > 0 ? F : 1));
             for (int ly = 0; ly < BLOCK_Y; ly++)
@@ -501,18 +504,23 @@ void orc_blend_backward(int W, int H, int F, const uint32_t* ranges, const uint3
                         const float* final_T, const uint32_t* n_contrib, const float* dL_dpixels,
                         const float* dL_dothers, const float* dL_dpixel_extras, float* dL_dtransMat,
                         float* dL_dmean2D /*[P][3]*/, float* dL_dnormal3D, float* dL_dopacity,
-                        float* dL_dcolors, float* dL_dextras) {
+                        float* dL_dcolors, float* dL_dextras, int tile_stride) {
     const int gx = (W + BLOCK_X - 1) / BLOCK_X, gy = (H + BLOCK_Y - 1) / BLOCK_Y;
     const size_t HW = (size_t)H * W;
     const float c1 = far_n / (far_n - near_n);
     const float c3 = (far_n * near_n) / (far_n - near_n);
     const int Fa = F > 0 ? F : 1;
-    /* serial over tiles: gradient accumulation order is then fully deterministic */
-    float* accum_ree = (float*)malloc(sizeof(float) * Fa);
-    float* last_extra = (float*)malloc(sizeof(float) * Fa);
-    float* dLdE = (float*)malloc(sizeof(float) * Fa);
+    if (tile_stride < 1) tile_stride = 1;
+    /* Tiles run in parallel; per-Gaussian sums use atomic adds (like the reference's float atomics the order is
+     * then unspecified).  With orc_set_num_threads(1) the order is tile-major, pixel-major, back-to-front. */
+#define ACC(lhs, val) do { const float v_ = (val); _Pragma("omp atomic") lhs += v_; } while (0)
+#pragma omp parallel for schedule(dynamic, 4) collapse(2)
     for (int ty = 0; ty < gy; ty++)
         for (int tx = 0; tx < gx; tx++) {
+            if ((ty * gx + tx) % tile_stride != 0) continue;
+            float* accum_ree = (float*)malloc(sizeof(float) * 3 * Fa);
+            float* last_extra = accum_ree + Fa;
+            float* dLdE = accum_ree + 2 * Fa;
             const uint32_t r0 = ranges[2 * ((size_t)ty * gx + tx)], r1 = ranges[2 * ((size_t)ty * gx + tx) + 1];
             for (int ly = 0; ly < BLOCK_Y; ly++)
                 for (int lx = 0; lx < BLOCK_X; lx++) {
@@ -563,7 +571,7 @@ void orc_blend_backward(int W, int H, int F, const uint32_t* ranges, const uint3
                             accum_rec[ch] = fmaf(last_alpha, last_color[ch], one_m_la * accum_rec[ch]);
                             last_color[ch] = col;
                             dL_dalpha = fmaf(col - accum_rec[ch], dL_dpixel[ch], dL_dalpha);
-                            dL_dcolors[3 * (size_t)g + ch] += w * dL_dpixel[ch];
+                            ACC(dL_dcolors[3 * (size_t)g + ch], w * dL_dpixel[ch]);
                         }
                         float dL_dz = 0.0f;
                         const float rcd = rcp_rn(c_d);
@@ -585,14 +593,14 @@ void orc_blend_backward(int W, int H, int F, const uint32_t* ranges, const uint3
                             accum_normal_rec[ch] = fmaf(last_alpha, last_normal[ch], one_m_la * accum_normal_rec[ch]);
                             last_normal[ch] = no[ch];
                             dL_dalpha = fmaf(no[ch] - accum_normal_rec[ch], dL_dnormal2D[ch], dL_dalpha);
-                            dL_dnormal3D[3 * (size_t)g + ch] += w * dL_dnormal2D[ch];
+                            ACC(dL_dnormal3D[3 * (size_t)g + ch], w * dL_dnormal2D[ch]);
                         }
                         for (int ch = 0; ch < F; ch++) {
                             const float ex = extras[(size_t)g * F + ch];
                             accum_ree[ch] = fmaf(last_alpha, last_extra[ch], one_m_la * accum_ree[ch]);
                             last_extra[ch] = ex;
                             dL_dalpha = fmaf(ex - accum_ree[ch], dLdE[ch], dL_dalpha);
-                            dL_dextras[(size_t)g * F + ch] += w * dLdE[ch];
+                            ACC(dL_dextras[(size_t)g * F + ch], w * dLdE[ch]);
                         }
                         dL_dalpha *= T;
                         last_alpha = alpha;
@@ -613,25 +621,24 @@ void orc_blend_backward(int W, int H, int F, const uint32_t* ranges, const uint3
                             const float dlx = fmaf(dpy, e.kz, -(dpz * e.ky));
                             const float dly = fmaf(dpz, e.kx, -(dpx * e.kz));
                             const float dlz = fmaf(dpx, e.ky, -(dpy * e.kx));
-                            dT[0] += -dkx; dT[1] += -dky; dT[2] += -dkz;
-                            dT[3] += -dlx; dT[4] += -dly; dT[5] += -dlz;
-                            dT[6] += fmaf(dL_dz, e.sx, fmaf(pixx, dkx, pixy * dlx));
-                            dT[7] += fmaf(dL_dz, e.sy, fmaf(pixx, dky, pixy * dly));
-                            dT[8] += fmaf(pixx, dkz, pixy * dlz) + dL_dz;
+                            ACC(dT[0], -dkx); ACC(dT[1], -dky); ACC(dT[2], -dkz);
+                            ACC(dT[3], -dlx); ACC(dT[4], -dly); ACC(dT[5], -dlz);
+                            ACC(dT[6], fmaf(dL_dz, e.sx, fmaf(pixx, dkx, pixy * dlx)));
+                            ACC(dT[7], fmaf(dL_dz, e.sy, fmaf(pixx, dky, pixy * dly)));
+                            ACC(dT[8], fmaf(pixx, dkz, pixy * dlz) + dL_dz);
                         } else {
                             const float dG_ddelx = (-G * FilterInvSquare) * e.ddx;
                             const float dG_ddely = (-G * FilterInvSquare) * e.ddy;
-                            dL_dmean2D[3 * (size_t)g + 0] += dL_dG * dG_ddelx;
-                            dL_dmean2D[3 * (size_t)g + 1] += dL_dG * dG_ddely;
-                            dT[8] += dL_dz;
+                            ACC(dL_dmean2D[3 * (size_t)g + 0], dL_dG * dG_ddelx);
+                            ACC(dL_dmean2D[3 * (size_t)g + 1], dL_dG * dG_ddely);
+                            ACC(dT[8], dL_dz);
                         }
-                        dL_dopacity[g] += G * dL_dalpha;
+                        ACC(dL_dopacity[g], G * dL_dalpha);
                     }
                 }
+            free(accum_ree);
         }
-    free(accum_ree);
-    free(last_extra);
-    free(dLdE);
+#undef ACC
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -66,7 +66,7 @@ def mark_visible(means3D, viewmatrix) -> np.ndarray:
 def forward(means3D, opacities, viewmatrix, projmatrix, campos, W: int, H: int, bg,
             scales=None, rotations=None, scale_modifier: float = 1.0, shs=None, sh_degree: int = 0,
             colors_precomp=None, transMat_precomp=None, extra_attrs=None,
-            want_pairs: bool = True, blend: bool = True) -> Dict[str, np.ndarray]:
+            want_pairs: bool = True, blend: bool = True, tile_stride: int = 1) -> Dict[str, np.ndarray]:
     """Full forward (K1..K6).  Returns every public output and every intermediate buffer."""
     L = lib()
     means3D, opacities = _f32(means3D), _f32(opacities).reshape(-1)
@@ -117,7 +117,7 @@ def forward(means3D, opacities, viewmatrix, projmatrix, campos, W: int, H: int, 
     L.orc_blend_forward(C.c_int(W), C.c_int(H), C.c_int(F), _p(ranges), _p(point_list), _p(means2D),
                         _p(colors), _p(tms), _p(extra_attrs if F else None), _p(normal_opacity), _p(bg),
                         _p(final_T), _p(n_contrib), _p(out_color), _p(out_others), _p(out_extra),
-                        _p(pairs) if want_pairs else C.c_void_p(0), C.c_int64(cap), C.byref(cnt))
+                        _p(pairs) if want_pairs else C.c_void_p(0), C.c_int64(cap), C.byref(cnt), C.c_int(tile_stride))
     out.update(final_T=final_T, n_contrib=n_contrib, color=out_color, others=out_others, extra=out_extra,
                pairs=pairs[: min(cnt.value, cap)], pair_count=int(cnt.value))
     return out
@@ -127,7 +127,7 @@ def backward(fwd: Dict[str, np.ndarray], means3D, viewmatrix, projmatrix, campos
              tan_fovx: float, tan_fovy: float, dL_dcolor, dL_dothers, dL_dextra=None,
              scales=None, rotations=None, scale_modifier: float = 1.0, shs=None, sh_degree: int = 0,
              colors_precomp=None, transMat_precomp=None, extra_attrs=None,
-             flags: int = FLAG_BWD_WH_QUIRK) -> Dict[str, np.ndarray]:
+             flags: int = FLAG_BWD_WH_QUIRK, tile_stride: int = 1) -> Dict[str, np.ndarray]:
     """Full backward (K7 + K8) from the buffers returned by forward()."""
     L = lib()
     means3D = _f32(means3D)
@@ -151,7 +151,7 @@ def backward(fwd: Dict[str, np.ndarray], means3D, viewmatrix, projmatrix, campos
                          _p(extra_attrs if F else None), _p(fwd["final_T"]), _p(fwd["n_contrib"]),
                          _p(dL_dcolor), _p(dL_dothers), _p(dL_dextra if F else None), _p(g["dL_dtransMat"]),
                          _p(g["dL_dmeans2D"]), _p(g["dL_dnormal"]), _p(g["dL_dopacity"]), _p(g["dL_dcolors"]),
-                         _p(g["dL_dextra"]))
+                         _p(g["dL_dextra"]), C.c_int(tile_stride))
     g["dL_dmeans2D_raw"] = g["dL_dmeans2D"].copy()
     g["dL_dtransMat_raw"] = g["dL_dtransMat"].copy()
     L.orc_preprocess_backward(C.c_int(P), C.c_int(sh_degree), C.c_int(M), _p(means3D), _p(fwd["radii"]),

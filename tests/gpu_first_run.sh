@@ -1,0 +1,6 @@
+#!/usr/bin/env bash
+# one gpurun call: parity tests + timing probe; logs into gpurun_out/
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+python -m pytest tests -m gpu -x -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+cat gpurun_out/pytest_gpu.log

@@ -1,0 +1,118 @@
+"""Shared test helpers: run the CUDA path (through the reference-shaped API / C ABI) and the oracle on the same
+seeded synthetic inputs and unpack the CUDA workspaces for field-by-field comparison."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from instascene_b200 import synth  # noqa: E402
+
+
+def scene_inputs(P, F, W, H, seed, view=1, n_views=4, sh_degree=3, scale_mult=1.0):
+    sc = synth.synth_scene(P, F=F, seed=seed, scale_mult=scale_mult)
+    cam = synth.ring_cameras(n_views, W, H)[view]
+    return dict(means3D=sc.xyz, opacities=sc.opacities(), scales=sc.scales(), rotations=sc.rotations(), shs=sc.shs(),
+                extra_attrs=sc.seg_features(), sh_degree=sh_degree, viewmatrix=cam.world_view_transform,
+                projmatrix=cam.full_proj_transform, campos=cam.camera_center, W=W, H=H,
+                tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=np.array([0.1, 0.2, 0.3], np.float32), cam=cam, scene=sc)
+
+
+def oracle_forward(orc, inp, **kw):
+    return orc.forward(inp["means3D"], inp["opacities"], inp["viewmatrix"], inp["projmatrix"], inp["campos"],
+                       inp["W"], inp["H"], inp["bg"], scales=inp["scales"], rotations=inp["rotations"], shs=inp["shs"],
+                       sh_degree=inp["sh_degree"], extra_attrs=inp["extra_attrs"], **kw)
+
+
+def oracle_backward(orc, inp, fwd, dcolor, dothers, dextra, flags=1):
+    return orc.backward(fwd, inp["means3D"], inp["viewmatrix"], inp["projmatrix"], inp["campos"], inp["W"], inp["H"],
+                        inp["bg"], inp["tanfovx"], inp["tanfovy"], dcolor, dothers, dextra, scales=inp["scales"],
+                        rotations=inp["rotations"], shs=inp["shs"], sh_degree=inp["sh_degree"],
+                        extra_attrs=inp["extra_attrs"], flags=flags)
+
+
+def cuda_forward(inp, want_pairs=True, device="cuda:0"):
+    """Runs c_rasterize_gaussians (the reference-shaped binding over the C ABI) and unpacks everything to numpy."""
+    import torch
+    from instascene_b200 import _lib
+    from instascene_b200.rasterizer import c_rasterize_gaussians
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    e = torch.empty(0, dtype=torch.float32, device=device)
+    F = 0 if inp["extra_attrs"] is None else inp["extra_attrs"].shape[1]
+    tens = dict(bg=t(inp["bg"]), means3D=t(inp["means3D"]), opacities=t(inp["opacities"]), scales=t(inp["scales"]),
+                rotations=t(inp["rotations"]), shs=t(inp["shs"]), extra=t(inp["extra_attrs"]) if F else e,
+                view=t(inp["viewmatrix"]), proj=t(inp["projmatrix"]), campos=t(inp["campos"]))
+    res = c_rasterize_gaussians(tens["bg"], tens["means3D"], e, tens["opacities"], tens["scales"], tens["rotations"], 1.0,
+                                e, tens["extra"], F, tens["view"], tens["proj"], inp["tanfovx"], inp["tanfovy"],
+                                inp["H"], inp["W"], tens["shs"], inp["sh_degree"], tens["campos"], False, False,
+                                want_pairs=want_pairs)
+    (R, color, others, radii, extra, geom, binning, img, pairs, pidx) = res
+    torch.cuda.synchronize()
+    L = _lib.lib()
+    P, W, H = inp["means3D"].shape[0], inp["W"], inp["H"]
+    HW, tiles = W * H, ((W + 15) // 16) * ((H + 15) // 16)
+    off = lambda f: int(L.isr_field_offset(f, P, R, W, H))
+    g, im, b = geom.cpu().numpy(), img.cpu().numpy(), binning.cpu().numpy()
+
+    def view(buf, o, dtype, count):
+        return np.frombuffer(buf.tobytes()[o:o + count * np.dtype(dtype).itemsize], dtype=dtype).copy()
+
+    splat = view(g, off(_lib.GEOM_SPLAT), np.float32, P * 16).reshape(P, 16)
+    rgb = view(g, off(_lib.GEOM_RGB), np.float32, P * 4).reshape(P, 4)[:, :3]
+    out = dict(num_rendered=R, color=color.cpu().numpy(), others=others.cpu().numpy(), radii=radii.cpu().numpy(),
+               extra=extra.cpu().numpy() if F else np.zeros((0, H, W), np.float32),
+               transMats=splat[:, :9].copy(), means2D=splat[:, 9:11].copy(),
+               normal_opacity=splat[:, 11:15].copy(), rgb=rgb.copy(),
+               depths=view(g, off(_lib.GEOM_DEPTH), np.float32, P),
+               tiles_touched=view(g, off(_lib.GEOM_TILES), np.uint32, P),
+               clamped_mask=view(g, off(_lib.GEOM_CLAMPED), np.uint8, P),
+               final_T=view(im, off(_lib.IMG_FINAL_T), np.float32, 3 * HW).reshape(3, H, W),
+               n_contrib=view(im, off(_lib.IMG_NCONTRIB), np.uint32, 2 * HW).reshape(2, H, W),
+               ranges=view(im, off(_lib.IMG_RANGES), np.uint32, 2 * tiles).reshape(tiles, 2),
+               point_list=view(b, off(_lib.BIN_POINT_LIST), np.uint32, R) if R else np.zeros(0, np.uint32))
+    if want_pairs:
+        n = int(pidx.item()) + 1
+        out["pairs"] = pairs[:n].cpu().numpy()
+        out["pair_count"] = n
+    out["_torch"] = dict(tens=tens, geom=geom, binning=binning, img=img, radii=radii, R=R)
+    return out
+
+
+def cuda_backward(inp, fwd, dcolor, dothers, dextra, grad_mask=15, sparse=None, flags=1):
+    import torch
+    from instascene_b200.rasterizer import c_rasterize_gaussians_backward
+    st = fwd["_torch"]
+    tens = st["tens"]
+    dev = tens["means3D"].device
+    t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    e = torch.empty(0, dtype=torch.float32, device=dev)
+    sp = None
+    if sparse is not None:
+        sp = (torch.from_numpy(sparse[0]).to(dev), torch.from_numpy(sparse[1]).to(dev))
+    res = c_rasterize_gaussians_backward(tens["bg"], tens["means3D"], st["radii"], e, tens["scales"], tens["rotations"],
+                                         tens["extra"], 1.0, e, tens["view"], tens["proj"], inp["tanfovx"], inp["tanfovy"],
+                                         t(dcolor), t(dothers), t(dextra), tens["shs"], inp["sh_degree"], tens["campos"],
+                                         st["geom"], st["R"], st["binning"], st["img"], False, grad_mask=grad_mask,
+                                         image_size=(inp["H"], inp["W"]), sparse_extra=sp, flags=flags)
+    torch.cuda.synchronize()
+    names = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dtransMat", "dL_dsh", "dL_dscales",
+             "dL_drotations", "dL_dextra"]
+    return {k: v.cpu().numpy() for k, v in zip(names, res)}
+
+
+def rel_err(a, b):
+    """max |a-b| / (max|b| + tiny): norm-wise relative error used for float gradients."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    if a.size == 0:
+        return 0.0
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def pair_set(pairs):
+    p = np.asarray(pairs, np.int64).reshape(-1, 2)
+    return set((p[:, 0] << 32 | p[:, 1]).tolist())

@@ -1,0 +1,231 @@
+"""CPU tests of the host-side logic: the C-ABI library loads and exports every declared symbol (no compute calls
+without a GPU), the Python mirrors keep the reference's interface, the oracle satisfies domain properties, and the
+data-parallel plumbing works over gloo with world_size 2."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_loads_and_exports_every_declared_symbol():
+    from instascene_b200 import _lib
+    L = _lib.lib()
+    header = open(os.path.join(ROOT, "include", "isr.h")).read()
+    declared = set(re.findall(r"\b(isr_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/isr.h but not exported by libisr.so"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    assert L.isr_version() == 100
+    assert L.isr_status_string(-3).decode() == "workspace too small"
+    # struct layout agreement between ctypes and the C header (sizes only; offsets follow from field order)
+    assert ctypes.sizeof(_lib.IsrForwardArgs) % 8 == 0 and ctypes.sizeof(_lib.IsrBackwardArgs) % 8 == 0
+
+
+def test_argument_validation_without_gpu():
+    from instascene_b200 import _lib
+    L = _lib.lib()
+    a = _lib.IsrForwardArgs()
+    a.P, a.W, a.H, a.F = 10, 64, 64, 40
+    assert L.isr_forward_geometry(ctypes.byref(a), None) == -2  # F > ISR_MAX_EXTRA_DIMS
+    a.F = 0
+    assert L.isr_forward_geometry(ctypes.byref(a), None) == -1  # null pointers
+    assert L.isr_forward_geometry(None, None) == -1
+    assert L.isr_knn_mean_dist2(-1, None, None, None, 0, None) == -1
+
+
+def test_product_has_no_cpu_fallback():
+    import torch
+    import instascene_b200 as isr
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    s = isr.GaussianRasterizationSettings(8, 8, 0.5, 0.5, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 0,
+                                          torch.zeros(3), False, False)
+    r = isr.GaussianRasterizer(s)
+    z = torch.zeros((4, 3))
+    with pytest.raises(Exception):
+        r(z, z, torch.zeros((4, 1)), colors_precomp=z, scales=torch.ones((4, 2)), rotations=torch.ones((4, 4)))
+    with pytest.raises(Exception):
+        isr.distCUDA2(torch.zeros((8, 3)))
+    # product sources never import the oracle
+    for root, _, files in os.walk(os.path.join(ROOT, "instascene_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                assert "oracle" not in open(os.path.join(root, f)).read().replace("oracle/isr_oracle.c", "").replace(
+                    "the oracle", "").replace("oracle:", "").replace("CPU oracle", ""), f
+
+
+def test_reference_interface_mirrors():
+    import inspect
+    import instascene_b200 as isr
+    assert isr.GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+        "sh_degree", "campos", "prefiltered", "debug")
+    sig = inspect.signature(isr.GaussianRasterizer.forward)
+    assert list(sig.parameters)[1:] == ["means3D", "means2D", "opacities", "shs", "colors_precomp", "scales",
+                                        "rotations", "cov3D_precomp", "extra_attrs"]
+    sig = inspect.signature(isr.render)
+    assert list(sig.parameters)[:7] == ["viewpoint_camera", "pc", "pipe", "bg_color", "scaling_modifier",
+                                        "override_color", "norm_seg_feat"]
+    sig = inspect.signature(isr.contrastive_loss)
+    assert list(sig.parameters)[:6] == ["features", "masks", "predef_u_list", "min_pixnum", "temp_lambda",
+                                        "consider_negative"]
+
+
+def test_synth_is_deterministic_and_matches_reference_conventions():
+    from instascene_b200 import synth
+    a, b = synth.synth_scene(1000, F=8, seed=5), synth.synth_scene(1000, F=8, seed=5)
+    assert np.array_equal(a.xyz, b.xyz) and np.array_equal(a.seg_feature_raw, b.seg_feature_raw)
+    cam = synth.ring_cameras(8, 640, 360)[3]
+    # camera centre maps to the view-space origin; the cloud centre is in front of the camera (+z)
+    c = np.append(cam.camera_center, 1.0) @ cam.world_view_transform
+    assert np.abs(c[:3]).max() < 1e-5
+    o = np.array([0, 0, 0, 1.0]) @ cam.world_view_transform
+    assert abs(o[2] - 4.0) < 1e-4
+    # full_proj: clip w equals view z
+    p = np.array([0.3, -0.2, 0.1, 1.0])
+    assert abs((p @ cam.full_proj_transform)[3] - (p @ cam.world_view_transform)[2]) < 1e-5
+
+
+def _small(oracle, P=800, F=4, W=48, H=32, seed=3):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import oracle_forward, scene_inputs
+    inp = scene_inputs(P, F, W, H, seed, scale_mult=1.5)
+    return inp, oracle_forward(oracle, inp)
+
+
+def test_oracle_forward_properties(oracle):
+    inp, o = _small(oracle)
+    # sortedness: the instance list is ordered by (tile, depth bits, id), ranges partition it
+    keys = o["keys"]
+    assert np.all(keys[1:] >= keys[:-1])
+    tiles = (keys >> np.uint64(32)).astype(np.int64)
+    same = tiles[1:] == tiles[:-1]
+    d = (keys & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    tie = same & (d[1:] == d[:-1])
+    assert np.all(o["point_list"][1:][tie] > o["point_list"][:-1][tie])  # stable: ties by ascending id
+    r = o["ranges"].astype(np.int64)
+    assert int((r[:, 1] - r[:, 0]).sum()) == o["num_rendered"] == int(o["tiles_touched"].sum())
+    # alpha = 1 - T_final, weights sum to alpha, <= 9 pairs per pixel
+    assert np.allclose(o["others"][1], 1.0 - o["final_T"][0], atol=1e-6)
+    assert np.all(o["final_T"][0] >= 1e-4 - 1e-9)
+    cnt = np.bincount(o["pairs"][:, 1], minlength=inp["W"] * inp["H"])
+    assert cnt.max() <= 9
+    # idempotence
+    o2 = _small(oracle)[1]
+    assert all(np.array_equal(o[k], o2[k]) for k in ("color", "others", "extra", "n_contrib", "point_list"))
+
+
+def test_oracle_backward_is_linear_in_cotangents_and_matches_finite_differences(oracle):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import oracle_backward, oracle_forward
+    inp, o = _small(oracle, P=300, F=4, W=32, H=32, seed=9)
+    W, H, F = inp["W"], inp["H"], 4
+    rng = np.random.default_rng(0)
+    c1 = [rng.standard_normal(s).astype(np.float32) for s in ((3, H, W), (7, H, W), (F, H, W))]
+    c2 = [rng.standard_normal(s).astype(np.float32) for s in ((3, H, W), (7, H, W), (F, H, W))]
+    g1, g2 = oracle_backward(oracle, inp, o, *c1), oracle_backward(oracle, inp, o, *c2)
+    g12 = oracle_backward(oracle, inp, o, *[a + 2 * b for a, b in zip(c1, c2)])
+    for k in ("dL_dextra", "dL_dopacity", "dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dsh"):
+        want = g1[k] + 2 * g2[k]
+        assert np.abs(g12[k] - want).max() <= 2e-4 * (np.abs(want).max() + 1e-12), k
+    # finite differences on the feature channels (the map is linear in the features: exact up to rounding)
+    cot = c1[2]
+    base = float((o["extra"].astype(np.float64) * cot).sum())
+    g = oracle_backward(oracle, inp, o, np.zeros_like(c1[0]), np.zeros_like(c1[1]), cot)
+    vis = np.flatnonzero(o["radii"] > 0)[:5]
+    for gi in vis:
+        for ch in (0, 3):
+            inp2 = dict(inp)
+            ea = inp["extra_attrs"].copy()
+            ea[gi, ch] += 0.25
+            inp2["extra_attrs"] = ea
+            o2 = oracle_forward(oracle, inp2)
+            fd = (float((o2["extra"].astype(np.float64) * cot).sum()) - base) / 0.25
+            assert abs(fd - g["dL_dextra"][gi, ch]) <= 1e-3 * (abs(fd) + 1e-3), (gi, ch, fd, g["dL_dextra"][gi, ch])
+    # finite differences on opacity (smooth away from the thresholds; loose tolerance)
+    cotc = c1[0]
+    basec = float((o["color"].astype(np.float64) * cotc).sum())
+    gc = oracle_backward(oracle, inp, o, cotc, np.zeros_like(c1[1]), np.zeros_like(c1[2]))
+    ok = 0
+    gmax = float(np.abs(gc["dL_dopacity"]).max())
+    for gi in np.argsort(-np.abs(gc["dL_dopacity"][:, 0]))[:6]:  # largest gradients: fp32 forward noise is negligible
+        inp2 = dict(inp)
+        op = inp["opacities"].copy()
+        op[gi] += 1e-3
+        inp2["opacities"] = op
+        o2 = oracle_forward(oracle, inp2)
+        if not np.array_equal(o2["n_contrib"], o["n_contrib"]):
+            continue  # crossed a threshold: not differentiable there
+        fd = (float((o2["color"].astype(np.float64) * cotc).sum()) - basec) / 1e-3
+        assert abs(fd - gc["dL_dopacity"][gi, 0]) <= 5e-2 * abs(fd) + 2e-2 * gmax, (gi, fd, gc["dL_dopacity"][gi, 0])
+        ok += 1
+    assert ok >= 1
+
+
+def test_contrastive_oracle_matches_closed_form():
+    import torch
+    from oracle.contrastive_ref import contrastive_loss_ref
+    torch.manual_seed(0)
+    f = torch.randn(64, 8, dtype=torch.float64)
+    lab = torch.randint(1, 5, (64,))
+    loss = contrastive_loss_ref(f, lab)
+    fh = f / f.norm(dim=1, keepdim=True)
+    ids = torch.unique(lab)
+    u = torch.stack([fh[lab == i].mean(0) for i in ids])
+    n = torch.tensor([(lab == i).sum() for i in ids], dtype=torch.float64)
+    y = torch.searchsorted(ids, lab)
+    phi = torch.stack([(fh[lab == i] - u[j]).norm(dim=1).sum() for j, i in enumerate(ids)]) / (n * torch.log(n + 1000))
+    phi = torch.clip(phi * 10, 0.5, 1.0)
+    z = fh @ u.T / phi
+    want = (torch.logsumexp(z, 1) - z[torch.arange(64), y]).sum()
+    assert abs(float(loss) - float(want)) < 1e-6 * abs(float(want))
+
+
+def test_view_sharding():
+    from instascene_b200 import dist as idist
+    for world in (1, 2, 8):
+        all_views = sorted(v for r in range(world) for v in idist.shard_views(200, r, world))
+        assert all_views == list(range(200))
+        step0 = [idist.step_views(0, 200, r, world) for r in range(world)]
+        assert len(set(step0)) == world
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, %r)
+from instascene_b200 import dist as idist
+rank, local_rank, world = idist.init("gloo")
+assert world == 2
+torch.manual_seed(0)
+P, F = 1000, 16
+per_view = [torch.randn(P, F) for _ in range(4)]          # "gradient of view v" (same on both ranks)
+mine = [v for v in range(4) if v %% world == rank]
+g = torch.zeros(P, F)
+for v in mine:
+    g += per_view[v]
+idist.allreduce_grads([g], world)
+want = sum(per_view)
+assert torch.allclose(g, want, atol=1e-5), (g - want).abs().max()
+t = idist.max_over_ranks(float(rank + 1), world, "cpu")
+assert t == 2.0
+idist.barrier(world)
+print("rank", rank, "ok")
+"""
+
+
+def test_gloo_world2_gradient_allreduce(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER % ROOT)
+    port = 29500 + (os.getpid() % 2000)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2

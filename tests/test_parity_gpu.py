@@ -1,0 +1,266 @@
+"""GPU parity tests (run with -m gpu on the B200 box): CUDA path through the C ABI vs the CPU oracle on the same
+seeded inputs.  Forward outputs -- floats AND every thresholded integer -- must be BIT-EXACT (the spec'd fp32
+arithmetic is identical on both sides); gradients are compared at 1e-4 norm-wise relative error (the summation
+order over pixels differs; the reference itself uses unordered float atomics)."""
+import numpy as np
+import pytest
+
+from helpers import (cuda_backward, cuda_forward, oracle_backward, oracle_forward, pair_set, rel_err, scene_inputs)
+
+pytestmark = pytest.mark.gpu
+
+GRAD_TOL = 1e-4
+
+CASES = [
+    # P, F, W, H, seed, scale_mult
+    (3000, 0, 96, 64, 11, 1.0),
+    (6000, 16, 160, 96, 12, 1.0),
+    (2000, 3, 70, 50, 13, 2.0),     # non-multiple-of-16 image, odd F
+    (20000, 32, 128, 128, 14, 0.7),  # F = 32 (beyond the reference's MAX_EXTRA_DIMS 24)
+    (500, 8, 33, 17, 15, 6.0),      # huge splats, long per-tile lists, tiny image
+]
+
+
+def _check_forward_exact(c, o, F):
+    for k in ["radii", "tiles_touched", "num_rendered"]:
+        assert np.array_equal(c[k], o[k]), k
+    vis = o["radii"] > 0
+    for k in ["depths", "transMats", "means2D", "normal_opacity", "rgb"]:
+        assert np.array_equal(c[k][vis].view(np.uint32), o[k][vis].view(np.uint32)), k
+    cm = np.packbits(o["clamped"][vis].astype(bool), axis=1, bitorder="little")[:, 0]
+    assert np.array_equal(c["clamped_mask"][vis], cm)
+    assert np.array_equal(c["point_list"], o["point_list"]), "sorted (tile, depth, id) instance list"
+    assert np.array_equal(c["ranges"], o["ranges"]), "tile ranges"
+    assert np.array_equal(c["n_contrib"], o["n_contrib"]), "n_contrib"
+    for k in ["final_T", "color", "others"] + (["extra"] if F else []):
+        assert np.array_equal(c[k].view(np.uint32), o[k].view(np.uint32)), k
+    assert c["pair_count"] == o["pair_count"]
+    assert pair_set(c["pairs"]) == pair_set(o["pairs"])
+
+
+@pytest.mark.parametrize("P,F,W,H,seed,sm", CASES)
+def test_forward_bit_exact(oracle, P, F, W, H, seed, sm):
+    inp = scene_inputs(P, F, W, H, seed, scale_mult=sm)
+    o = oracle_forward(oracle, inp)
+    c = cuda_forward(inp)
+    _check_forward_exact(c, o, F)
+
+
+@pytest.mark.parametrize("P,F,W,H,seed,sm", CASES)
+def test_backward_dense(oracle, P, F, W, H, seed, sm):
+    inp = scene_inputs(P, F, W, H, seed, scale_mult=sm)
+    rng = np.random.default_rng(seed + 1)
+    dcolor = rng.standard_normal((3, H, W)).astype(np.float32)
+    dothers = rng.standard_normal((7, H, W)).astype(np.float32)
+    dextra = rng.standard_normal((F, H, W)).astype(np.float32) if F else None
+    o = oracle_forward(oracle, inp)
+    og = oracle_backward(oracle, inp, o, dcolor, dothers, dextra)
+    c = cuda_forward(inp)
+    cg = cuda_backward(inp, c, dcolor, dothers, dextra)
+    for k in ["dL_dcolors", "dL_dopacity", "dL_dtransMat", "dL_dmeans2D", "dL_dmeans3D", "dL_dscales", "dL_drotations",
+              "dL_dsh"] + (["dL_dextra"] if F else []):
+        assert np.isfinite(cg[k]).all(), k
+        assert rel_err(cg[k], og[k].reshape(cg[k].shape)) < GRAD_TOL, (k, rel_err(cg[k], og[k].reshape(cg[k].shape)))
+
+
+def test_backward_sparse_equals_dense(oracle):
+    P, F, W, H, seed = 6000, 16, 160, 96, 21
+    inp = scene_inputs(P, F, W, H, seed)
+    rng = np.random.default_rng(seed)
+    n = 700
+    pix = rng.integers(0, W * H, size=n).astype(np.int32)  # with replacement -> duplicates
+    rows = rng.standard_normal((n, F)).astype(np.float32)
+    dense = np.zeros((F, H * W), np.float32)
+    np.add.at(dense.T, pix, rows)
+    dense = dense.reshape(F, H, W)
+    o = oracle_forward(oracle, inp)
+    og = oracle_backward(oracle, inp, o, np.zeros((3, H, W), np.float32), np.zeros((7, H, W), np.float32), dense)
+    c = cuda_forward(inp, want_pairs=False)
+    g_sparse = cuda_backward(inp, c, None, None, None, grad_mask=8, sparse=(pix, rows))
+    g_dense = cuda_backward(inp, c, None, None, dense, grad_mask=8)
+    assert rel_err(g_sparse["dL_dextra"], og["dL_dextra"]) < GRAD_TOL
+    assert rel_err(g_dense["dL_dextra"], og["dL_dextra"]) < GRAD_TOL
+
+
+def test_wh_quirk_flag(oracle):
+    """Q5: backward's W,H = int(focal*tan*2) can be W-1; both settings must match the oracle."""
+    P, F, W, H, seed = 1500, 0, 64, 48, 31
+    inp = scene_inputs(P, F, W, H, seed)
+    rng = np.random.default_rng(seed)
+    dcolor = rng.standard_normal((3, H, W)).astype(np.float32)
+    dothers = rng.standard_normal((7, H, W)).astype(np.float32)
+    o = oracle_forward(oracle, inp)
+    c = cuda_forward(inp, want_pairs=False)
+    for flags in (0, 1):
+        og = oracle_backward(oracle, inp, o, dcolor, dothers, None, flags=flags)
+        cg = cuda_backward(inp, c, dcolor, dothers, None, flags=flags)
+        for k in ["dL_dmeans2D", "dL_dmeans3D", "dL_dscales", "dL_drotations"]:
+            assert rel_err(cg[k], og[k]) < GRAD_TOL, (flags, k)
+
+
+def test_empty_and_culled(oracle):
+    import torch
+    import instascene_b200 as isr
+    dev = "cuda:0"
+    # P = 0
+    s = isr.GaussianRasterizationSettings(32, 48, 0.5, 0.4, torch.zeros(3, device=dev), 1.0, torch.eye(4, device=dev),
+                                          torch.eye(4, device=dev), 0, torch.zeros(3, device=dev), False, False)
+    r = isr.GaussianRasterizer(s)
+    z = torch.zeros((0, 3), device=dev)
+    color, radii, allmap, extra, pairs = r(z, z, torch.zeros((0, 1), device=dev), colors_precomp=z,
+                                            scales=torch.zeros((0, 2), device=dev), rotations=torch.zeros((0, 4), device=dev))
+    assert color.shape == (3, 32, 48) and float(color.abs().max()) == 0.0 and pairs.shape[0] == 0
+    # everything behind the camera: R = 0, colour = background
+    inp = scene_inputs(300, 4, 48, 32, 41)
+    inp["means3D"] = inp["means3D"] + np.array([100.0, 0, 0], np.float32) * 0  # keep
+    inp["viewmatrix"] = inp["viewmatrix"].copy()
+    inp["viewmatrix"][3, 2] -= 50.0  # push the scene far behind the camera (z_view <= 0.2)
+    o = oracle_forward(oracle, inp)
+    c = cuda_forward(inp)
+    assert o["num_rendered"] == 0 and c["num_rendered"] == 0
+    assert np.array_equal(c["color"], o["color"]) and np.array_equal(c["others"], o["others"])
+    with pytest.raises(Exception):
+        r(z, z, torch.zeros((0, 1), device=dev))  # neither SHs nor colours
+
+
+def test_mark_visible(oracle):
+    import torch
+    import instascene_b200 as isr
+    inp = scene_inputs(5000, 0, 64, 64, 51)
+    inp["viewmatrix"] = inp["viewmatrix"].copy()
+    inp["viewmatrix"][3, 2] -= 4.0  # camera plane cuts through the cloud
+    dev = "cuda:0"
+    t = lambda a: torch.from_numpy(a).to(dev)
+    s = isr.GaussianRasterizationSettings(64, 64, 0.5, 0.5, torch.zeros(3, device=dev), 1.0, t(inp["viewmatrix"]),
+                                          t(inp["projmatrix"]), 0, t(inp["campos"]), False, False)
+    vis = isr.GaussianRasterizer(s).markVisible(t(inp["means3D"])).cpu().numpy()
+    ref = oracle.mark_visible(inp["means3D"], inp["viewmatrix"])
+    assert np.array_equal(vis, ref) and 0 < vis.sum() < vis.size
+
+
+def test_knn(oracle):
+    import torch
+    import instascene_b200 as isr
+    rng = np.random.default_rng(5)
+    for P in (3, 100, 5000):
+        pts = rng.standard_normal((P, 3)).astype(np.float32)
+        pts[: P // 3] *= 0.01  # a dense cluster
+        got = isr.distCUDA2(torch.from_numpy(pts).cuda()).cpu().numpy()
+        want = oracle.knn_mean_dist2(pts)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), P
+
+
+@pytest.mark.parametrize("predef,consider_negative", [(False, False), (True, False), (False, True)])
+def test_contrastive_loss(predef, consider_negative):
+    import torch
+    import instascene_b200 as isr
+    from instascene_b200 import synth
+    from oracle.contrastive_ref import contrastive_loss_ref
+    rng = np.random.default_rng(7)
+    N, F, K = 4096, 16, 37
+    feats = rng.standard_normal((N, F)).astype(np.float32)
+    labels = rng.integers(0, K + 1, size=N).astype(np.int64)  # 0 = unlabelled
+    labels[labels == 5] = 6                                   # an absent id in the middle
+    proto = synth.gram_schmidt_prototypes(K + 1, F, 3) if predef else None
+    f64 = torch.tensor(feats, dtype=torch.float64, requires_grad=True)
+    want = contrastive_loss_ref(f64, torch.tensor(labels), None if proto is None else torch.tensor(proto, dtype=torch.float64),
+                                consider_negative=consider_negative)
+    want.backward()
+    fc = torch.tensor(feats, device="cuda", requires_grad=True)
+    got = isr.contrastive_loss(fc, torch.tensor(labels, device="cuda"),
+                               None if proto is None else torch.tensor(proto, device="cuda"),
+                               consider_negative=consider_negative)
+    (got * 0.5).backward()
+    assert abs(float(got) - float(want)) / abs(float(want)) < 1e-4
+    assert rel_err(fc.grad.cpu().numpy() * 2.0, f64.grad.numpy()) < 1e-4
+
+
+def test_autograd_render_sample_loss(oracle):
+    """render() -> sample_pixels -> contrastive_loss -> backward: gradient w.r.t. the raw seg feature parameter
+    through the sparse path equals the oracle's dense backward composed with torch autograd on the CPU."""
+    import torch
+    import instascene_b200 as isr
+    from instascene_b200 import synth
+    from oracle.contrastive_ref import contrastive_loss_ref
+    P, F, W, H, seed = 5000, 16, 128, 80, 61
+    inp = scene_inputs(P, F, W, H, seed)
+    sc, cam = inp["scene"], inp["cam"]
+    dev = "cuda:0"
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    class PC:
+        active_sh_degree, max_sh_degree = 3, 3
+        get_xyz = t(sc.xyz)
+        get_opacity = t(sc.opacities()).reshape(-1, 1)
+        get_scaling = t(sc.scales())
+        get_rotation = t(sc.rotations())
+        get_features = t(sc.shs())
+        _seg = t(sc.seg_feature_raw).requires_grad_(True)
+
+        @property
+        def get_seg_feature(self):
+            return self._seg / (torch.norm(self._seg, p=2, dim=1, keepdim=True) + 1e-6)
+
+    class Cam:
+        FoVx, FoVy, image_width, image_height = cam.FoVx, cam.FoVy, W, H
+        world_view_transform, full_proj_transform, camera_center = t(cam.world_view_transform), t(cam.full_proj_transform), t(cam.camera_center)
+        znear, zfar = 0.01, 100.0
+
+    class Pipe:
+        compute_cov3D_python, convert_SHs_python, depth_ratio = False, False, 1.0
+
+    pc = PC()
+    pkg = isr.render(Cam(), pc, Pipe(), t(inp["bg"]))
+    assert set(pkg) == {"render", "viewspace_points", "visibility_filter", "radii", "seg_feature", "gau_related_pixels",
+                        "rend_alpha", "rend_normal", "rend_dist", "surf_depth", "surf_normal", "rend_depth",
+                        "rend_median_depth"}
+    lab = synth.label_map(W, H, seed + 2)
+    valid = np.flatnonzero(lab.reshape(-1) > 0)
+    rng = np.random.default_rng(seed + 3)
+    pix = valid[rng.integers(0, valid.size, size=2048)]
+    labels = lab.reshape(-1)[pix].astype(np.int64)
+    feats = isr.sample_pixels(pkg["seg_feature"], t(pix.astype(np.int64)))
+    loss = isr.contrastive_loss(feats, t(labels)) * 1e-3
+    loss.backward()
+    got = pc._seg.grad.cpu().numpy()
+
+    # oracle: CPU forward, torch-CPU loss, oracle dense backward, torch-CPU activation chain
+    # the oracle gets the feature rows exactly as the GPU normalised them (torch-CUDA and numpy norms differ by ulps)
+    with torch.no_grad():
+        segn = pc.get_seg_feature
+        segn = segn / (segn.norm(dim=-1, keepdim=True) + 1e-9)
+    inp["extra_attrs"] = segn.cpu().numpy()
+    o = oracle_forward(oracle, inp)
+    assert np.array_equal(pkg["seg_feature"].detach().cpu().numpy().view(np.uint32), o["extra"].view(np.uint32))
+    emap = torch.tensor(o["extra"], requires_grad=True)
+    f_o = emap.reshape(F, -1)[:, torch.tensor(pix)].t()
+    l_o = contrastive_loss_ref(f_o, torch.tensor(labels)) * 1e-3
+    l_o.backward()
+    assert abs(float(loss) - float(l_o)) / abs(float(l_o)) < 1e-4
+    og = oracle_backward(oracle, inp, o, np.zeros((3, H, W), np.float32), np.zeros((7, H, W), np.float32), emap.grad.numpy())
+    raw = torch.tensor(sc.seg_feature_raw, requires_grad=True)
+    a = raw / (torch.norm(raw, p=2, dim=1, keepdim=True) + 1e-6)
+    a = a / (a.norm(dim=-1, keepdim=True) + 1e-9)
+    a.backward(torch.tensor(og["dL_dextra"]))
+    assert rel_err(got, raw.grad.numpy()) < 2e-4
+
+
+def _golden_paths():
+    import glob
+    import os
+    return sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", _golden_paths(), ids=lambda p: p.split("/")[-1][:-4])
+def test_cuda_matches_reference_goldens(path):
+    """CUDA path vs outputs of the unmodified reference CUDA rasterizer (tests/golden/*.npz, generated on a B200 by
+    tests/golden/make_golden.py): integers exact, floats / gradients within 1e-4."""
+    from test_golden_cpu import SEEDS, check_against_reference, cotangents, load_fixture
+    inp, ref = load_fixture(path)
+    name = path.split("/")[-1][:-4]
+    F = 0 if inp["extra_attrs"] is None else inp["extra_attrs"].shape[1]
+    c = cuda_forward(inp)
+    dcolor, dothers, dextra = cotangents(F, inp["W"], inp["H"], SEEDS[name])
+    g = cuda_backward(inp, c, dcolor, dothers, dextra)
+    c["clamped"] = None
+    check_against_reference(c, ref, F, g)
