@@ -29,6 +29,7 @@
  *                                                 DSR/cuda_rasterizer/rasterizer_impl.h:29-72
  *   isr_contrastive_forward / _backward        <- utils/contrastive_utils.py:18-73 (contrastive_loss)
  *   isr_gather_pixels                          <- train_semantic.py:124-129 (boolean-mask gather + index)
+ *   isr_rownorm_forward / _backward            <- scene/gaussian_model.py:121-125 + gaussian_renderer/__init__.py:60-62
  *   isr_knn_mean_dist2                         <- SimpleKNN::knn submodules/simple-knn/simple_knn.cu:186-222
  *                                                 (distCUDA2, submodules/simple-knn/spatial.cu:15-25)
  */
@@ -202,6 +203,14 @@ int isr_contrastive_forward(int N, int F, int K, const float* features, const in
 int isr_contrastive_backward(int N, int F, int K, const float* features, const int* labels,
                              const float* predef_u, const void* ws, const float* grad_scale,
                              float* dL_dfeatures, void* stream);
+
+/* ---- seg-feature activation ------------------------------------------------------------------------------ */
+/* Row normalisation y = x / (|x| + eps1), optionally followed by a second one with eps2 (stages = 2): the two
+ * L2 normalisations applied to _seg_feature before rasterisation (scene/gaussian_model.py:121-125 then
+ * gaussian_renderer/__init__.py:60-62), fused into one pass each way.  x, y, dy, dx are [P,F]. */
+int isr_rownorm_forward(int P, int F, const float* x, float eps1, float eps2, int stages, float* y, void* stream);
+int isr_rownorm_backward(int P, int F, const float* x, const float* dy, float eps1, float eps2, int stages, float* dx,
+                         void* stream);
 
 /* ---- simple-knn ------------------------------------------------------------------------------------- */
 size_t isr_knn_workspace_bytes(int P);

@@ -23,6 +23,8 @@ int launch_contrastive_fwd(int N, int F, int K, const float* features, const int
                            float temp_lambda, void* ws, float* loss, cudaStream_t stream);
 int launch_contrastive_bwd(int N, int F, int K, const int* labels, const float* predef_u, const void* ws,
                            const float* grad_scale, float* dfeat, cudaStream_t stream);
+int launch_rownorm(bool fwd, int P, int F, const float* x, const float* dy, float e1, float e2, int stages, float* out,
+                   cudaStream_t stream);
 size_t knn_ws_bytes(int P);
 int launch_knn(int P, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
 }  // namespace isr
@@ -203,6 +205,23 @@ int isr_contrastive_backward(int N, int F, int K, const float* features, const i
     if (N > 0 && (!labels || !ws || !dL_dfeatures)) return ISR_ERR_INVALID_ARG;
     return launch_contrastive_bwd(N, F, K, labels, predef_u, ws, grad_scale, dL_dfeatures,
                                   static_cast<cudaStream_t>(stream_));
+}
+
+int isr_rownorm_forward(int P, int F, const float* x, float eps1, float eps2, int stages, float* y, void* stream_) {
+    if (P < 0 || F < 0 || stages < 1 || stages > 2) return ISR_ERR_INVALID_ARG;
+    if (F > ISR_MAX_EXTRA_DIMS) return ISR_ERR_UNSUPPORTED;
+    if (P == 0 || F == 0) return ISR_OK;
+    if (!x || !y) return ISR_ERR_INVALID_ARG;
+    return launch_rownorm(true, P, F, x, nullptr, eps1, eps2, stages, y, static_cast<cudaStream_t>(stream_));
+}
+
+int isr_rownorm_backward(int P, int F, const float* x, const float* dy, float eps1, float eps2, int stages, float* dx,
+                         void* stream_) {
+    if (P < 0 || F < 0 || stages < 1 || stages > 2) return ISR_ERR_INVALID_ARG;
+    if (F > ISR_MAX_EXTRA_DIMS) return ISR_ERR_UNSUPPORTED;
+    if (P == 0 || F == 0) return ISR_OK;
+    if (!x || !dy || !dx) return ISR_ERR_INVALID_ARG;
+    return launch_rownorm(false, P, F, x, dy, eps1, eps2, stages, dx, static_cast<cudaStream_t>(stream_));
 }
 
 size_t isr_knn_workspace_bytes(int P) { return P < 0 ? 0 : knn_ws_bytes(P) + 256; }

@@ -311,11 +311,13 @@ extra_sparse_bwd_kernel(int n, const int* __restrict__ pix_ids, const float* __r
         // sequential-exact transmittance: T_i = T_{i-1} * (1 - alpha_{i-1}) in list order, same roundings as
         // the forward (a left-to-right product), obtained by passing the running value lane to lane.
         float Tin = T;
-#pragma unroll
-        for (int l = 0; l < 32; l++) {
+        unsigned contrib = __ballot_sync(0xffffffffu, alpha != 0.0f);
+        while (contrib) {  // contributing lanes only, in list order
+            const int l = __ffs(contrib) - 1;
+            contrib &= contrib - 1;
             const float a_l = __shfl_sync(0xffffffffu, alpha, l);
             if (lane == l) Tin = T;
-            if (a_l != 0.0f) T = mul(T, sub(1.0f, a_l));
+            T = mul(T, sub(1.0f, a_l));
         }
         if (alpha != 0.0f && g >= 0) {
             const float w = mul(alpha, Tin);

@@ -1,28 +1,37 @@
 // isr_blend_fwd.cu -- K6: per-tile front-to-back alpha compositing of RGB + 7 auxiliary maps + F semantic
 // feature channels + the (gaussian, pixel) pair list.   Reference: DSR/cuda_rasterizer/forward.cu:256-462.
 //
-// Mapping: one CTA (256 threads) per 16x16 tile, one thread per pixel, a warp covers an 8x4 pixel block.
-// Per batch of 256 list entries every thread stages ONE instance into shared memory (splat record 64 B,
-// cull rect 16 B, rgb 16 B, features 4F B -- all 16-byte vector loads), so the inner loop issues no global
-// loads (the reference fetches rgb and features from global per contributing (pixel, Gaussian) pair).
-// Each warp first tests 32 staged Gaussians at a time against its own 8x4 pixel block with the conservative
-// cull rectangle computed in K1 (one lane per Gaussian, one ballot), and only walks the survivors in list
-// order -- exact, because a culled Gaussian provably fails the alpha >= 1/255 test on every pixel of the block.
-// Pair-list entries are staged per warp in shared memory and flushed with one global atomic per 32+ pairs
-// (the reference does one global atomic per pair on a single counter).
+// Mapping: one CTA (256 threads) per 16x16 tile, one thread per pixel, a warp per 8x4 pixel block.  Warps are
+// autonomous (see blend_fwd_kernel): per-warp exact culling against a conservative per-Gaussian rectangle computed
+// in K1, cp.async staging of the surviving records (splat 64 B, rgb 16 B, features 4F B) into warp-private shared
+// memory, broadcast reads in the inner loop (the reference fetches rgb and features from global per contributing
+// (pixel, Gaussian) pair), no block-wide barriers.  Pair-list entries are staged per warp in shared memory and
+// flushed with one global atomic per <= 96 pairs (the reference: one global atomic per pair on a single counter).
 #include "isr_common.cuh"
 
 namespace isr {
 
-constexpr int kBatch = 256;
 constexpr int kPairStage = 96;  // per-warp staging slots (int2)
 
 template <int FP>  // feature dim padded to a multiple of 4 (0, 4, 8, 16, 24, 32)
 struct FwdSmem {
-    static constexpr int kFeatVec = FP / 4;
-    static constexpr size_t bytes = (size_t)kBatch * (64 + 16 + 16 + 4 * FP + 4) + 8 * kPairStage * 8;
+    static constexpr int kRecF4 = 4 + 1 + FP / 4;  // splat (4 x float4) + rgb (1) + features
+    static constexpr size_t per_warp = (size_t)32 * kRecF4 * 16 + 32 * 8 + kPairStage * 8;
+    static constexpr size_t bytes = 8 * per_warp;
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// Warp-autonomous blend: every warp owns an 8x4 pixel block and walks its tile's list on its own, 32 entries at a
+// time: (1) ids and cull rectangles of the NEXT chunks are prefetched into registers, (2) one lane per entry tests
+// the cull rectangle against the warp's pixel block, (3) only the survivors' records are copied (cp.async, 16-byte
+// LDGSTS, no registers) into the warp's private shared-memory slots, (4) the survivors are blended in list order
+// with broadcast shared-memory reads.  There is no block-wide barrier: warps of a tile neither wait for each other
+// nor for the slowest pixel of the tile, and a warp stops as soon as its own 32 pixels are saturated.
 template <int FP, bool kPairs>
 __global__ void __launch_bounds__(256)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int F,
@@ -31,30 +40,28 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                  uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, float* __restrict__ out_others,
                  float* __restrict__ out_extra, int2* __restrict__ pairs, int64_t pair_cap, int* __restrict__ pair_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* s_splat = reinterpret_cast<float4*>(smem_raw);                 // [kBatch][4]
-    float4* s_cull = s_splat + kBatch * 4;                                 // [kBatch]
-    float4* s_rgb = s_cull + kBatch;                                       // [kBatch]
-    float4* s_feat = s_rgb + kBatch;                                       // [kBatch][FP/4]
-    int* s_id = reinterpret_cast<int*>(s_feat + kBatch * (FP / 4));        // [kBatch]
-    int2* s_pairs = reinterpret_cast<int2*>(s_id + kBatch);                // [8][kPairStage]
-
+    constexpr int REC = FwdSmem<FP>::kRecF4;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    unsigned char* wbase = smem_raw + (size_t)warp * FwdSmem<FP>::per_warp;
+    float4* slots = reinterpret_cast<float4*>(wbase);                       // [32][REC]
+    int2* meta = reinterpret_cast<int2*>(wbase + (size_t)32 * REC * 16);    // [32] (gaussian id, list index)
+    int2* my_pairs = meta + 32;                                              // [kPairStage]
+
     const int tiles_x = (W + TILE - 1) / TILE;
     const int tile_id = blockIdx.y * tiles_x + blockIdx.x;
-    // warp -> 8x4 block inside the tile
     const int wx0 = blockIdx.x * TILE + (warp & 1) * 8;
     const int wy0 = blockIdx.y * TILE + (warp >> 1) * 4;
     const int pxi = wx0 + (lane & 7), pyi = wy0 + (lane >> 3);
     const bool inside = pxi < W && pyi < H;
     const uint32_t pix_id = (uint32_t)W * (uint32_t)pyi + (uint32_t)pxi;
     const float pixx = (float)pxi, pixy = (float)pyi;
-    // pixel block bounds of this warp (inclusive), clipped to the image
     const float bx0 = (float)wx0, by0 = (float)wy0;
     const float bx1 = (float)min(wx0 + 7, W - 1), by1 = (float)min(wy0 + 3, H - 1);
 
     const uint2 range = ranges[tile_id];
     const int n_total = (int)(range.y - range.x);
+    const uint32_t* __restrict__ plist = point_list + range.x;
     const float c1 = __fdiv_rn(kFar, __fsub_rn(kFar, kNear));
 
     bool done = !inside;
@@ -65,111 +72,115 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 #pragma unroll
     for (int ch = 0; ch < FP; ch++) E[ch] = 0.0f;
     int wcount = 0;  // staged pairs of this warp (warp-uniform)
-    int2* my_pairs = s_pairs + warp * kPairStage;
 
-    for (int base = 0; base < n_total; base += kBatch) {
-        // whole-block early exit (forward.cu:331-333)
-        if (__syncthreads_count(done) == 256) break;
-        const int n_batch = min(kBatch, n_total - base);
-        if (tid < n_batch) {
-            const int g = (int)point_list[range.x + base + tid];
-            s_id[tid] = g;
-            const float4* sp = splats + (size_t)g * 4;
-            s_splat[tid * 4 + 0] = __ldg(sp + 0);
-            s_splat[tid * 4 + 1] = __ldg(sp + 1);
-            s_splat[tid * 4 + 2] = __ldg(sp + 2);
-            s_splat[tid * 4 + 3] = __ldg(sp + 3);
-            s_cull[tid] = __ldg(cull4 + g);
-            s_rgb[tid] = __ldg(rgb4 + g);
+    const float4 kEmpty = make_float4(1e30f, 1e30f, -1e30f, -1e30f);
+    // software pipeline registers: ids of chunk c+1 / c+2, cull rect of chunk c+1
+    int id1 = (lane < n_total) ? (int)__ldg(plist + lane) : -1;
+    float4 cr1 = (id1 >= 0) ? __ldg(cull4 + id1) : kEmpty;
+    int id2 = (32 + lane < n_total) ? (int)__ldg(plist + 32 + lane) : -1;
+
+    for (int base = 0; base < n_total; base += 32) {
+        if (__all_sync(0xffffffffu, done)) break;
+        const int id = id1;
+        const float4 cr = cr1;
+        id1 = id2;
+        cr1 = (id1 >= 0) ? __ldg(cull4 + id1) : kEmpty;
+        id2 = (base + 64 + lane < n_total) ? (int)__ldg(plist + base + 64 + lane) : -1;
+
+        const bool ov = (id >= 0) && !(cr.z < bx0 || cr.x > bx1 || cr.w < by0 || cr.y > by1);
+        const unsigned m = __ballot_sync(0xffffffffu, ov);
+        if (m == 0) continue;
+        if (ov) {
+            const int rank = __popc(m & ((1u << lane) - 1u));
+            float4* dst = slots + rank * REC;
+            const float4* sp = splats + (size_t)id * 4;
+            cp_async16(dst + 0, sp + 0);
+            cp_async16(dst + 1, sp + 1);
+            cp_async16(dst + 2, sp + 2);
+            cp_async16(dst + 3, sp + 3);
+            cp_async16(dst + 4, rgb4 + id);
             if (FP > 0) {
                 if ((F & 3) == 0) {
-                    const float4* fp = reinterpret_cast<const float4*>(extras + (size_t)g * F);
+                    const float4* fp = reinterpret_cast<const float4*>(extras + (size_t)id * F);
 #pragma unroll
-                    for (int v = 0; v < FP / 4; v++)
-                        s_feat[tid * (FP / 4) + v] = (v * 4 < F) ? __ldg(fp + v) : make_float4(0, 0, 0, 0);
+                    for (int v = 0; v < FP / 4; v++) {
+                        if (v * 4 < F) cp_async16(dst + 5 + v, fp + v);
+                        else dst[5 + v] = make_float4(0, 0, 0, 0);
+                    }
                 } else {
-                    float* dstf = reinterpret_cast<float*>(s_feat + tid * (FP / 4));
+                    float* dstf = reinterpret_cast<float*>(dst + 5);
 #pragma unroll
-                    for (int ch = 0; ch < FP; ch++) dstf[ch] = (ch < F) ? __ldg(extras + (size_t)g * F + ch) : 0.0f;
+                    for (int ch = 0; ch < FP; ch++) dstf[ch] = (ch < F) ? __ldg(extras + (size_t)id * F + ch) : 0.0f;
                 }
             }
+            meta[rank] = make_int2(id, base + lane);
         }
-        __syncthreads();
-
-        for (int j0 = 0; j0 < n_batch; j0 += 32) {
-            if (__all_sync(0xffffffffu, done)) break;
-            // one lane per staged Gaussian: does its cull rect overlap this warp's pixel block?
-            bool ov = false;
-            if (j0 + lane < n_batch) {
-                const float4 cr = s_cull[j0 + lane];
-                ov = !(cr.z < bx0 || cr.x > bx1 || cr.w < by0 || cr.y > by1);
-            }
-            unsigned todo = __ballot_sync(0xffffffffu, ov);
-            while (todo) {
-                const int j = j0 + __ffs(todo) - 1;
-                todo &= todo - 1;
-                bool hit = false;
-                float w = 0.0f;
-                if (!done) {
-                    const float* s = reinterpret_cast<const float*>(s_splat + j * 4);
-                    PairEval e;
-                    if (eval_pair<false>(pixx, pixy, s, e)) {
-                        const float test_T = mul(T, sub(1.0f, e.alpha));
-                        if (test_T < kTMin) {
-                            done = true;
-                        } else {
-                            hit = true;
-                            const uint32_t contributor = (uint32_t)(base + j + 1);
-                            w = mul(e.alpha, T);
-                            const float A = sub(1.0f, T);
-                            const float m = mul(c1, sub(1.0f, mul(kNear, rcp(e.depth))));
-                            const float mm = mul(m, m);
-                            const float dt = fma_(-add(m, m), M1, fma_(mm, A, M2));
-                            dist = fma_(dt, w, dist);
-                            D = fma_(e.depth, w, D);
-                            M1 = fma_(m, w, M1);
-                            M2 = fma_(mm, w, M2);
-                            if (T > 0.5f) { median_depth = e.depth; median_contributor = contributor; }
-                            N0 = fma_(s[11], w, N0); N1 = fma_(s[12], w, N1); N2 = fma_(s[13], w, N2);
-                            if (FP > 0) {
-                                const float4* f4 = s_feat + j * (FP / 4);
+        cp_async_wait_all();
+        __syncwarp();
+        const int n_surv = __popc(m);
+        for (int r = 0; r < n_surv; r++) {
+            bool hit = false;
+            float w = 0.0f;
+            if (!done) {
+                const float* s = reinterpret_cast<const float*>(slots + r * REC);
+                PairEval e;
+                if (eval_pair<false>(pixx, pixy, s, e)) {
+                    const float test_T = mul(T, sub(1.0f, e.alpha));
+                    if (test_T < kTMin) {
+                        done = true;
+                    } else {
+                        hit = true;
+                        const uint32_t contributor = (uint32_t)(meta[r].y + 1);
+                        w = mul(e.alpha, T);
+                        const float A = sub(1.0f, T);
+                        const float mdep = mul(c1, sub(1.0f, mul(kNear, rcp(e.depth))));
+                        const float mm = mul(mdep, mdep);
+                        const float dt = fma_(-add(mdep, mdep), M1, fma_(mm, A, M2));
+                        dist = fma_(dt, w, dist);
+                        D = fma_(e.depth, w, D);
+                        M1 = fma_(mdep, w, M1);
+                        M2 = fma_(mm, w, M2);
+                        if (T > 0.5f) { median_depth = e.depth; median_contributor = contributor; }
+                        N0 = fma_(s[11], w, N0); N1 = fma_(s[12], w, N1); N2 = fma_(s[13], w, N2);
+                        if (FP > 0) {
+                            const float4* f4 = slots + r * REC + 5;
 #pragma unroll
-                                for (int v = 0; v < FP / 4; v++) {
-                                    const float4 f = f4[v];
-                                    E[4 * v + 0] = fma_(f.x, w, E[4 * v + 0]);
-                                    E[4 * v + 1] = fma_(f.y, w, E[4 * v + 1]);
-                                    E[4 * v + 2] = fma_(f.z, w, E[4 * v + 2]);
-                                    E[4 * v + 3] = fma_(f.w, w, E[4 * v + 3]);
-                                }
+                            for (int v = 0; v < FP / 4; v++) {
+                                const float4 f = f4[v];
+                                E[4 * v + 0] = fma_(f.x, w, E[4 * v + 0]);
+                                E[4 * v + 1] = fma_(f.y, w, E[4 * v + 1]);
+                                E[4 * v + 2] = fma_(f.z, w, E[4 * v + 2]);
+                                E[4 * v + 3] = fma_(f.w, w, E[4 * v + 3]);
                             }
-                            const float4 c = s_rgb[j];
-                            C0 = fma_(c.x, w, C0); C1 = fma_(c.y, w, C1); C2 = fma_(c.z, w, C2);
-                            T = test_T;
-                            last_contributor = contributor;
                         }
-                    }
-                }
-                if (kPairs) {
-                    const bool emit = hit && (w >= 0.1f);  // reference: (double)w > 0.1 (forward.cu:422)
-                    const unsigned m_emit = __ballot_sync(0xffffffffu, emit);
-                    if (m_emit) {
-                        const int n_new = __popc(m_emit);
-                        if (wcount + n_new > kPairStage) {
-                            int gbase = 0;
-                            if (lane == 0) gbase = atomicAdd(pair_count, wcount);
-                            gbase = __shfl_sync(0xffffffffu, gbase, 0);
-                            for (int i = lane; i < wcount; i += 32)
-                                if ((int64_t)gbase + i < pair_cap) pairs[gbase + i] = my_pairs[i];
-                            __syncwarp();
-                            wcount = 0;
-                        }
-                        if (emit) my_pairs[wcount + __popc(m_emit & ((1u << lane) - 1u))] = make_int2(s_id[j], (int)pix_id);
-                        wcount += n_new;
-                        __syncwarp();
+                        const float4 c = slots[r * REC + 4];
+                        C0 = fma_(c.x, w, C0); C1 = fma_(c.y, w, C1); C2 = fma_(c.z, w, C2);
+                        T = test_T;
+                        last_contributor = contributor;
                     }
                 }
             }
+            if (kPairs) {
+                const bool emit = hit && (w >= 0.1f);  // reference: (double)w > 0.1 (forward.cu:422)
+                const unsigned m_emit = __ballot_sync(0xffffffffu, emit);
+                if (m_emit) {
+                    const int n_new = __popc(m_emit);
+                    if (wcount + n_new > kPairStage) {
+                        int gbase = 0;
+                        if (lane == 0) gbase = atomicAdd(pair_count, wcount);
+                        gbase = __shfl_sync(0xffffffffu, gbase, 0);
+                        for (int i = lane; i < wcount; i += 32)
+                            if ((int64_t)gbase + i < pair_cap) pairs[gbase + i] = my_pairs[i];
+                        __syncwarp();
+                        wcount = 0;
+                    }
+                    if (emit) my_pairs[wcount + __popc(m_emit & ((1u << lane) - 1u))] = make_int2(meta[r].x, (int)pix_id);
+                    wcount += n_new;
+                    __syncwarp();
+                }
+            }
         }
+        __syncwarp();  // all lanes are done reading the slots before the next chunk overwrites them
     }
     if (kPairs && wcount > 0) {
         int gbase = 0;
@@ -208,7 +219,6 @@ template <int FP, bool kPairs>
 static int launch_one(const IsrForwardArgs& a, cudaStream_t stream) {
     GeomLayout gl(a.P);
     ImageLayout il(a.W, a.H);
-    BinLayout bl(a.P, 1, a.W, a.H);  // point_list is at offset 0 regardless of R
     const char* g = static_cast<const char*>(a.geom);
     char* im = static_cast<char*>(a.image);
     const char* b = static_cast<const char*>(a.binning);
@@ -217,7 +227,7 @@ static int launch_one(const IsrForwardArgs& a, cudaStream_t stream) {
     auto kern = blend_fwd_kernel<FP, kPairs>;
     ISR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 256, smem, stream>>>(
-        reinterpret_cast<const uint2*>(im + il.ranges), reinterpret_cast<const uint32_t*>(b ? b + bl.point_list : nullptr),
+        reinterpret_cast<const uint2*>(im + il.ranges), reinterpret_cast<const uint32_t*>(b),  // point_list sits at offset 0 of the binning workspace
         a.W, a.H, a.F, reinterpret_cast<const float4*>(g + gl.splat), reinterpret_cast<const float4*>(g + gl.cull),
         reinterpret_cast<const float4*>(g + gl.rgb), a.extra_attrs, a.background,
         reinterpret_cast<float*>(im + il.final_T), reinterpret_cast<uint32_t*>(im + il.n_contrib), a.out_color,

@@ -142,29 +142,18 @@ contrast_loss_kernel(int N, int F, int K, const float* __restrict__ fhat, const 
     }
 }
 
-// dU[k][c] = sum_i coef[i][k] * fhat[i][c]      one block per cluster
+// dU[k][c] = sum_i coef[i][k] * fhat[i][c]: each block reduces a slab of 64 samples for all K*F entries (entry e =
+// k*F + c owned by thread e mod 256), then adds its partial sums to dU with one atomic per entry.
 __global__ void __launch_bounds__(256)
 contrast_dU_kernel(int N, int F, int K, const float* __restrict__ coef, const float* __restrict__ fhat,
                    float* __restrict__ dU) {
-    const int k = blockIdx.x;
-    float acc[ISR_MAX_EXTRA_DIMS];
-    for (int c = 0; c < F; c++) acc[c] = 0.0f;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const float cf = coef[(size_t)i * K + k];
-        if (cf != 0.0f)
-            for (int c = 0; c < F; c++) acc[c] = fmaf(cf, fhat[(size_t)i * F + c], acc[c]);
-    }
-    __shared__ float s_red[8][ISR_MAX_EXTRA_DIMS];
-    for (int c = 0; c < F; c++) {
-        float v = acc[c];
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][c] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < F) {
-        float v = 0.0f;
-        for (int w = 0; w < 8; w++) v += s_red[w][threadIdx.x];
-        dU[(size_t)k * F + threadIdx.x] = v;
+    const int i0 = blockIdx.x * 64, i1 = min(N, i0 + 64);
+    const int KF = K * F;
+    for (int e = threadIdx.x; e < KF; e += 256) {
+        const int k = e / F, cch = e - k * F;
+        float acc = 0.0f;
+        for (int i = i0; i < i1; i++) acc = fmaf(__ldg(coef + (size_t)i * K + k), __ldg(fhat + (size_t)i * F + cch), acc);
+        if (acc != 0.0f) atomicAdd(dU + e, acc);
     }
 }
 
@@ -194,6 +183,127 @@ contrast_dfeat_kernel(int N, int F, int K, const float* __restrict__ coef, const
     }
     const float sc = (grad_scale ? *grad_scale : 1.0f) * inv_norm[i];
     for (int c = 0; c < F; c++) dfeat[(size_t)i * F + c] = g[c] * sc;
+}
+
+// ---- fused row normalisation (one thread per row, F <= 32 values in registers) ---------------------------------
+template <int FP>
+__global__ void __launch_bounds__(256)
+rownorm_fwd_kernel(int P, int F, const float* __restrict__ x, float eps1, float eps2, int stages, float* __restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float v[FP];
+    const bool vec = (F & 3) == 0;
+#pragma unroll
+    for (int c = 0; c < FP; c += 4) {
+        if (vec && c < F) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(x + (size_t)i * F + c));
+            v[c] = t.x; v[c + 1] = t.y; v[c + 2] = t.z; v[c + 3] = t.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[c + k] = (c + k < F) ? __ldg(x + (size_t)i * F + c + k) : 0.0f;
+        }
+    }
+    float ss = 0.0f;
+#pragma unroll
+    for (int c = 0; c < FP; c++) ss = fmaf(v[c], v[c], ss);
+    float inv = 1.0f / (sqrtf(ss) + eps1);
+#pragma unroll
+    for (int c = 0; c < FP; c++) v[c] *= inv;
+    if (stages > 1) {
+        ss = 0.0f;
+#pragma unroll
+        for (int c = 0; c < FP; c++) ss = fmaf(v[c], v[c], ss);
+        inv = 1.0f / (sqrtf(ss) + eps2);
+#pragma unroll
+        for (int c = 0; c < FP; c++) v[c] *= inv;
+    }
+#pragma unroll
+    for (int c = 0; c < FP; c += 4) {
+        if (vec && c < F) {
+            *reinterpret_cast<float4*>(y + (size_t)i * F + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (c + k < F) y[(size_t)i * F + c + k] = v[c + k];
+        }
+    }
+}
+
+// d/dx of y = x / (n + eps), n = |x|:  dx = dy/(n+eps) - x (x.dy) / (n (n+eps)^2)
+template <int FP>
+__device__ __forceinline__ void rownorm_vjp(const float* x, float* d, float eps) {
+    float ss = 0.0f, xd = 0.0f;
+#pragma unroll
+    for (int c = 0; c < FP; c++) { ss = fmaf(x[c], x[c], ss); xd = fmaf(x[c], d[c], xd); }
+    const float n = sqrtf(ss), ne = n + eps;
+    const float a = 1.0f / ne;
+    const float b = n > 0.0f ? xd / (n * ne * ne) : 0.0f;
+#pragma unroll
+    for (int c = 0; c < FP; c++) d[c] = fmaf(-b, x[c], a * d[c]);
+}
+
+template <int FP>
+__global__ void __launch_bounds__(256)
+rownorm_bwd_kernel(int P, int F, const float* __restrict__ x, const float* __restrict__ dy, float eps1, float eps2,
+                   int stages, float* __restrict__ dx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float v[FP], d[FP];
+    const bool vec = (F & 3) == 0;
+#pragma unroll
+    for (int c = 0; c < FP; c += 4) {
+        if (vec && c < F) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(x + (size_t)i * F + c));
+            const float4 u = __ldg(reinterpret_cast<const float4*>(dy + (size_t)i * F + c));
+            v[c] = t.x; v[c + 1] = t.y; v[c + 2] = t.z; v[c + 3] = t.w;
+            d[c] = u.x; d[c + 1] = u.y; d[c + 2] = u.z; d[c + 3] = u.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                v[c + k] = (c + k < F) ? __ldg(x + (size_t)i * F + c + k) : 0.0f;
+                d[c + k] = (c + k < F) ? __ldg(dy + (size_t)i * F + c + k) : 0.0f;
+            }
+        }
+    }
+    if (stages > 1) {
+        float a1[FP];
+        float ss = 0.0f;
+#pragma unroll
+        for (int c = 0; c < FP; c++) ss = fmaf(v[c], v[c], ss);
+        const float inv = 1.0f / (sqrtf(ss) + eps1);
+#pragma unroll
+        for (int c = 0; c < FP; c++) a1[c] = v[c] * inv;
+        rownorm_vjp<FP>(a1, d, eps2);
+    }
+    rownorm_vjp<FP>(v, d, eps1);
+#pragma unroll
+    for (int c = 0; c < FP; c += 4) {
+        if (vec && c < F) {
+            *reinterpret_cast<float4*>(dx + (size_t)i * F + c) = make_float4(d[c], d[c + 1], d[c + 2], d[c + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (c + k < F) dx[(size_t)i * F + c + k] = d[c + k];
+        }
+    }
+}
+
+template <int FP>
+static int rownorm_launch(bool fwd, int P, int F, const float* x, const float* dy, float e1, float e2, int stages,
+                          float* out, cudaStream_t stream) {
+    if (fwd) rownorm_fwd_kernel<FP><<<(P + 255) / 256, 256, 0, stream>>>(P, F, x, e1, e2, stages, out);
+    else rownorm_bwd_kernel<FP><<<(P + 255) / 256, 256, 0, stream>>>(P, F, x, dy, e1, e2, stages, out);
+    ISR_CUDA_TRY(cudaGetLastError());
+    return ISR_OK;
+}
+
+int launch_rownorm(bool fwd, int P, int F, const float* x, const float* dy, float e1, float e2, int stages, float* out,
+                   cudaStream_t stream) {
+    if (P <= 0 || F <= 0) return ISR_OK;
+    if (F <= 4) return rownorm_launch<4>(fwd, P, F, x, dy, e1, e2, stages, out, stream);
+    if (F <= 8) return rownorm_launch<8>(fwd, P, F, x, dy, e1, e2, stages, out, stream);
+    if (F <= 16) return rownorm_launch<16>(fwd, P, F, x, dy, e1, e2, stages, out, stream);
+    if (F <= 24) return rownorm_launch<24>(fwd, P, F, x, dy, e1, e2, stages, out, stream);
+    if (F <= 32) return rownorm_launch<32>(fwd, P, F, x, dy, e1, e2, stages, out, stream);
+    return ISR_ERR_UNSUPPORTED;
 }
 
 size_t contrastive_ws_bytes(int N, int F, int K) { return ContrastWs(N, F, K).total; }
@@ -241,9 +351,11 @@ int launch_contrastive_bwd(int N, int F, int K, const int* labels, const float* 
     const char* w = static_cast<const char*>(ws);
     const bool means = predef_u == nullptr;
     float* dU = reinterpret_cast<float*>(const_cast<char*>(w) + L.dU);
-    if (means && K > 0)
-        contrast_dU_kernel<<<K, 256, 0, stream>>>(N, F, K, reinterpret_cast<const float*>(w + L.coef),
-                                                  reinterpret_cast<const float*>(w + L.fhat), dU);
+    if (means && K > 0) {
+        ISR_CUDA_TRY(cudaMemsetAsync(dU, 0, (size_t)K * F * sizeof(float), stream));
+        contrast_dU_kernel<<<(N + 63) / 64, 256, 0, stream>>>(N, F, K, reinterpret_cast<const float*>(w + L.coef),
+                                                                reinterpret_cast<const float*>(w + L.fhat), dU);
+    }
     const size_t smem = (size_t)(K > 0 ? K : 1) * F * sizeof(float);
     ISR_CUDA_TRY(cudaFuncSetAttribute(contrast_dfeat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     contrast_dfeat_kernel<<<(N + 255) / 256, 256, smem, stream>>>(

@@ -264,8 +264,11 @@ class _RasterizeGaussians(torch.autograd.Function):
             res = c_rasterize_gaussians(*args, want_pairs=want_pairs)
         (num_rendered, color, depth, radii, extra, geomBuffer, binningBuffer, imgBuffer, gau_related_pixels,
          gau_pixel_indices) = res
-        if want_pairs:
+        if want_pairs and not getattr(raster_settings, "defer_pairs", False):
             gau_related_pixels = gau_related_pixels[:(int(gau_pixel_indices.item()) + 1)]
+        elif want_pairs:
+            # render() slices lazily on first access (avoids a host sync right after the blend)
+            gau_related_pixels._isr_count_minus_1 = gau_pixel_indices
         ctx.raster_settings = raster_settings
         ctx.num_rendered = num_rendered
         ctx.set_materialize_grads(False)
@@ -402,6 +405,40 @@ class _SamplePixels(torch.autograd.Function):
         g = torch.sparse_coo_tensor(pix_ids.reshape(1, -1).to(torch.int64), grad_out.contiguous(), size=ctx.shape,
                                     check_invariants=False)
         return g, None, None
+
+
+class _RowNorm(torch.autograd.Function):
+    """y = x / (|x| + eps1) [then y / (|y| + eps2)] over the rows of [P,F], one fused kernel each way."""
+
+    @staticmethod
+    def forward(ctx, x, eps1, eps2, stages):
+        L = _require_cuda_lib()
+        xc = _f32c(x.detach(), "x")
+        P, F = int(xc.shape[0]), int(xc.shape[1])
+        y = torch.empty_like(xc)
+        _lib.check(L.isr_rownorm_forward(P, F, _ptr(xc), float(eps1), float(eps2), int(stages), _ptr(y), _stream()),
+                   "isr_rownorm_forward")
+        ctx.save_for_backward(xc)
+        ctx.cfg = (float(eps1), float(eps2), int(stages))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _require_cuda_lib()
+        (xc,) = ctx.saved_tensors
+        e1, e2, stages = ctx.cfg
+        dyc = _f32c(dy, "dy")
+        dx = torch.empty_like(xc)
+        _lib.check(L.isr_rownorm_backward(int(xc.shape[0]), int(xc.shape[1]), _ptr(xc), _ptr(dyc), e1, e2, stages,
+                                          _ptr(dx), _stream()), "isr_rownorm_backward")
+        return dx, None, None, None
+
+
+def normalize_rows(x: torch.Tensor, eps1: float, eps2: float = 0.0, stages: int = 1) -> torch.Tensor:
+    """Fused `x / (x.norm(dim=-1, keepdim=True) + eps1)`, optionally applied twice (second eps = eps2)."""
+    if x.numel() == 0:
+        return x
+    return _RowNorm.apply(x, eps1, eps2, stages)
 
 
 def sample_pixels(extra_map: torch.Tensor, pix_ids: torch.Tensor) -> torch.Tensor:

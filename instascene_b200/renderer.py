@@ -14,12 +14,69 @@ import math
 
 import torch
 
-from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, normalize_rows
 
 
 class _SettingsNoPairs(GaussianRasterizationSettings):
     """Same 12 fields; tells the rasterizer not to emit gau_related_pixels (no post-blend host sync)."""
     want_pairs = False
+
+
+class _SettingsDeferPairs(GaussianRasterizationSettings):
+    """Same 12 fields; the pair list comes back unsliced with its device-side count (sliced lazily)."""
+    defer_pairs = True
+
+
+class RenderPackage(dict):
+    """The reference's 13-key result dict.  The six rasterizer outputs are stored eagerly; the seven derived maps
+    (gaussian_renderer/__init__.py:127-167) and the sliced pair list are computed on FIRST ACCESS -- the semantic
+    training loop (train_semantic.py:102-108) never reads them, the RGB loop (train.py) reads them all.  Values,
+    autograd history and key set are identical to the eager reference dict."""
+    _LAZY = ("rend_alpha", "rend_normal", "rend_dist", "surf_depth", "surf_normal", "rend_depth", "rend_median_depth")
+
+    def __init__(self, eager, aux_fn, pairs_fn):
+        super().__init__(eager)
+        self._aux_fn, self._pairs_fn = aux_fn, pairs_fn
+
+    def _materialise(self, key):
+        if key == "gau_related_pixels" and self._pairs_fn is not None:
+            fn, self._pairs_fn = self._pairs_fn, None
+            super().__setitem__("gau_related_pixels", fn())
+        elif key in self._LAZY and self._aux_fn is not None:
+            fn, self._aux_fn = self._aux_fn, None
+            for k, v in fn().items():
+                super().__setitem__(k, v)
+
+    def materialise(self):
+        self._materialise("gau_related_pixels")
+        self._materialise("rend_alpha")
+        return self
+
+    def __getitem__(self, key):
+        self._materialise(key)
+        return super().__getitem__(key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def __contains__(self, key):
+        return super().__contains__(key) or (key in self._LAZY and self._aux_fn is not None)
+
+    def keys(self):
+        return self.materialise() and super().keys()
+
+    def items(self):
+        return self.materialise() and super().items()
+
+    def values(self):
+        return self.materialise() and super().values()
+
+    def __iter__(self):
+        self.materialise()
+        return super().__iter__()
+
+    def __len__(self):
+        return super().__len__() + (len(self._LAZY) if self._aux_fn is not None else 0)
 
 
 def depths_to_points(view, depthmap):
@@ -60,7 +117,7 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
 
     tanfovx = math.tan(viewpoint_camera.FoVx * 0.5)
     tanfovy = math.tan(viewpoint_camera.FoVy * 0.5)
-    cls = GaussianRasterizationSettings if want_pairs else _SettingsNoPairs
+    cls = _SettingsDeferPairs if want_pairs else _SettingsNoPairs
     raster_settings = cls(
         image_height=int(viewpoint_camera.image_height),
         image_width=int(viewpoint_camera.image_width),
@@ -80,9 +137,16 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
     means3D = pc.get_xyz
     means2D = screenspace_points
     opacity = pc.get_opacity
-    seg_feature = pc.get_seg_feature
-    if seg_feature is not None and norm_seg_feat:
-        seg_feature = seg_feature / (seg_feature.norm(dim=-1, keepdim=True) + 1e-9)
+    raw = getattr(pc, "_seg_feature", None)
+    if norm_seg_feat and raw is not None and getattr(pipe, "fused_seg_activation", True) \
+            and getattr(pc, "seg_feature_eps", 1e-6) is not None:
+        # get_seg_feature (x / (|x| + 1e-6), scene/gaussian_model.py:121-125) and the renormalisation below it in the
+        # reference render() (eps 1e-9) fused into one kernel each way (SURVEY.md Q9 / build-plan step 7)
+        seg_feature = normalize_rows(raw, getattr(pc, "seg_feature_eps", 1e-6), 1e-9, stages=2)
+    else:
+        seg_feature = pc.get_seg_feature
+        if seg_feature is not None and norm_seg_feat:
+            seg_feature = normalize_rows(seg_feature, 1e-9)
 
     scales = None
     rotations = None
@@ -111,20 +175,27 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
         means3D=means3D, means2D=means2D, shs=shs, colors_precomp=colors_precomp, opacities=opacity, scales=scales,
         rotations=rotations, cov3D_precomp=cov3D_precomp, extra_attrs=seg_feature)
 
-    rets = {"render": rendered_image, "viewspace_points": means2D, "visibility_filter": radii > 0, "radii": radii,
-            "seg_feature": extra_attrs, "gau_related_pixels": gau_related_pixels}
+    eager = {"render": rendered_image, "viewspace_points": means2D, "visibility_filter": radii > 0, "radii": radii,
+             "seg_feature": extra_attrs, "gau_related_pixels": gau_related_pixels}
 
-    render_alpha = allmap[1:2]
-    render_normal = allmap[2:5]
-    render_normal = (render_normal.permute(1, 2, 0) @ (viewpoint_camera.world_view_transform[:3, :3].T)).permute(2, 0, 1)
-    render_depth_median = torch.nan_to_num(allmap[5:6], 0, 0)
-    render_depth_expected = torch.nan_to_num(allmap[0:1] / render_alpha, 0, 0)
-    render_dist = allmap[6:7]
-    surf_depth = render_depth_expected * (1 - pipe.depth_ratio) + (pipe.depth_ratio) * render_depth_median
-    surf_normal = depth_to_normal(viewpoint_camera, surf_depth).permute(2, 0, 1)
-    surf_normal = surf_normal * (render_alpha).detach()
+    def aux():
+        render_alpha = allmap[1:2]
+        render_normal = allmap[2:5]
+        render_normal = (render_normal.permute(1, 2, 0) @ (viewpoint_camera.world_view_transform[:3, :3].T)).permute(2, 0, 1)
+        render_depth_median = torch.nan_to_num(allmap[5:6], 0, 0)
+        render_depth_expected = torch.nan_to_num(allmap[0:1] / render_alpha, 0, 0)
+        render_dist = allmap[6:7]
+        surf_depth = render_depth_expected * (1 - pipe.depth_ratio) + (pipe.depth_ratio) * render_depth_median
+        surf_normal = depth_to_normal(viewpoint_camera, surf_depth).permute(2, 0, 1)
+        surf_normal = surf_normal * (render_alpha).detach()
+        return {'rend_alpha': render_alpha, 'rend_normal': render_normal, 'rend_dist': render_dist,
+                'surf_depth': surf_depth, 'surf_normal': surf_normal, "rend_depth": render_depth_expected,
+                "rend_median_depth": render_depth_median}
 
-    rets.update({'rend_alpha': render_alpha, 'rend_normal': render_normal, 'rend_dist': render_dist,
-                 'surf_depth': surf_depth, 'surf_normal': surf_normal, "rend_depth": render_depth_expected,
-                 "rend_median_depth": render_depth_median})
-    return rets
+    pairs_fn = None
+    cnt = getattr(gau_related_pixels, "_isr_count_minus_1", None)
+    if cnt is not None:
+        pairs_fn = lambda: gau_related_pixels[:(int(cnt.item()) + 1)]
+    if not getattr(pipe, "lazy_outputs", True):
+        return RenderPackage(eager, aux, pairs_fn).materialise()
+    return RenderPackage(eager, aux, pairs_fn)
