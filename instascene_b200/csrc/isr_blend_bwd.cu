@@ -16,8 +16,6 @@
 
 namespace isr {
 
-constexpr int kBatchB = 128;
-
 template <int N, int OFF>
 struct Butterfly {
     __device__ __forceinline__ static void run(float* v, int lane) {
@@ -45,22 +43,36 @@ __device__ __forceinline__ float warp_transpose_reduce(float* v, int lane) {
 }
 
 template <int FP>
+struct BwdSmem {
+    static constexpr int kRecF4 = 4 + 1 + FP / 4;  // splat (4 x float4) + rgb (1) + features
+    static constexpr size_t per_warp = (size_t)32 * kRecF4 * 16 + 32 * 8;
+    static constexpr size_t bytes = 8 * per_warp;
+};
+
+__device__ __forceinline__ void cp_async16_b(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+
+// Same warp-autonomous structure as blend_fwd_kernel, walking the list BACK to front: per-warp cull-rectangle test
+// (exact: a culled Gaussian contributed to no pixel of the block in the forward), cp.async staging of survivors.
+template <int FP>
 __global__ void __launch_bounds__(256)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int F,
-                 const float* __restrict__ bg, const float4* __restrict__ splats, const float4* __restrict__ rgb4,
-                 const float* __restrict__ extras, const float* __restrict__ final_Ts,
+                 const float* __restrict__ bg, const float4* __restrict__ splats, const float4* __restrict__ cull4,
+                 const float4* __restrict__ rgb4, const float* __restrict__ extras, const float* __restrict__ final_Ts,
                  const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
                  const float* __restrict__ dL_dothers, const float* __restrict__ dL_dpix_extra,
                  float* __restrict__ dL_dtransMat, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dnormal3D,
                  float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolors, float* __restrict__ dL_dextras) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* s_splat = reinterpret_cast<float4*>(smem_raw);           // [kBatchB][4]
-    float4* s_rgb = s_splat + kBatchB * 4;                           // [kBatchB]
-    float4* s_feat = s_rgb + kBatchB;                                // [kBatchB][FP/4]
-    int* s_id = reinterpret_cast<int*>(s_feat + kBatchB * (FP / 4)); // [kBatchB]
-
+    constexpr int REC = BwdSmem<FP>::kRecF4;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    unsigned char* wbase = smem_raw + (size_t)warp * BwdSmem<FP>::per_warp;
+    float4* slots = reinterpret_cast<float4*>(wbase);                     // [32][REC]
+    int2* meta = reinterpret_cast<int2*>(wbase + (size_t)32 * REC * 16);  // [32] (gaussian id, list index)
+
     const int tiles_x = (W + TILE - 1) / TILE;
     const int tile_id = blockIdx.y * tiles_x + blockIdx.x;
     const int wx0 = blockIdx.x * TILE + (warp & 1) * 8;
@@ -70,9 +82,12 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     const size_t HW = (size_t)H * W;
     const size_t pix_id = (size_t)W * pyi + pxi;
     const float pixx = (float)pxi, pixy = (float)pyi;
+    const float bx0 = (float)wx0, by0 = (float)wy0;
+    const float bx1 = (float)min(wx0 + 7, W - 1), by1 = (float)min(wy0 + 3, H - 1);
 
     const uint2 range = ranges[tile_id];
     const int n_total = (int)(range.y - range.x);
+    const uint32_t* __restrict__ plist = point_list + range.x;
     const float c1 = __fdiv_rn(kFar, __fsub_rn(kFar, kNear));
     const float c3 = __fdiv_rn(__fmul_rn(kFar, kNear), __fsub_rn(kFar, kNear));
 
@@ -112,51 +127,66 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     for (int ch = 0; ch < FP; ch++) { acc_e[ch] = 0.0f; last_e[ch] = 0.0f; }
     float last_dL_dT = 0, last_alpha = 0;
 
-    // the highest list index any pixel of this CTA needs
-    __shared__ int s_max_contrib;
-    if (tid == 0) s_max_contrib = 0;
-    __syncthreads();
-    if (last_contributor > 0) atomicMax(&s_max_contrib, (int)last_contributor);
-    __syncthreads();
-    const int n_need = min(n_total, s_max_contrib);
+    // the highest list index any pixel of this WARP needs
+    int n_need = (int)last_contributor;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) n_need = max(n_need, __shfl_xor_sync(0xffffffffu, n_need, off));
+    n_need = min(n_need, n_total);
 
-    // batches walk the list from index n_need-1 down to 0
-    for (int top = n_need; top > 0; top -= kBatchB) {
-        const int n_batch = min(kBatchB, top);
-        __syncthreads();
-        if (tid < n_batch) {
-            const int g = (int)point_list[range.x + top - 1 - tid];  // slot t <-> list index top-1-t
-            s_id[tid] = g;
-            const float4* sp = splats + (size_t)g * 4;
-            s_splat[tid * 4 + 0] = __ldg(sp + 0);
-            s_splat[tid * 4 + 1] = __ldg(sp + 1);
-            s_splat[tid * 4 + 2] = __ldg(sp + 2);
-            s_splat[tid * 4 + 3] = __ldg(sp + 3);
-            s_rgb[tid] = __ldg(rgb4 + g);
+    const float4 kEmpty = make_float4(1e30f, 1e30f, -1e30f, -1e30f);
+    // chunk with top index `top` covers list indices top-1-lane (lane 0 = last entry); pipeline registers as in fwd
+    auto idx_of = [&](int top) { return top - 1 - lane; };
+    int id1 = (idx_of(n_need) >= 0) ? (int)__ldg(plist + idx_of(n_need)) : -1;
+    float4 cr1 = (id1 >= 0) ? __ldg(cull4 + id1) : kEmpty;
+    int id2 = (idx_of(n_need - 32) >= 0) ? (int)__ldg(plist + idx_of(n_need - 32)) : -1;
+
+    for (int top = n_need; top > 0; top -= 32) {
+        const int id = id1;
+        const float4 cr = cr1;
+        id1 = id2;
+        cr1 = (id1 >= 0) ? __ldg(cull4 + id1) : kEmpty;
+        id2 = (idx_of(top - 64) >= 0) ? (int)__ldg(plist + idx_of(top - 64)) : -1;
+
+        const bool ov = (id >= 0) && !(cr.z < bx0 || cr.x > bx1 || cr.w < by0 || cr.y > by1);
+        const unsigned m = __ballot_sync(0xffffffffu, ov);
+        if (m == 0) continue;
+        if (ov) {
+            const int rank = __popc(m & ((1u << lane) - 1u));
+            float4* dst = slots + rank * REC;
+            const float4* sp = splats + (size_t)id * 4;
+            cp_async16_b(dst + 0, sp + 0);
+            cp_async16_b(dst + 1, sp + 1);
+            cp_async16_b(dst + 2, sp + 2);
+            cp_async16_b(dst + 3, sp + 3);
+            cp_async16_b(dst + 4, rgb4 + id);
             if (FP > 0) {
                 if ((F & 3) == 0) {
-                    const float4* fp = reinterpret_cast<const float4*>(extras + (size_t)g * F);
+                    const float4* fp = reinterpret_cast<const float4*>(extras + (size_t)id * F);
 #pragma unroll
-                    for (int v = 0; v < FP / 4; v++)
-                        s_feat[tid * (FP / 4) + v] = (v * 4 < F) ? __ldg(fp + v) : make_float4(0, 0, 0, 0);
+                    for (int v = 0; v < FP / 4; v++) {
+                        if (v * 4 < F) cp_async16_b(dst + 5 + v, fp + v);
+                        else dst[5 + v] = make_float4(0, 0, 0, 0);
+                    }
                 } else {
-                    float* dstf = reinterpret_cast<float*>(s_feat + tid * (FP / 4));
+                    float* dstf = reinterpret_cast<float*>(dst + 5);
 #pragma unroll
-                    for (int ch = 0; ch < FP; ch++) dstf[ch] = (ch < F) ? __ldg(extras + (size_t)g * F + ch) : 0.0f;
+                    for (int ch = 0; ch < FP; ch++) dstf[ch] = (ch < F) ? __ldg(extras + (size_t)id * F + ch) : 0.0f;
                 }
             }
+            meta[rank] = make_int2(id, idx_of(top));
         }
-        __syncthreads();
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+        __syncwarp();
+        const int n_surv = __popc(m);
 
-        for (int t = 0; t < n_batch; t++) {
-            const uint32_t contributor = (uint32_t)(top - 1 - t);  // 0-based list index
+        for (int t = 0; t < n_surv; t++) {
+            const int2 mt = meta[t];
+            const uint32_t contributor = (uint32_t)mt.y;  // 0-based list index
             const bool active = contributor < last_contributor;
-            if (!__any_sync(0xffffffffu, active)) continue;
-            const float* s = reinterpret_cast<const float*>(s_splat + t * 4);
+            const float* s = reinterpret_cast<const float*>(slots + t * REC);
             PairEval e;
             const bool hit = active && eval_pair<true>(pixx, pixy, s, e);
             if (!__any_sync(0xffffffffu, hit)) continue;
-
             // per-lane partial gradients (0 when this lane does not contribute)
             float v[32];
 #pragma unroll
@@ -171,7 +201,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                 const float w = mul(alpha, T);
                 float dL_dalpha = 0.0f;
                 const float one_m_la = sub(1.0f, last_alpha);
-                const float4 col = s_rgb[t];
+                const float4 col = slots[t * REC + 4];
                 acc_c0 = fma_(last_alpha, last_c0, mul(one_m_la, acc_c0)); last_c0 = col.x;
                 dL_dalpha = fma_(sub(col.x, acc_c0), dLdC0, dL_dalpha);
                 acc_c1 = fma_(last_alpha, last_c1, mul(one_m_la, acc_c1)); last_c1 = col.y;
@@ -204,7 +234,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                 dL_dalpha = fma_(sub(s[13], acc_n2), dLdN2, dL_dalpha);
                 v[3] = mul(w, dLdN0); v[4] = mul(w, dLdN1); v[5] = mul(w, dLdN2);
                 if (FP > 0) {
-                    const float* f = reinterpret_cast<const float*>(s_feat + t * (FP / 4));
+                    const float* f = reinterpret_cast<const float*>(slots + t * REC + 5);
 #pragma unroll
                     for (int ch = 0; ch < FP; ch++) {
                         const float ex = f[ch];
@@ -244,7 +274,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                 }
                 v[17] = mul(G, dL_dalpha);
             }
-            const int g = s_id[t];
+            const int g = mt.x;
             const float tot = warp_transpose_reduce<32>(v, lane);
             if (lane < 18 && tot != 0.0f) {
                 float* dst;
@@ -267,6 +297,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                     atomicAdd(dL_dextras + (size_t)g * F + ch, tote);
             }
         }
+        __syncwarp();  // slots are reused by the next chunk
     }
 }
 
@@ -277,8 +308,8 @@ template <int FP>
 __global__ void __launch_bounds__(256)
 extra_sparse_bwd_kernel(int n, const int* __restrict__ pix_ids, const float* __restrict__ dLdE_samples, int W, int H,
                         int F, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                        const float4* __restrict__ splats, const uint32_t* __restrict__ n_contrib,
-                        float* __restrict__ dL_dextras) {
+                        const float4* __restrict__ splats, const float4* __restrict__ cull4,
+                        const uint32_t* __restrict__ n_contrib, float* __restrict__ dL_dextras) {
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp_global >= n) return;
@@ -297,8 +328,13 @@ extra_sparse_bwd_kernel(int n, const int* __restrict__ pix_ids, const float* __r
         const int i = base + lane;
         float alpha = 0.0f;
         int g = -1;
-        if (i < last) {
-            g = (int)point_list[range.x + i];
+        if (i < last) g = (int)point_list[range.x + i];
+        bool cand = false;
+        if (g >= 0) {  // exact pre-test: the pixel lies outside the Gaussian's conservative cull rectangle
+            const float4 cr = __ldg(cull4 + g);
+            cand = !(cr.z < pixx || cr.x > pixx || cr.w < pixy || cr.y > pixy);
+        }
+        if (cand) {
             float s[16];
             const float4* sp = splats + (size_t)g * 4;
             *reinterpret_cast<float4*>(s + 0) = __ldg(sp + 0);
@@ -339,14 +375,14 @@ static int launch_bwd_one(const IsrBackwardArgs& a, cudaStream_t stream) {
     const char* im = static_cast<const char*>(a.image);
     const char* b = static_cast<const char*>(a.binning);
     const dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE);
-    const size_t smem = (size_t)kBatchB * (64 + 16 + 4 * FP + 4);
+    const size_t smem = BwdSmem<FP>::bytes;
     auto kern = blend_bwd_kernel<FP>;
     ISR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned m = a.grad_mask;
     kern<<<grid, 256, smem, stream>>>(
         reinterpret_cast<const uint2*>(im + il.ranges), reinterpret_cast<const uint32_t*>(b), a.W, a.H, a.F, a.background,
-        reinterpret_cast<const float4*>(g + gl.splat), reinterpret_cast<const float4*>(g + gl.rgb), a.extra_attrs,
-        reinterpret_cast<const float*>(im + il.final_T), reinterpret_cast<const uint32_t*>(im + il.n_contrib), a.dL_dcolor,
+        reinterpret_cast<const float4*>(g + gl.splat), reinterpret_cast<const float4*>(g + gl.cull),
+        reinterpret_cast<const float4*>(g + gl.rgb), a.extra_attrs, reinterpret_cast<const float*>(im + il.final_T), reinterpret_cast<const uint32_t*>(im + il.n_contrib), a.dL_dcolor,
         a.dL_dothers, a.dL_dextra_pix, (m & ISR_GRAD_GEOMETRY) ? a.dL_dtransMat : nullptr,
         (m & ISR_GRAD_GEOMETRY) ? a.dL_dmeans2D : nullptr, (m & ISR_GRAD_GEOMETRY) ? a.dL_dnormal : nullptr,
         (m & ISR_GRAD_OPACITY) ? a.dL_dopacity : nullptr, (m & ISR_GRAD_COLOR) ? a.dL_dcolors : nullptr,
@@ -378,7 +414,7 @@ static int launch_sparse_one(int P, int F, int W, int H, const void* geom, const
     extra_sparse_bwd_kernel<FP><<<(n + warps_per_block - 1) / warps_per_block, 256, 0, stream>>>(
         n, pix_ids, dLdE, W, H, F, reinterpret_cast<const uint2*>(im + il.ranges),
         reinterpret_cast<const uint32_t*>(binning), reinterpret_cast<const float4*>(g + gl.splat),
-        reinterpret_cast<const uint32_t*>(im + il.n_contrib), dL_dextra);
+        reinterpret_cast<const float4*>(g + gl.cull), reinterpret_cast<const uint32_t*>(im + il.n_contrib), dL_dextra);
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }
