@@ -155,9 +155,7 @@ def run_ours(args):
                  center=torch.from_numpy(c.camera_center).pin_memory())
         if args.workload == "cfg3":
             lab = synth.label_map(W, H, wl["seed"] + 2 + v)
-            valid = np.flatnonzero(lab.reshape(-1) > 0).astype(np.int32)
-            h["labels"] = torch.from_numpy(lab.reshape(-1).astype(np.int16)).pin_memory()
-            h["valid"] = torch.from_numpy(valid).pin_memory()
+            h["labels"] = torch.from_numpy(lab.reshape(-1).astype(np.int16)).pin_memory()  # the view's segmap
         else:
             rng = np.random.default_rng(wl["seed"] + 1 + v)
             h["dcolor"] = torch.from_numpy(rng.standard_normal((3, H, W)).astype(np.float32)).pin_memory()
@@ -182,10 +180,7 @@ def run_ours(args):
         cam = _Cam(cams[v], data["wvt"], data["fpt"], data["center"])
         if args.workload == "cfg3":
             pkg = isr.render(cam, pc, _Pipe, bg)
-            n_valid = int(data["valid"].numel())
-            sel = torch.randint(0, n_valid, (wl["samples"],), device=dev, generator=gen)
-            pix = data["valid"][sel].long()
-            labels = data["labels"][pix]
+            pix, labels = isr.sample_labelled_pixels(data["labels"], wl["samples"], generator=gen)
             feats = isr.sample_pixels(pkg["seg_feature"], pix)
             loss = isr.contrastive_loss(feats, labels, num_labels=wl["labels"]) * (1e-6 * 0.5)
             loss.backward()

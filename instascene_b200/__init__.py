@@ -2,10 +2,11 @@
 the reference InstaScene interfaces (diff_surfel_rasterization, gaussian_renderer.render, contrastive_loss,
 distCUDA2).  Host side = Python mirror of the reference API; device side = libisr.so (C ABI, include/isr.h)."""
 from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians, sample_pixels, normalize_rows,  # noqa: F401
+                         sample_labelled_pixels,
                          _C)
 from .renderer import render, depth_to_normal  # noqa: F401
 from .contrastive import contrastive_loss  # noqa: F401
 from .knn import distCUDA2  # noqa: F401
 
-__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "sample_pixels", "normalize_rows", "render",
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "sample_pixels", "sample_labelled_pixels", "normalize_rows", "render",
            "depth_to_normal", "contrastive_loss", "distCUDA2"]

@@ -57,10 +57,11 @@ __device__ __forceinline__ void cp_async16_b(void* smem_dst, const void* gmem_sr
 // Same warp-autonomous structure as blend_fwd_kernel, walking the list BACK to front: per-warp cull-rectangle test
 // (exact: a culled Gaussian contributed to no pixel of the block in the forward), cp.async staging of survivors.
 template <int FP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, FP == 0 ? 3 : 1)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int F,
                  const float* __restrict__ bg, const float4* __restrict__ splats, const float4* __restrict__ cull4,
-                 const float4* __restrict__ rgb4, const float* __restrict__ extras, const float* __restrict__ final_Ts,
+                 const float4* __restrict__ cullq, const float4* __restrict__ rgb4, const float* __restrict__ extras,
+                 const float* __restrict__ final_Ts,
                  const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
                  const float* __restrict__ dL_dothers, const float* __restrict__ dL_dpix_extra,
                  float* __restrict__ dL_dtransMat, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dnormal3D,
@@ -84,6 +85,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     const float pixx = (float)pxi, pixy = (float)pyi;
     const float bx0 = (float)wx0, by0 = (float)wy0;
     const float bx1 = (float)min(wx0 + 7, W - 1), by1 = (float)min(wy0 + 3, H - 1);
+    const float bcx = 0.5f * (bx0 + bx1), bcy = 0.5f * (by0 + by1), bhx = 0.5f * (bx1 - bx0), bhy = 0.5f * (by1 - by0);
 
     const uint2 range = ranges[tile_id];
     const int n_total = (int)(range.y - range.x);
@@ -147,7 +149,11 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         cr1 = (id1 >= 0) ? __ldg(cull4 + id1) : kEmpty;
         id2 = (idx_of(top - 64) >= 0) ? (int)__ldg(plist + idx_of(top - 64)) : -1;
 
-        const bool ov = (id >= 0) && !(cr.z < bx0 || cr.x > bx1 || cr.w < by0 || cr.y > by1);
+        bool ov = (id >= 0) && !(cr.z < bx0 || cr.x > bx1 || cr.w < by0 || cr.y > by1);
+        if (ov) {
+            const float4* q = cullq + (size_t)id * 3;
+            ov = !block_outside(__ldg(q), __ldg(q + 1), __ldg(q + 2).x, bcx, bcy, bhx, bhy);
+        }
         const unsigned m = __ballot_sync(0xffffffffu, ov);
         if (m == 0) continue;
         if (ov) {
@@ -188,15 +194,17 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
             const bool hit = active && eval_pair<true>(pixx, pixy, s, e);
             if (!__any_sync(0xffffffffu, hit)) continue;
             // per-lane partial gradients (0 when this lane does not contribute)
-            float v[32];
+            // v[0..2] colour, v[3..5] normal, v[6..14] transMat, v[15] opacity; mean2D (2D-filter branch only) apart
+            float v[16];
 #pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = 0.0f;
+            for (int i = 0; i < 16; i++) v[i] = 0.0f;
+            float m2x = 0.0f, m2y = 0.0f;
             float ve[FP > 0 ? FP : 1];
 #pragma unroll
             for (int ch = 0; ch < FP; ch++) ve[ch] = 0.0f;
             if (hit) {
                 const float alpha = e.alpha, G = e.G, c_d = e.depth;
-                const float ra = rcp(sub(1.0f, alpha));
+                const float ra = rcp_fast(sub(1.0f, alpha));
                 T = mul(T, ra);
                 const float w = mul(alpha, T);
                 float dL_dalpha = 0.0f;
@@ -211,7 +219,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                 v[0] = mul(w, dLdC0); v[1] = mul(w, dLdC1); v[2] = mul(w, dLdC2);
 
                 float dL_dz = 0.0f;
-                const float rcd = rcp(c_d);
+                const float rcd = rcp_fast(c_d);
                 const float m_d = mul(c1, sub(1.0f, mul(kNear, rcd)));
                 const float dmd_dd = mul(mul(c3, rcd), rcd);
                 if (contributor == median_contributor - 1u) dL_dz = add(dL_dz, dL_dmedian);
@@ -268,22 +276,35 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                     v[14] = add(fma_(pixx, dkz, mul(pixy, dlz)), dL_dz);
                 } else {
                     const float nG2 = mul(-G, kFilterInvSquare);
-                    v[15] = mul(dL_dG, mul(nG2, e.ddx));
-                    v[16] = mul(dL_dG, mul(nG2, e.ddy));
+                    m2x = mul(dL_dG, mul(nG2, e.ddx));
+                    m2y = mul(dL_dG, mul(nG2, e.ddy));
                     v[14] = dL_dz;
                 }
-                v[17] = mul(G, dL_dalpha);
+                v[15] = mul(G, dL_dalpha);
             }
             const int g = mt.x;
-            const float tot = warp_transpose_reduce<32>(v, lane);
-            if (lane < 18 && tot != 0.0f) {
+            // 16-value transposing butterfly: afterwards lanes 2i and 2i+1 both hold the total of value i
+            const float tot = warp_transpose_reduce<16>(v, lane);
+            if ((lane & 1) == 0 && tot != 0.0f) {
+                const int vi = lane >> 1;
                 float* dst;
-                if (lane < 3) dst = dL_dcolors ? dL_dcolors + (size_t)g * 3 + lane : nullptr;
-                else if (lane < 6) dst = dL_dnormal3D ? dL_dnormal3D + (size_t)g * 3 + (lane - 3) : nullptr;
-                else if (lane < 15) dst = dL_dtransMat ? dL_dtransMat + (size_t)g * 9 + (lane - 6) : nullptr;
-                else if (lane < 17) dst = dL_dmean2D ? dL_dmean2D + (size_t)g * 3 + (lane - 15) : nullptr;
+                if (vi < 3) dst = dL_dcolors ? dL_dcolors + (size_t)g * 3 + vi : nullptr;
+                else if (vi < 6) dst = dL_dnormal3D ? dL_dnormal3D + (size_t)g * 3 + (vi - 3) : nullptr;
+                else if (vi < 15) dst = dL_dtransMat ? dL_dtransMat + (size_t)g * 9 + (vi - 6) : nullptr;
                 else dst = dL_dopacity ? dL_dopacity + g : nullptr;
                 if (dst) atomicAdd(dst, tot);
+            }
+            // the low-pass (2D) branch is rare: reduce its two values only when some lane took it
+            if (__any_sync(0xffffffffu, hit && !e.use3d)) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    m2x += __shfl_xor_sync(0xffffffffu, m2x, off);
+                    m2y += __shfl_xor_sync(0xffffffffu, m2y, off);
+                }
+                if (lane == 0 && dL_dmean2D) {
+                    if (m2x != 0.0f) atomicAdd(dL_dmean2D + (size_t)g * 3 + 0, m2x);
+                    if (m2y != 0.0f) atomicAdd(dL_dmean2D + (size_t)g * 3 + 1, m2y);
+                }
             }
             if (FP > 0) {
                 constexpr int NE = FP <= 8 ? 8 : (FP <= 16 ? 16 : 32);
@@ -324,16 +345,22 @@ extra_sparse_bwd_kernel(int n, const int* __restrict__ pix_ids, const float* __r
 #pragma unroll
     for (int ch = 0; ch < FP; ch++) dE[ch] = (ch < F) ? dLdE_samples[(size_t)warp_global * F + ch] : 0.0f;
     float T = 1.0f;  // transmittance in front of the current group of 32 (warp-uniform)
+    const uint32_t* __restrict__ plist = point_list + range.x;
+    const float4 kEmpty = make_float4(1e30f, 1e30f, -1e30f, -1e30f);
+    // software pipeline (as in blend_fwd_kernel): ids two chunks ahead, cull rectangles one chunk ahead
+    int id1 = (lane < last) ? (int)__ldg(plist + lane) : -1;
+    float4 cr1 = (id1 >= 0) ? __ldg(cull4 + id1) : kEmpty;
+    int id2 = (32 + lane < last) ? (int)__ldg(plist + 32 + lane) : -1;
     for (int base = 0; base < last; base += 32) {
-        const int i = base + lane;
+        const int g = id1;
+        const float4 cr = cr1;
+        id1 = id2;
+        cr1 = (id1 >= 0) ? __ldg(cull4 + id1) : kEmpty;
+        id2 = (base + 64 + lane < last) ? (int)__ldg(plist + base + 64 + lane) : -1;
         float alpha = 0.0f;
-        int g = -1;
-        if (i < last) g = (int)point_list[range.x + i];
-        bool cand = false;
-        if (g >= 0) {  // exact pre-test: the pixel lies outside the Gaussian's conservative cull rectangle
-            const float4 cr = __ldg(cull4 + g);
-            cand = !(cr.z < pixx || cr.x > pixx || cr.w < pixy || cr.y > pixy);
-        }
+        // exact pre-test: the pixel lies outside the Gaussian's conservative cull rectangle
+        const bool cand = (g >= 0) && !(cr.z < pixx || cr.x > pixx || cr.w < pixy || cr.y > pixy);
+        if (!__any_sync(0xffffffffu, cand)) continue;
         if (cand) {
             float s[16];
             const float4* sp = splats + (size_t)g * 4;
@@ -357,12 +384,21 @@ extra_sparse_bwd_kernel(int n, const int* __restrict__ pix_ids, const float* __r
         }
         if (alpha != 0.0f && g >= 0) {
             const float w = mul(alpha, Tin);
+            if ((F & 3) == 0) {  // 16-byte vector reductions (red.global.add.v4.f32): 4x fewer atomic operations
+                float4* dst = reinterpret_cast<float4*>(dL_dextras + (size_t)g * F);
 #pragma unroll
-            for (int ch = 0; ch < FP; ch++)
-                if (ch < F) {
-                    const float val = mul(w, dE[ch]);
-                    if (val != 0.0f) atomicAdd(dL_dextras + (size_t)g * F + ch, val);
-                }
+                for (int v4 = 0; v4 < FP / 4; v4++)
+                    if (v4 * 4 < F)
+                        atomicAdd(dst + v4, make_float4(mul(w, dE[4 * v4]), mul(w, dE[4 * v4 + 1]), mul(w, dE[4 * v4 + 2]),
+                                                        mul(w, dE[4 * v4 + 3])));
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < FP; ch++)
+                    if (ch < F) {
+                        const float val = mul(w, dE[ch]);
+                        if (val != 0.0f) atomicAdd(dL_dextras + (size_t)g * F + ch, val);
+                    }
+            }
         }
     }
 }
@@ -382,7 +418,8 @@ static int launch_bwd_one(const IsrBackwardArgs& a, cudaStream_t stream) {
     kern<<<grid, 256, smem, stream>>>(
         reinterpret_cast<const uint2*>(im + il.ranges), reinterpret_cast<const uint32_t*>(b), a.W, a.H, a.F, a.background,
         reinterpret_cast<const float4*>(g + gl.splat), reinterpret_cast<const float4*>(g + gl.cull),
-        reinterpret_cast<const float4*>(g + gl.rgb), a.extra_attrs, reinterpret_cast<const float*>(im + il.final_T), reinterpret_cast<const uint32_t*>(im + il.n_contrib), a.dL_dcolor,
+        reinterpret_cast<const float4*>(g + gl.cullq), reinterpret_cast<const float4*>(g + gl.rgb), a.extra_attrs,
+        reinterpret_cast<const float*>(im + il.final_T), reinterpret_cast<const uint32_t*>(im + il.n_contrib), a.dL_dcolor,
         a.dL_dothers, a.dL_dextra_pix, (m & ISR_GRAD_GEOMETRY) ? a.dL_dtransMat : nullptr,
         (m & ISR_GRAD_GEOMETRY) ? a.dL_dmeans2D : nullptr, (m & ISR_GRAD_GEOMETRY) ? a.dL_dnormal : nullptr,
         (m & ISR_GRAD_OPACITY) ? a.dL_dopacity : nullptr, (m & ISR_GRAD_COLOR) ? a.dL_dcolors : nullptr,

@@ -7,6 +7,8 @@
 // memory, broadcast reads in the inner loop (the reference fetches rgb and features from global per contributing
 // (pixel, Gaussian) pair), no block-wide barriers.  Pair-list entries are staged per warp in shared memory and
 // flushed with one global atomic per <= 96 pairs (the reference: one global atomic per pair on a single counter).
+#include <cstdlib>
+
 #include "isr_common.cuh"
 
 namespace isr {
@@ -32,11 +34,12 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // LDGSTS, no registers) into the warp's private shared-memory slots, (4) the survivors are blended in list order
 // with broadcast shared-memory reads.  There is no block-wide barrier: warps of a tile neither wait for each other
 // nor for the slowest pixel of the tile, and a warp stops as soon as its own 32 pixels are saturated.
-template <int FP, bool kPairs>
-__global__ void __launch_bounds__(256)
+template <int FP, bool kPairs, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int F,
-                 const float4* __restrict__ splats, const float4* __restrict__ cull4, const float4* __restrict__ rgb4,
-                 const float* __restrict__ extras, const float* __restrict__ bg, float* __restrict__ final_T,
+                 const float4* __restrict__ splats, const float4* __restrict__ cull4, const float4* __restrict__ cullq,
+                 const float4* __restrict__ rgb4, const float* __restrict__ extras, const float* __restrict__ bg,
+                 float* __restrict__ final_T,
                  uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, float* __restrict__ out_others,
                  float* __restrict__ out_extra, int2* __restrict__ pairs, int64_t pair_cap, int* __restrict__ pair_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -58,6 +61,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     const float pixx = (float)pxi, pixy = (float)pyi;
     const float bx0 = (float)wx0, by0 = (float)wy0;
     const float bx1 = (float)min(wx0 + 7, W - 1), by1 = (float)min(wy0 + 3, H - 1);
+    const float bcx = 0.5f * (bx0 + bx1), bcy = 0.5f * (by0 + by1), bhx = 0.5f * (bx1 - bx0), bhy = 0.5f * (by1 - by0);
 
     const uint2 range = ranges[tile_id];
     const int n_total = (int)(range.y - range.x);
@@ -87,7 +91,11 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         cr1 = (id1 >= 0) ? __ldg(cull4 + id1) : kEmpty;
         id2 = (base + 64 + lane < n_total) ? (int)__ldg(plist + base + 64 + lane) : -1;
 
-        const bool ov = (id >= 0) && !(cr.z < bx0 || cr.x > bx1 || cr.w < by0 || cr.y > by1);
+        bool ov = (id >= 0) && !(cr.z < bx0 || cr.x > bx1 || cr.w < by0 || cr.y > by1);
+        if (ov) {  // second stage: the conic itself against the block (corner overlaps of the rectangle)
+            const float4* q = cullq + (size_t)id * 3;
+            ov = !block_outside(__ldg(q), __ldg(q + 1), __ldg(q + 2).x, bcx, bcy, bhx, bhy);
+        }
         const unsigned m = __ballot_sync(0xffffffffu, ov);
         if (m == 0) continue;
         if (ov) {
@@ -133,7 +141,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                         const uint32_t contributor = (uint32_t)(meta[r].y + 1);
                         w = mul(e.alpha, T);
                         const float A = sub(1.0f, T);
-                        const float mdep = mul(c1, sub(1.0f, mul(kNear, rcp(e.depth))));
+                        const float mdep = mul(c1, sub(1.0f, mul(kNear, rcp_fast(e.depth))));
                         const float mm = mul(mdep, mdep);
                         const float dt = fma_(-add(mdep, mdep), M1, fma_(mm, A, M2));
                         dist = fma_(dt, w, dist);
@@ -224,12 +232,15 @@ static int launch_one(const IsrForwardArgs& a, cudaStream_t stream) {
     const char* b = static_cast<const char*>(a.binning);
     const dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE);
     const size_t smem = FwdSmem<FP>::bytes;
-    auto kern = blend_fwd_kernel<FP, kPairs>;
+    // occupancy variant: 4 CTAs/SM (64 registers) or 3 CTAs/SM (80 registers, no spills); ISR_FWD_MINBLOCKS overrides
+    static const int env_mb = [] { const char* e = getenv("ISR_FWD_MINBLOCKS"); return e ? atoi(e) : 0; }();
+    const int mb = env_mb ? env_mb : (FP < 16 ? 4 : 3);  // measured at cfg3 (F=16): 3 CTAs/SM, no spills, is 6% faster
+    auto kern = (mb >= 4) ? blend_fwd_kernel<FP, kPairs, 4> : blend_fwd_kernel<FP, kPairs, 3>;
     ISR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 256, smem, stream>>>(
         reinterpret_cast<const uint2*>(im + il.ranges), reinterpret_cast<const uint32_t*>(b),  // point_list sits at offset 0 of the binning workspace
         a.W, a.H, a.F, reinterpret_cast<const float4*>(g + gl.splat), reinterpret_cast<const float4*>(g + gl.cull),
-        reinterpret_cast<const float4*>(g + gl.rgb), a.extra_attrs, a.background,
+        reinterpret_cast<const float4*>(g + gl.cullq), reinterpret_cast<const float4*>(g + gl.rgb), a.extra_attrs, a.background,
         reinterpret_cast<float*>(im + il.final_T), reinterpret_cast<uint32_t*>(im + il.n_contrib), a.out_color,
         a.out_others, a.out_extra, reinterpret_cast<int2*>(a.pairs), a.pair_capacity, a.pair_count);
     ISR_CUDA_TRY(cudaGetLastError());

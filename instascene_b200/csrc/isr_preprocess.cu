@@ -43,25 +43,45 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
                       const float* __restrict__ opacities, const float* __restrict__ shs,
                       const float* __restrict__ transMat_precomp, const float* __restrict__ colors_precomp,
                       const Camera cam, int W, int H, int gx, int gy, int* __restrict__ radii,
-                      Splat* __restrict__ splats, float4* __restrict__ cull4, float4* __restrict__ rgb4,
+                      Splat* __restrict__ splats, float4* __restrict__ cull4, float4* __restrict__ cullq,
+                      float4* __restrict__ rgb4,
                       float* __restrict__ depths,
                       uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ tiles_touched,
                       uint8_t* __restrict__ clamped) {
+    // SH coefficients of the block's 256 Gaussians are one contiguous 48 KB range: stage them with fully coalesced
+    // 16-byte cp.async copies into per-Gaussian slots padded to 13 x 16 B (conflict-free LDS), overlapped with the
+    // projection math below.  (Per-thread strided loads of the 192-byte rows ran K1 at 48% of the HBM roofline.)
+    extern __shared__ __align__(16) float4 s_sh[];
+    const bool stage_sh = (shs != nullptr) && (M == 16) && (colors_precomp == nullptr);
+    if (stage_sh) {
+        const int block_base = blockIdx.x * blockDim.x;
+        const int n_chunks = min((int)blockDim.x, P - block_base) * 12;
+        const float4* src = reinterpret_cast<const float4*>(shs + (size_t)block_base * 48);
+        for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) {
+            const int row = c / 12, col = c - row * 12;
+            const unsigned d = (unsigned)__cvta_generic_to_shared(s_sh + row * 13 + col);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src + c));
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    }
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
     int radius_i = 0;
     uint32_t tiles = 0, dkey = 0xFFFFFFFFu;
     uint8_t clamp_mask = 0;
+    bool visible = false;
+    float p0 = 0, p1 = 0, p2 = 0, pvz = 0, cx = 0, cy = 0;
+    float T[9], nrm[3];
+    int ri = 0, ntiles = 0;
     do {
-        const float p0 = means3D[3 * (size_t)idx], p1 = means3D[3 * (size_t)idx + 1], p2 = means3D[3 * (size_t)idx + 2];
+        if (idx >= P) break;
+        p0 = means3D[3 * (size_t)idx]; p1 = means3D[3 * (size_t)idx + 1]; p2 = means3D[3 * (size_t)idx + 2];
         float view[16], proj[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) { view[i] = __ldg(cam.view + i); proj[i] = __ldg(cam.proj + i); }
         const float pvx = add(dot3c(view[0], p0, view[4], p1, view[8], p2), view[12]);
         const float pvy = add(dot3c(view[1], p0, view[5], p1, view[9], p2), view[13]);
-        const float pvz = add(dot3c(view[2], p0, view[6], p1, view[10], p2), view[14]);
+        pvz = add(dot3c(view[2], p0, view[6], p1, view[10], p2), view[14]);
         if (pvz <= 0.2f) break;
-        float T[9], nrm[3];
         if (transMat_precomp == nullptr) {
             const float2 sc = scales[idx];
             const float sx = mul(scale_modifier, sc.x), sy = mul(scale_modifier, sc.y);
@@ -102,25 +122,31 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
         if (d == 0.0f) break;
         const float inv_d = rcp(d);
         const float f9 = mul(inv_d, 9.0f);
-        const float cx = fma_(mul(Tu[2], Tw[2]), -inv_d, fma_(f9, mul(Tu[1], Tw[1]), mul(f9, mul(Tu[0], Tw[0]))));
-        const float cy = fma_(mul(Tv[2], Tw[2]), -inv_d, fma_(f9, mul(Tv[1], Tw[1]), mul(f9, mul(Tv[0], Tw[0]))));
+        cx = fma_(mul(Tu[2], Tw[2]), -inv_d, fma_(f9, mul(Tu[1], Tw[1]), mul(f9, mul(Tu[0], Tw[0]))));
+        cy = fma_(mul(Tv[2], Tw[2]), -inv_d, fma_(f9, mul(Tv[1], Tw[1]), mul(f9, mul(Tv[0], Tw[0]))));
         const float ngx = fma_(mul(Tu[2], Tu[2]), inv_d, -fma_(f9, mul(Tu[1], Tu[1]), mul(f9, mul(Tu[0], Tu[0]))));
         const float ngy = fma_(mul(Tv[2], Tv[2]), inv_d, -fma_(f9, mul(Tv[1], Tv[1]), mul(f9, mul(Tv[0], Tv[0]))));
         const float ex = sqrt_(fmaxf(1e-4f, fma_(cx, cx, ngx)));
         const float ey = sqrt_(fmaxf(1e-4f, fma_(cy, cy, ngy)));
         const float radius = ceilf(fmaxf(fmaxf(ex, ey), mul(3.0f, kFilterSize)));
-        const int ri = __float2int_rz(radius);
+        ri = __float2int_rz(radius);
         int mnx, mny, mxx, mxy;
         get_rect(cx, cy, ri, gx, gy, mnx, mny, mxx, mxy);
-        const int ntiles = (mxx - mnx) * (mxy - mny);
+        ntiles = (mxx - mnx) * (mxy - mny);
         if (ntiles == 0) break;
-
+        visible = true;
+    } while (false);
+    if (stage_sh) {
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+        __syncthreads();
+    }
+    if (visible) {
+        const float* Tu = T; const float* Tv = T + 3; const float* Tw = T + 6;
         float rgb[3];
         if (colors_precomp == nullptr) {
             // computeColorFromSH (forward.cu:20-71)
-            const float4* sh4 = reinterpret_cast<const float4*>(shs + (size_t)idx * M * 3);
-            const float* sh = shs + (size_t)idx * M * 3;
-            (void)sh4;
+            const float* sh = stage_sh ? reinterpret_cast<const float*>(s_sh + threadIdx.x * 13)
+                                       : shs + (size_t)idx * M * 3;
             const float dx = sub(p0, __ldg(cam.campos)), dy = sub(p1, __ldg(cam.campos + 1)), dz = sub(p2, __ldg(cam.campos + 2));
             const float len = sqrt_(fma_(dz, dz, fma_(dx, dx, mul(dy, dy))));
             const float x = __fdiv_rn(dx, len), y = __fdiv_rn(dy, len), z = __fdiv_rn(dz, len);
@@ -233,12 +259,46 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
             }
         }
         cull4[idx] = cr;
+        // Normalised conic of the same region for the second-stage block test (isr::block_outside), in fp64:
+        // p(x,y) = A x + B y + C with A = Tv x Tw, B = Tw x Tu, C = Tu x Tv (k x l expanded), re-centred at (cx,cy).
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = make_float4(0.f, -1.f, cx, cy);  // Q == -1: never "outside"
+        float r2 = __int_as_float(0x7f800000);
+        if (rho_max > 0.0f && cr.x > -1e29f) {
+            const double rho = (double)rho_max * 1.0002;
+            const double tu0 = Tu[0], tu1 = Tu[1], tu2 = Tu[2], tv0 = Tv[0], tv1 = Tv[1], tv2 = Tv[2];
+            const double tw0 = Tw[0], tw1 = Tw[1], tw2 = Tw[2];
+            const double Ax = tv1 * tw2 - tv2 * tw1, Ay = tv2 * tw0 - tv0 * tw2, Az = tv0 * tw1 - tv1 * tw0;
+            const double Bx = tw1 * tu2 - tw2 * tu1, By = tw2 * tu0 - tw0 * tu2, Bz = tw0 * tu1 - tw1 * tu0;
+            const double Cx = tu1 * tv2 - tu2 * tv1, Cy = tu2 * tv0 - tu0 * tv2, Cz = tu0 * tv1 - tu1 * tv0;
+            const double mx = cx, my = cy;
+            const double cpx = Ax * mx + Bx * my + Cx, cpy = Ay * mx + By * my + Cy, cpz = Az * mx + Bz * my + Cz;
+            const double qxx = Ax * Ax + Ay * Ay - rho * Az * Az, qyy = Bx * Bx + By * By - rho * Bz * Bz;
+            const double qxy = 2.0 * (Ax * Bx + Ay * By - rho * Az * Bz);
+            const double qx = 2.0 * (Ax * cpx + Ay * cpy - rho * Az * cpz), qy = 2.0 * (Bx * cpx + By * cpy - rho * Bz * cpz);
+            const double qc = cpx * cpx + cpy * cpy - rho * cpz * cpz;
+            const double nrm2 = rho * cpz * cpz;
+            // usable only for a proper ellipse that contains its own centre
+            if (nrm2 > 0.0 && qc < 0.0 && qxx > 0.0 && 4.0 * qxx * qyy - qxy * qxy > 0.0) {
+                const double sc = 1.0 / nrm2;
+                q0 = make_float4((float)(qxx * sc), (float)(qxy * sc), (float)(qyy * sc), (float)(qx * sc));
+                q1 = make_float4((float)(qy * sc), (float)(qc * sc), cx, cy);
+            }
+            const float rd = sqrtf(0.5f * rho_max) + 0.5f;
+            r2 = rd * rd;
+        } else if (!(rho_max > 0.0f)) {
+            q1.y = 1e30f;  // never contributes: Q huge, disk empty
+            r2 = -1.0f;
+        }
+        cullq[3 * (size_t)idx + 0] = q0;
+        cullq[3 * (size_t)idx + 1] = q1;
+        cullq[3 * (size_t)idx + 2] = make_float4(r2, 0.f, 0.f, 0.f);
         rgb4[idx] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
         depths[idx] = pvz;
         dkey = __float_as_uint(pvz);
         radius_i = ri;
         tiles = (uint32_t)ntiles;
-    } while (false);
+    }
+    if (idx >= P) return;
     radii[idx] = radius_i;
     tiles_touched[idx] = tiles;
     depth_keys[idx] = dkey;
@@ -258,70 +318,67 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
 // K8: backward of the per-Gaussian projection (backward.cu:469-656) + SH backward (backward.cu:20-139).
 // Float-only results; written as plain expressions (tolerance-compared with the oracle / reference).
 // ---------------------------------------------------------------------------------------------------------
+// SH backward (reference: backward.cu:20-139) written as "basis + basis gradient":
+//   rgb = sum_i Y_i(d) * sh_i + 0.5,  d = (pos - campos)/|pos - campos|
+//   dL/dsh_i = Y_i * dL/drgb (clamped channels masked),   dL/dd = sum_i gradY_i * (sh_i . dL/drgb)
+// followed by the Jacobian of the normalisation (auxiliary.h:129-139).
+__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float* Y, float* Yx, float* Yy, float* Yz) {
+    for (int i = 0; i < 16; i++) { Y[i] = 0.0f; Yx[i] = 0.0f; Yy[i] = 0.0f; Yz[i] = 0.0f; }
+    Y[0] = SH_C0;
+    if (deg < 1) return;
+    Y[1] = -SH_C1 * y; Yy[1] = -SH_C1;
+    Y[2] = SH_C1 * z;  Yz[2] = SH_C1;
+    Y[3] = -SH_C1 * x; Yx[3] = -SH_C1;
+    if (deg < 2) return;
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    Y[4] = SH_C2[0] * xy;                   Yx[4] = SH_C2[0] * y;          Yy[4] = SH_C2[0] * x;
+    Y[5] = SH_C2[1] * yz;                   Yy[5] = SH_C2[1] * z;          Yz[5] = SH_C2[1] * y;
+    Y[6] = SH_C2[2] * (2.f * zz - xx - yy); Yx[6] = -2.f * SH_C2[2] * x;   Yy[6] = -2.f * SH_C2[2] * y;  Yz[6] = 4.f * SH_C2[2] * z;
+    Y[7] = SH_C2[3] * xz;                   Yx[7] = SH_C2[3] * z;          Yz[7] = SH_C2[3] * x;
+    Y[8] = SH_C2[4] * (xx - yy);            Yx[8] = 2.f * SH_C2[4] * x;    Yy[8] = -2.f * SH_C2[4] * y;
+    if (deg < 3) return;
+    Y[9] = SH_C3[0] * y * (3.f * xx - yy);
+    Yx[9] = SH_C3[0] * 6.f * xy;            Yy[9] = SH_C3[0] * 3.f * (xx - yy);
+    Y[10] = SH_C3[1] * xy * z;
+    Yx[10] = SH_C3[1] * yz;                 Yy[10] = SH_C3[1] * xz;        Yz[10] = SH_C3[1] * xy;
+    Y[11] = SH_C3[2] * y * (4.f * zz - xx - yy);
+    Yx[11] = SH_C3[2] * -2.f * xy;          Yy[11] = SH_C3[2] * (4.f * zz - xx - 3.f * yy);  Yz[11] = SH_C3[2] * 8.f * yz;
+    Y[12] = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+    Yx[12] = SH_C3[3] * -6.f * xz;          Yy[12] = SH_C3[3] * -6.f * yz; Yz[12] = SH_C3[3] * 3.f * (2.f * zz - xx - yy);
+    Y[13] = SH_C3[4] * x * (4.f * zz - xx - yy);
+    Yx[13] = SH_C3[4] * (4.f * zz - 3.f * xx - yy);  Yy[13] = SH_C3[4] * -2.f * xy;  Yz[13] = SH_C3[4] * 8.f * xz;
+    Y[14] = SH_C3[5] * z * (xx - yy);
+    Yx[14] = SH_C3[5] * 2.f * xz;           Yy[14] = SH_C3[5] * -2.f * yz; Yz[14] = SH_C3[5] * (xx - yy);
+    Y[15] = SH_C3[6] * x * (xx - 3.f * yy);
+    Yx[15] = SH_C3[6] * 3.f * (xx - yy);    Yy[15] = SH_C3[6] * -6.f * xy;
+}
+
 __device__ void sh_backward(int idx, int deg, int M, const float* __restrict__ means, const float* campos,
                             const float* __restrict__ shs, uint8_t clamp_mask, const float* __restrict__ dL_dcolor,
                             float* __restrict__ dL_dmeans, float* __restrict__ dL_dshs) {
-    const float dox = means[3 * (size_t)idx] - campos[0], doy = means[3 * (size_t)idx + 1] - campos[1],
-                doz = means[3 * (size_t)idx + 2] - campos[2];
-    const float len = sqrtf(dox * dox + doy * doy + doz * doz);
-    const float x = dox / len, y = doy / len, z = doz / len;
+    const float ox = means[3 * (size_t)idx] - __ldg(campos), oy = means[3 * (size_t)idx + 1] - __ldg(campos + 1),
+                oz = means[3 * (size_t)idx + 2] - __ldg(campos + 2);
+    const float len2 = ox * ox + oy * oy + oz * oz;
+    const float inv_len = 1.0f / sqrtf(len2);
+    float Y[16], Yx[16], Yy[16], Yz[16];
+    sh_basis(deg, ox * inv_len, oy * inv_len, oz * inv_len, Y, Yx, Yy, Yz);
+    float g[3];  // dL/drgb with the clamp mask applied (PyTorch clamp rule: zero gradient where clamped)
+    for (int c = 0; c < 3; c++) g[c] = ((clamp_mask >> c) & 1) ? 0.0f : dL_dcolor[3 * (size_t)idx + c];
     const float* sh = shs + (size_t)idx * M * 3;
-    float dRGB[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) dRGB[c] = ((clamp_mask >> c) & 1) ? 0.0f : dL_dcolor[3 * (size_t)idx + c];
-    float dx[3] = {0, 0, 0}, dy[3] = {0, 0, 0}, dz[3] = {0, 0, 0};
     float* dsh = dL_dshs + (size_t)idx * M * 3;
-#define SH(i, c) sh[3 * (i) + (c)]
-#define DSH(i, v)                                                   \
-    {                                                               \
-        const float _v = (v);                                       \
-        for (int c = 0; c < 3; c++) dsh[3 * (i) + c] = _v * dRGB[c]; \
+    const int n = (deg + 1) * (deg + 1);
+    float ddx = 0.0f, ddy = 0.0f, ddz = 0.0f;  // dL/d(direction)
+    for (int i = 0; i < n; i++) {
+        const float proj = sh[3 * i] * g[0] + sh[3 * i + 1] * g[1] + sh[3 * i + 2] * g[2];
+        ddx += Yx[i] * proj; ddy += Yy[i] * proj; ddz += Yz[i] * proj;
+        dsh[3 * i] = Y[i] * g[0]; dsh[3 * i + 1] = Y[i] * g[1]; dsh[3 * i + 2] = Y[i] * g[2];
     }
-    DSH(0, SH_C0);
-    if (deg > 0) {
-        DSH(1, -SH_C1 * y); DSH(2, SH_C1 * z); DSH(3, -SH_C1 * x);
-        for (int c = 0; c < 3; c++) { dx[c] = -SH_C1 * SH(3, c); dy[c] = -SH_C1 * SH(1, c); dz[c] = SH_C1 * SH(2, c); }
-        if (deg > 1) {
-            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-            DSH(4, SH_C2[0] * xy); DSH(5, SH_C2[1] * yz); DSH(6, SH_C2[2] * (2.f * zz - xx - yy));
-            DSH(7, SH_C2[3] * xz); DSH(8, SH_C2[4] * (xx - yy));
-            for (int c = 0; c < 3; c++) {
-                dx[c] += SH_C2[0] * y * SH(4, c) + SH_C2[2] * 2.f * -x * SH(6, c) + SH_C2[3] * z * SH(7, c) + SH_C2[4] * 2.f * x * SH(8, c);
-                dy[c] += SH_C2[0] * x * SH(4, c) + SH_C2[1] * z * SH(5, c) + SH_C2[2] * 2.f * -y * SH(6, c) + SH_C2[4] * 2.f * -y * SH(8, c);
-                dz[c] += SH_C2[1] * y * SH(5, c) + SH_C2[2] * 2.f * 2.f * z * SH(6, c) + SH_C2[3] * x * SH(7, c);
-            }
-            if (deg > 2) {
-                DSH(9, SH_C3[0] * y * (3.f * xx - yy)); DSH(10, SH_C3[1] * xy * z);
-                DSH(11, SH_C3[2] * y * (4.f * zz - xx - yy));
-                DSH(12, SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy));
-                DSH(13, SH_C3[4] * x * (4.f * zz - xx - yy)); DSH(14, SH_C3[5] * z * (xx - yy));
-                DSH(15, SH_C3[6] * x * (xx - 3.f * yy));
-                for (int c = 0; c < 3; c++) {
-                    dx[c] += (SH_C3[0] * SH(9, c) * 3.f * 2.f * xy + SH_C3[1] * SH(10, c) * yz +
-                              SH_C3[2] * SH(11, c) * -2.f * xy + SH_C3[3] * SH(12, c) * -3.f * 2.f * xz +
-                              SH_C3[4] * SH(13, c) * (-3.f * xx + 4.f * zz - yy) + SH_C3[5] * SH(14, c) * 2.f * xz +
-                              SH_C3[6] * SH(15, c) * 3.f * (xx - yy));
-                    dy[c] += (SH_C3[0] * SH(9, c) * 3.f * (xx - yy) + SH_C3[1] * SH(10, c) * xz +
-                              SH_C3[2] * SH(11, c) * (-3.f * yy + 4.f * zz - xx) + SH_C3[3] * SH(12, c) * -3.f * 2.f * yz +
-                              SH_C3[4] * SH(13, c) * -2.f * xy + SH_C3[5] * SH(14, c) * -2.f * yz +
-                              SH_C3[6] * SH(15, c) * -3.f * 2.f * xy);
-                    dz[c] += (SH_C3[1] * SH(10, c) * xy + SH_C3[2] * SH(11, c) * 4.f * 2.f * yz +
-                              SH_C3[3] * SH(12, c) * 3.f * (2.f * zz - xx - yy) + SH_C3[4] * SH(13, c) * 4.f * 2.f * xz +
-                              SH_C3[5] * SH(14, c) * (xx - yy));
-                }
-            }
-        }
-    }
-#undef SH
-#undef DSH
-    const float ddx = dx[0] * dRGB[0] + dx[1] * dRGB[1] + dx[2] * dRGB[2];
-    const float ddy = dy[0] * dRGB[0] + dy[1] * dRGB[1] + dy[2] * dRGB[2];
-    const float ddz = dz[0] * dRGB[0] + dz[1] * dRGB[1] + dz[2] * dRGB[2];
-    const float sum2 = dox * dox + doy * doy + doz * doz;
-    const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
-    dL_dmeans[3 * (size_t)idx + 0] += ((+sum2 - dox * dox) * ddx - doy * dox * ddy - doz * dox * ddz) * invsum32;
-    dL_dmeans[3 * (size_t)idx + 1] += (-dox * doy * ddx + (sum2 - doy * doy) * ddy - doz * doy * ddz) * invsum32;
-    dL_dmeans[3 * (size_t)idx + 2] += (-dox * doz * ddx - doy * doz * ddy + (sum2 - doz * doz) * ddz) * invsum32;
+    // d(v/|v|)/dv applied to (ddx, ddy, ddz):  (|v|^2 I - v v^T) dd / |v|^3
+    const float inv3 = inv_len * inv_len * inv_len;
+    const float vd = ox * ddx + oy * ddy + oz * ddz;
+    dL_dmeans[3 * (size_t)idx + 0] += (len2 * ddx - ox * vd) * inv3;
+    dL_dmeans[3 * (size_t)idx + 1] += (len2 * ddy - oy * vd) * inv3;
+    dL_dmeans[3 * (size_t)idx + 2] += (len2 * ddz - oz * vd) * inv3;
 }
 
 __global__ void __launch_bounds__(256)
@@ -442,11 +499,13 @@ int launch_preprocess_fwd(const IsrForwardArgs& a, cudaStream_t stream) {
     char* g = static_cast<char*>(a.geom);
     const int gx = (a.W + TILE - 1) / TILE, gy = (a.H + TILE - 1) / TILE;
     Camera cam{a.viewmatrix, a.projmatrix, a.campos};
-    preprocess_fwd_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(
+    const size_t sh_smem = (a.shs != nullptr && a.sh_coeffs == 16 && a.colors_precomp == nullptr) ? 256 * 13 * 16 : 0;
+    ISR_CUDA_TRY(cudaFuncSetAttribute(preprocess_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 13 * 16));
+    preprocess_fwd_kernel<<<(a.P + 255) / 256, 256, sh_smem, stream>>>(
         a.P, a.sh_degree, a.sh_coeffs, a.means3D, reinterpret_cast<const float2*>(a.scales), a.scale_modifier,
         reinterpret_cast<const float4*>(a.rotations), a.opacities, a.shs, a.transMat_precomp, a.colors_precomp, cam,
         a.W, a.H, gx, gy, a.radii, reinterpret_cast<Splat*>(g + gl.splat), reinterpret_cast<float4*>(g + gl.cull),
-        reinterpret_cast<float4*>(g + gl.rgb),
+        reinterpret_cast<float4*>(g + gl.cullq), reinterpret_cast<float4*>(g + gl.rgb),
         reinterpret_cast<float*>(g + gl.depth), reinterpret_cast<uint32_t*>(g + gl.depth_key),
         reinterpret_cast<uint32_t*>(g + gl.tiles), reinterpret_cast<uint8_t*>(g + gl.clamped));
     ISR_CUDA_TRY(cudaGetLastError());

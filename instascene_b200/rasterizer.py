@@ -163,12 +163,16 @@ def c_rasterize_gaussians_backward(background, means3D, radii, colors, scales, r
         H, W = image_size
     F = int(extra_attrs.shape[1]) if extra_attrs.numel() else 0
     M = int(sh.shape[1]) if sh.numel() else 0
-    z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
     geo, col, opa, ext = (bool(grad_mask & m) for m in (_lib.GRAD_GEOMETRY, _lib.GRAD_COLOR, _lib.GRAD_OPACITY, _lib.GRAD_EXTRA))
-    dL_dmeans3D, dL_dmeans2D = z(P, 3), z(P, 3)
-    dL_dcolors, dL_dnormal, dL_dopacity, dL_dtransMat = z(P, 3), z(P, 3), z(P, 1), z(P, 9)
-    dL_dsh, dL_dscales, dL_drotations = z(P, M, 3), z(P, 2), z(P, 4)
-    dL_dextra = z(P, F) if F > 0 else torch.empty(0, dtype=torch.float32, device=dev)
+    none = torch.empty(0, dtype=torch.float32, device=dev)
+    # the reference zero-fills all ten buffers (304+4F bytes per Gaussian) on every backward; only requested ones here
+    z = lambda on, *s: torch.zeros(s, dtype=torch.float32, device=dev) if on else none
+    dL_dmeans3D, dL_dmeans2D = z(geo, P, 3), z(geo, P, 3)
+    dL_dnormal, dL_dtransMat = z(geo, P, 3), z(geo, P, 9)
+    dL_dscales, dL_drotations = z(geo, P, 2), z(geo, P, 4)
+    dL_dcolors, dL_dsh = z(col or geo, P, 3), z(col or geo, P, M, 3)
+    dL_dopacity = z(opa, P, 1)
+    dL_dextra = z(ext and F > 0, P, F)
     if P == 0:
         return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dscales, dL_drotations, dL_dextra
     means3D = _f32c(means3D, "means3D")
@@ -448,3 +452,18 @@ def sample_pixels(extra_map: torch.Tensor, pix_ids: torch.Tensor) -> torch.Tenso
     if handle is None or not handle.requires_grad:
         return extra_map.reshape(extra_map.shape[0], -1)[:, pix_ids.long()].t()
     return _SamplePixels.apply(handle, extra_map, pix_ids)
+
+
+def sample_labelled_pixels(labels_flat: torch.Tensor, n: int, generator=None):
+    """Draw `n` pixel ids uniformly WITH replacement among the pixels whose label is > 0 -- the sampling of
+    train_semantic.py:118-129 (`valid = segmap > 0; idx = randint(0, len(valid), (n,))`) without the boolean-mask
+    gather of the [F,H,W] map and without a host sync: inclusive scan of the mask + searchsorted.
+    Returns (pix_ids int64 [n], labels [n])."""
+    mask = labels_flat > 0
+    csum = torch.cumsum(mask, dim=0, dtype=torch.int32)
+    n_valid = csum[-1]
+    u = torch.rand(n, device=labels_flat.device, generator=generator)
+    target = torch.clamp((u * n_valid).to(torch.int32), max=n_valid - 1) + 1  # rank (1-based) of the chosen valid pixel
+    pix = torch.searchsorted(csum, target, right=False)
+    pix = torch.clamp(pix, max=labels_flat.numel() - 1)
+    return pix, labels_flat[pix]

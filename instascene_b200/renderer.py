@@ -1,12 +1,14 @@
-"""Drop-in mirror of the reference ``gaussian_renderer.render`` (gaussian_renderer/__init__.py:20-169) and of
-``utils.point_utils.depth_to_normal`` (utils/point_utils.py:10-40) on top of the B200 rasterizer.
+"""`render()` with the interface of the reference's gaussian_renderer.render (gaussian_renderer/__init__.py:20-169)
+on top of the B200 rasterizer, plus `depth_to_normal` (utils/point_utils.py:10-40).
 
-`viewpoint_camera`, `pc` and `pipe` are duck-typed exactly like the reference uses them:
-  camera: FoVx, FoVy, image_height, image_width, world_view_transform, full_proj_transform, camera_center
-  pc:     get_xyz, get_opacity, get_seg_feature, get_scaling, get_rotation, get_features, active_sh_degree,
-          max_sh_degree, get_covariance(scaling_modifier)
-  pipe:   compute_cov3D_python, convert_SHs_python (forced False, Q10), depth_ratio
-The returned dict has the reference's 13 keys.
+Duck-typed inputs, exactly the attributes the reference touches:
+  camera  FoVx, FoVy, image_height, image_width, world_view_transform, full_proj_transform, camera_center
+          (znear/zfar only with pipe.compute_cov3D_python)
+  pc      get_xyz, get_opacity, get_seg_feature (or the raw parameter `_seg_feature`), get_scaling, get_rotation,
+          get_features, active_sh_degree, get_covariance(scaling_modifier)
+  pipe    compute_cov3D_python, convert_SHs_python (forced to False like the reference does, Q10), depth_ratio;
+          optional switches of this implementation: lazy_outputs (default True), fused_seg_activation (default True)
+Result: a dict-like `RenderPackage` with the reference's 13 keys.
 """
 from __future__ import annotations
 
@@ -15,6 +17,8 @@ import math
 import torch
 
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, normalize_rows
+
+_AUX_KEYS = ("rend_alpha", "rend_normal", "rend_dist", "surf_depth", "surf_normal", "rend_depth", "rend_median_depth")
 
 
 class _SettingsNoPairs(GaussianRasterizationSettings):
@@ -28,11 +32,9 @@ class _SettingsDeferPairs(GaussianRasterizationSettings):
 
 
 class RenderPackage(dict):
-    """The reference's 13-key result dict.  The six rasterizer outputs are stored eagerly; the seven derived maps
-    (gaussian_renderer/__init__.py:127-167) and the sliced pair list are computed on FIRST ACCESS -- the semantic
-    training loop (train_semantic.py:102-108) never reads them, the RGB loop (train.py) reads them all.  Values,
-    autograd history and key set are identical to the eager reference dict."""
-    _LAZY = ("rend_alpha", "rend_normal", "rend_dist", "surf_depth", "surf_normal", "rend_depth", "rend_median_depth")
+    """The 13-key result of render().  The six rasterizer outputs are stored eagerly; the seven derived maps and the
+    sliced pair list are produced on FIRST ACCESS: the semantic training loop (train_semantic.py:102-108) never reads
+    them, the RGB loop (train.py) reads them all.  Values, autograd history and key set equal the eager dict."""
 
     def __init__(self, eager, aux_fn, pairs_fn):
         super().__init__(eager)
@@ -42,14 +44,14 @@ class RenderPackage(dict):
         if key == "gau_related_pixels" and self._pairs_fn is not None:
             fn, self._pairs_fn = self._pairs_fn, None
             super().__setitem__("gau_related_pixels", fn())
-        elif key in self._LAZY and self._aux_fn is not None:
+        elif key in _AUX_KEYS and self._aux_fn is not None:
             fn, self._aux_fn = self._aux_fn, None
             for k, v in fn().items():
                 super().__setitem__(k, v)
 
     def materialise(self):
         self._materialise("gau_related_pixels")
-        self._materialise("rend_alpha")
+        self._materialise(_AUX_KEYS[0])
         return self
 
     def __getitem__(self, key):
@@ -60,7 +62,7 @@ class RenderPackage(dict):
         return self[key] if key in self else default
 
     def __contains__(self, key):
-        return super().__contains__(key) or (key in self._LAZY and self._aux_fn is not None)
+        return super().__contains__(key) or (key in _AUX_KEYS and self._aux_fn is not None)
 
     def keys(self):
         return self.materialise() and super().keys()
@@ -76,126 +78,108 @@ class RenderPackage(dict):
         return super().__iter__()
 
     def __len__(self):
-        return super().__len__() + (len(self._LAZY) if self._aux_fn is not None else 0)
+        return super().__len__() + (len(_AUX_KEYS) if self._aux_fn is not None else 0)
+
+
+# ---- geometry helpers (utils/point_utils.py) ---------------------------------------------------------------------
+def _pixel_rays(view, device):
+    """Per-pixel ray directions (world space, un-normalised, z_view = 1) and the camera origin."""
+    c2w = view.world_view_transform.T.inverse()
+    W, H = view.image_width, view.image_height
+    ndc2pix = torch.tensor([[W / 2, 0, 0, W / 2], [0, H / 2, 0, H / 2], [0, 0, 0, 1]], dtype=torch.float32, device=device).T
+    intrins = ((c2w.T @ view.full_proj_transform) @ ndc2pix)[:3, :3].T
+    xs = torch.arange(W, device=device, dtype=torch.float32)
+    ys = torch.arange(H, device=device, dtype=torch.float32)
+    gx, gy = torch.meshgrid(xs, ys, indexing="xy")
+    pix_h = torch.stack([gx, gy, torch.ones_like(gx)], dim=-1).reshape(-1, 3)
+    return pix_h @ intrins.inverse().T @ c2w[:3, :3].T, c2w[:3, 3]
 
 
 def depths_to_points(view, depthmap):
-    """utils/point_utils.py:10-26"""
-    dev = depthmap.device
-    c2w = (view.world_view_transform.T).inverse()
-    W, H = view.image_width, view.image_height
-    ndc2pix = torch.tensor([[W / 2, 0, 0, W / 2], [0, H / 2, 0, H / 2], [0, 0, 0, 1]], dtype=torch.float32, device=dev).T
-    projection_matrix = c2w.T @ view.full_proj_transform
-    intrins = (projection_matrix @ ndc2pix)[:3, :3].T
-    grid_x, grid_y = torch.meshgrid(torch.arange(W, device=dev).float(), torch.arange(H, device=dev).float(),
-                                    indexing='xy')
-    points = torch.stack([grid_x, grid_y, torch.ones_like(grid_x)], dim=-1).reshape(-1, 3)
-    rays_d = points @ intrins.inverse().T @ c2w[:3, :3].T
-    rays_o = c2w[:3, 3]
+    rays_d, rays_o = _pixel_rays(view, depthmap.device)
     return depthmap.reshape(-1, 1) * rays_d + rays_o
 
 
 def depth_to_normal(view, depth):
-    """utils/point_utils.py:29-40"""
-    points = depths_to_points(view, depth).reshape(*depth.shape[1:], 3)
-    output = torch.zeros_like(points)
-    dx = points[2:, 1:-1] - points[:-2, 1:-1]
-    dy = points[1:-1, 2:] - points[1:-1, :-2]
-    normal_map = torch.nn.functional.normalize(torch.cross(dx, dy, dim=-1), dim=-1)
-    output[1:-1, 1:-1, :] = normal_map
-    return output
+    """Finite-difference normals of the back-projected depth map; the one-pixel border stays zero."""
+    pts = depths_to_points(view, depth).reshape(*depth.shape[1:], 3)
+    normals = torch.zeros_like(pts)
+    d_row = pts[2:, 1:-1] - pts[:-2, 1:-1]
+    d_col = pts[1:-1, 2:] - pts[1:-1, :-2]
+    normals[1:-1, 1:-1, :] = torch.nn.functional.normalize(torch.cross(d_row, d_col, dim=-1), dim=-1)
+    return normals
+
+
+def _derived_maps(allmap, camera, depth_ratio):
+    """allmap channels: 0 depth*w, 1 alpha, 2-4 view-space normal, 5 median depth, 6 distortion
+    (DSR/cuda_rasterizer/auxiliary.h:24-28); post-processing of gaussian_renderer/__init__.py:127-156."""
+    alpha = allmap[1:2]
+    world_normal = (allmap[2:5].permute(1, 2, 0) @ camera.world_view_transform[:3, :3].T).permute(2, 0, 1)
+    median = torch.nan_to_num(allmap[5:6], 0, 0)
+    expected = torch.nan_to_num(allmap[0:1] / alpha, 0, 0)
+    surf_depth = expected * (1 - depth_ratio) + depth_ratio * median
+    surf_normal = depth_to_normal(camera, surf_depth).permute(2, 0, 1) * alpha.detach()
+    return {"rend_alpha": alpha, "rend_normal": world_normal, "rend_dist": allmap[6:7], "surf_depth": surf_depth,
+            "surf_normal": surf_normal, "rend_depth": expected, "rend_median_depth": median}
+
+
+def _seg_features_for_raster(pc, pipe, norm_seg_feat):
+    """get_seg_feature (x/(|x|+1e-6), scene/gaussian_model.py:121-125) followed by render()'s own renormalisation
+    (eps 1e-9, gaussian_renderer/__init__.py:60-62) -- Q9.  With the raw parameter available both are one kernel."""
+    raw = getattr(pc, "_seg_feature", None)
+    if norm_seg_feat and raw is not None and getattr(pipe, "fused_seg_activation", True):
+        return normalize_rows(raw, getattr(pc, "seg_feature_eps", 1e-6), 1e-9, stages=2)
+    feats = pc.get_seg_feature
+    if feats is not None and norm_seg_feat:
+        feats = normalize_rows(feats, 1e-9)
+    return feats
+
+
+def _precomputed_transmats(camera, pc, scaling_modifier, device):
+    """pipe.compute_cov3D_python branch (gaussian_renderer/__init__.py:69-81)."""
+    splat2world = pc.get_covariance(scaling_modifier)
+    W, H = camera.image_width, camera.image_height
+    near, far = camera.znear, camera.zfar
+    ndc2pix = torch.tensor([[W / 2, 0, 0, (W - 1) / 2], [0, H / 2, 0, (H - 1) / 2], [0, 0, far - near, near], [0, 0, 0, 1]],
+                           dtype=torch.float32, device=device).T
+    world2pix = camera.full_proj_transform @ ndc2pix
+    return (splat2world[:, [0, 1, 3]] @ world2pix[:, [0, 1, 3]]).permute(0, 2, 1).reshape(-1, 9)
 
 
 def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
            norm_seg_feat=True, want_pairs: bool = True):
-    """Render the scene (reference signature + `want_pairs`).  Background tensor (bg_color) must be on GPU!"""
-    screenspace_points = torch.zeros_like(pc.get_xyz, dtype=pc.get_xyz.dtype, requires_grad=True, device=pc.get_xyz.device)
+    """Rasterise `pc` from `viewpoint_camera`.  `bg_color` must live on the GPU."""
+    xyz = pc.get_xyz
+    # dummy leaf that receives the densification proxy dL/dmean2D (reference :29-33)
+    screen_pts = torch.zeros_like(xyz, requires_grad=True)
     try:
-        screenspace_points.retain_grad()
+        screen_pts.retain_grad()
     except Exception:
         pass
 
-    tanfovx = math.tan(viewpoint_camera.FoVx * 0.5)
-    tanfovy = math.tan(viewpoint_camera.FoVy * 0.5)
-    cls = _SettingsDeferPairs if want_pairs else _SettingsNoPairs
-    raster_settings = cls(
-        image_height=int(viewpoint_camera.image_height),
-        image_width=int(viewpoint_camera.image_width),
-        tanfovx=tanfovx,
-        tanfovy=tanfovy,
-        bg=bg_color,
-        scale_modifier=scaling_modifier,
-        viewmatrix=viewpoint_camera.world_view_transform,
-        projmatrix=viewpoint_camera.full_proj_transform,
-        sh_degree=pc.active_sh_degree,
-        campos=viewpoint_camera.camera_center,
-        prefiltered=False,
-        debug=False,
-    )
-    rasterizer = GaussianRasterizer(raster_settings=raster_settings)
+    settings_cls = _SettingsDeferPairs if want_pairs else _SettingsNoPairs
+    settings = settings_cls(
+        image_height=int(viewpoint_camera.image_height), image_width=int(viewpoint_camera.image_width),
+        tanfovx=math.tan(viewpoint_camera.FoVx * 0.5), tanfovy=math.tan(viewpoint_camera.FoVy * 0.5), bg=bg_color,
+        scale_modifier=scaling_modifier, viewmatrix=viewpoint_camera.world_view_transform,
+        projmatrix=viewpoint_camera.full_proj_transform, sh_degree=pc.active_sh_degree,
+        campos=viewpoint_camera.camera_center, prefiltered=False, debug=False)
 
-    means3D = pc.get_xyz
-    means2D = screenspace_points
-    opacity = pc.get_opacity
-    raw = getattr(pc, "_seg_feature", None)
-    if norm_seg_feat and raw is not None and getattr(pipe, "fused_seg_activation", True) \
-            and getattr(pc, "seg_feature_eps", 1e-6) is not None:
-        # get_seg_feature (x / (|x| + 1e-6), scene/gaussian_model.py:121-125) and the renormalisation below it in the
-        # reference render() (eps 1e-9) fused into one kernel each way (SURVEY.md Q9 / build-plan step 7)
-        seg_feature = normalize_rows(raw, getattr(pc, "seg_feature_eps", 1e-6), 1e-9, stages=2)
-    else:
-        seg_feature = pc.get_seg_feature
-        if seg_feature is not None and norm_seg_feat:
-            seg_feature = normalize_rows(seg_feature, 1e-9)
-
-    scales = None
-    rotations = None
-    cov3D_precomp = None
+    geometry = {}
     if pipe.compute_cov3D_python:
-        splat2world = pc.get_covariance(scaling_modifier)
-        W, H = viewpoint_camera.image_width, viewpoint_camera.image_height
-        near, far = viewpoint_camera.znear, viewpoint_camera.zfar
-        ndc2pix = torch.tensor([[W / 2, 0, 0, (W - 1) / 2], [0, H / 2, 0, (H - 1) / 2], [0, 0, far - near, near],
-                                [0, 0, 0, 1]], dtype=torch.float32, device=means3D.device).T
-        world2pix = viewpoint_camera.full_proj_transform @ ndc2pix
-        cov3D_precomp = (splat2world[:, [0, 1, 3]] @ world2pix[:, [0, 1, 3]]).permute(0, 2, 1).reshape(-1, 9)
+        geometry["cov3D_precomp"] = _precomputed_transmats(viewpoint_camera, pc, scaling_modifier, xyz.device)
     else:
-        scales = pc.get_scaling
-        rotations = pc.get_rotation
+        geometry["scales"], geometry["rotations"] = pc.get_scaling, pc.get_rotation
+    pipe.convert_SHs_python = False  # the reference mutates the caller's object in the same way (Q10)
+    appearance = {"shs": pc.get_features} if override_color is None else {"colors_precomp": override_color}
 
-    pipe.convert_SHs_python = False  # Q10: the reference mutates the caller's object too
-    shs = None
-    colors_precomp = None
-    if override_color is None:
-        shs = pc.get_features
-    else:
-        colors_precomp = override_color
+    image, radii, allmap, seg_map, pairs = GaussianRasterizer(raster_settings=settings)(
+        means3D=xyz, means2D=screen_pts, opacities=pc.get_opacity,
+        extra_attrs=_seg_features_for_raster(pc, pipe, norm_seg_feat), **geometry, **appearance)
 
-    rendered_image, radii, allmap, extra_attrs, gau_related_pixels = rasterizer(
-        means3D=means3D, means2D=means2D, shs=shs, colors_precomp=colors_precomp, opacities=opacity, scales=scales,
-        rotations=rotations, cov3D_precomp=cov3D_precomp, extra_attrs=seg_feature)
-
-    eager = {"render": rendered_image, "viewspace_points": means2D, "visibility_filter": radii > 0, "radii": radii,
-             "seg_feature": extra_attrs, "gau_related_pixels": gau_related_pixels}
-
-    def aux():
-        render_alpha = allmap[1:2]
-        render_normal = allmap[2:5]
-        render_normal = (render_normal.permute(1, 2, 0) @ (viewpoint_camera.world_view_transform[:3, :3].T)).permute(2, 0, 1)
-        render_depth_median = torch.nan_to_num(allmap[5:6], 0, 0)
-        render_depth_expected = torch.nan_to_num(allmap[0:1] / render_alpha, 0, 0)
-        render_dist = allmap[6:7]
-        surf_depth = render_depth_expected * (1 - pipe.depth_ratio) + (pipe.depth_ratio) * render_depth_median
-        surf_normal = depth_to_normal(viewpoint_camera, surf_depth).permute(2, 0, 1)
-        surf_normal = surf_normal * (render_alpha).detach()
-        return {'rend_alpha': render_alpha, 'rend_normal': render_normal, 'rend_dist': render_dist,
-                'surf_depth': surf_depth, 'surf_normal': surf_normal, "rend_depth": render_depth_expected,
-                "rend_median_depth": render_depth_median}
-
-    pairs_fn = None
-    cnt = getattr(gau_related_pixels, "_isr_count_minus_1", None)
-    if cnt is not None:
-        pairs_fn = lambda: gau_related_pixels[:(int(cnt.item()) + 1)]
-    if not getattr(pipe, "lazy_outputs", True):
-        return RenderPackage(eager, aux, pairs_fn).materialise()
-    return RenderPackage(eager, aux, pairs_fn)
+    eager = {"render": image, "viewspace_points": screen_pts, "visibility_filter": radii > 0, "radii": radii,
+             "seg_feature": seg_map, "gau_related_pixels": pairs}
+    count_m1 = getattr(pairs, "_isr_count_minus_1", None)
+    pairs_fn = None if count_m1 is None else (lambda: pairs[:(int(count_m1.item()) + 1)])
+    pkg = RenderPackage(eager, lambda: _derived_maps(allmap, viewpoint_camera, pipe.depth_ratio), pairs_fn)
+    return pkg if getattr(pipe, "lazy_outputs", True) else pkg.materialise()

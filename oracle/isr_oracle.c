@@ -390,10 +390,13 @@ static inline int eval_pair(float pixx, float pixy, const float* xy, const float
     e->py = fmaf(e->kz, e->lx, -(e->kx * e->lz));
     e->pz = fmaf(e->kx, e->ly, -(e->ky * e->lx));
     if (e->pz == 0.0f) return 0;
-    e->rpz = rcp_rn(e->pz);
+    /* spec: the 3D intersection is used only for 1e-30 <= |pz| <= 1e30 (else rho3d = +inf: low-pass path only);
+     * the reference divides by any non-zero pz, which differs only for geometry beyond fp32's useful range */
+    const int pz_ok = fabsf(e->pz) >= 1e-30f && fabsf(e->pz) <= 1e30f;
+    e->rpz = rcp_rn(pz_ok ? e->pz : 1.0f);
     e->sx = e->px * e->rpz;
     e->sy = e->py * e->rpz;
-    e->rho3d = fmaf(e->sx, e->sx, e->sy * e->sy);
+    e->rho3d = pz_ok ? fmaf(e->sx, e->sx, e->sy * e->sy) : INFINITY;
     e->ddx = xy[0] - pixx;
     e->ddy = xy[1] - pixy;
     e->rho2d = FilterInvSquare * fmaf(e->ddx, e->ddx, e->ddy * e->ddy);

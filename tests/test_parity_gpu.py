@@ -324,3 +324,18 @@ def test_lazy_render_package_equals_eager():
             assert pair_set(a.cpu().numpy()) == pair_set(b.cpu().numpy())
             continue
         assert a.shape == b.shape and torch.equal(torch.nan_to_num(a.float()), torch.nan_to_num(b.float())), k
+
+
+def test_sample_labelled_pixels_is_uniform_over_valid():
+    import torch
+    import instascene_b200 as isr
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0)
+    lab = torch.zeros(10000, dtype=torch.int16, device="cuda")
+    valid = torch.tensor([3, 17, 4000, 9999], device="cuda")
+    lab[valid] = torch.tensor([5, 6, 7, 8], dtype=torch.int16, device="cuda")
+    pix, labels = isr.sample_labelled_pixels(lab, 40000, generator=g)
+    assert set(pix.cpu().tolist()) == set(valid.cpu().tolist())
+    assert torch.equal(labels, lab[pix])
+    counts = torch.bincount(pix, minlength=10000)[valid].float()
+    assert float((counts / 10000.0 - 1.0).abs().max()) < 0.05
