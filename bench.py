@@ -35,7 +35,7 @@ WORKLOADS = {
     "cfg2": dict(P=500_000, F=0, W=1920, H=1080, seed=1002, n_views=200, samples=0, labels=0,
                  desc="cfg2: 500k Gaussians @1920x1080, RGB+depth+normal forward + backward of all gradients"),
 }
-KERNELS_PER_STEP = {"cfg3": 19, "cfg2": 9}  # our own kernels per step (see DESIGN.md "launch list")
+KERNELS_PER_STEP = {"cfg3": 19, "cfg2": 11}  # our own kernels per step (see DESIGN.md "launch list")
 
 
 # ----------------------------------------------------------------------------------------------------------------

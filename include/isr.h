@@ -29,6 +29,7 @@
  *                                                 DSR/cuda_rasterizer/rasterizer_impl.h:29-72
  *   isr_contrastive_forward / _backward        <- utils/contrastive_utils.py:18-73 (contrastive_loss)
  *   isr_gather_pixels                          <- train_semantic.py:124-129 (boolean-mask gather + index)
+ *   isr_aux_maps_forward / _backward           <- gaussian_renderer/__init__.py:127-156 + utils/point_utils.py:10-40
  *   isr_rownorm_forward / _backward            <- scene/gaussian_model.py:121-125 + gaussian_renderer/__init__.py:60-62
  *   isr_knn_mean_dist2                         <- SimpleKNN::knn submodules/simple-knn/simple_knn.cu:186-222
  *                                                 (distCUDA2, submodules/simple-knn/spatial.cu:15-25)
@@ -211,6 +212,20 @@ int isr_contrastive_backward(int N, int F, int K, const float* features, const i
 int isr_rownorm_forward(int P, int F, const float* x, float eps1, float eps2, int stages, float* y, void* stream);
 int isr_rownorm_backward(int P, int F, const float* x, const float* dy, float eps1, float eps2, int stages, float* dx,
                          void* stream);
+
+/* ---- derived maps of render() ------------------------------------------------------------------------------- */
+/* Fused post-processing of allmap[7,H,W] (gaussian_renderer/__init__.py:127-156, utils/point_utils.py:10-40):
+ * world-space normals, nan-cleaned median / expected depth, surf_depth and the finite-difference surf_normal.
+ * normal_rot_host[9] (row-major M, n_world = n_view @ M = world_view_transform[:3,:3].T) and ray_mat_host[9]
+ * (row-major K, ray = [x, y, 1] @ K) are HOST arrays (per-camera constants).  Outputs / gradient maps are CHW;
+ * NULL gradient pointers mean zeros; g_allmap[7,H,W] is fully written. */
+int isr_aux_maps_forward(int W, int H, const float* allmap, const float* normal_rot_host, const float* ray_mat_host,
+                         float depth_ratio, float* rend_normal, float* rend_depth, float* rend_median, float* surf_depth,
+                         float* surf_normal, void* stream);
+int isr_aux_maps_backward(int W, int H, const float* allmap, const float* normal_rot_host, const float* ray_mat_host,
+                          float depth_ratio, const float* g_rend_normal, const float* g_rend_depth,
+                          const float* g_rend_median, const float* g_surf_depth, const float* g_surf_normal,
+                          float* g_allmap, void* stream);
 
 /* ---- simple-knn ------------------------------------------------------------------------------------- */
 size_t isr_knn_workspace_bytes(int P);

@@ -25,6 +25,12 @@ int launch_contrastive_bwd(int N, int F, int K, const int* labels, const float* 
                            const float* grad_scale, float* dfeat, cudaStream_t stream);
 int launch_rownorm(bool fwd, int P, int F, const float* x, const float* dy, float e1, float e2, int stages, float* out,
                    cudaStream_t stream);
+int launch_aux_fwd(int W, int H, const float* allmap, const float* M_host, const float* K_host, float depth_ratio,
+                   float* rend_normal, float* rend_depth, float* rend_median, float* surf_depth, float* surf_normal,
+                   cudaStream_t stream);
+int launch_aux_bwd(int W, int H, const float* allmap, const float* M_host, const float* K_host, float depth_ratio,
+                   const float* g_rend_normal, const float* g_rend_depth, const float* g_rend_median,
+                   const float* g_surf_depth, const float* g_surf_normal, float* g_allmap, cudaStream_t stream);
 size_t knn_ws_bytes(int P);
 int launch_knn(int P, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
 }  // namespace isr
@@ -222,6 +228,26 @@ int isr_rownorm_backward(int P, int F, const float* x, const float* dy, float ep
     if (P == 0 || F == 0) return ISR_OK;
     if (!x || !dy || !dx) return ISR_ERR_INVALID_ARG;
     return launch_rownorm(false, P, F, x, dy, eps1, eps2, stages, dx, static_cast<cudaStream_t>(stream_));
+}
+
+int isr_aux_maps_forward(int W, int H, const float* allmap, const float* normal_rot_host, const float* ray_mat_host,
+                         float depth_ratio, float* rend_normal, float* rend_depth, float* rend_median, float* surf_depth,
+                         float* surf_normal, void* stream_) {
+    if (W <= 0 || H <= 0) return ISR_ERR_INVALID_ARG;
+    if (!allmap || !normal_rot_host || !ray_mat_host || !rend_normal || !rend_depth || !rend_median || !surf_depth || !surf_normal)
+        return ISR_ERR_INVALID_ARG;
+    return launch_aux_fwd(W, H, allmap, normal_rot_host, ray_mat_host, depth_ratio, rend_normal, rend_depth, rend_median,
+                          surf_depth, surf_normal, static_cast<cudaStream_t>(stream_));
+}
+
+int isr_aux_maps_backward(int W, int H, const float* allmap, const float* normal_rot_host, const float* ray_mat_host,
+                          float depth_ratio, const float* g_rend_normal, const float* g_rend_depth,
+                          const float* g_rend_median, const float* g_surf_depth, const float* g_surf_normal,
+                          float* g_allmap, void* stream_) {
+    if (W <= 0 || H <= 0) return ISR_ERR_INVALID_ARG;
+    if (!allmap || !normal_rot_host || !ray_mat_host || !g_allmap) return ISR_ERR_INVALID_ARG;
+    return launch_aux_bwd(W, H, allmap, normal_rot_host, ray_mat_host, depth_ratio, g_rend_normal, g_rend_depth,
+                          g_rend_median, g_surf_depth, g_surf_normal, g_allmap, static_cast<cudaStream_t>(stream_));
 }
 
 size_t isr_knn_workspace_bytes(int P) { return P < 0 ? 0 : knn_ws_bytes(P) + 256; }

@@ -16,7 +16,11 @@ import math
 
 import torch
 
-from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, normalize_rows
+import ctypes as C
+
+from . import _lib
+from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, normalize_rows, _ptr, _require_cuda_lib,
+                         _stream)
 
 _AUX_KEYS = ("rend_alpha", "rend_normal", "rend_dist", "surf_depth", "surf_normal", "rend_depth", "rend_median_depth")
 
@@ -110,6 +114,66 @@ def depth_to_normal(view, depth):
     return normals
 
 
+def _camera_aux_constants(camera):
+    """Per-camera constants of the fused aux kernel as host arrays: M = world_view_transform[:3,:3].T (view->world
+    normal rotation) and K with ray = [x, y, 1] @ K (utils/point_utils.py:10-24).  Cached on the camera object and
+    keyed on the transforms' storage + version, so a static camera costs one device->host copy in its lifetime."""
+    wvt, fpt = camera.world_view_transform, camera.full_proj_transform
+    key = (wvt.data_ptr(), wvt._version, fpt.data_ptr(), fpt._version, int(camera.image_width), int(camera.image_height))
+    cached = getattr(camera, "_isr_aux_consts", None)
+    if cached is not None and cached[0] == key:
+        return cached[1], cached[2]
+    c2w = wvt.T.inverse()
+    W, H = camera.image_width, camera.image_height
+    ndc2pix = torch.tensor([[W / 2, 0, 0, W / 2], [0, H / 2, 0, H / 2], [0, 0, 0, 1]], dtype=torch.float32, device=wvt.device).T
+    intrins = ((c2w.T @ fpt) @ ndc2pix)[:3, :3].T
+    K = (intrins.inverse().T @ c2w[:3, :3].T).contiguous().cpu().reshape(-1).tolist()
+    M = wvt[:3, :3].T.contiguous().cpu().reshape(-1).tolist()
+    M_c, K_c = (C.c_float * 9)(*M), (C.c_float * 9)(*K)
+    try:
+        camera._isr_aux_consts = (key, M_c, K_c)
+    except Exception:
+        pass
+    return M_c, K_c
+
+
+class _AuxMaps(torch.autograd.Function):
+    """allmap[7,H,W] -> (rend_normal, rend_depth, rend_median_depth, surf_depth, surf_normal), one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, allmap, M_c, K_c, depth_ratio):
+        L = _require_cuda_lib()
+        am = allmap.detach().contiguous()
+        H, W = int(am.shape[1]), int(am.shape[2])
+        new = lambda ch: torch.empty((ch, H, W), dtype=torch.float32, device=am.device)
+        rn, rd, rm, sd, sn = new(3), new(1), new(1), new(1), new(3)
+        _lib.check(L.isr_aux_maps_forward(W, H, _ptr(am), M_c, K_c, float(depth_ratio), _ptr(rn), _ptr(rd), _ptr(rm), _ptr(sd),
+                                          _ptr(sn), _stream()), "isr_aux_maps_forward")
+        ctx.save_for_backward(am)
+        ctx.consts = (M_c, K_c, float(depth_ratio))
+        ctx.set_materialize_grads(False)
+        return rn, rd, rm, sd, sn
+
+    @staticmethod
+    def backward(ctx, g_rn, g_rd, g_rm, g_sd, g_sn):
+        L = _require_cuda_lib()
+        (am,) = ctx.saved_tensors
+        M_c, K_c, ratio = ctx.consts
+        H, W = int(am.shape[1]), int(am.shape[2])
+        gs = [None if g is None else g.contiguous().float() for g in (g_rn, g_rd, g_rm, g_sd, g_sn)]
+        g_allmap = torch.empty_like(am)
+        _lib.check(L.isr_aux_maps_backward(W, H, _ptr(am), M_c, K_c, ratio, _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), _ptr(gs[3]),
+                                           _ptr(gs[4]), _ptr(g_allmap), _stream()), "isr_aux_maps_backward")
+        return g_allmap, None, None, None
+
+
+def _derived_maps_fused(allmap, camera, depth_ratio):
+    M_c, K_c = _camera_aux_constants(camera)
+    rn, rd, rm, sd, sn = _AuxMaps.apply(allmap, M_c, K_c, depth_ratio)
+    return {"rend_alpha": allmap[1:2], "rend_normal": rn, "rend_dist": allmap[6:7], "surf_depth": sd, "surf_normal": sn,
+            "rend_depth": rd, "rend_median_depth": rm}
+
+
 def _derived_maps(allmap, camera, depth_ratio):
     """allmap channels: 0 depth*w, 1 alpha, 2-4 view-space normal, 5 median depth, 6 distortion
     (DSR/cuda_rasterizer/auxiliary.h:24-28); post-processing of gaussian_renderer/__init__.py:127-156."""
@@ -181,5 +245,6 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
              "seg_feature": seg_map, "gau_related_pixels": pairs}
     count_m1 = getattr(pairs, "_isr_count_minus_1", None)
     pairs_fn = None if count_m1 is None else (lambda: pairs[:(int(count_m1.item()) + 1)])
-    pkg = RenderPackage(eager, lambda: _derived_maps(allmap, viewpoint_camera, pipe.depth_ratio), pairs_fn)
+    aux = _derived_maps_fused if getattr(pipe, "fused_aux_maps", True) else _derived_maps
+    pkg = RenderPackage(eager, lambda: aux(allmap, viewpoint_camera, pipe.depth_ratio), pairs_fn)
     return pkg if getattr(pipe, "lazy_outputs", True) else pkg.materialise()

@@ -339,3 +339,46 @@ def test_sample_labelled_pixels_is_uniform_over_valid():
     assert torch.equal(labels, lab[pix])
     counts = torch.bincount(pix, minlength=10000)[valid].float()
     assert float((counts / 10000.0 - 1.0).abs().max()) < 0.05
+
+
+def test_fused_aux_maps_match_torch_glue():
+    """isr_aux_maps_forward/backward vs the reference's torch post-processing (values and gradients wrt allmap)."""
+    import torch
+    from instascene_b200 import synth
+    from instascene_b200.renderer import _derived_maps, _derived_maps_fused
+    torch.manual_seed(0)
+    W, H = 97, 61
+    cam = synth.ring_cameras(5, W, H)[2]
+    dev = "cuda:0"
+
+    class Cam:
+        image_width, image_height = W, H
+        world_view_transform = torch.from_numpy(cam.world_view_transform).to(dev)
+        full_proj_transform = torch.from_numpy(cam.full_proj_transform).to(dev)
+
+    base = torch.rand(7, H, W, device=dev)
+    base[0] = base[0] * 3 + 0.5          # depth*w
+    base[1] = base[1] * 0.9 + 0.05       # alpha
+    base[5] = base[5] * 3 + 0.5          # median depth
+    base[1, 5:9, 7:12] = 0.0             # uncovered pixels: D = 0, alpha = 0 -> 0/0
+    base[0, 5:9, 7:12] = 0.0
+    base[5, 5:9, 7:12] = 0.0
+    for ratio in (0.0, 1.0, 0.3):
+        a = base.clone().requires_grad_(True)
+        b = base.clone().requires_grad_(True)
+        fa = _derived_maps_fused(a, Cam, ratio)
+        fb = _derived_maps(b, Cam, ratio)
+        loss_a = loss_b = 0.0
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1)
+        for k in ("rend_alpha", "rend_normal", "rend_dist", "surf_depth", "surf_normal", "rend_depth", "rend_median_depth"):
+            assert fa[k].shape == fb[k].shape, k
+            assert float((fa[k] - fb[k]).abs().max()) <= 2e-5 * (float(fb[k].abs().max()) + 1e-6), (k, ratio)
+            wgt = torch.randn(fa[k].shape, device=dev, generator=gen)
+            loss_a = loss_a + (fa[k] * wgt).sum()
+            loss_b = loss_b + (fb[k] * wgt).sum()
+        loss_a.backward()
+        loss_b.backward()
+        ga, gb = a.grad, torch.nan_to_num(b.grad, 0.0, 0.0, 0.0)  # torch yields 0/0 on the uncovered pixels
+        covered = (base[1] > 0).expand_as(ga)
+        assert rel_err(ga[covered].cpu().numpy(), gb[covered].cpu().numpy()) < 2e-4, ratio
