@@ -129,6 +129,20 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     for (int ch = 0; ch < FP; ch++) { acc_e[ch] = 0.0f; last_e[ch] = 0.0f; }
     float last_dL_dT = 0, last_alpha = 0;
 
+    // Destination of the butterfly result held by this lane (loop invariant): lanes 2i and 2i+1 end up with the total
+    // of value i = lane>>1: 0-2 colour, 3-5 normal, 6-14 transMat, 15 opacity.
+    float* lane_dst = nullptr;
+    int lane_stride = 0;
+    {
+        const int vi = lane >> 1;
+        if ((lane & 1) == 0) {
+            if (vi < 3) { lane_dst = dL_dcolors ? dL_dcolors + vi : nullptr; lane_stride = 3; }
+            else if (vi < 6) { lane_dst = dL_dnormal3D ? dL_dnormal3D + (vi - 3) : nullptr; lane_stride = 3; }
+            else if (vi < 15) { lane_dst = dL_dtransMat ? dL_dtransMat + (vi - 6) : nullptr; lane_stride = 9; }
+            else { lane_dst = dL_dopacity; lane_stride = 1; }
+        }
+    }
+
     // the highest list index any pixel of this WARP needs
     int n_need = (int)last_contributor;
 #pragma unroll
@@ -285,15 +299,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
             const int g = mt.x;
             // 16-value transposing butterfly: afterwards lanes 2i and 2i+1 both hold the total of value i
             const float tot = warp_transpose_reduce<16>(v, lane);
-            if ((lane & 1) == 0 && tot != 0.0f) {
-                const int vi = lane >> 1;
-                float* dst;
-                if (vi < 3) dst = dL_dcolors ? dL_dcolors + (size_t)g * 3 + vi : nullptr;
-                else if (vi < 6) dst = dL_dnormal3D ? dL_dnormal3D + (size_t)g * 3 + (vi - 3) : nullptr;
-                else if (vi < 15) dst = dL_dtransMat ? dL_dtransMat + (size_t)g * 9 + (vi - 6) : nullptr;
-                else dst = dL_dopacity ? dL_dopacity + g : nullptr;
-                if (dst) atomicAdd(dst, tot);
-            }
+            if (lane_dst != nullptr && tot != 0.0f) atomicAdd(lane_dst + (size_t)g * lane_stride, tot);
             // the low-pass (2D) branch is rare: reduce its two values only when some lane took it
             if (__any_sync(0xffffffffu, hit && !e.use3d)) {
 #pragma unroll

@@ -23,34 +23,43 @@ def scene_inputs(P, F, W, H, seed, view=1, n_views=4, sh_degree=3, scale_mult=1.
                 tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=np.array([0.1, 0.2, 0.3], np.float32), cam=cam, scene=sc)
 
 
+def _variant_kwargs(inp):
+    cp, tp = inp.get("colors_precomp"), inp.get("transMat_precomp")
+    return dict(scales=None if tp is not None else inp["scales"], rotations=None if tp is not None else inp["rotations"],
+                shs=None if cp is not None else inp["shs"], colors_precomp=cp, transMat_precomp=tp,
+                scale_modifier=inp.get("scale_modifier", 1.0), sh_degree=inp["sh_degree"], extra_attrs=inp["extra_attrs"])
+
+
 def oracle_forward(orc, inp, **kw):
     return orc.forward(inp["means3D"], inp["opacities"], inp["viewmatrix"], inp["projmatrix"], inp["campos"],
-                       inp["W"], inp["H"], inp["bg"], scales=inp["scales"], rotations=inp["rotations"], shs=inp["shs"],
-                       sh_degree=inp["sh_degree"], extra_attrs=inp["extra_attrs"], **kw)
+                       inp["W"], inp["H"], inp["bg"], **_variant_kwargs(inp), **kw)
 
 
 def oracle_backward(orc, inp, fwd, dcolor, dothers, dextra, flags=1):
     return orc.backward(fwd, inp["means3D"], inp["viewmatrix"], inp["projmatrix"], inp["campos"], inp["W"], inp["H"],
-                        inp["bg"], inp["tanfovx"], inp["tanfovy"], dcolor, dothers, dextra, scales=inp["scales"],
-                        rotations=inp["rotations"], shs=inp["shs"], sh_degree=inp["sh_degree"],
-                        extra_attrs=inp["extra_attrs"], flags=flags)
+                        inp["bg"], inp["tanfovx"], inp["tanfovy"], dcolor, dothers, dextra, flags=flags,
+                        **_variant_kwargs(inp))
 
 
 def cuda_forward(inp, want_pairs=True, device="cuda:0"):
-    """Runs c_rasterize_gaussians (the reference-shaped binding over the C ABI) and unpacks everything to numpy."""
+    """Runs c_rasterize_gaussians (the reference-shaped binding over the C ABI) and unpacks everything to numpy.
+    Optional keys of `inp`: colors_precomp [P,3], transMat_precomp [P,9], scale_modifier."""
     import torch
     from instascene_b200 import _lib
     from instascene_b200.rasterizer import c_rasterize_gaussians
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
     e = torch.empty(0, dtype=torch.float32, device=device)
     F = 0 if inp["extra_attrs"] is None else inp["extra_attrs"].shape[1]
-    tens = dict(bg=t(inp["bg"]), means3D=t(inp["means3D"]), opacities=t(inp["opacities"]), scales=t(inp["scales"]),
-                rotations=t(inp["rotations"]), shs=t(inp["shs"]), extra=t(inp["extra_attrs"]) if F else e,
+    cp, tp = inp.get("colors_precomp"), inp.get("transMat_precomp")
+    tens = dict(bg=t(inp["bg"]), means3D=t(inp["means3D"]), opacities=t(inp["opacities"]),
+                scales=e if tp is not None else t(inp["scales"]), rotations=e if tp is not None else t(inp["rotations"]),
+                shs=e if cp is not None else t(inp["shs"]), extra=t(inp["extra_attrs"]) if F else e,
+                colors=t(cp) if cp is not None else e, transmat=t(tp) if tp is not None else e,
                 view=t(inp["viewmatrix"]), proj=t(inp["projmatrix"]), campos=t(inp["campos"]))
-    res = c_rasterize_gaussians(tens["bg"], tens["means3D"], e, tens["opacities"], tens["scales"], tens["rotations"], 1.0,
-                                e, tens["extra"], F, tens["view"], tens["proj"], inp["tanfovx"], inp["tanfovy"],
-                                inp["H"], inp["W"], tens["shs"], inp["sh_degree"], tens["campos"], False, False,
-                                want_pairs=want_pairs)
+    res = c_rasterize_gaussians(tens["bg"], tens["means3D"], tens["colors"], tens["opacities"], tens["scales"],
+                                tens["rotations"], inp.get("scale_modifier", 1.0), tens["transmat"], tens["extra"], F,
+                                tens["view"], tens["proj"], inp["tanfovx"], inp["tanfovy"], inp["H"], inp["W"], tens["shs"],
+                                inp["sh_degree"], tens["campos"], False, False, want_pairs=want_pairs)
     (R, color, others, radii, extra, geom, binning, img, pairs, pidx) = res
     torch.cuda.synchronize()
     L = _lib.lib()
@@ -94,8 +103,9 @@ def cuda_backward(inp, fwd, dcolor, dothers, dextra, grad_mask=15, sparse=None, 
     sp = None
     if sparse is not None:
         sp = (torch.from_numpy(sparse[0]).to(dev), torch.from_numpy(sparse[1]).to(dev))
-    res = c_rasterize_gaussians_backward(tens["bg"], tens["means3D"], st["radii"], e, tens["scales"], tens["rotations"],
-                                         tens["extra"], 1.0, e, tens["view"], tens["proj"], inp["tanfovx"], inp["tanfovy"],
+    res = c_rasterize_gaussians_backward(tens["bg"], tens["means3D"], st["radii"], tens["colors"], tens["scales"],
+                                         tens["rotations"], tens["extra"], inp.get("scale_modifier", 1.0), tens["transmat"],
+                                         tens["view"], tens["proj"], inp["tanfovx"], inp["tanfovy"],
                                          t(dcolor), t(dothers), t(dextra), tens["shs"], inp["sh_degree"], tens["campos"],
                                          st["geom"], st["R"], st["binning"], st["img"], False, grad_mask=grad_mask,
                                          image_size=(inp["H"], inp["W"]), sparse_extra=sp, flags=flags)

@@ -382,3 +382,70 @@ def test_fused_aux_maps_match_torch_glue():
         ga, gb = a.grad, torch.nan_to_num(b.grad, 0.0, 0.0, 0.0)  # torch yields 0/0 on the uncovered pixels
         covered = (base[1] > 0).expand_as(ga)
         assert rel_err(ga[covered].cpu().numpy(), gb[covered].cpu().numpy()) < 2e-4, ratio
+
+
+def _fwd_bwd_variant(oracle, inp, F, grads):
+    H, W = inp["H"], inp["W"]
+    rng = np.random.default_rng(5)
+    dcolor = rng.standard_normal((3, H, W)).astype(np.float32)
+    dothers = rng.standard_normal((7, H, W)).astype(np.float32)
+    dextra = rng.standard_normal((F, H, W)).astype(np.float32) if F else None
+    o = oracle_forward(oracle, inp)
+    c = cuda_forward(inp)
+    assert np.array_equal(c["radii"], o["radii"]) and c["num_rendered"] == o["num_rendered"] > 0
+    assert np.array_equal(c["point_list"], o["point_list"]) and np.array_equal(c["n_contrib"], o["n_contrib"])
+    for k in ["color", "others"] + (["extra"] if F else []):
+        assert np.array_equal(c[k].view(np.uint32), o[k].view(np.uint32)), k
+    og = oracle_backward(oracle, inp, o, dcolor, dothers, dextra)
+    cg = cuda_backward(inp, c, dcolor, dothers, dextra)
+    for k in grads:
+        assert rel_err(cg[k], og[k].reshape(cg[k].shape)) < GRAD_TOL, (k, rel_err(cg[k], og[k].reshape(cg[k].shape)))
+    return o, c
+
+
+def test_variant_colors_precomp_and_low_sh_degree(oracle):
+    inp = scene_inputs(2500, 4, 80, 64, 81)
+    rng = np.random.default_rng(1)
+    inp["colors_precomp"] = rng.uniform(0, 1, size=(2500, 3)).astype(np.float32)   # override_color path
+    _fwd_bwd_variant(oracle, inp, 4, ["dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dextra"])
+    for deg in (0, 1, 2):                                                           # active_sh_degree < max
+        inp2 = scene_inputs(2500, 0, 80, 64, 82, sh_degree=deg)
+        _fwd_bwd_variant(oracle, inp2, 0, ["dL_dsh", "dL_dmeans3D", "dL_dopacity"])
+
+
+def test_variant_scale_modifier(oracle):
+    inp = scene_inputs(2500, 0, 80, 64, 83)
+    inp["scale_modifier"] = 0.6   # Q6: forward uses it, backward ignores it -- in the oracle and here alike
+    _fwd_bwd_variant(oracle, inp, 0, ["dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dscales", "dL_drotations"])
+
+
+def test_variant_transmat_precomp(oracle):
+    """cov3D_precomp path (pipe.compute_cov3D_python): T given, normals (0,0,1), gradient returned in dL_dtransMat."""
+    base = scene_inputs(2000, 0, 80, 64, 84)
+    o = oracle_forward(oracle, base, blend=False)
+    inp = dict(base)
+    inp["transMat_precomp"] = o["transMats"].copy()
+    inp["transMat_precomp"][o["radii"] == 0] = 0.0   # culled rows were never written by the oracle
+    _fwd_bwd_variant(oracle, inp, 0, ["dL_dcolors", "dL_dopacity", "dL_dtransMat", "dL_dsh"])
+
+
+def test_module_api_noncontiguous_inputs_and_flags(oracle):
+    """GaussianRasterizer with non-contiguous / strided inputs (Q17), F = 1, debug=True, prefiltered=True."""
+    import torch
+    import instascene_b200 as isr
+    inp = scene_inputs(1500, 1, 64, 48, 85)
+    dev = "cuda:0"
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    s = isr.GaussianRasterizationSettings(48, 64, inp["tanfovx"], inp["tanfovy"], t(inp["bg"]), 1.0, t(inp["viewmatrix"]),
+                                          t(inp["projmatrix"]), 3, t(inp["campos"]), True, True)
+    wide = torch.zeros((1500, 6), device=dev)
+    wide[:, ::2] = t(inp["means3D"])
+    means_nc = wide[:, ::2]                                   # stride-2 view
+    assert not means_nc.is_contiguous()
+    scales_nc = t(inp["scales"]).t().contiguous().t()         # column-major
+    out = isr.GaussianRasterizer(s)(means_nc, torch.zeros_like(means_nc), t(inp["opacities"]).reshape(-1, 1), shs=t(inp["shs"]),
+                                    scales=scales_nc, rotations=t(inp["rotations"]), extra_attrs=t(inp["extra_attrs"]))
+    o = oracle_forward(oracle, inp)
+    assert np.array_equal(out[0].cpu().numpy().view(np.uint32), o["color"].view(np.uint32))
+    assert np.array_equal(out[3].cpu().numpy().view(np.uint32), o["extra"].view(np.uint32))
+    assert np.array_equal(out[1].cpu().numpy(), o["radii"]) and out[4].shape[0] == o["pair_count"]
