@@ -213,6 +213,14 @@ int isr_rownorm_forward(int P, int F, const float* x, float eps1, float eps2, in
 int isr_rownorm_backward(int P, int F, const float* x, const float* dy, float eps1, float eps2, int stages, float* dx,
                          void* stream);
 
+/* ---- optimizer step of the trainable tensor ------------------------------------------------------------------- */
+/* One fused pass of torch.optim.Adam's update (no weight decay / amsgrad / maximize) over n fp32 elements:
+ * exp_avg = b1*exp_avg + (1-b1)*g; exp_avg_sq = b2*exp_avg_sq + (1-b2)*g*g;
+ * param -= lr/(1-b1^step) * exp_avg / (sqrt(exp_avg_sq)/sqrt(1-b2^step) + eps).   `step` is the 1-based step count.
+ * (scene/gaussian_model.py:217-249 trains _seg_feature with Adam(lr=0.025, eps=1e-15)) */
+int isr_adam_step(size_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
+                  float beta2, float eps, int step, void* stream);
+
 /* ---- derived maps of render() ------------------------------------------------------------------------------- */
 /* Fused post-processing of allmap[7,H,W] (gaussian_renderer/__init__.py:127-156, utils/point_utils.py:10-40):
  * world-space normals, nan-cleaned median / expected depth, surf_depth and the finite-difference surf_normal.

@@ -7,6 +7,7 @@ from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rast
 from .renderer import render, depth_to_normal  # noqa: F401
 from .contrastive import contrastive_loss  # noqa: F401
 from .knn import distCUDA2  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "sample_pixels", "sample_labelled_pixels", "normalize_rows", "render",
-           "depth_to_normal", "contrastive_loss", "distCUDA2"]
+           "depth_to_normal", "contrastive_loss", "distCUDA2", "FusedAdam"]

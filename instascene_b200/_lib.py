@@ -58,7 +58,7 @@ EXPORTED_SYMBOLS = [
     "isr_geom_bytes", "isr_image_bytes", "isr_binning_bytes", "isr_field_offset",
     "isr_forward_geometry", "isr_forward_render", "isr_backward", "isr_backward_extra_sparse", "isr_mark_visible",
     "isr_gather_pixels", "isr_contrastive_workspace_bytes", "isr_contrastive_forward", "isr_contrastive_backward",
-    "isr_rownorm_forward", "isr_rownorm_backward", "isr_aux_maps_forward", "isr_aux_maps_backward", "isr_knn_workspace_bytes", "isr_knn_mean_dist2",
+    "isr_rownorm_forward", "isr_rownorm_backward", "isr_aux_maps_forward", "isr_aux_maps_backward", "isr_adam_step", "isr_knn_workspace_bytes", "isr_knn_mean_dist2",
 ]
 
 _lib = None
@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
                                        _fp, _fp, C.c_void_p]
     L.isr_aux_maps_backward.argtypes = [C.c_int, C.c_int, _fp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, _fp, _fp, _fp,
                                         _fp, _fp, _fp, C.c_void_p]
+    L.isr_adam_step.argtypes = [C.c_size_t, _fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p]
     L.isr_knn_workspace_bytes.restype = C.c_size_t
     L.isr_knn_workspace_bytes.argtypes = [C.c_int]
     L.isr_knn_mean_dist2.argtypes = [C.c_int, _fp, _fp, _vp, C.c_size_t, C.c_void_p]

@@ -31,6 +31,8 @@ int launch_aux_fwd(int W, int H, const float* allmap, const float* M_host, const
 int launch_aux_bwd(int W, int H, const float* allmap, const float* M_host, const float* K_host, float depth_ratio,
                    const float* g_rend_normal, const float* g_rend_depth, const float* g_rend_median,
                    const float* g_surf_depth, const float* g_surf_normal, float* g_allmap, cudaStream_t stream);
+int launch_adam(size_t n, float* p, const float* g, float* m, float* v, float lr, float beta1, float beta2, float eps,
+                int step, cudaStream_t stream);
 size_t knn_ws_bytes(int P);
 int launch_knn(int P, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
 }  // namespace isr
@@ -248,6 +250,15 @@ int isr_aux_maps_backward(int W, int H, const float* allmap, const float* normal
     if (!allmap || !normal_rot_host || !ray_mat_host || !g_allmap) return ISR_ERR_INVALID_ARG;
     return launch_aux_bwd(W, H, allmap, normal_rot_host, ray_mat_host, depth_ratio, g_rend_normal, g_rend_depth,
                           g_rend_median, g_surf_depth, g_surf_normal, g_allmap, static_cast<cudaStream_t>(stream_));
+}
+
+int isr_adam_step(size_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
+                  float beta2, float eps, int step, void* stream_) {
+    if (step < 1) return ISR_ERR_INVALID_ARG;
+    if (n == 0) return ISR_OK;
+    if (!param || !grad || !exp_avg || !exp_avg_sq) return ISR_ERR_INVALID_ARG;
+    if (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) return ISR_ERR_INVALID_ARG;
+    return launch_adam(n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, static_cast<cudaStream_t>(stream_));
 }
 
 size_t isr_knn_workspace_bytes(int P) { return P < 0 ? 0 : knn_ws_bytes(P) + 256; }

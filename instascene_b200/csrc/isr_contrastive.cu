@@ -10,19 +10,21 @@
 //   loss  = - sum_i log( exp(f^_i.u_{y_i}/phi_{y_i}) / (sum_k exp(f^_i.u_k/phi_k) + 1e-9) )       (:68-71)
 // The [N,F]x[F,K] logits contraction is ~70 MFLOP at N=32768,K=64,F=16: it is evaluated in exact fp32 FFMA
 // (u_k staged in shared memory), one sample per thread.
+#include <cmath>
+
 #include "isr_common.cuh"
 
 namespace isr {
 
+// Workspace: f^ [N,F], 1/(|f|+eps) [N], counts [K], u [K,F], phi [K], coefT [K,N] (softmax coefficients, CLUSTER-major
+// so that both the per-cluster reductions and the per-sample reads are coalesced), dU [K,F].
 struct ContrastWs {
-    size_t fhat, inv_norm, counts, usum, u, phisum, phi, coef, dU, total;
+    size_t fhat, inv_norm, counts, u, phi, coef, dU, total;
     ContrastWs(int N, int F, int K) {
         size_t o = 0;
         fhat = o;     o = align_up(o + (size_t)N * F * 4, 256);
         inv_norm = o; o = align_up(o + (size_t)N * 4, 256);
         counts = o;   o = align_up(o + (size_t)K * 4, 256);
-        usum = o;     o = align_up(o + (size_t)K * F * 4, 256);
-        phisum = o;   o = align_up(o + (size_t)K * 4, 256);   // counts..phisum are zero-filled together
         u = o;        o = align_up(o + (size_t)K * F * 4, 256);
         phi = o;      o = align_up(o + (size_t)K * 4, 256);
         coef = o;     o = align_up(o + (size_t)N * K * 4, 256);
@@ -40,97 +42,116 @@ __global__ void gather_pixels_kernel(int F, int64_t HW, const float* __restrict_
     out[i] = (pix >= 0 && pix < HW) ? map[(size_t)ch * HW + pix] : 0.0f;
 }
 
-// pass 1: normalise, count, (optionally) accumulate cluster sums
-__global__ void contrast_normalise_kernel(int N, int F, int K, const float* __restrict__ feat,
-                                          const int* __restrict__ labels, bool need_means, float* __restrict__ fhat,
-                                          float* __restrict__ inv_norm, int* __restrict__ counts,
-                                          float* __restrict__ usum) {
+// 1. per sample: f^ = f / (|f| + 1e-9)
+__global__ void contrast_normalise_kernel(int N, int F, const float* __restrict__ feat, float* __restrict__ fhat,
+                                          float* __restrict__ inv_norm) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const int y = labels[i];
     float ss = 0.0f;
     for (int c = 0; c < F; c++) { const float v = feat[(size_t)i * F + c]; ss = fmaf(v, v, ss); }
     const float inv = 1.0f / (sqrtf(ss) + 1e-9f);
     inv_norm[i] = inv;
     for (int c = 0; c < F; c++) fhat[(size_t)i * F + c] = feat[(size_t)i * F + c] * inv;
-    if (y >= 0 && y < K) {
-        atomicAdd(counts + y, 1);
-        if (need_means)
-            for (int c = 0; c < F; c++) atomicAdd(usum + (size_t)y * F + c, feat[(size_t)i * F + c] * inv);
+}
+
+// sum over the whole block (up to 1024 threads); s_red must hold 32 floats
+__device__ __forceinline__ float block_sum(float v, float* s_red) {
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.0f;
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int w = 0; w < nw; w++) t += s_red[w];
+    return t;
+}
+
+// 2. one block per cluster k: count, centre u_k (mean of members or predefined prototype), temperature phi_k.
+//    No atomics, deterministic; the label vector (N ints) is re-read by every block from L2.
+__global__ void __launch_bounds__(1024)
+contrast_cluster_kernel(int N, int F, int K, const float* __restrict__ fhat, const int* __restrict__ labels,
+                        const float* __restrict__ predef_u, float temp_lambda, int* __restrict__ counts,
+                        float* __restrict__ u, float* __restrict__ phi) {
+    __shared__ float s_red[32];
+    __shared__ float s_u[ISR_MAX_EXTRA_DIMS];
+    const int k = blockIdx.x;
+    float cnt = 0.0f, acc[ISR_MAX_EXTRA_DIMS];
+    for (int c = 0; c < F; c++) acc[c] = 0.0f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+        if (__ldg(labels + i) == k) {
+            cnt += 1.0f;
+            if (predef_u == nullptr)
+                for (int c = 0; c < F; c++) acc[c] += fhat[(size_t)i * F + c];
+        }
+    const float n = block_sum(cnt, s_red);
+    for (int c = 0; c < F; c++) {
+        float m;
+        if (predef_u != nullptr) m = predef_u[(size_t)k * F + c];
+        else { const float t = block_sum(acc[c], s_red); m = n > 0.0f ? t / n : 0.0f; }
+        if (threadIdx.x == 0) { s_u[c] = m; u[(size_t)k * F + c] = m; }
+    }
+    __syncthreads();
+    float spread = 0.0f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+        if (__ldg(labels + i) == k) {
+            float ss = 0.0f;
+            for (int c = 0; c < F; c++) { const float d = fhat[(size_t)i * F + c] - s_u[c]; ss = fmaf(d, d, ss); }
+            spread += sqrtf(ss);
+        }
+    const float tot = block_sum(spread, s_red);
+    if (threadIdx.x == 0) {
+        counts[k] = (int)n;
+        phi[k] = n > 0.0f ? fminf(fmaxf(10.0f * (tot / (n * logf(n + temp_lambda))), 0.5f), 1.0f) : 1.0f;
     }
 }
 
-__global__ void contrast_means_kernel(int F, int K, const int* __restrict__ counts, const float* __restrict__ usum,
-                                      const float* __restrict__ predef_u, float* __restrict__ u) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= K * F) return;
-    const int k = i / F;
-    if (predef_u) u[i] = predef_u[i];
-    else u[i] = counts[k] > 0 ? usum[i] / (float)counts[k] : 0.0f;
-}
-
-__global__ void contrast_phisum_kernel(int N, int F, int K, const float* __restrict__ fhat,
-                                       const int* __restrict__ labels, const float* __restrict__ u,
-                                       float* __restrict__ phisum) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const int y = labels[i];
-    if (y < 0 || y >= K) return;
-    float ss = 0.0f;
-    for (int c = 0; c < F; c++) { const float d = fhat[(size_t)i * F + c] - u[(size_t)y * F + c]; ss = fmaf(d, d, ss); }
-    atomicAdd(phisum + y, sqrtf(ss));
-}
-
-__global__ void contrast_phi_kernel(int K, float temp_lambda, const int* __restrict__ counts,
-                                    const float* __restrict__ phisum, float* __restrict__ phi) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= K) return;
-    const float n = (float)counts[k];
-    float p = 1.0f;
-    if (counts[k] > 0) p = fminf(fmaxf(10.0f * (phisum[k] / (n * logf(n + temp_lambda))), 0.5f), 1.0f);
-    phi[k] = p;
-}
-
-// loss + softmax coefficients  coef[i][k] = (p_ik - [k == y_i]) / phi_k   (0 for absent clusters / invalid samples)
+// 3. loss + softmax coefficients coefT[k][i] = (p_ik - [k == y_i]) / phi_k (0 for absent clusters / ignored samples).
+//    Four lanes per sample, each covering a quarter of the clusters; u and phi staged in shared memory.
 __global__ void __launch_bounds__(256)
 contrast_loss_kernel(int N, int F, int K, const float* __restrict__ fhat, const int* __restrict__ labels,
                      const float* __restrict__ u, const float* __restrict__ phi, const int* __restrict__ counts,
-                     float* __restrict__ coef, float* __restrict__ loss) {
+                     float* __restrict__ coefT, float* __restrict__ loss) {
     extern __shared__ float s_u[];  // [K][F] then phi[K] (0 marks an absent cluster)
-    float* s_iphi = s_u + (size_t)K * F;
+    float* s_phi = s_u + (size_t)K * F;
     for (int i = threadIdx.x; i < K * F; i += blockDim.x) s_u[i] = u[i];
-    for (int k = threadIdx.x; k < K; k += blockDim.x) s_iphi[k] = counts[k] > 0 ? phi[k] : 0.0f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) s_phi[k] = counts[k] > 0 ? phi[k] : 0.0f;
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = threadIdx.x & 3;                          // quarter of the clusters
+    const int i = blockIdx.x * 64 + (threadIdx.x >> 2);     // sample
+    const int kq = (K + 3) / 4, k0 = q * kq, k1 = min(K, k0 + kq);
     float li = 0.0f;
-    if (i < N) {
-        const int y = labels[i];
-        const bool valid = (y >= 0 && y < K);
-        float f[ISR_MAX_EXTRA_DIMS];
-        for (int c = 0; c < F; c++) f[c] = fhat[(size_t)i * F + c];
-        float sum = 0.0f, dy = 0.0f;
-        if (valid) {
-            for (int k = 0; k < K; k++) {
-                if (s_iphi[k] == 0.0f) continue;
+    const bool in_range = i < N;
+    const int y = in_range ? labels[i] : -1;
+    const bool valid = in_range && y >= 0 && y < K;
+    float f[ISR_MAX_EXTRA_DIMS];
+    if (in_range) for (int c = 0; c < F; c++) f[c] = fhat[(size_t)i * F + c];
+    float sum = 0.0f, dy = 0.0f;
+    if (valid)
+        for (int k = k0; k < k1; k++) {
+            const float ph = s_phi[k];
+            float e = 0.0f;
+            if (ph != 0.0f) {
                 float dot = 0.0f;
                 for (int c = 0; c < F; c++) dot = fmaf(f[c], s_u[(size_t)k * F + c], dot);
-                const float e = expf(dot / s_iphi[k]);
+                e = expf(dot / ph);
                 sum += e;
                 if (k == y) dy = e;
-                coef[(size_t)i * K + k] = e;
             }
-            const float denom = sum + 1e-9f;
-            li = -logf(dy / denom);
-            for (int k = 0; k < K; k++) {
-                const float ip = s_iphi[k];
-                const float p = ip == 0.0f ? 0.0f : coef[(size_t)i * K + k] / denom;
-                coef[(size_t)i * K + k] = ip == 0.0f ? 0.0f : (p - (k == y ? 1.0f : 0.0f)) / ip;
-            }
-        } else {
-            for (int k = 0; k < K; k++) coef[(size_t)i * K + k] = 0.0f;
+            coefT[(size_t)k * N + i] = e;
+        }
+    // combine the four quarters (lanes 4j..4j+3 of a warp belong to one sample)
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1); sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    dy += __shfl_xor_sync(0xffffffffu, dy, 1);   dy += __shfl_xor_sync(0xffffffffu, dy, 2);
+    if (in_range) {
+        const float denom = sum + 1e-9f;
+        if (valid && q == 0) li = -logf(dy / denom);
+        for (int k = k0; k < k1; k++) {
+            const float ph = s_phi[k];
+            float cf = 0.0f;
+            if (valid && ph != 0.0f) cf = (coefT[(size_t)k * N + i] / denom - (k == y ? 1.0f : 0.0f)) / ph;
+            coefT[(size_t)k * N + i] = cf;
         }
     }
-    // block reduction of the loss
     __shared__ float s_red[8];
     for (int off = 16; off > 0; off >>= 1) li += __shfl_xor_sync(0xffffffffu, li, off);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = li;
@@ -142,23 +163,38 @@ contrast_loss_kernel(int N, int F, int K, const float* __restrict__ fhat, const 
     }
 }
 
-// dU[k][c] = sum_i coef[i][k] * fhat[i][c]: each block reduces a slab of 64 samples for all K*F entries (entry e =
-// k*F + c owned by thread e mod 256), then adds its partial sums to dU with one atomic per entry.
+// 4. dU[k][c] = sum_i coefT[k][i] * f^[i][c]: split over slabs of 128 samples; a thread owns the entries e = k*F + c with
+//    e = tid (mod 256): its coefficient reads run along the contiguous sample axis of coefT (16-byte loads, shared by
+//    the F threads of a cluster), its feature reads are coalesced across c.  One atomic per entry per slab.
 __global__ void __launch_bounds__(256)
-contrast_dU_kernel(int N, int F, int K, const float* __restrict__ coef, const float* __restrict__ fhat,
+contrast_dU_kernel(int N, int F, int K, const float* __restrict__ coefT, const float* __restrict__ fhat,
                    float* __restrict__ dU) {
-    const int i0 = blockIdx.x * 64, i1 = min(N, i0 + 64);
+    constexpr int SLAB = 128;
+    const int i0 = blockIdx.x * SLAB, i1 = min(N, i0 + SLAB);
     const int KF = K * F;
+    const bool vec = ((N & 3) == 0) && (i1 - i0 == SLAB);
     for (int e = threadIdx.x; e < KF; e += 256) {
         const int k = e / F, cch = e - k * F;
+        const float* cr = coefT + (size_t)k * N;
         float acc = 0.0f;
-        for (int i = i0; i < i1; i++) acc = fmaf(__ldg(coef + (size_t)i * K + k), __ldg(fhat + (size_t)i * F + cch), acc);
+        if (vec) {
+            for (int i = i0; i < i1; i += 4) {
+                const float4 cf = __ldg(reinterpret_cast<const float4*>(cr + i));
+                acc = fmaf(cf.x, __ldg(fhat + (size_t)i * F + cch), acc);
+                acc = fmaf(cf.y, __ldg(fhat + (size_t)(i + 1) * F + cch), acc);
+                acc = fmaf(cf.z, __ldg(fhat + (size_t)(i + 2) * F + cch), acc);
+                acc = fmaf(cf.w, __ldg(fhat + (size_t)(i + 3) * F + cch), acc);
+            }
+        } else {
+            for (int i = i0; i < i1; i++) acc = fmaf(__ldg(cr + i), __ldg(fhat + (size_t)i * F + cch), acc);
+        }
         if (acc != 0.0f) atomicAdd(dU + e, acc);
     }
 }
 
+// 5. dL/df_i = grad_scale / (|f_i| + eps) * ( sum_k coefT[k][i] u_k  +  [means] dU[y_i] / n_{y_i} )
 __global__ void __launch_bounds__(256)
-contrast_dfeat_kernel(int N, int F, int K, const float* __restrict__ coef, const int* __restrict__ labels,
+contrast_dfeat_kernel(int N, int F, int K, const float* __restrict__ coefT, const int* __restrict__ labels,
                       const float* __restrict__ u, const float* __restrict__ dU, const int* __restrict__ counts,
                       const float* __restrict__ inv_norm, bool means, const float* __restrict__ grad_scale,
                       float* __restrict__ dfeat) {
@@ -172,7 +208,7 @@ contrast_dfeat_kernel(int N, int F, int K, const float* __restrict__ coef, const
     for (int c = 0; c < F; c++) g[c] = 0.0f;
     if (y >= 0 && y < K) {
         for (int k = 0; k < K; k++) {
-            const float cf = coef[(size_t)i * K + k];
+            const float cf = __ldg(coefT + (size_t)k * N + i);
             if (cf != 0.0f)
                 for (int c = 0; c < F; c++) g[c] = fmaf(cf, s_u[(size_t)k * F + c], g[c]);
         }
@@ -306,6 +342,40 @@ int launch_rownorm(bool fwd, int P, int F, const float* x, const float* dy, floa
     return ISR_ERR_UNSUPPORTED;
 }
 
+// ---- fused Adam step (one pass over param / grad / exp_avg / exp_avg_sq; torch.optim.Adam semantics, no amsgrad) ----
+__global__ void __launch_bounds__(256)
+adam_step_kernel(size_t n4, size_t n, float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                 float4* __restrict__ v, float beta1, float beta2, float eps, float step_size, float inv_sqrt_bias2) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+        mm = beta1 * mm + (1.0f - beta1) * gg;
+        vv = beta2 * vv + (1.0f - beta2) * gg * gg;
+        pp -= step_size * mm / (sqrtf(vv) * inv_sqrt_bias2 + eps);
+    };
+    if (i < n4) {
+        float4 P = p[i], M = m[i], V = v[i];
+        const float4 G = g[i];
+        upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
+        p[i] = P; m[i] = M; v[i] = V;
+    } else if (i == n4) {  // tail (n not a multiple of 4)
+        float* ps = reinterpret_cast<float*>(p); const float* gs = reinterpret_cast<const float*>(g);
+        float* ms = reinterpret_cast<float*>(m); float* vs = reinterpret_cast<float*>(v);
+        for (size_t j = n4 * 4; j < n; j++) upd(ps[j], gs[j], ms[j], vs[j]);
+    }
+}
+
+int launch_adam(size_t n, float* p, const float* g, float* m, float* v, float lr, float beta1, float beta2, float eps,
+                int step, cudaStream_t stream) {
+    if (n == 0) return ISR_OK;
+    const double b1 = 1.0 - pow((double)beta1, (double)step), b2 = 1.0 - pow((double)beta2, (double)step);
+    const size_t n4 = n / 4;
+    adam_step_kernel<<<(unsigned)((n4 + 1 + 255) / 256), 256, 0, stream>>>(
+        n4, n, reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+        reinterpret_cast<float4*>(v), beta1, beta2, eps, (float)((double)lr / b1), (float)(1.0 / sqrt(b2)));
+    ISR_CUDA_TRY(cudaGetLastError());
+    return ISR_OK;
+}
+
 size_t contrastive_ws_bytes(int N, int F, int K) { return ContrastWs(N, F, K).total; }
 
 int launch_gather_pixels(int F, int64_t HW, const float* map, int n, const int* pix_ids, float* out, cudaStream_t stream) {
@@ -320,26 +390,18 @@ int launch_contrastive_fwd(int N, int F, int K, const float* features, const int
                            float temp_lambda, void* ws, float* loss, cudaStream_t stream) {
     ContrastWs L(N, F, K);
     char* w = static_cast<char*>(ws);
-    ISR_CUDA_TRY(cudaMemsetAsync(w + L.counts, 0, L.u - L.counts, stream));
     ISR_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), stream));
     if (N <= 0 || K <= 0) return ISR_OK;
     float* fhat = reinterpret_cast<float*>(w + L.fhat);
     int* counts = reinterpret_cast<int*>(w + L.counts);
     float* u = reinterpret_cast<float*>(w + L.u);
     float* phi = reinterpret_cast<float*>(w + L.phi);
-    contrast_normalise_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, F, K, features, labels, predef_u == nullptr, fhat,
-                                                                   reinterpret_cast<float*>(w + L.inv_norm), counts,
-                                                                   reinterpret_cast<float*>(w + L.usum));
-    contrast_means_kernel<<<(K * F + 255) / 256, 256, 0, stream>>>(F, K, counts, reinterpret_cast<float*>(w + L.usum),
-                                                                   predef_u, u);
-    contrast_phisum_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, F, K, fhat, labels, u,
-                                                                reinterpret_cast<float*>(w + L.phisum));
-    contrast_phi_kernel<<<(K + 255) / 256, 256, 0, stream>>>(K, temp_lambda, counts,
-                                                             reinterpret_cast<float*>(w + L.phisum), phi);
+    contrast_normalise_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, F, features, fhat, reinterpret_cast<float*>(w + L.inv_norm));
+    contrast_cluster_kernel<<<K, 1024, 0, stream>>>(N, F, K, fhat, labels, predef_u, temp_lambda, counts, u, phi);
     const size_t smem = ((size_t)K * F + K) * sizeof(float);
     ISR_CUDA_TRY(cudaFuncSetAttribute(contrast_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    contrast_loss_kernel<<<(N + 255) / 256, 256, smem, stream>>>(N, F, K, fhat, labels, u, phi, counts,
-                                                                 reinterpret_cast<float*>(w + L.coef), loss);
+    contrast_loss_kernel<<<(N + 63) / 64, 256, smem, stream>>>(N, F, K, fhat, labels, u, phi, counts,
+                                                               reinterpret_cast<float*>(w + L.coef), loss);
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }
@@ -353,7 +415,7 @@ int launch_contrastive_bwd(int N, int F, int K, const int* labels, const float* 
     float* dU = reinterpret_cast<float*>(const_cast<char*>(w) + L.dU);
     if (means && K > 0) {
         ISR_CUDA_TRY(cudaMemsetAsync(dU, 0, (size_t)K * F * sizeof(float), stream));
-        contrast_dU_kernel<<<(N + 63) / 64, 256, 0, stream>>>(N, F, K, reinterpret_cast<const float*>(w + L.coef),
+        contrast_dU_kernel<<<(N + 127) / 128, 256, 0, stream>>>(N, F, K, reinterpret_cast<const float*>(w + L.coef),
                                                                 reinterpret_cast<const float*>(w + L.fhat), dU);
     }
     const size_t smem = (size_t)(K > 0 ? K : 1) * F * sizeof(float);

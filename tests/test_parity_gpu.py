@@ -449,3 +449,19 @@ def test_module_api_noncontiguous_inputs_and_flags(oracle):
     assert np.array_equal(out[0].cpu().numpy().view(np.uint32), o["color"].view(np.uint32))
     assert np.array_equal(out[3].cpu().numpy().view(np.uint32), o["extra"].view(np.uint32))
     assert np.array_equal(out[1].cpu().numpy(), o["radii"]) and out[4].shape[0] == o["pair_count"]
+
+
+def test_fused_adam_matches_torch():
+    import torch
+    import instascene_b200 as isr
+    torch.manual_seed(0)
+    for shape in ((1000, 16), (333, 3)):
+        a = torch.randn(shape, device="cuda").requires_grad_(True)
+        b = a.detach().clone().requires_grad_(True)
+        oa = isr.FusedAdam([a], lr=0.025, eps=1e-15)
+        ob = torch.optim.Adam([b], lr=0.025, eps=1e-15)
+        for it in range(5):
+            g = torch.randn(shape, device="cuda") * (0.0 if it == 2 else 1.0)
+            a.grad, b.grad = g.clone(), g.clone()
+            oa.step(); ob.step()
+        assert float((a - b).abs().max()) < 1e-5 * float(b.abs().max())
