@@ -28,6 +28,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: NCCL's own banner / debug output (it prints "NCCL version ..." to stdout by
+# default) is sent to stderr unless the caller chose a file
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 WORKLOADS = {
     "cfg3": dict(P=2_000_000, F=16, W=1920, H=1080, seed=1003, n_views=200, samples=32768, labels=64,
@@ -172,6 +175,9 @@ def run_ours(args):
         opt = isr.FusedAdam([pc._seg_feature], lr=0.025, eps=1e-15)  # scene/gaussian_model.py:217-249
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    import collections
+    held = collections.deque(maxlen=2)
     geo_params = []
     if args.workload == "cfg2":
         for name in ("get_xyz", "get_scaling", "get_rotation", "get_opacity", "get_features"):
@@ -187,9 +193,24 @@ def run_ours(args):
             feats = isr.sample_pixels(pkg["seg_feature"], pix)
             loss = isr.contrastive_loss(feats, labels, num_labels=wl["labels"]) * (1e-6 * 0.5)
             loss.backward()
-            idist.allreduce_grads([pc._seg_feature.grad], world)
-            opt.step()
-            opt.zero_grad(set_to_none=True)
+            if world > 1:
+                # gradient all-reduce + Adam on a side stream; the next render() launches its geometry phase first and
+                # waits for this event only before it reads the features (renderer.py)
+                g = pc._seg_feature.grad
+                comm.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(comm):
+                    idist.allreduce_grads([g], world)
+                    opt.step()
+                    ev = torch.cuda.Event()
+                    ev.record(comm)
+                pc._seg_feature.grad = None
+                pc._isr_param_ready_event = ev
+                # keep the gradient buffer alive until the main stream has waited for `ev` (next render) instead of
+                # record_stream(): its deferred frees made the caching allocator grow for dozens of steps
+                held.append(g)
+            else:
+                opt.step()
+                opt.zero_grad(set_to_none=True)
             return loss
         else:
             pkg = isr.render(cam, pc, _Pipe, bg)
@@ -222,6 +243,8 @@ def run_ours(args):
             if e2e:
                 last = float(loss.detach().to("cpu", non_blocking=False))  # device -> host read of the step's result
                 d2h = 4
+        if comm is not None:  # the last step's all-reduce + optimizer step belong to the timed region
+            torch.cuda.current_stream().wait_stream(comm)
         e1.record()
         torch.cuda.synchronize()
         idist.barrier(world)

@@ -66,14 +66,102 @@ def _require_cuda_lib():
 # --------------------------------------------------------------------------------------------------------------
 # _C-level functions: same signatures / returns as the reference pybind module (DSR/rasterize_points.h:17-73)
 # --------------------------------------------------------------------------------------------------------------
+class _ForwardState:
+    """Everything between the two phases of the forward (isr_forward_geometry -> isr_forward_render)."""
+    __slots__ = ("args", "keep", "P", "H", "W", "dev", "want_pairs", "out_color", "out_others", "radii", "geom", "img",
+                 "pairs", "pair_count", "nr_host")
+
+
+def launch_geometry(background, means3D, colors, opacity, scales, rotations, scale_modifier, transMat_precomp, viewmatrix,
+                    projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
+                    want_pairs: bool = True) -> Optional[_ForwardState]:
+    """Phase A of the forward: K1 projection + depth order + offsets, enqueued asynchronously on the current stream.
+    Nothing here depends on extra_attrs (the semantic features), so a caller may start it before the features of the
+    step are final (e.g. while the previous step's gradient all-reduce / optimizer step runs on another stream)."""
+    L = _require_cuda_lib()
+    if means3D.dim() != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    P, H, W = int(means3D.shape[0]), int(image_height), int(image_width)
+    if P == 0:
+        return None
+    dev = means3D.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    background = _f32c(background, "background")
+    means3D = _f32c(means3D, "means3D")
+    opacity = _f32c(opacity, "opacity")
+    viewmatrix = _f32c(viewmatrix, "viewmatrix")
+    projmatrix = _f32c(projmatrix, "projmatrix")
+    campos = _f32c(campos, "campos")
+    colors = _f32c(colors, "colors") if colors.numel() else colors
+    scales = _f32c(scales, "scales") if scales.numel() else scales
+    rotations = _f32c(rotations, "rotations") if rotations.numel() else rotations
+    transMat_precomp = _f32c(transMat_precomp, "transMat_precomp") if transMat_precomp.numel() else transMat_precomp
+    sh = _f32c(sh, "sh") if sh.numel() else sh
+    M = int(sh.shape[1]) if sh.numel() else 0
+    st = _ForwardState()
+    st.P, st.H, st.W, st.dev, st.want_pairs = P, H, W, dev, want_pairs
+    st.out_color = torch.empty((3, H, W), **f32)
+    st.out_others = torch.empty((7, H, W), **f32)
+    st.radii = torch.empty(P, dtype=torch.int32, device=dev)
+    geom_bytes, img_bytes = L.isr_geom_bytes(P), L.isr_image_bytes(W, H)
+    st.geom = torch.empty(geom_bytes, dtype=torch.uint8, device=dev)
+    st.img = torch.empty(img_bytes, dtype=torch.uint8, device=dev)
+    pair_cap = 9 * H * W if want_pairs else 0
+    st.pairs = torch.empty((pair_cap, 2), dtype=torch.int32, device=dev)
+    st.pair_count = torch.zeros(1, dtype=torch.int32, device=dev)
+    st.nr_host = _pinned_i64(dev)
+    a = _lib.IsrForwardArgs()
+    a.P, a.sh_degree, a.sh_coeffs, a.F, a.W, a.H = P, int(degree), M, 0, W, H
+    a.flags = 0 if want_pairs else _lib.FLAG_NO_PAIRS
+    a.tan_fovx, a.tan_fovy, a.scale_modifier = float(tan_fovx), float(tan_fovy), float(scale_modifier)
+    a.background, a.viewmatrix, a.projmatrix, a.campos = _ptr(background), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos)
+    a.means3D, a.opacities = _ptr(means3D), _ptr(opacity)
+    a.scales, a.rotations, a.transMat_precomp = _ptr(scales), _ptr(rotations), _ptr(transMat_precomp)
+    a.shs, a.colors_precomp, a.extra_attrs = _ptr(sh), _ptr(colors), None
+    a.geom, a.geom_bytes, a.image, a.image_bytes = st.geom.data_ptr(), geom_bytes, st.img.data_ptr(), img_bytes
+    a.radii, a.out_color, a.out_others, a.out_extra = st.radii.data_ptr(), st.out_color.data_ptr(), st.out_others.data_ptr(), None
+    a.pairs, a.pair_capacity, a.pair_count = _ptr(st.pairs), pair_cap, st.pair_count.data_ptr()
+    a.num_rendered_host = st.nr_host.data_ptr()
+    st.args = a
+    st.keep = (background, means3D, colors, opacity, scales, rotations, transMat_precomp, sh, viewmatrix, projmatrix, campos)
+    _lib.check(L.isr_forward_geometry(C.byref(a), _stream()), "isr_forward_geometry")
+    return st
+
+
+def finish_render(st: _ForwardState, extra_attrs, F: int, debug: bool = False, return_args: bool = False):
+    """Phase B: wait for the instance count, size the binning workspace, emit + tile-sort + blend."""
+    L = _require_cuda_lib()
+    a, dev = st.args, st.dev
+    if F > 0:
+        extra_attrs = _f32c(extra_attrs, "extra_attrs")
+        out_extra = torch.empty((F, st.H, st.W), dtype=torch.float32, device=dev)
+        a.F, a.extra_attrs, a.out_extra = F, extra_attrs.data_ptr(), out_extra.data_ptr()
+    else:
+        out_extra = torch.empty(0, dtype=torch.float32, device=dev)
+    torch.cuda.current_stream().synchronize()  # the reference blocks on a cudaMemcpy here (rasterizer_impl.cu:287)
+    num_rendered = int(st.nr_host.item())
+    bin_bytes = L.isr_binning_bytes(st.P, num_rendered, st.W, st.H)
+    binningBuffer = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
+    a.binning, a.binning_bytes = binningBuffer.data_ptr(), bin_bytes
+    _lib.check(L.isr_forward_render(C.byref(a), num_rendered, _stream()), "isr_forward_render")
+    if debug:
+        torch.cuda.synchronize()
+    res = (num_rendered, st.out_color, st.out_others, st.radii, out_extra, st.geom, binningBuffer, st.img, st.pairs,
+           st.pair_count - 1)
+    if return_args:  # profiling hook (bench.py roofline leg); keeps every tensor the struct points to alive
+        a._keepalive = st.keep + (extra_attrs, st.pair_count, st.nr_host) + res[1:9]
+        return res + (a,)
+    return res
+
+
 def c_rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, transMat_precomp,
                           extra_attrs, attr_degree, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
                           image_width, sh, degree, campos, prefiltered, debug, want_pairs: bool = True,
-                          return_args: bool = False):
+                          return_args: bool = False, geom_state: Optional[_ForwardState] = None):
     """RasterizeGaussiansCUDA (DSR/rasterize_points.cu:39-151).  Returns the reference's 10-tuple
     (num_rendered, out_color, out_others, radii, out_extra, geomBuffer, binningBuffer, imgBuffer,
-     gau_related_pixels [cap,2], gau_pixel_indices [1] = count-1)."""
-    L = _require_cuda_lib()
+     gau_related_pixels [cap,2], gau_pixel_indices [1] = count-1).  `geom_state`: phase A already launched."""
+    _require_cuda_lib()
     if means3D.dim() != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     dev = means3D.device
@@ -87,63 +175,11 @@ def c_rasterize_gaussians(background, means3D, colors, opacity, scales, rotation
         return (0, out_color, out_others, torch.zeros(0, dtype=torch.int32, device=dev), out_extra, empty_u8,
                 empty_u8.clone(), empty_u8.clone(), torch.empty((0, 2), dtype=torch.int32, device=dev),
                 torch.full((1,), -1, dtype=torch.int32, device=dev))
-    background = _f32c(background, "background")
-    means3D = _f32c(means3D, "means3D")
-    opacity = _f32c(opacity, "opacity")
-    viewmatrix = _f32c(viewmatrix, "viewmatrix")
-    projmatrix = _f32c(projmatrix, "projmatrix")
-    campos = _f32c(campos, "campos")
-    colors = _f32c(colors, "colors") if colors.numel() else colors
-    scales = _f32c(scales, "scales") if scales.numel() else scales
-    rotations = _f32c(rotations, "rotations") if rotations.numel() else rotations
-    transMat_precomp = _f32c(transMat_precomp, "transMat_precomp") if transMat_precomp.numel() else transMat_precomp
-    sh = _f32c(sh, "sh") if sh.numel() else sh
-    if F > 0:
-        extra_attrs = _f32c(extra_attrs, "extra_attrs")
-    M = int(sh.shape[1]) if sh.numel() else 0
-
-    out_color = torch.empty((3, H, W), **f32)
-    out_others = torch.empty((7, H, W), **f32)
-    out_extra = torch.empty((F, H, W), **f32) if F > 0 else torch.empty(0, **f32)
-    radii = torch.empty(P, dtype=torch.int32, device=dev)
-    geom_bytes, img_bytes = L.isr_geom_bytes(P), L.isr_image_bytes(W, H)
-    geomBuffer = torch.empty(geom_bytes, dtype=torch.uint8, device=dev)
-    imgBuffer = torch.empty(img_bytes, dtype=torch.uint8, device=dev)
-    pair_cap = 9 * H * W if want_pairs else 0
-    pairs = torch.empty((pair_cap, 2), dtype=torch.int32, device=dev)
-    pair_count = torch.zeros(1, dtype=torch.int32, device=dev)
-    nr_host = _pinned_i64(dev)
-
-    a = _lib.IsrForwardArgs()
-    a.P, a.sh_degree, a.sh_coeffs, a.F, a.W, a.H = P, int(degree), M, F, W, H
-    a.flags = 0 if want_pairs else _lib.FLAG_NO_PAIRS
-    a.tan_fovx, a.tan_fovy, a.scale_modifier = float(tan_fovx), float(tan_fovy), float(scale_modifier)
-    a.background, a.viewmatrix, a.projmatrix, a.campos = _ptr(background), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos)
-    a.means3D, a.opacities = _ptr(means3D), _ptr(opacity)
-    a.scales, a.rotations, a.transMat_precomp = _ptr(scales), _ptr(rotations), _ptr(transMat_precomp)
-    a.shs, a.colors_precomp, a.extra_attrs = _ptr(sh), _ptr(colors), (_ptr(extra_attrs) if F > 0 else None)
-    a.geom, a.geom_bytes, a.image, a.image_bytes = geomBuffer.data_ptr(), geom_bytes, imgBuffer.data_ptr(), img_bytes
-    a.radii, a.out_color, a.out_others, a.out_extra = radii.data_ptr(), out_color.data_ptr(), out_others.data_ptr(), _ptr(out_extra)
-    a.pairs, a.pair_capacity, a.pair_count = _ptr(pairs), pair_cap, pair_count.data_ptr()
-    a.num_rendered_host = nr_host.data_ptr()
-
-    stream = _stream()
-    _lib.check(L.isr_forward_geometry(C.byref(a), stream), "isr_forward_geometry")
-    torch.cuda.current_stream().synchronize()  # the reference blocks on a cudaMemcpy here (rasterizer_impl.cu:287)
-    num_rendered = int(nr_host.item())
-    bin_bytes = L.isr_binning_bytes(P, num_rendered, W, H)
-    binningBuffer = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
-    a.binning, a.binning_bytes = binningBuffer.data_ptr(), bin_bytes
-    _lib.check(L.isr_forward_render(C.byref(a), num_rendered, stream), "isr_forward_render")
-    if debug:
-        torch.cuda.synchronize()
-    res = (num_rendered, out_color, out_others, radii, out_extra, geomBuffer, binningBuffer, imgBuffer, pairs,
-           pair_count - 1)
-    if return_args:  # profiling hook (bench.py roofline leg); keeps every tensor the struct points to alive
-        a._keepalive = (background, means3D, colors, opacity, scales, rotations, transMat_precomp, sh, extra_attrs,
-                        viewmatrix, projmatrix, campos, pair_count, nr_host) + res[1:9]
-        return res + (a,)
-    return res
+    st = geom_state
+    if st is None:
+        st = launch_geometry(background, means3D, colors, opacity, scales, rotations, scale_modifier, transMat_precomp,
+                             viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, sh, degree, campos, want_pairs=want_pairs)
+    return finish_render(st, extra_attrs, F, debug=debug, return_args=return_args)
 
 
 def c_rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, extra_attrs, scale_modifier,
@@ -256,6 +292,11 @@ class _RasterizeGaussians(torch.autograd.Function):
                 raster_settings.tanfovy, raster_settings.image_height, raster_settings.image_width, sh,
                 raster_settings.sh_degree, raster_settings.campos, raster_settings.prefiltered, raster_settings.debug)
         want_pairs = getattr(raster_settings, "want_pairs", True)
+        geom_state = getattr(raster_settings, "_geom_state", None)  # phase A launched early by render()
+        if geom_state is not None:
+            # ctx keeps raster_settings alive and the state owns this Function's output tensors: drop the link, or
+            # ctx <-> outputs form a reference cycle that only the cyclic GC frees (hundreds of MB per view)
+            raster_settings._geom_state = None
         if raster_settings.debug:
             cpu_args = cpu_deep_copy_tuple(args)
             try:
@@ -265,7 +306,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise ex
         else:
-            res = c_rasterize_gaussians(*args, want_pairs=want_pairs)
+            res = c_rasterize_gaussians(*args, want_pairs=want_pairs, geom_state=geom_state)
         (num_rendered, color, depth, radii, extra, geomBuffer, binningBuffer, imgBuffer, gau_related_pixels,
          gau_pixel_indices) = res
         if want_pairs and not getattr(raster_settings, "defer_pairs", False):

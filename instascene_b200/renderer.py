@@ -19,9 +19,12 @@ import torch
 import ctypes as C
 
 from . import _lib
-from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, normalize_rows, _ptr, _require_cuda_lib,
-                         _stream)
+from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, launch_geometry, normalize_rows, _ptr,
+                         _require_cuda_lib, _stream)
 
+import os
+
+_GEOMETRY_FIRST = os.environ.get("ISR_GEOMETRY_FIRST", "1") != "0"
 _AUX_KEYS = ("rend_alpha", "rend_normal", "rend_dist", "surf_depth", "surf_normal", "rend_depth", "rend_median_depth")
 
 
@@ -237,8 +240,24 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
     pipe.convert_SHs_python = False  # the reference mutates the caller's object in the same way (Q10)
     appearance = {"shs": pc.get_features} if override_color is None else {"colors_precomp": override_color}
 
+    # Phase A (projection, depth order, offsets) does not read the semantic features: launch it first so that it can
+    # overlap whatever still produces them (pc._isr_param_ready_event: e.g. the previous step's gradient all-reduce +
+    # optimizer step running on another stream).  Same kernels, same order of results.
+    opacity = pc.get_opacity
+    none = torch.empty(0, dtype=torch.float32, device=xyz.device)
+    if getattr(pipe, "geometry_first", _GEOMETRY_FIRST):
+        settings._geom_state = launch_geometry(
+            bg_color, xyz, appearance.get("colors_precomp", none), opacity, geometry.get("scales", none),
+            geometry.get("rotations", none), scaling_modifier, geometry.get("cov3D_precomp", none),
+            viewpoint_camera.world_view_transform, viewpoint_camera.full_proj_transform, settings.tanfovx,
+            settings.tanfovy, settings.image_height, settings.image_width, appearance.get("shs", none),
+            pc.active_sh_degree, viewpoint_camera.camera_center, want_pairs=want_pairs)
+    ready = getattr(pc, "_isr_param_ready_event", None)
+    if ready is not None:
+        torch.cuda.current_stream().wait_event(ready)
+
     image, radii, allmap, seg_map, pairs = GaussianRasterizer(raster_settings=settings)(
-        means3D=xyz, means2D=screen_pts, opacities=pc.get_opacity,
+        means3D=xyz, means2D=screen_pts, opacities=opacity,
         extra_attrs=_seg_features_for_raster(pc, pipe, norm_seg_feat), **geometry, **appearance)
 
     eager = {"render": image, "viewspace_points": screen_pts, "visibility_filter": radii > 0, "radii": radii,

@@ -465,3 +465,45 @@ def test_fused_adam_matches_torch():
             a.grad, b.grad = g.clone(), g.clone()
             oa.step(); ob.step()
         assert float((a - b).abs().max()) < 1e-5 * float(b.abs().max())
+
+
+def test_render_geometry_first_and_param_ready_event():
+    """render() launches the geometry phase before it touches the features and honours pc._isr_param_ready_event:
+    a parameter update enqueued on a side stream is visible to the render that follows."""
+    import torch
+    import instascene_b200 as isr
+    inp = scene_inputs(4000, 8, 96, 64, 91)
+    sc, cam = inp["scene"], inp["cam"]
+    dev = "cuda:0"
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    class PC:
+        active_sh_degree, max_sh_degree = 3, 3
+        get_xyz, get_opacity = t(sc.xyz), t(sc.opacities()).reshape(-1, 1)
+        get_scaling, get_rotation, get_features = t(sc.scales()), t(sc.rotations()), t(sc.shs())
+        _seg_feature = t(sc.seg_feature_raw).clone()
+
+    class Cam:
+        FoVx, FoVy, image_width, image_height = cam.FoVx, cam.FoVy, 96, 64
+        world_view_transform, full_proj_transform, camera_center = t(cam.world_view_transform), t(cam.full_proj_transform), t(cam.camera_center)
+
+    class Pipe:
+        compute_cov3D_python, convert_SHs_python, depth_ratio = False, False, 1.0
+
+    pc = PC()
+    new_feat = torch.rand_like(pc._seg_feature) + 0.1
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        big = torch.randn(4096, 4096, device=dev)
+        for _ in range(20):
+            big = big @ big * 1e-4          # keep the side stream busy so that a missing wait would be visible
+        pc._seg_feature.copy_(new_feat)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    pc._isr_param_ready_event = ev
+    got = isr.render(Cam(), pc, Pipe(), t(inp["bg"]), want_pairs=False)["seg_feature"].clone()
+    torch.cuda.synchronize()
+    pc._isr_param_ready_event = None
+    want = isr.render(Cam(), pc, Pipe(), t(inp["bg"]), want_pairs=False)["seg_feature"]
+    assert torch.equal(got, want)
