@@ -28,9 +28,28 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line: NCCL's own banner / debug output (it prints "NCCL version ..." to stdout by
-# default) is sent to stderr unless the caller chose a file
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line.  Native libraries write to fd 1 behind Python's back (NCCL prints its
+# "NCCL version ..." banner there at NCCL_DEBUG=VERSION and ignores NCCL_DEBUG_FILE at that level), so fd 1 points at
+# stderr while the bench runs and is restored only to emit the result line.
+_REAL_STDOUT_FD = None
+
+
+def _quiet_stdout():
+    global _REAL_STDOUT_FD
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.flush()
+        _REAL_STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT_FD is not None:
+        os.dup2(_REAL_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+    if _REAL_STDOUT_FD is not None:
+        os.dup2(2, 1)
+
 
 WORKLOADS = {
     "cfg3": dict(P=2_000_000, F=16, W=1920, H=1080, seed=1003, n_views=200, samples=32768, labels=64,
@@ -280,7 +299,7 @@ def run_ours(args):
             rc = ref_cuda_leg(args, wl, pc, cams, devdata, my_views, dev)
             if rc is not None:
                 line["ref_cuda"] = rc
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     idist.barrier(world)
 
 
@@ -409,7 +428,7 @@ def run_reference_arm(args):
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.time() - t0, "world_size_env": world}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -478,6 +497,7 @@ def main():
     ap.add_argument("--no-ref-cuda", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
