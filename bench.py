@@ -335,7 +335,7 @@ def measure_roofline(args, wl, pc, cams, devdata, my_views, dev):
     for i in range(8):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _lib.check(L.isr_forward_render(C.byref(a), R, stream), "isr_forward_render(blend only)")
+        _lib.check(L.isr_forward_render(C.byref(a), a._n_inst, stream), "isr_forward_render(blend only)")
         e1.record()
         torch.cuda.synchronize()
         if i >= 3:
@@ -355,7 +355,7 @@ def measure_roofline(args, wl, pc, cams, devdata, my_views, dev):
     return {"bound": "hbm", "kernel": "blend_fwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "peak_source": "measured" if peaks else "fallback",
             "traffic": NCU_TRAFFIC_BYTES.get(args.workload),
-            "kernel_ms": ms, "algorithmic_bytes": alg, "R": R, "V": V, "pairs": G,
+            "kernel_ms": ms, "algorithmic_bytes": alg, "R": R, "R_emitted": int(a._n_inst), "V": V, "pairs": G,
             "note": "instruction-issue bound (75% of issue slots, DRAM 4% of peak): every pixel walks its tile list; "
                     "algorithmic bytes count one record gather per (tile, Gaussian) instance, most of which hit L2"}
 

@@ -79,7 +79,8 @@ int isr_device_sm_count(void);              /* SM count of the current device, o
 /* ---- workspace sizes --------------------------------------------------------------------------------- */
 size_t isr_geom_bytes(int P);               /* per-Gaussian state saved for backward                       */
 size_t isr_image_bytes(int W, int H);       /* per-pixel state saved for backward + per-tile ranges        */
-size_t isr_binning_bytes(int P, int64_t R, int W, int H);  /* sorted instance list + sort scratch          */
+size_t isr_binning_bytes(int P, int64_t R, int W, int H);  /* sorted instance list + sort scratch; R = the
+                                                             * emitted instance count num_rendered_host[1]  */
 
 /* Offsets (in bytes) of the fields inside the geometry / image / binning workspaces, so that tests and
  * tools can compare intermediates with the oracle.  Field ids: */
@@ -90,11 +91,13 @@ enum IsrField {
     ISR_GEOM_TILES = 3,      /* uint32[P] tiles_touched                                                   */
     ISR_GEOM_CLAMPED = 4,    /* uint8[P]  bit c set <=> SH colour channel c was clamped                    */
     ISR_GEOM_DEPTH_ORDER = 5,/* uint32[P] Gaussian ids in ascending (depth bits, id) order                */
-    ISR_GEOM_OFFSETS = 6,    /* uint32[P] exclusive scan of tiles_touched in depth order                  */
+    ISR_GEOM_OFFSETS = 6,    /* uint32[P+1] exclusive scan of the emitted-tile counts in depth order      */
+    ISR_GEOM_TILE_COUNT = 7, /* uint32[P] tiles actually emitted (<= tiles_touched): footprint-culled      */
     ISR_IMG_FINAL_T = 16,    /* float[3][H*W]: T, M1, M2                                                  */
     ISR_IMG_NCONTRIB = 17,   /* uint32[2][H*W]: last contributor, median contributor                      */
     ISR_IMG_RANGES = 18,     /* uint32[tiles][2]                                                          */
-    ISR_BIN_POINT_LIST = 32  /* uint32[R] Gaussian ids sorted by (tile, depth bits, id)                    */
+    ISR_BIN_POINT_LIST = 32  /* uint32[R] Gaussian ids sorted by (tile, depth bits, id): per tile the      *
+                              * reference's list minus entries that provably reach none of its pixels     */
 };
 int64_t isr_field_offset(int field, int P, int64_t R, int W, int H);   /* <0: unknown field               */
 
@@ -135,16 +138,18 @@ typedef struct IsrForwardArgs {
     int* pairs;                 /* [pair_capacity,2] (gaussian id, pixel id) or NULL                      */
     int64_t pair_capacity;      /* 9*H*W always suffices (sum of weights <= 1, each weight > 0.1)         */
     int* pair_count;            /* device int32: number of pairs written (NOT count-1 as in the reference)*/
-    int64_t* num_rendered_host; /* pinned HOST int64 written asynchronously by isr_forward_geometry       */
+    int64_t* num_rendered_host; /* pinned HOST int64[2] written asynchronously by isr_forward_geometry:   *
+                                 * [0] = the reference's num_rendered (sum of tiles_touched),              *
+                                 * [1] = R, the emitted instance count that sizes the binning workspace    */
 } IsrForwardArgs;
 
-/* Phase A: K1 preprocess + depth ordering + offsets.  Enqueues an async copy of R (= num_rendered) into
- * *num_rendered_host; the caller synchronises `stream`, sizes the binning workspace with
- * isr_binning_bytes(P, R, W, H) and calls phase B.  (The reference blocks on a cudaMemcpy at the same
- * point, rasterizer_impl.cu:287.) */
+/* Phase A: K1 preprocess (incl. per-Gaussian tile footprints) + depth ordering + offsets.  Enqueues an async
+ * copy of the two instance counts into num_rendered_host[0..1]; the caller synchronises `stream`, sizes the
+ * binning workspace with isr_binning_bytes(P, R = num_rendered_host[1], W, H) and calls phase B with that R.
+ * (The reference blocks on a cudaMemcpy at the same point, rasterizer_impl.cu:287.) */
 int isr_forward_geometry(const IsrForwardArgs* args, void* stream);
 /* Phase B: instance emission, stable tile sort, tile ranges, front-to-back blend. */
-int isr_forward_render(const IsrForwardArgs* args, int64_t num_rendered, void* stream);
+int isr_forward_render(const IsrForwardArgs* args, int64_t R, void* stream);
 
 /* ---- backward ---------------------------------------------------------------------------------------- */
 typedef struct IsrBackwardArgs {

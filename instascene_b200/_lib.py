@@ -16,7 +16,7 @@ GRAD_GEOMETRY, GRAD_COLOR, GRAD_OPACITY, GRAD_EXTRA, GRAD_ALL = 1, 2, 4, 8, 15
 MAX_EXTRA_DIMS = 32
 
 # enum IsrField
-GEOM_SPLAT, GEOM_RGB, GEOM_DEPTH, GEOM_TILES, GEOM_CLAMPED, GEOM_DEPTH_ORDER, GEOM_OFFSETS = 0, 1, 2, 3, 4, 5, 6
+GEOM_SPLAT, GEOM_RGB, GEOM_DEPTH, GEOM_TILES, GEOM_CLAMPED, GEOM_DEPTH_ORDER, GEOM_OFFSETS, GEOM_TILE_COUNT = 0, 1, 2, 3, 4, 5, 6, 7
 IMG_FINAL_T, IMG_NCONTRIB, IMG_RANGES = 16, 17, 18
 BIN_POINT_LIST = 32
 

@@ -77,6 +77,7 @@ int64_t isr_field_offset(int field, int P, int64_t R, int W, int H) {
         case ISR_GEOM_CLAMPED: return (int64_t)GeomLayout(P).clamped;
         case ISR_GEOM_DEPTH_ORDER: return (int64_t)GeomLayout(P).order;
         case ISR_GEOM_OFFSETS: return (int64_t)GeomLayout(P).offsets;
+        case ISR_GEOM_TILE_COUNT: return (int64_t)GeomLayout(P).tcount;
         case ISR_IMG_FINAL_T: return (int64_t)ImageLayout(W, H).final_T;
         case ISR_IMG_NCONTRIB: return (int64_t)ImageLayout(W, H).n_contrib;
         case ISR_IMG_RANGES: return (int64_t)ImageLayout(W, H).ranges;
@@ -109,7 +110,7 @@ int isr_forward_geometry(const IsrForwardArgs* a, void* stream_) {
     if (st != ISR_OK) return st;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (a->P == 0) {
-        if (a->num_rendered_host) *a->num_rendered_host = 0;
+        if (a->num_rendered_host) a->num_rendered_host[0] = a->num_rendered_host[1] = 0;
         return ISR_OK;
     }
     st = launch_preprocess_fwd(*a, stream);

@@ -4,14 +4,19 @@
 // one 64-bit key (tile<<32 | depth bits) per (Gaussian, tile) instance, ONE stable radix sort of R 12-byte
 // pairs over 32+log2(tiles) bits (6 onesweep passes at 1080p), then identifyTileRanges.
 //
-// Here (same resulting order, bit for bit):
+// Here:
+//   0. (K1) per Gaussian, a 64-bit mask of the tiles of its getRect rectangle that its footprint can reach at all
+//      (conservative conic / low-pass-disk test, isr::rect_may_touch): the reference's square of side 2*radius
+//      emits many tiles an elongated or small splat provably never touches
 //   1. stable sort of the P Gaussians by depth bits (culled ones carry key 0xFFFFFFFF and sink to the end)
-//   2. exclusive scan of tiles_touched in that depth order -> instance offsets, R
-//   3. emission of (tile id, Gaussian id) in depth order
-//   4. stable sort of the R instances by tile id ONLY (13 bits at 1080p = 2 onesweep passes of 8-byte pairs)
+//   2. exclusive scan of the emitted-tile counts in that depth order -> instance offsets, R_emit
+//   3. emission of (tile id, Gaussian id) in depth order for the tiles in the mask
+//   4. stable sort of the instances by tile id ONLY (13 bits at 1080p = 2 onesweep passes of 8-byte pairs)
 //   5. tile ranges from the sorted tile ids
-// Because both sorts are stable, instances of a tile end up ordered by (depth bits, Gaussian id) -- exactly
-// the reference's (tile, depth, id) order (ties: SURVEY.md Q2) -- while the R-sized traffic drops ~6x.
+// Because both sorts are stable, instances of a tile end up ordered by (depth bits, Gaussian id): each tile list
+// is exactly the reference's list (ties: SURVEY.md Q2) minus entries that contribute to none of the tile's pixels
+// -- skipping those never changes a result -- while the instance-sized traffic drops by an order of magnitude.
+// The reference's num_rendered (sum of tiles_touched) is still computed and reported at the boundary.
 // The radix-sort/scan primitives are CUB (CUDA toolkit), as in the reference.
 #include <cub/cub.cuh>
 
@@ -31,7 +36,10 @@ size_t sort_temp_bytes_gauss(int P) {
     cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
                                     (uint32_t*)nullptr, P, 0, 32);
     cub::DeviceScan::ExclusiveSum(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr, P + 1);
-    return align_up((a > b ? a : b) + 256, 256);
+    size_t c = 0;
+    cub::DeviceReduce::Sum(nullptr, c, (const uint32_t*)nullptr, (uint32_t*)nullptr, P);
+    a = a > b ? a : b;
+    return align_up((a > c ? a : c) + 256, 256);
 }
 
 size_t sort_temp_bytes_inst(int64_t R, int num_tiles) {
@@ -58,22 +66,28 @@ __global__ void gather_tiles_kernel(int P, const uint32_t* __restrict__ tiles, c
     else if (i == P) gathered[i] = 0;
 }
 
-__global__ void copy_count_kernel(const uint32_t* __restrict__ offsets, int P, int64_t* __restrict__ out) {
-    *out = (int64_t)offsets[P];
+// out[0] = the reference's num_rendered (all tiles of every getRect rectangle), out[1] = emitted instances
+__global__ void copy_count_kernel(const uint32_t* __restrict__ offsets, int P, const uint32_t* __restrict__ tile_total,
+                                  int64_t* __restrict__ out) {
+    out[0] = (int64_t)*tile_total;
+    out[1] = (int64_t)offsets[P];
 }
 
 // Instance emission (DSR duplicateWithKeys, rasterizer_impl.cu:70-111) in depth order.  A warp takes 32 consecutive
-// Gaussians; each lane fetches one Gaussian's rectangle and offset, then the warp writes the Gaussians' (tile id,
-// Gaussian id) runs one after the other with all lanes (contiguous, fully used sectors) instead of 32 lanes each
-// walking its own run with 4-byte scattered stores.
+// Gaussians; each lane fetches one Gaussian's rectangle, tile mask and offset, then the warp writes the Gaussians'
+// (tile id, Gaussian id) runs one after the other with all lanes (contiguous, fully used sectors) instead of 32
+// lanes each walking its own run with 4-byte scattered stores.  Tile t of the rectangle (row-major, the reference's
+// order) is emitted iff bit t of the mask is set; rectangles of more than 64 tiles are emitted whole.
 __global__ void __launch_bounds__(256)
 emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
-                      const int* __restrict__ radii, const Splat* __restrict__ splats, int gx, int gy,
+                      const int* __restrict__ radii, const Splat* __restrict__ splats,
+                      const unsigned long long* __restrict__ tile_mask, int gx, int gy,
                       uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ gauss_ids) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     uint32_t g = 0, off = 0;
     int mnx = 0, mny = 0, w = 0, n = 0;
+    unsigned long long mask = 0ull;
     float inv_w = 0.0f;
     if (i < P) {
         g = order[i];
@@ -85,6 +99,8 @@ emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t*
             n = w * (mxy - mny);
             inv_w = 1.0f / (float)w;
             off = offsets[i];
+            mask = tile_mask[g];
+            if (mask == 0ull) n = 0;
         }
     }
     unsigned todo = __ballot_sync(0xffffffffu, n > 0);
@@ -95,12 +111,24 @@ emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t*
         const int mnx_s = __shfl_sync(0xffffffffu, mnx, src), mny_s = __shfl_sync(0xffffffffu, mny, src);
         const int w_s = __shfl_sync(0xffffffffu, w, src), n_s = __shfl_sync(0xffffffffu, n, src);
         const float iw_s = __shfl_sync(0xffffffffu, inv_w, src);
-        for (int t = lane; t < n_s; t += 32) {  // t-th tile of the rectangle, row-major (same order as the reference)
-            // t / w without an integer division: (t + 0.5) / w is at least 0.5/w away from an integer, far more than
-            // the fp32 error for any t below ~1e6 tiles
-            const int ty = __float2int_rd(((float)t + 0.5f) * iw_s), tx = t - ty * w_s;
-            tile_keys[off_s + t] = (uint32_t)((mny_s + ty) * gx + (mnx_s + tx));
-            gauss_ids[off_s + t] = g_s;
+        const unsigned long long m_s = __shfl_sync(0xffffffffu, mask, src);
+        if (n_s <= 64) {
+            for (int t = lane; t < n_s; t += 32) {
+                if ((m_s >> t) & 1ull) {
+                    const int ty = __float2int_rd(((float)t + 0.5f) * iw_s), tx = t - ty * w_s;
+                    const uint32_t dst = off_s + (uint32_t)__popcll(m_s & ((1ull << t) - 1ull));
+                    tile_keys[dst] = (uint32_t)((mny_s + ty) * gx + (mnx_s + tx));
+                    gauss_ids[dst] = g_s;
+                }
+            }
+        } else {
+            for (int t = lane; t < n_s; t += 32) {  // t-th tile of the rectangle, row-major
+                // t / w without an integer division: (t + 0.5) / w is at least 0.5/w away from an integer, far more
+                // than the fp32 error for any t below ~1e6 tiles
+                const int ty = __float2int_rd(((float)t + 0.5f) * iw_s), tx = t - ty * w_s;
+                tile_keys[off_s + t] = (uint32_t)((mny_s + ty) * gx + (mnx_s + tx));
+                gauss_ids[off_s + t] = g_s;
+            }
         }
     }
 }
@@ -131,24 +159,29 @@ int launch_depth_order_and_offsets(const IsrForwardArgs& a, cudaStream_t stream)
     uint32_t* keys = reinterpret_cast<uint32_t*>(g + gl.depth_key);
     uint32_t* keys_alt = reinterpret_cast<uint32_t*>(g + gl.keys_alt);
     uint32_t* tiles = reinterpret_cast<uint32_t*>(g + gl.tiles);
+    uint32_t* tcount = reinterpret_cast<uint32_t*>(g + gl.tcount);
+    uint32_t* tile_total = reinterpret_cast<uint32_t*>(g + gl.counters);
     uint32_t* offsets = reinterpret_cast<uint32_t*>(g + gl.offsets);
     void* temp = g + gl.sort_temp;
     size_t temp_bytes = gl.sort_temp_bytes;
+    if (a.num_rendered_host != nullptr)  // only the boundary's num_rendered needs the reference's count
+        ISR_CUDA_TRY(cub::DeviceReduce::Sum(temp, temp_bytes, tiles, tile_total, P, stream));
+    temp_bytes = gl.sort_temp_bytes;
     iota_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, order_alt);
     ISR_CUDA_TRY(cudaGetLastError());
     // stable: equal depth bits keep ascending Gaussian id
     ISR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_alt, order_alt, order, P, 0, 32, stream));
     // keys_alt now holds sorted keys (unused afterwards) -> reuse it for the gathered tile counts
-    gather_tiles_kernel<<<(P + 1 + 255) / 256, 256, 0, stream>>>(P, tiles, order, keys_alt);
+    gather_tiles_kernel<<<(P + 1 + 255) / 256, 256, 0, stream>>>(P, tcount, order, keys_alt);
     ISR_CUDA_TRY(cudaGetLastError());
     temp_bytes = gl.sort_temp_bytes;
     ISR_CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, keys_alt, offsets, P + 1, stream));
     if (a.num_rendered_host != nullptr) {
-        // offsets[P] (uint32) -> int64 on the host; widen on the device into the scratch first
+        // both counts -> int64[2] on the host; widened on the device into the scratch first
         int64_t* wide = reinterpret_cast<int64_t*>(temp);
-        copy_count_kernel<<<1, 1, 0, stream>>>(offsets, P, wide);
+        copy_count_kernel<<<1, 1, 0, stream>>>(offsets, P, tile_total, wide);
         ISR_CUDA_TRY(cudaGetLastError());
-        ISR_CUDA_TRY(cudaMemcpyAsync(a.num_rendered_host, wide, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+        ISR_CUDA_TRY(cudaMemcpyAsync(a.num_rendered_host, wide, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
     }
     return ISR_OK;
 }
@@ -173,7 +206,8 @@ int launch_binning(const IsrForwardArgs& a, int64_t R, cudaStream_t stream) {
     uint32_t* tile_keys_alt = reinterpret_cast<uint32_t*>(b + bl.tile_keys_alt);
     emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
         P, reinterpret_cast<const uint32_t*>(g + gl.order), reinterpret_cast<const uint32_t*>(g + gl.offsets), a.radii,
-        reinterpret_cast<const Splat*>(g + gl.splat), gx, gy, tile_keys_alt, point_list_alt);
+        reinterpret_cast<const Splat*>(g + gl.splat), reinterpret_cast<const unsigned long long*>(g + gl.tmask), gx, gy,
+        tile_keys_alt, point_list_alt);
     ISR_CUDA_TRY(cudaGetLastError());
     int bits = 1;
     while ((1 << bits) < num_tiles) bits++;

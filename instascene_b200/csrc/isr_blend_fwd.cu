@@ -19,7 +19,6 @@ template <int FP>  // feature dim padded to a multiple of 4 (0, 4, 8, 16, 24, 32
 struct FwdSmem {
     static constexpr int kRecF4 = 4 + 1 + FP / 4;  // splat (4 x float4) + rgb (1) + features
     static constexpr size_t per_warp = (size_t)32 * kRecF4 * 16 + 32 * 8 + kPairStage * 8;
-    static constexpr size_t bytes = 8 * per_warp;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -34,8 +33,11 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // LDGSTS, no registers) into the warp's private shared-memory slots, (4) the survivors are blended in list order
 // with broadcast shared-memory reads.  There is no block-wide barrier: warps of a tile neither wait for each other
 // nor for the slowest pixel of the tile, and a warp stops as soon as its own 32 pixels are saturated.
-template <int FP, bool kPairs, int kMinBlocks>
-__global__ void __launch_bounds__(256, kMinBlocks)
+// kWarps: warps (8x4 pixel blocks) per CTA; the warps never cooperate, so a CTA is just a scheduling unit: with 8 a
+// CTA is a whole tile and its slot stays occupied until the slowest of its 8 blocks is done.  kWarpsPerSM: occupancy
+// target that sets the register budget (24 -> 80 registers, 32 -> 64).
+template <int FP, bool kPairs, int kWarpsPerSM, int kWarps>
+__global__ void __launch_bounds__(32 * kWarps, kWarpsPerSM / kWarps)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int F,
                  const float4* __restrict__ splats, const float4* __restrict__ cull4, const float4* __restrict__ cullq,
                  const float4* __restrict__ rgb4, const float* __restrict__ extras, const float* __restrict__ bg,
@@ -45,16 +47,19 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int REC = FwdSmem<FP>::kRecF4;
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    unsigned char* wbase = smem_raw + (size_t)warp * FwdSmem<FP>::per_warp;
+    const int lane = tid & 31;
+    unsigned char* wbase = smem_raw + (size_t)(tid >> 5) * FwdSmem<FP>::per_warp;
     float4* slots = reinterpret_cast<float4*>(wbase);                       // [32][REC]
     int2* meta = reinterpret_cast<int2*>(wbase + (size_t)32 * REC * 16);    // [32] (gaussian id, list index)
     int2* my_pairs = meta + 32;                                              // [kPairStage]
 
     const int tiles_x = (W + TILE - 1) / TILE;
-    const int tile_id = blockIdx.y * tiles_x + blockIdx.x;
-    const int wx0 = blockIdx.x * TILE + (warp & 1) * 8;
-    const int wy0 = blockIdx.y * TILE + (warp >> 1) * 4;
+    constexpr int kCtasPerTile = 8 / kWarps;
+    const int tile_id = blockIdx.x / kCtasPerTile;
+    const int warp = (blockIdx.x % kCtasPerTile) * kWarps + (tid >> 5);  // 8x4 block of the tile: 2 across, 4 down
+    const int tile_x = tile_id % tiles_x, tile_y = tile_id / tiles_x;
+    const int wx0 = tile_x * TILE + (warp & 1) * 8;
+    const int wy0 = tile_y * TILE + (warp >> 1) * 4;
     const int pxi = wx0 + (lane & 7), pyi = wy0 + (lane >> 3);
     const bool inside = pxi < W && pyi < H;
     const uint32_t pix_id = (uint32_t)W * (uint32_t)pyi + (uint32_t)pxi;
@@ -70,11 +75,13 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 
     bool done = !inside;
     float T = 1.0f;
-    float C0 = 0, C1 = 0, C2 = 0, N0 = 0, N1 = 0, N2 = 0, D = 0, M1 = 0, M2 = 0, dist = 0, median_depth = 0;
+    // accumulators live in register pairs so that one FFMA2 updates two of them (isr::fma2, bit-identical to two FFMAs)
+    float2 C01 = make_float2(0.f, 0.f), C2x = C01, N12 = C01, DM1 = C01, M2dist = C01;  // C2x.y, see below, stays 0
+    float N0 = 0, median_depth = 0;
     uint32_t last_contributor = 0, median_contributor = 0;
-    float E[FP > 0 ? FP : 1];
+    float2 E[FP > 0 ? FP / 2 : 1];
 #pragma unroll
-    for (int ch = 0; ch < FP; ch++) E[ch] = 0.0f;
+    for (int ch = 0; ch < FP / 2; ch++) E[ch] = make_float2(0.f, 0.f);
     int wcount = 0;  // staged pairs of this warp (warp-uniform)
 
     const float4 kEmpty = make_float4(1e30f, 1e30f, -1e30f, -1e30f);
@@ -127,8 +134,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         __syncwarp();
         const int n_surv = __popc(m);
         for (int r = 0; r < n_surv; r++) {
-            bool hit = false;
-            float w = 0.0f;
+            float w = 0.0f;  // blend weight of this (pixel, Gaussian) pair; stays 0 if the pair does not contribute
             if (!done) {
                 const float* s = reinterpret_cast<const float*>(slots + r * REC);
                 PairEval e;
@@ -137,39 +143,36 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                     if (test_T < kTMin) {
                         done = true;
                     } else {
-                        hit = true;
                         const uint32_t contributor = (uint32_t)(meta[r].y + 1);
                         w = mul(e.alpha, T);
                         const float A = sub(1.0f, T);
                         const float mdep = mul(c1, sub(1.0f, mul(kNear, rcp_fast(e.depth))));
                         const float mm = mul(mdep, mdep);
-                        const float dt = fma_(-add(mdep, mdep), M1, fma_(mm, A, M2));
-                        dist = fma_(dt, w, dist);
-                        D = fma_(e.depth, w, D);
-                        M1 = fma_(mdep, w, M1);
-                        M2 = fma_(mm, w, M2);
+                        const float dt = fma_(-add(mdep, mdep), DM1.y, fma_(mm, A, M2dist.x));
+                        M2dist = fma2(make_float2(mm, dt), w, M2dist);       // M2 += mm*w, dist += dt*w
+                        DM1 = fma2(make_float2(e.depth, mdep), w, DM1);      // D += depth*w, M1 += mdep*w
                         if (T > 0.5f) { median_depth = e.depth; median_contributor = contributor; }
-                        N0 = fma_(s[11], w, N0); N1 = fma_(s[12], w, N1); N2 = fma_(s[13], w, N2);
+                        N0 = fma_(s[11], w, N0);
+                        N12 = fma2(*reinterpret_cast<const float2*>(s + 12), w, N12);
                         if (FP > 0) {
                             const float4* f4 = slots + r * REC + 5;
 #pragma unroll
                             for (int v = 0; v < FP / 4; v++) {
                                 const float4 f = f4[v];
-                                E[4 * v + 0] = fma_(f.x, w, E[4 * v + 0]);
-                                E[4 * v + 1] = fma_(f.y, w, E[4 * v + 1]);
-                                E[4 * v + 2] = fma_(f.z, w, E[4 * v + 2]);
-                                E[4 * v + 3] = fma_(f.w, w, E[4 * v + 3]);
+                                E[2 * v + 0] = fma2(make_float2(f.x, f.y), w, E[2 * v + 0]);
+                                E[2 * v + 1] = fma2(make_float2(f.z, f.w), w, E[2 * v + 1]);
                             }
                         }
-                        const float4 c = slots[r * REC + 4];
-                        C0 = fma_(c.x, w, C0); C1 = fma_(c.y, w, C1); C2 = fma_(c.z, w, C2);
+                        const float4 c = slots[r * REC + 4];  // (r, g, b, 0)
+                        C01 = fma2(make_float2(c.x, c.y), w, C01);
+                        C2x = fma2(make_float2(c.z, c.w), w, C2x);
                         T = test_T;
                         last_contributor = contributor;
                     }
                 }
             }
             if (kPairs) {
-                const bool emit = hit && (w >= 0.1f);  // reference: (double)w > 0.1 (forward.cu:422)
+                const bool emit = w >= 0.1f;  // reference: (double)w > 0.1 (forward.cu:422)
                 const unsigned m_emit = __ballot_sync(0xffffffffu, emit);
                 if (m_emit) {
                     const int n_new = __popc(m_emit);
@@ -201,24 +204,24 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     if (inside) {
         const size_t HW = (size_t)H * W;
         final_T[pix_id] = T;
-        final_T[pix_id + HW] = M1;
-        final_T[pix_id + 2 * HW] = M2;
+        final_T[pix_id + HW] = DM1.y;
+        final_T[pix_id + 2 * HW] = M2dist.x;
         n_contrib[pix_id] = last_contributor;
         n_contrib[pix_id + HW] = median_contributor;
-        out_color[pix_id] = fma_(T, __ldg(bg + 0), C0);
-        out_color[pix_id + HW] = fma_(T, __ldg(bg + 1), C1);
-        out_color[pix_id + 2 * HW] = fma_(T, __ldg(bg + 2), C2);
-        out_others[pix_id + 0 * HW] = D;
+        out_color[pix_id] = fma_(T, __ldg(bg + 0), C01.x);
+        out_color[pix_id + HW] = fma_(T, __ldg(bg + 1), C01.y);
+        out_color[pix_id + 2 * HW] = fma_(T, __ldg(bg + 2), C2x.x);
+        out_others[pix_id + 0 * HW] = DM1.x;
         out_others[pix_id + 1 * HW] = sub(1.0f, T);
         out_others[pix_id + 2 * HW] = N0;
-        out_others[pix_id + 3 * HW] = N1;
-        out_others[pix_id + 4 * HW] = N2;
+        out_others[pix_id + 3 * HW] = N12.x;
+        out_others[pix_id + 4 * HW] = N12.y;
         out_others[pix_id + 5 * HW] = median_depth;
-        out_others[pix_id + 6 * HW] = dist;
+        out_others[pix_id + 6 * HW] = M2dist.y;
         if (FP > 0) {
 #pragma unroll
             for (int ch = 0; ch < FP; ch++)
-                if (ch < F) out_extra[(size_t)ch * HW + pix_id] = E[ch];
+                if (ch < F) out_extra[(size_t)ch * HW + pix_id] = (ch & 1) ? E[ch >> 1].y : E[ch >> 1].x;
         }
     }
 }
@@ -230,21 +233,27 @@ static int launch_one(const IsrForwardArgs& a, cudaStream_t stream) {
     const char* g = static_cast<const char*>(a.geom);
     char* im = static_cast<char*>(a.image);
     const char* b = static_cast<const char*>(a.binning);
-    const dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE);
-    const size_t smem = FwdSmem<FP>::bytes;
-    // occupancy variant: 4 CTAs/SM (64 registers) or 3 CTAs/SM (80 registers, no spills); ISR_FWD_MINBLOCKS overrides
+    const int num_tiles = ((a.W + TILE - 1) / TILE) * ((a.H + TILE - 1) / TILE);
+    // occupancy variant: 32 warps/SM (64 registers) or 24 warps/SM (80 registers, no spills); ISR_FWD_MINBLOCKS
+    // (4 or 3 CTAs of 8 warps) and ISR_FWD_WARPS (warps per CTA) override
     static const int env_mb = [] { const char* e = getenv("ISR_FWD_MINBLOCKS"); return e ? atoi(e) : 0; }();
-    const int mb = env_mb ? env_mb : (FP < 16 ? 4 : 3);  // measured at cfg3 (F=16): 3 CTAs/SM, no spills, is 6% faster
-    auto kern = (mb >= 4) ? blend_fwd_kernel<FP, kPairs, 4> : blend_fwd_kernel<FP, kPairs, 3>;
-    ISR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 256, smem, stream>>>(
-        reinterpret_cast<const uint2*>(im + il.ranges), reinterpret_cast<const uint32_t*>(b),  // point_list sits at offset 0 of the binning workspace
-        a.W, a.H, a.F, reinterpret_cast<const float4*>(g + gl.splat), reinterpret_cast<const float4*>(g + gl.cull),
-        reinterpret_cast<const float4*>(g + gl.cullq), reinterpret_cast<const float4*>(g + gl.rgb), a.extra_attrs, a.background,
-        reinterpret_cast<float*>(im + il.final_T), reinterpret_cast<uint32_t*>(im + il.n_contrib), a.out_color,
-        a.out_others, a.out_extra, reinterpret_cast<int2*>(a.pairs), a.pair_capacity, a.pair_count);
-    ISR_CUDA_TRY(cudaGetLastError());
-    return ISR_OK;
+    static const int env_w = [] { const char* e = getenv("ISR_FWD_WARPS"); return e ? atoi(e) : 0; }();
+    const int mb = env_mb ? env_mb : (FP < 16 ? 4 : 3);  // measured at cfg3 (F=16): 24 warps/SM, no spills, is 6% faster
+    const int warps = (env_w == 8 || env_w == 2) ? env_w : 2;
+    auto launch = [&](auto kern, int w) -> int {
+        const size_t smem = (size_t)w * FwdSmem<FP>::per_warp;
+        ISR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<num_tiles * (8 / w), 32 * w, smem, stream>>>(
+            reinterpret_cast<const uint2*>(im + il.ranges), reinterpret_cast<const uint32_t*>(b),  // point_list sits at offset 0 of the binning workspace
+            a.W, a.H, a.F, reinterpret_cast<const float4*>(g + gl.splat), reinterpret_cast<const float4*>(g + gl.cull),
+            reinterpret_cast<const float4*>(g + gl.cullq), reinterpret_cast<const float4*>(g + gl.rgb), a.extra_attrs, a.background,
+            reinterpret_cast<float*>(im + il.final_T), reinterpret_cast<uint32_t*>(im + il.n_contrib), a.out_color,
+            a.out_others, a.out_extra, reinterpret_cast<int2*>(a.pairs), a.pair_capacity, a.pair_count);
+        ISR_CUDA_TRY(cudaGetLastError());
+        return ISR_OK;
+    };
+    if (warps == 8) return (mb >= 4) ? launch(blend_fwd_kernel<FP, kPairs, 32, 8>, 8) : launch(blend_fwd_kernel<FP, kPairs, 24, 8>, 8);
+    return (mb >= 4) ? launch(blend_fwd_kernel<FP, kPairs, 32, 2>, 2) : launch(blend_fwd_kernel<FP, kPairs, 24, 2>, 2);
 }
 
 template <bool kPairs>

@@ -47,7 +47,8 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
                       float4* __restrict__ rgb4,
                       float* __restrict__ depths,
                       uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ tiles_touched,
-                      uint8_t* __restrict__ clamped) {
+                      uint8_t* __restrict__ clamped, unsigned long long* __restrict__ tile_mask,
+                      uint32_t* __restrict__ tile_count) {
     // SH coefficients of the block's 256 Gaussians are one contiguous 48 KB range: stage them with fully coalesced
     // 16-byte cp.async copies into per-Gaussian slots padded to 13 x 16 B (conflict-free LDS), overlapped with the
     // projection math below.  (Per-thread strided loads of the 192-byte rows ran K1 at 48% of the HBM roofline.)
@@ -66,7 +67,8 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
     }
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     int radius_i = 0;
-    uint32_t tiles = 0, dkey = 0xFFFFFFFFu;
+    uint32_t tiles = 0, dkey = 0xFFFFFFFFu, tcount = 0;
+    unsigned long long tmask = 0ull;
     uint8_t clamp_mask = 0;
     bool visible = false;
     float p0 = 0, p1 = 0, p2 = 0, pvz = 0, cx = 0, cy = 0;
@@ -217,7 +219,8 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
         const float opa = opacities[idx];
         // conservative alpha cut: alpha = opa*exp(power) < 1/255  <=  power < -ln(255*opa) - margin
         float power_cut = __int_as_float(0x7f800000);  // +inf: never contributes (opa <= 0)
-        if (opa > 0.0f) power_cut = -__logf(255.0f * opa) - 1e-3f;
+        // (never below -80: there the specified exp is 0, so alpha = 0 and the pair is skipped anyway)
+        if (opa > 0.0f) power_cut = fmaxf(-__logf(255.0f * opa) - 1e-3f, -80.0f);
         Splat s;
         s.Tu[0] = T[0]; s.Tu[1] = T[1]; s.Tu[2] = T[2];
         s.Tv[0] = T[3]; s.Tv[1] = T[4]; s.Tv[2] = T[5];
@@ -292,6 +295,21 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
         cullq[3 * (size_t)idx + 0] = q0;
         cullq[3 * (size_t)idx + 1] = q1;
         cullq[3 * (size_t)idx + 2] = make_float4(r2, 0.f, 0.f, 0.f);
+        // Tile footprint for the binning (isr_binning.cu): bit t of the mask = tile t (row-major) of the reference's
+        // getRect rectangle may receive something from this Gaussian; the others are never emitted (skipping them
+        // cannot change a result).  Rectangles of more than 64 tiles are emitted whole.
+        if (ntiles <= 64) {
+            int mnx, mny, mxx, mxy;
+            get_rect(cx, cy, ri, gx, gy, mnx, mny, mxx, mxy);
+            int t = 0;
+            for (int ty = mny; ty < mxy; ty++)
+                for (int tx = mnx; tx < mxx; tx++, t++)
+                    if (rect_may_touch(tx * TILE, ty * TILE, TILE, TILE, W, H, cr, q0, q1, r2)) tmask |= 1ull << t;
+            tcount = (uint32_t)__popcll(tmask);
+        } else {
+            tmask = ~0ull;
+            tcount = (uint32_t)ntiles;
+        }
         rgb4[idx] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
         depths[idx] = pvz;
         dkey = __float_as_uint(pvz);
@@ -303,6 +321,8 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
     tiles_touched[idx] = tiles;
     depth_keys[idx] = dkey;
     clamped[idx] = clamp_mask;
+    tile_mask[idx] = tmask;
+    tile_count[idx] = tcount;
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const Camera cam,
@@ -507,7 +527,8 @@ int launch_preprocess_fwd(const IsrForwardArgs& a, cudaStream_t stream) {
         a.W, a.H, gx, gy, a.radii, reinterpret_cast<Splat*>(g + gl.splat), reinterpret_cast<float4*>(g + gl.cull),
         reinterpret_cast<float4*>(g + gl.cullq), reinterpret_cast<float4*>(g + gl.rgb),
         reinterpret_cast<float*>(g + gl.depth), reinterpret_cast<uint32_t*>(g + gl.depth_key),
-        reinterpret_cast<uint32_t*>(g + gl.tiles), reinterpret_cast<uint8_t*>(g + gl.clamped));
+        reinterpret_cast<uint32_t*>(g + gl.tiles), reinterpret_cast<uint8_t*>(g + gl.clamped),
+        reinterpret_cast<unsigned long long*>(g + gl.tmask), reinterpret_cast<uint32_t*>(g + gl.tcount));
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }

@@ -43,7 +43,7 @@ def _pinned_i64(device: torch.device) -> torch.Tensor:
     key = (device.index, torch.cuda.current_stream().cuda_stream)
     t = _pinned_cache.get(key)
     if t is None:
-        t = torch.zeros(1, dtype=torch.int64).pin_memory()
+        t = torch.zeros(2, dtype=torch.int64).pin_memory()  # [reference num_rendered, emitted instances]
         _pinned_cache[key] = t
     return t
 
@@ -139,17 +139,19 @@ def finish_render(st: _ForwardState, extra_attrs, F: int, debug: bool = False, r
     else:
         out_extra = torch.empty(0, dtype=torch.float32, device=dev)
     torch.cuda.current_stream().synchronize()  # the reference blocks on a cudaMemcpy here (rasterizer_impl.cu:287)
-    num_rendered = int(st.nr_host.item())
-    bin_bytes = L.isr_binning_bytes(st.P, num_rendered, st.W, st.H)
+    # [0]: what the reference reports as num_rendered (all tiles of every rectangle); [1]: instances actually binned
+    num_rendered, n_inst = int(st.nr_host[0]), int(st.nr_host[1])
+    bin_bytes = L.isr_binning_bytes(st.P, n_inst, st.W, st.H)
     binningBuffer = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
     a.binning, a.binning_bytes = binningBuffer.data_ptr(), bin_bytes
-    _lib.check(L.isr_forward_render(C.byref(a), num_rendered, _stream()), "isr_forward_render")
+    _lib.check(L.isr_forward_render(C.byref(a), n_inst, _stream()), "isr_forward_render")
     if debug:
         torch.cuda.synchronize()
     res = (num_rendered, st.out_color, st.out_others, st.radii, out_extra, st.geom, binningBuffer, st.img, st.pairs,
            st.pair_count - 1)
     if return_args:  # profiling hook (bench.py roofline leg); keeps every tensor the struct points to alive
         a._keepalive = st.keep + (extra_attrs, st.pair_count, st.nr_host) + res[1:9]
+        a._n_inst = n_inst
         return res + (a,)
     return res
 
@@ -344,9 +346,12 @@ class _RasterizeGaussians(torch.autograd.Function):
             mask |= _lib.GRAD_EXTRA
         sparse = None
         if grad_handle is not None:
-            if grad_handle.is_sparse:
+            if grad_handle.is_sparse and (mask & ~_lib.GRAD_EXTRA) == 0:
+                # only the features are trainable: their gradient needs just the sampled pixels
                 sparse = (grad_handle._indices()[0], grad_handle._values())
-            else:  # someone densified it: fold into the dense cotangent
+            else:  # other gradients are wanted too (or someone densified it): fold into the dense cotangent
+                if grad_handle.is_sparse:
+                    grad_handle = grad_handle.to_dense()
                 F = extra_attrs.shape[1]
                 dense = grad_handle[:, :F].t().reshape(F, rs.image_height, rs.image_width)
                 grad_out_extra = dense if grad_out_extra is None else grad_out_extra + dense

@@ -217,13 +217,6 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
            norm_seg_feat=True, want_pairs: bool = True):
     """Rasterise `pc` from `viewpoint_camera`.  `bg_color` must live on the GPU."""
     xyz = pc.get_xyz
-    # dummy leaf that receives the densification proxy dL/dmean2D (reference :29-33)
-    screen_pts = torch.zeros_like(xyz, requires_grad=True)
-    try:
-        screen_pts.retain_grad()
-    except Exception:
-        pass
-
     settings_cls = _SettingsDeferPairs if want_pairs else _SettingsNoPairs
     settings = settings_cls(
         image_height=int(viewpoint_camera.image_height), image_width=int(viewpoint_camera.image_width),
@@ -244,6 +237,13 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
     # overlap whatever still produces them (pc._isr_param_ready_event: e.g. the previous step's gradient all-reduce +
     # optimizer step running on another stream).  Same kernels, same order of results.
     opacity = pc.get_opacity
+    # Dummy leaf that receives the densification proxy dL/dmean2D (reference :29-33).  The reference makes it require
+    # grad unconditionally; here only when some geometry/appearance input does (the proxy is read by densification,
+    # which optimises those).  With frozen geometry -- train_semantic.py -- that keeps the backward on the
+    # feature-only path instead of computing and zero-filling ten per-Gaussian gradient buffers nobody reads.
+    geom_trainable = torch.is_grad_enabled() and any(
+        t.requires_grad for t in (xyz, opacity, *geometry.values(), *appearance.values()))
+    screen_pts = torch.zeros_like(xyz, requires_grad=bool(geom_trainable))
     none = torch.empty(0, dtype=torch.float32, device=xyz.device)
     if getattr(pipe, "geometry_first", _GEOMETRY_FIRST):
         settings._geom_state = launch_geometry(

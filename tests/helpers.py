@@ -82,14 +82,48 @@ def cuda_forward(inp, want_pairs=True, device="cuda:0"):
                clamped_mask=view(g, off(_lib.GEOM_CLAMPED), np.uint8, P),
                final_T=view(im, off(_lib.IMG_FINAL_T), np.float32, 3 * HW).reshape(3, H, W),
                n_contrib=view(im, off(_lib.IMG_NCONTRIB), np.uint32, 2 * HW).reshape(2, H, W),
-               ranges=view(im, off(_lib.IMG_RANGES), np.uint32, 2 * tiles).reshape(tiles, 2),
-               point_list=view(b, off(_lib.BIN_POINT_LIST), np.uint32, R) if R else np.zeros(0, np.uint32))
+               tiles_emitted=view(g, off(_lib.GEOM_TILE_COUNT), np.uint32, P),
+               ranges=view(im, off(_lib.IMG_RANGES), np.uint32, 2 * tiles).reshape(tiles, 2))
+    # the CUDA path emits only the tiles a Gaussian's footprint can reach: the list is shorter than num_rendered
+    n_inst = int(out["tiles_emitted"].sum())
+    out["point_list"] = view(b, off(_lib.BIN_POINT_LIST), np.uint32, n_inst) if n_inst else np.zeros(0, np.uint32)
     if want_pairs:
         n = int(pidx.item()) + 1
         out["pairs"] = pairs[:n].cpu().numpy()
         out["pair_count"] = n
     out["_torch"] = dict(tens=tens, geom=geom, binning=binning, img=img, radii=radii, R=R)
     return out
+
+
+def check_tile_lists(c, o, W, H):
+    """The CUDA path never emits a (tile, Gaussian) instance whose footprint provably misses the tile; the oracle (like
+    the reference) emits every tile of the getRect rectangle.  Checks that
+    (1) the tile ranges partition the CUDA instance list, whose length is the sum of the per-Gaussian emitted counts,
+        and no Gaussian is emitted into more tiles than the reference touches,
+    (2) every CUDA tile list is an ordered SUBSEQUENCE of the oracle's list of the same tile (same (depth, id) order),
+    (3) the per-pixel last / median contributor indices, mapped from CUDA-list to oracle-list positions, are
+        bit-identical to the oracle's n_contrib (both stop at the same Gaussian for every pixel)."""
+    tiles_x, tiles_y = (W + 15) // 16, (H + 15) // 16
+    cr, cl = c["ranges"].astype(np.int64), c["point_list"].astype(np.int64)
+    orr, ol = o["ranges"].astype(np.int64), o["point_list"].astype(np.int64)
+    assert np.all(c["tiles_emitted"] <= c["tiles_touched"])
+    assert int((cr[:, 1] - cr[:, 0]).sum()) == len(cl), "ranges partition the list"
+    mapped = np.zeros_like(c["n_contrib"])
+    for t in range(tiles_x * tiles_y):
+        tl = ol[orr[t, 0]:orr[t, 1]]
+        pos = {int(g): i for i, g in enumerate(tl)}
+        assert len(pos) == len(tl)
+        sub = cl[cr[t, 0]:cr[t, 1]]
+        idx = np.array([pos.get(int(g), -1) for g in sub], dtype=np.int64)
+        assert np.all(idx >= 0), "emitted instance missing from the reference's tile list"
+        assert np.all(np.diff(idx) > 0), "tile list is not in the reference's (depth, id) order"
+        ty, tx = divmod(t, tiles_x)
+        y0, x0 = ty * 16, tx * 16
+        nb = c["n_contrib"][:, y0:y0 + 16, x0:x0 + 16].astype(np.int64)
+        assert nb.max(initial=0) <= len(sub)
+        lut = np.concatenate([[0], idx + 1]).astype(np.int64)  # CUDA position (1-based, 0 = none) -> oracle position
+        mapped[:, y0:y0 + 16, x0:x0 + 16] = lut[nb]
+    assert np.array_equal(mapped, o["n_contrib"]), "last/median contributor (mapped to the reference's list positions)"
 
 
 def cuda_backward(inp, fwd, dcolor, dothers, dextra, grad_mask=15, sparse=None, flags=1):

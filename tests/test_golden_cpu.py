@@ -34,11 +34,18 @@ def cotangents(F, W, H, seed):
 SEEDS = {"g0_rgb": 101, "g1_feat16": 102, "g2_feat24_odd": 103, "g3_big_splats": 104}
 
 
-def check_against_reference(got, ref, F, grads=None):
-    """Shared by the CPU (oracle) and GPU (CUDA) golden tests."""
+def check_against_reference(got, ref, F, grads=None, culled_lists=False):
+    """Shared by the CPU (oracle) and GPU (CUDA) golden tests.  culled_lists: `got` comes from the CUDA path, whose
+    tile lists omit instances that provably miss the tile; they are compared with the reference's lists through
+    helpers.check_tile_lists."""
     assert int(got["num_rendered"]) == int(ref["num_rendered"])
-    for k in ("radii", "tiles_touched", "point_list", "ranges", "n_contrib"):
+    for k in ("radii", "tiles_touched") + (() if culled_lists else ("point_list", "ranges", "n_contrib")):
         assert np.array_equal(np.asarray(got[k]).astype(np.int64), np.asarray(ref[k]).astype(np.int64)), k
+    if culled_lists:
+        from helpers import check_tile_lists
+        refd = {"point_list": np.asarray(ref["point_list"]), "ranges": np.asarray(ref["ranges"]).reshape(-1, 2),
+                "n_contrib": np.asarray(ref["n_contrib"]).reshape(np.asarray(got["n_contrib"]).shape)}
+        check_tile_lists(got, refd, np.asarray(got["color"]).shape[2], np.asarray(got["color"]).shape[1])
     vis = ref["radii"] > 0
     # per-Gaussian intermediates: 1e-4 relative, with an absolute floor of 1e-5 of the field's magnitude (the AABB
     # centre of a huge splat is a difference of large terms: a 3e-5 px deviation on a 0.01 px value is rounding)

@@ -5,7 +5,7 @@ order over pixels differs; the reference itself uses unordered float atomics).""
 import numpy as np
 import pytest
 
-from helpers import (cuda_backward, cuda_forward, oracle_backward, oracle_forward, pair_set, rel_err, scene_inputs)
+from helpers import (check_tile_lists, cuda_backward, cuda_forward, oracle_backward, oracle_forward, pair_set, rel_err, scene_inputs)
 
 pytestmark = pytest.mark.gpu
 
@@ -29,9 +29,7 @@ def _check_forward_exact(c, o, F):
         assert np.array_equal(c[k][vis].view(np.uint32), o[k][vis].view(np.uint32)), k
     cm = np.packbits(o["clamped"][vis].astype(bool), axis=1, bitorder="little")[:, 0]
     assert np.array_equal(c["clamped_mask"][vis], cm)
-    assert np.array_equal(c["point_list"], o["point_list"]), "sorted (tile, depth, id) instance list"
-    assert np.array_equal(c["ranges"], o["ranges"]), "tile ranges"
-    assert np.array_equal(c["n_contrib"], o["n_contrib"]), "n_contrib"
+    check_tile_lists(c, o, c["color"].shape[2], c["color"].shape[1])
     for k in ["final_T", "color", "others"] + (["extra"] if F else []):
         assert np.array_equal(c[k].view(np.uint32), o[k].view(np.uint32)), k
     assert c["pair_count"] == o["pair_count"]
@@ -265,7 +263,7 @@ def test_cuda_matches_reference_goldens(path):
     dcolor, dothers, dextra = cotangents(F, inp["W"], inp["H"], SEEDS[name])
     g = cuda_backward(inp, c, dcolor, dothers, dextra)
     c["clamped"] = None
-    check_against_reference(c, ref, F, g)
+    check_against_reference(c, ref, F, g, culled_lists=True)
 
 
 def test_normalize_rows_matches_torch():
@@ -393,7 +391,7 @@ def _fwd_bwd_variant(oracle, inp, F, grads):
     o = oracle_forward(oracle, inp)
     c = cuda_forward(inp)
     assert np.array_equal(c["radii"], o["radii"]) and c["num_rendered"] == o["num_rendered"] > 0
-    assert np.array_equal(c["point_list"], o["point_list"]) and np.array_equal(c["n_contrib"], o["n_contrib"])
+    check_tile_lists(c, o, W, H)
     for k in ["color", "others"] + (["extra"] if F else []):
         assert np.array_equal(c[k].view(np.uint32), o[k].view(np.uint32)), k
     og = oracle_backward(oracle, inp, o, dcolor, dothers, dextra)
@@ -507,3 +505,60 @@ def test_render_geometry_first_and_param_ready_event():
     pc._isr_param_ready_event = None
     want = isr.render(Cam(), pc, Pipe(), t(inp["bg"]), want_pairs=False)["seg_feature"]
     assert torch.equal(got, want)
+
+
+def test_sampled_loss_with_trainable_geometry_uses_dense_backward():
+    """A loss on sampled feature pixels (hybrid-sparse gradient on the hidden handle) while the geometry is trainable
+    too: every gradient must equal the plain dense formulation `seg_map.reshape(F,-1)[:, ids]`; with frozen geometry the
+    means2D proxy does not require grad and the feature gradient is the same."""
+    import torch
+    import instascene_b200 as isr
+    P, F, W, H, seed = 3000, 8, 96, 64, 77
+    inp = scene_inputs(P, F, W, H, seed)
+    sc, cam = inp["scene"], inp["cam"]
+    dev = "cuda:0"
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    class Cam:
+        FoVx, FoVy, image_width, image_height = cam.FoVx, cam.FoVy, W, H
+        world_view_transform, full_proj_transform, camera_center = t(cam.world_view_transform), t(cam.full_proj_transform), t(cam.camera_center)
+        znear, zfar = 0.01, 100.0
+
+    class Pipe:
+        compute_cov3D_python, convert_SHs_python, depth_ratio = False, False, 1.0
+
+    def make_pc(train_geometry):
+        class PC:
+            active_sh_degree, max_sh_degree = 3, 3
+            get_xyz = t(sc.xyz).requires_grad_(train_geometry)
+            get_opacity = t(sc.opacities()).reshape(-1, 1).requires_grad_(train_geometry)
+            get_scaling = t(sc.scales()).requires_grad_(train_geometry)
+            get_rotation = t(sc.rotations())
+            get_features = t(sc.shs())
+            _seg_feature = t(sc.seg_feature_raw).requires_grad_(True)
+            get_seg_feature = _seg_feature
+        return PC()
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    ids = torch.randint(0, W * H, (4096,), device=dev, generator=g)
+    coef = torch.randn((4096, F), device=dev, generator=g)
+    bg = torch.zeros(3, device=dev)
+    grads = {}
+    for mode in ("sampled", "dense", "sampled_frozen"):
+        pc = make_pc(mode != "sampled_frozen")
+        pkg = isr.render(Cam(), pc, Pipe(), bg, norm_seg_feat=False, want_pairs=False)
+        seg = pkg["seg_feature"]
+        feats = isr.sample_pixels(seg, ids) if mode != "dense" else seg.reshape(F, -1)[:, ids].t()
+        (feats * coef).sum().backward()
+        assert pkg["viewspace_points"].requires_grad == (mode != "sampled_frozen")
+        grads[mode] = {k: getattr(pc, k).grad for k in ("get_xyz", "get_opacity", "get_scaling", "_seg_feature")}
+        if mode != "sampled_frozen":
+            grads[mode]["means2D"] = pkg["viewspace_points"].grad
+    for k, ref in grads["dense"].items():
+        got = grads["sampled"][k]
+        assert got is not None and ref is not None, k
+        assert ref.abs().max() > 0, k
+        assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 1e-4, k
+    assert grads["sampled_frozen"]["get_xyz"] is None
+    assert rel_err(grads["sampled_frozen"]["_seg_feature"].cpu().numpy(), grads["dense"]["_seg_feature"].cpu().numpy()) < 1e-4
