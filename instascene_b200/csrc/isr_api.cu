@@ -201,7 +201,7 @@ int isr_contrastive_forward(int N, int F, int K, const float* features, const in
     if (F > ISR_MAX_EXTRA_DIMS) return ISR_ERR_UNSUPPORTED;
     if (N > 0 && (!features || !labels || !ws)) return ISR_ERR_INVALID_ARG;
     if (ws_bytes < contrastive_ws_bytes(N, F, K)) return ISR_ERR_WORKSPACE;
-    if ((size_t)K * (F + 1) * sizeof(float) > 200 * 1024) return ISR_ERR_UNSUPPORTED;
+    if ((size_t)K * (F + 1) * sizeof(float) > 120 * 1024) return ISR_ERR_UNSUPPORTED;  // centres live in shared memory
     return launch_contrastive_fwd(N, F, K, features, labels, predef_u, temp_lambda, ws, loss,
                                   static_cast<cudaStream_t>(stream_));
 }

@@ -24,6 +24,11 @@
 
 namespace isr {
 
+bool entries_packed(int P) {
+    static const bool plain = [] { const char* e = getenv("ISR_PLAIN_ENTRIES"); return e && e[0] == '1'; }();
+    return !plain && P < (1 << kIdBits);
+}
+
 struct TilesInDepthOrder {
     const uint32_t* tiles;
     const uint32_t* order;
@@ -73,62 +78,146 @@ __global__ void copy_count_kernel(const uint32_t* __restrict__ offsets, int P, c
     out[1] = (int64_t)offsets[P];
 }
 
-// Instance emission (DSR duplicateWithKeys, rasterizer_impl.cu:70-111) in depth order.  A warp takes 32 consecutive
-// Gaussians; each lane fetches one Gaussian's rectangle, tile mask and offset, then the warp writes the Gaussians'
-// (tile id, Gaussian id) runs one after the other with all lanes (contiguous, fully used sectors) instead of 32
-// lanes each walking its own run with 4-byte scattered stores.  Tile t of the rectangle (row-major, the reference's
-// order) is emitted iff bit t of the mask is set; rectangles of more than 64 tiles are emitted whole.
+// One list entry: Gaussian id, plus (packed entries) the per-block footprint bits of tile (tile_x, tile_y): the test
+// of isr::rect_may_touch / block_outside for the tile's 2 x 4 blocks of 8x4 pixels, with the conic evaluated
+// incrementally over the block-centre grid (Q = a x^2 + (b y + d) x + (c y^2 + e y + f) per row) and UNCLIPPED block
+// extents at the image border (a larger block only makes the test more conservative).
+__device__ __forceinline__ uint32_t make_entry(uint32_t g, int tile_x, int tile_y, int packed, const float4 cr,
+                                               const float4 q0, const float4 q1, float r2) {
+    if (!packed) return g;
+    const float X0 = (float)(tile_x * TILE), Y0 = (float)(tile_y * TILE);
+    const float x0 = X0 + 3.5f - q1.z, y0 = Y0 + 1.5f - q1.w;  // centre of block (0,0) relative to the Gaussian's centre
+    const float a2 = q0.x + q0.x, c2 = q0.z + q0.z;
+    uint32_t bits = 0;
+#pragma unroll
+    for (int by = 0; by < 4; by++) {
+        const float y = y0 + 4.0f * (float)by;
+        const float py0 = Y0 + 4.0f * (float)by;
+        const bool yin = !(cr.w < py0 || cr.y > py0 + 3.0f);
+        const float lin = fmaf(q0.y, y, q0.w);                 // b y + d
+        const float cst = fmaf(fmaf(q0.z, y, q1.x), y, q1.y);  // c y^2 + e y + f
+        const float gy0 = fmaf(c2, y, q1.x);                   // 2 c y + e
+        const float ey = fmaxf(fabsf(y) - 1.5f, 0.0f), ey2 = ey * ey;
+#pragma unroll
+        for (int bx = 0; bx < 2; bx++) {
+            const float x = x0 + 8.0f * (float)bx;
+            const float px0 = X0 + 8.0f * (float)bx;
+            const bool xin = !(cr.z < px0 || cr.x > px0 + 7.0f);
+            const float Qc = fmaf(fmaf(q0.x, x, lin), x, cst);
+            const float gxx = fmaf(a2, x, lin), gyy = fmaf(q0.y, x, gy0);
+            const bool out3d = Qc - fmaf(fabsf(gxx), 3.5f, fabsf(gyy) * 1.5f) > 0.02f;
+            const float ex = fmaxf(fabsf(x) - 3.5f, 0.0f);
+            const bool out2d = fmaf(ex, ex, ey2) > r2;
+            if (xin && yin && !(out3d && out2d)) bits |= 1u << (by * 2 + bx);
+        }
+    }
+    return g | (bits << kIdBits);
+}
+
+// Instance emission (DSR duplicateWithKeys, rasterizer_impl.cu:70-111) in depth order.  A warp owns 32 consecutive
+// Gaussians of the depth order.  Footprints of up to 64 tiles (K1 mask): the lanes take consecutive instances of the
+// warp's Gaussians -- each finds the owning Gaussian by a 5-step search over the warp's running counts (shuffles), the
+// tile as the k-th set bit of that Gaussian's mask, evaluates the 8 per-block footprint bits of that tile and writes
+// (tile id, Gaussian id | block bits << 24): coalesced stores, no per-Gaussian serial loop, all lanes busy.  Larger
+// footprints are only queued here (id, offset) and expanded by emit_big_kernel with a whole CTA each, so that one
+// screen-filling splat does not serialise thousands of instances on a single warp.  Tile t of a rectangle is numbered
+// row-major (the reference's order); the order of one Gaussian's instances is irrelevant for the result (distinct
+// tiles), the order ACROSS Gaussians is the depth order.
 __global__ void __launch_bounds__(256)
 emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
                       const int* __restrict__ radii, const Splat* __restrict__ splats,
-                      const unsigned long long* __restrict__ tile_mask, int gx, int gy,
-                      uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ gauss_ids) {
+                      const unsigned long long* __restrict__ tile_mask, const uint32_t* __restrict__ tile_count,
+                      const float4* __restrict__ cull4, const float4* __restrict__ cullq, int gx, int gy, int W, int H,
+                      int packed, uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ gauss_ids,
+                      uint32_t* __restrict__ big_count, uint2* __restrict__ big_list) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    uint32_t g = 0, off = 0;
-    int mnx = 0, mny = 0, w = 0, n = 0;
+    uint32_t g = 0, off = 0, cnt = 0, rect = 0, w = 1;
     unsigned long long mask = 0ull;
-    float inv_w = 0.0f;
     if (i < P) {
         g = order[i];
-        const int r = radii[g];
-        if (r > 0) {
-            int mxx, mxy;
-            get_rect(splats[g].mx, splats[g].my, r, gx, gy, mnx, mny, mxx, mxy);
-            w = mxx - mnx;
-            n = w * (mxy - mny);
-            inv_w = 1.0f / (float)w;
+        cnt = tile_count[g];
+        if (cnt > 0) {
             off = offsets[i];
-            mask = tile_mask[g];
-            if (mask == 0ull) n = 0;
+            int mnx, mny, mxx, mxy;
+            get_rect(splats[g].mx, splats[g].my, radii[g], gx, gy, mnx, mny, mxx, mxy);
+            w = (uint32_t)(mxx - mnx);
+            if ((mxx - mnx) * (mxy - mny) > 64) {  // expanded by emit_big_kernel
+                big_list[atomicAdd(big_count, 1u)] = make_uint2(g, off);
+                cnt = 0;
+            } else {
+                rect = (uint32_t)mnx | ((uint32_t)mny << 16);
+                mask = tile_mask[g];
+            }
         }
     }
-    unsigned todo = __ballot_sync(0xffffffffu, n > 0);
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint32_t g_s = __shfl_sync(0xffffffffu, g, src), off_s = __shfl_sync(0xffffffffu, off, src);
-        const int mnx_s = __shfl_sync(0xffffffffu, mnx, src), mny_s = __shfl_sync(0xffffffffu, mny, src);
-        const int w_s = __shfl_sync(0xffffffffu, w, src), n_s = __shfl_sync(0xffffffffu, n, src);
-        const float iw_s = __shfl_sync(0xffffffffu, inv_w, src);
-        const unsigned long long m_s = __shfl_sync(0xffffffffu, mask, src);
-        if (n_s <= 64) {
-            for (int t = lane; t < n_s; t += 32) {
-                if ((m_s >> t) & 1ull) {
-                    const int ty = __float2int_rd(((float)t + 0.5f) * iw_s), tx = t - ty * w_s;
-                    const uint32_t dst = off_s + (uint32_t)__popcll(m_s & ((1ull << t) - 1ull));
-                    tile_keys[dst] = (uint32_t)((mny_s + ty) * gx + (mnx_s + tx));
-                    gauss_ids[dst] = g_s;
-                }
-            }
-        } else {
-            for (int t = lane; t < n_s; t += 32) {  // t-th tile of the rectangle, row-major
-                // t / w without an integer division: (t + 0.5) / w is at least 0.5/w away from an integer, far more
-                // than the fp32 error for any t below ~1e6 tiles
-                const int ty = __float2int_rd(((float)t + 0.5f) * iw_s), tx = t - ty * w_s;
-                tile_keys[off_s + t] = (uint32_t)((mny_s + ty) * gx + (mnx_s + tx));
-                gauss_ids[off_s + t] = g_s;
-            }
+    // running instance count over the warp's Gaussians (inclusive scan), c_excl = instances before this lane's
+    uint32_t c_incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, c_incl, d);
+        if (lane >= d) c_incl += v;
+    }
+    const uint32_t c_excl = c_incl - cnt;
+    const uint32_t total = __shfl_sync(0xffffffffu, c_incl, 31);
+    const uint32_t mlo = (uint32_t)mask, mhi = (uint32_t)(mask >> 32);
+    for (uint32_t jb = 0; jb < total; jb += 32) {
+        const uint32_t j = jb + lane;
+        int lo = 0;  // owner = last lane whose exclusive count is <= j (lanes with no instances share their successor's)
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const uint32_t o = __shfl_sync(0xffffffffu, c_excl, lo + step);
+            if (o <= j) lo += step;
+        }
+        const uint32_t g_o = __shfl_sync(0xffffffffu, g, lo), off_o = __shfl_sync(0xffffffffu, off, lo);
+        const uint32_t ce_o = __shfl_sync(0xffffffffu, c_excl, lo);
+        const uint32_t rect_o = __shfl_sync(0xffffffffu, rect, lo), w_o = __shfl_sync(0xffffffffu, w, lo);
+        const uint32_t mlo_o = __shfl_sync(0xffffffffu, mlo, lo), mhi_o = __shfl_sync(0xffffffffu, mhi, lo);
+        if (j >= total) continue;
+        const int k = (int)(j - ce_o);
+        unsigned long long m = (unsigned long long)mlo_o | ((unsigned long long)mhi_o << 32);
+        for (int q = 0; q < k; q++) m &= m - 1;  // drop the k lowest set bits
+        const int t = __ffsll((long long)m) - 1;
+        // t / w without an integer division: (t + 0.5) / w is at least 0.5/w away from an integer
+        const int ty = __float2int_rd(((float)t + 0.5f) * (1.0f / (float)w_o)), tx = t - ty * (int)w_o;
+        const int tile_x = (int)(rect_o & 0xffffu) + tx, tile_y = (int)(rect_o >> 16) + ty;
+        float4 cr = make_float4(0.f, 0.f, 0.f, 0.f), q0 = cr, q1 = cr;
+        float r2 = 0.0f;
+        if (packed) {
+            cr = __ldg(cull4 + g_o);
+            const float4* q = cullq + (size_t)g_o * 3;
+            q0 = __ldg(q); q1 = __ldg(q + 1); r2 = __ldg(q + 2).x;
+        }
+        tile_keys[off_o + k] = (uint32_t)(tile_y * gx + tile_x);
+        gauss_ids[off_o + k] = make_entry(g_o, tile_x, tile_y, packed, cr, q0, q1, r2);
+    }
+}
+
+// Footprints of more than 64 tiles: one CTA per queued Gaussian, every tile of its getRect rectangle (row-major).
+__global__ void __launch_bounds__(256)
+emit_big_kernel(const uint32_t* __restrict__ big_count, const uint2* __restrict__ big_list,
+                const int* __restrict__ radii, const Splat* __restrict__ splats, const float4* __restrict__ cull4,
+                const float4* __restrict__ cullq, int gx, int gy, int W, int H, int packed,
+                uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ gauss_ids) {
+    const uint32_t n_big = *big_count;
+    for (uint32_t e = blockIdx.x; e < n_big; e += gridDim.x) {
+        const uint2 it = big_list[e];
+        const uint32_t g = it.x, off = it.y;
+        int mnx, mny, mxx, mxy;
+        get_rect(splats[g].mx, splats[g].my, radii[g], gx, gy, mnx, mny, mxx, mxy);
+        const int w = mxx - mnx, n = w * (mxy - mny);
+        const float inv_w = 1.0f / (float)w;
+        float4 cr = make_float4(0.f, 0.f, 0.f, 0.f), q0 = cr, q1 = cr;
+        float r2 = 0.0f;
+        if (packed) {
+            cr = __ldg(cull4 + g);
+            const float4* q = cullq + (size_t)g * 3;
+            q0 = __ldg(q); q1 = __ldg(q + 1); r2 = __ldg(q + 2).x;
+        }
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            const int ty = __float2int_rd(((float)t + 0.5f) * inv_w), tx = t - ty * w;
+            tile_keys[off + t] = (uint32_t)((mny + ty) * gx + (mnx + tx));
+            gauss_ids[off + t] = make_entry(g, mnx + tx, mny + ty, packed, cr, q0, q1, r2);
         }
     }
 }
@@ -204,10 +293,21 @@ int launch_binning(const IsrForwardArgs& a, int64_t R, cudaStream_t stream) {
     uint32_t* point_list_alt = reinterpret_cast<uint32_t*>(b + bl.point_list_alt);
     uint32_t* tile_keys = reinterpret_cast<uint32_t*>(b + bl.tile_keys);
     uint32_t* tile_keys_alt = reinterpret_cast<uint32_t*>(b + bl.tile_keys_alt);
+    uint32_t* big_count = reinterpret_cast<uint32_t*>(g + gl.counters) + 1;
+    uint2* big_list = reinterpret_cast<uint2*>(g + gl.big_list);
+    const int packed = entries_packed(P) ? 1 : 0;
+    ISR_CUDA_TRY(cudaMemsetAsync(big_count, 0, sizeof(uint32_t), stream));
     emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
         P, reinterpret_cast<const uint32_t*>(g + gl.order), reinterpret_cast<const uint32_t*>(g + gl.offsets), a.radii,
-        reinterpret_cast<const Splat*>(g + gl.splat), reinterpret_cast<const unsigned long long*>(g + gl.tmask), gx, gy,
-        tile_keys_alt, point_list_alt);
+        reinterpret_cast<const Splat*>(g + gl.splat), reinterpret_cast<const unsigned long long*>(g + gl.tmask),
+        reinterpret_cast<const uint32_t*>(g + gl.tcount), reinterpret_cast<const float4*>(g + gl.cull),
+        reinterpret_cast<const float4*>(g + gl.cullq), gx, gy, a.W, a.H, packed, tile_keys_alt, point_list_alt, big_count,
+        big_list);
+    ISR_CUDA_TRY(cudaGetLastError());
+    emit_big_kernel<<<592, 256, 0, stream>>>(big_count, big_list, a.radii, reinterpret_cast<const Splat*>(g + gl.splat),
+                                             reinterpret_cast<const float4*>(g + gl.cull),
+                                             reinterpret_cast<const float4*>(g + gl.cullq), gx, gy, a.W, a.H, packed,
+                                             tile_keys_alt, point_list_alt);
     ISR_CUDA_TRY(cudaGetLastError());
     int bits = 1;
     while ((1 << bits) < num_tiles) bits++;

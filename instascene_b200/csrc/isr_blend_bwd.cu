@@ -46,7 +46,6 @@ template <int FP>
 struct BwdSmem {
     static constexpr int kRecF4 = 4 + 1 + FP / 4;  // splat (4 x float4) + rgb (1) + features
     static constexpr size_t per_warp = (size_t)32 * kRecF4 * 16 + 32 * 8;
-    static constexpr size_t bytes = 8 * per_warp;
 };
 
 __device__ __forceinline__ void cp_async16_b(void* smem_dst, const void* gmem_src) {
@@ -56,8 +55,9 @@ __device__ __forceinline__ void cp_async16_b(void* smem_dst, const void* gmem_sr
 
 // Same warp-autonomous structure as blend_fwd_kernel, walking the list BACK to front: per-warp cull-rectangle test
 // (exact: a culled Gaussian contributed to no pixel of the block in the forward), cp.async staging of survivors.
-template <int FP>
-__global__ void __launch_bounds__(256, FP == 0 ? 3 : 1)
+// kWarps: warps (8x4 pixel blocks) per CTA, as in blend_fwd_kernel (the warps never cooperate).
+template <int FP, int kWarps>
+__global__ void __launch_bounds__(32 * kWarps, (FP == 0 ? 24 : 8) / kWarps)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int F,
                  const float* __restrict__ bg, const float4* __restrict__ splats, const float4* __restrict__ cull4,
                  const float4* __restrict__ cullq, const float4* __restrict__ rgb4, const float* __restrict__ extras,
@@ -65,19 +65,22 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                  const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
                  const float* __restrict__ dL_dothers, const float* __restrict__ dL_dpix_extra,
                  float* __restrict__ dL_dtransMat, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dnormal3D,
-                 float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolors, float* __restrict__ dL_dextras) {
+                 float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolors, float* __restrict__ dL_dextras,
+                 int packed) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int REC = BwdSmem<FP>::kRecF4;
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    unsigned char* wbase = smem_raw + (size_t)warp * BwdSmem<FP>::per_warp;
+    const int lane = tid & 31;
+    unsigned char* wbase = smem_raw + (size_t)(tid >> 5) * BwdSmem<FP>::per_warp;
     float4* slots = reinterpret_cast<float4*>(wbase);                     // [32][REC]
     int2* meta = reinterpret_cast<int2*>(wbase + (size_t)32 * REC * 16);  // [32] (gaussian id, list index)
 
     const int tiles_x = (W + TILE - 1) / TILE;
-    const int tile_id = blockIdx.y * tiles_x + blockIdx.x;
-    const int wx0 = blockIdx.x * TILE + (warp & 1) * 8;
-    const int wy0 = blockIdx.y * TILE + (warp >> 1) * 4;
+    constexpr int kCtasPerTile = 8 / kWarps;
+    const int tile_id = blockIdx.x / kCtasPerTile;
+    const int warp = (blockIdx.x % kCtasPerTile) * kWarps + (tid >> 5);  // 8x4 block of the tile: 2 across, 4 down
+    const int wx0 = (tile_id % tiles_x) * TILE + (warp & 1) * 8;
+    const int wy0 = (tile_id / tiles_x) * TILE + (warp >> 1) * 4;
     const int pxi = wx0 + (lane & 7), pyi = wy0 + (lane >> 3);
     const bool inside = pxi < W && pyi < H;
     const size_t HW = (size_t)H * W;
@@ -149,24 +152,30 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     for (int off = 16; off > 0; off >>= 1) n_need = max(n_need, __shfl_xor_sync(0xffffffffu, n_need, off));
     n_need = min(n_need, n_total);
 
-    const float4 kEmpty = make_float4(1e30f, 1e30f, -1e30f, -1e30f);
-    // chunk with top index `top` covers list indices top-1-lane (lane 0 = last entry); pipeline registers as in fwd
+    // chunk with top index `top` covers list indices top-1-lane (lane 0 = last entry); entries one chunk ahead
     auto idx_of = [&](int top) { return top - 1 - lane; };
-    int id1 = (idx_of(n_need) >= 0) ? (int)__ldg(plist + idx_of(n_need)) : -1;
-    float4 cr1 = (id1 >= 0) ? __ldg(cull4 + id1) : kEmpty;
-    int id2 = (idx_of(n_need - 32) >= 0) ? (int)__ldg(plist + idx_of(n_need - 32)) : -1;
+    uint32_t ent_next = (idx_of(n_need) >= 0) ? __ldg(plist + idx_of(n_need)) : 0u;
 
     for (int top = n_need; top > 0; top -= 32) {
-        const int id = id1;
-        const float4 cr = cr1;
-        id1 = id2;
-        cr1 = (id1 >= 0) ? __ldg(cull4 + id1) : kEmpty;
-        id2 = (idx_of(top - 64) >= 0) ? (int)__ldg(plist + idx_of(top - 64)) : -1;
-
-        bool ov = (id >= 0) && !(cr.z < bx0 || cr.x > bx1 || cr.w < by0 || cr.y > by1);
-        if (ov) {
-            const float4* q = cullq + (size_t)id * 3;
-            ov = !block_outside(__ldg(q), __ldg(q + 1), __ldg(q + 2).x, bcx, bcy, bhx, bhy);
+        const uint32_t ent = ent_next;
+        const bool have = idx_of(top) >= 0;
+        ent_next = (idx_of(top - 32) >= 0) ? __ldg(plist + idx_of(top - 32)) : 0u;
+        int id;
+        bool ov;
+        if (packed) {  // per-block footprint bits computed at emission (isr_common.cuh)
+            id = (int)(ent & kIdMask);
+            ov = have && ((ent >> (kIdBits + warp)) & 1u);
+        } else {
+            id = (int)ent;
+            ov = have;
+            if (ov) {
+                const float4 cr = __ldg(cull4 + id);
+                ov = !(cr.z < bx0 || cr.x > bx1 || cr.w < by0 || cr.y > by1);
+            }
+            if (ov) {
+                const float4* q = cullq + (size_t)id * 3;
+                ov = !block_outside(__ldg(q), __ldg(q + 1), __ldg(q + 2).x, bcx, bcy, bhx, bhy);
+            }
         }
         const unsigned m = __ballot_sync(0xffffffffu, ov);
         if (m == 0) continue;
@@ -336,7 +345,7 @@ __global__ void __launch_bounds__(256)
 extra_sparse_bwd_kernel(int n, const int* __restrict__ pix_ids, const float* __restrict__ dLdE_samples, int W, int H,
                         int F, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                         const float4* __restrict__ splats, const float4* __restrict__ cull4,
-                        const uint32_t* __restrict__ n_contrib, float* __restrict__ dL_dextras) {
+                        const uint32_t* __restrict__ n_contrib, float* __restrict__ dL_dextras, int packed) {
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp_global >= n) return;
@@ -352,20 +361,26 @@ extra_sparse_bwd_kernel(int n, const int* __restrict__ pix_ids, const float* __r
     for (int ch = 0; ch < FP; ch++) dE[ch] = (ch < F) ? dLdE_samples[(size_t)warp_global * F + ch] : 0.0f;
     float T = 1.0f;  // transmittance in front of the current group of 32 (warp-uniform)
     const uint32_t* __restrict__ plist = point_list + range.x;
-    const float4 kEmpty = make_float4(1e30f, 1e30f, -1e30f, -1e30f);
-    // software pipeline (as in blend_fwd_kernel): ids two chunks ahead, cull rectangles one chunk ahead
-    int id1 = (lane < last) ? (int)__ldg(plist + lane) : -1;
-    float4 cr1 = (id1 >= 0) ? __ldg(cull4 + id1) : kEmpty;
-    int id2 = (32 + lane < last) ? (int)__ldg(plist + 32 + lane) : -1;
+    const int blk = ((pyi % TILE) / 4) * 2 + (pxi % TILE) / 8;  // the pixel's 8x4 block of its tile
+    uint32_t ent_next = (lane < last) ? __ldg(plist + lane) : 0u;  // entries one chunk ahead
     for (int base = 0; base < last; base += 32) {
-        const int g = id1;
-        const float4 cr = cr1;
-        id1 = id2;
-        cr1 = (id1 >= 0) ? __ldg(cull4 + id1) : kEmpty;
-        id2 = (base + 64 + lane < last) ? (int)__ldg(plist + base + 64 + lane) : -1;
+        const uint32_t ent = ent_next;
+        const bool have = base + lane < last;
+        ent_next = (base + 32 + lane < last) ? __ldg(plist + base + 32 + lane) : 0u;
         float alpha = 0.0f;
-        // exact pre-test: the pixel lies outside the Gaussian's conservative cull rectangle
-        const bool cand = (g >= 0) && !(cr.z < pixx || cr.x > pixx || cr.w < pixy || cr.y > pixy);
+        int g;
+        bool cand;
+        if (packed) {  // the entry says whether the Gaussian can reach this pixel's block at all
+            g = (int)(ent & kIdMask);
+            cand = have && ((ent >> (kIdBits + blk)) & 1u);
+        } else {  // exact pre-test: the pixel lies outside the Gaussian's conservative cull rectangle
+            g = (int)ent;
+            cand = have;
+            if (cand) {
+                const float4 cr = __ldg(cull4 + g);
+                cand = !(cr.z < pixx || cr.x > pixx || cr.w < pixy || cr.y > pixy);
+            }
+        }
         if (!__any_sync(0xffffffffu, cand)) continue;
         if (cand) {
             float s[16];
@@ -388,7 +403,7 @@ extra_sparse_bwd_kernel(int n, const int* __restrict__ pix_ids, const float* __r
             if (lane == l) Tin = T;
             T = mul(T, sub(1.0f, a_l));
         }
-        if (alpha != 0.0f && g >= 0) {
+        if (alpha != 0.0f) {
             const float w = mul(alpha, Tin);
             if ((F & 3) == 0) {  // 16-byte vector reductions (red.global.add.v4.f32): 4x fewer atomic operations
                 float4* dst = reinterpret_cast<float4*>(dL_dextras + (size_t)g * F);
@@ -416,22 +431,24 @@ static int launch_bwd_one(const IsrBackwardArgs& a, cudaStream_t stream) {
     const char* g = static_cast<const char*>(a.geom);
     const char* im = static_cast<const char*>(a.image);
     const char* b = static_cast<const char*>(a.binning);
-    const dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE);
-    const size_t smem = BwdSmem<FP>::bytes;
-    auto kern = blend_bwd_kernel<FP>;
-    ISR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int num_tiles = ((a.W + TILE - 1) / TILE) * ((a.H + TILE - 1) / TILE);
     const unsigned m = a.grad_mask;
-    kern<<<grid, 256, smem, stream>>>(
-        reinterpret_cast<const uint2*>(im + il.ranges), reinterpret_cast<const uint32_t*>(b), a.W, a.H, a.F, a.background,
-        reinterpret_cast<const float4*>(g + gl.splat), reinterpret_cast<const float4*>(g + gl.cull),
-        reinterpret_cast<const float4*>(g + gl.cullq), reinterpret_cast<const float4*>(g + gl.rgb), a.extra_attrs,
-        reinterpret_cast<const float*>(im + il.final_T), reinterpret_cast<const uint32_t*>(im + il.n_contrib), a.dL_dcolor,
-        a.dL_dothers, a.dL_dextra_pix, (m & ISR_GRAD_GEOMETRY) ? a.dL_dtransMat : nullptr,
-        (m & ISR_GRAD_GEOMETRY) ? a.dL_dmeans2D : nullptr, (m & ISR_GRAD_GEOMETRY) ? a.dL_dnormal : nullptr,
-        (m & ISR_GRAD_OPACITY) ? a.dL_dopacity : nullptr, (m & ISR_GRAD_COLOR) ? a.dL_dcolors : nullptr,
-        (m & ISR_GRAD_EXTRA) ? a.dL_dextra : nullptr);
-    ISR_CUDA_TRY(cudaGetLastError());
-    return ISR_OK;
+    auto launch = [&](auto kern, int w) -> int {
+        const size_t smem = (size_t)w * BwdSmem<FP>::per_warp;
+        ISR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<num_tiles * (8 / w), 32 * w, smem, stream>>>(
+            reinterpret_cast<const uint2*>(im + il.ranges), reinterpret_cast<const uint32_t*>(b), a.W, a.H, a.F, a.background,
+            reinterpret_cast<const float4*>(g + gl.splat), reinterpret_cast<const float4*>(g + gl.cull),
+            reinterpret_cast<const float4*>(g + gl.cullq), reinterpret_cast<const float4*>(g + gl.rgb), a.extra_attrs,
+            reinterpret_cast<const float*>(im + il.final_T), reinterpret_cast<const uint32_t*>(im + il.n_contrib), a.dL_dcolor,
+            a.dL_dothers, a.dL_dextra_pix, (m & ISR_GRAD_GEOMETRY) ? a.dL_dtransMat : nullptr,
+            (m & ISR_GRAD_GEOMETRY) ? a.dL_dmeans2D : nullptr, (m & ISR_GRAD_GEOMETRY) ? a.dL_dnormal : nullptr,
+            (m & ISR_GRAD_OPACITY) ? a.dL_dopacity : nullptr, (m & ISR_GRAD_COLOR) ? a.dL_dcolors : nullptr,
+            (m & ISR_GRAD_EXTRA) ? a.dL_dextra : nullptr, entries_packed(a.P) ? 1 : 0);
+        ISR_CUDA_TRY(cudaGetLastError());
+        return ISR_OK;
+    };
+    return launch(blend_bwd_kernel<FP, 2>, 2);  // measured at cfg2: 2-warp CTAs are 8% faster than whole-tile CTAs
 }
 
 int launch_blend_bwd(const IsrBackwardArgs& a, cudaStream_t stream) {
@@ -457,7 +474,8 @@ static int launch_sparse_one(int P, int F, int W, int H, const void* geom, const
     extra_sparse_bwd_kernel<FP><<<(n + warps_per_block - 1) / warps_per_block, 256, 0, stream>>>(
         n, pix_ids, dLdE, W, H, F, reinterpret_cast<const uint2*>(im + il.ranges),
         reinterpret_cast<const uint32_t*>(binning), reinterpret_cast<const float4*>(g + gl.splat),
-        reinterpret_cast<const float4*>(g + gl.cull), reinterpret_cast<const uint32_t*>(im + il.n_contrib), dL_dextra);
+        reinterpret_cast<const float4*>(g + gl.cull), reinterpret_cast<const uint32_t*>(im + il.n_contrib), dL_dextra,
+        entries_packed(P) ? 1 : 0);
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }

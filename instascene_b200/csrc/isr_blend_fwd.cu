@@ -2,8 +2,8 @@
 // feature channels + the (gaussian, pixel) pair list.   Reference: DSR/cuda_rasterizer/forward.cu:256-462.
 //
 // Mapping: one CTA (256 threads) per 16x16 tile, one thread per pixel, a warp per 8x4 pixel block.  Warps are
-// autonomous (see blend_fwd_kernel): per-warp exact culling against a conservative per-Gaussian rectangle computed
-// in K1, cp.async staging of the surviving records (splat 64 B, rgb 16 B, features 4F B) into warp-private shared
+// autonomous (see blend_fwd_kernel): per-warp culling by the per-block footprint bits carried in the list entries
+// (computed at emission from a conservative per-Gaussian footprint of K1), cp.async staging of the surviving records (splat 64 B, rgb 16 B, features 4F B) into warp-private shared
 // memory, broadcast reads in the inner loop (the reference fetches rgb and features from global per contributing
 // (pixel, Gaussian) pair), no block-wide barriers.  Pair-list entries are staged per warp in shared memory and
 // flushed with one global atomic per <= 96 pairs (the reference: one global atomic per pair on a single counter).
@@ -34,8 +34,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // with broadcast shared-memory reads.  There is no block-wide barrier: warps of a tile neither wait for each other
 // nor for the slowest pixel of the tile, and a warp stops as soon as its own 32 pixels are saturated.
 // kWarps: warps (8x4 pixel blocks) per CTA; the warps never cooperate, so a CTA is just a scheduling unit: with 8 a
-// CTA is a whole tile and its slot stays occupied until the slowest of its 8 blocks is done.  kWarpsPerSM: occupancy
-// target that sets the register budget (24 -> 80 registers, 32 -> 64).
+// CTA is a whole tile and its slot stays occupied until the slowest of its 8 blocks is done (measured: 2-warp CTAs are
+// 3.5% faster at cfg3).  kWarpsPerSM: occupancy target that sets the register budget (24 -> 80 registers, 28 -> 72,
+// 32 -> 64).
 template <int FP, bool kPairs, int kWarpsPerSM, int kWarps>
 __global__ void __launch_bounds__(32 * kWarps, kWarpsPerSM / kWarps)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int F,
@@ -43,7 +44,8 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                  const float4* __restrict__ rgb4, const float* __restrict__ extras, const float* __restrict__ bg,
                  float* __restrict__ final_T,
                  uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, float* __restrict__ out_others,
-                 float* __restrict__ out_extra, int2* __restrict__ pairs, int64_t pair_cap, int* __restrict__ pair_count) {
+                 float* __restrict__ out_extra, int2* __restrict__ pairs, int64_t pair_cap, int* __restrict__ pair_count,
+                 int packed) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int REC = FwdSmem<FP>::kRecF4;
     const int tid = threadIdx.x;
@@ -84,24 +86,31 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     for (int ch = 0; ch < FP / 2; ch++) E[ch] = make_float2(0.f, 0.f);
     int wcount = 0;  // staged pairs of this warp (warp-uniform)
 
-    const float4 kEmpty = make_float4(1e30f, 1e30f, -1e30f, -1e30f);
-    // software pipeline registers: ids of chunk c+1 / c+2, cull rect of chunk c+1
-    int id1 = (lane < n_total) ? (int)__ldg(plist + lane) : -1;
-    float4 cr1 = (id1 >= 0) ? __ldg(cull4 + id1) : kEmpty;
-    int id2 = (32 + lane < n_total) ? (int)__ldg(plist + 32 + lane) : -1;
+    // list entries are fetched one chunk ahead.  Packed entries (isr_common.cuh) carry the "may reach block b of the
+    // tile" bits computed at emission; plain entries (>= 2^24 Gaussians) are tested against the footprint data here.
+    uint32_t ent_next = (lane < n_total) ? __ldg(plist + lane) : 0u;
 
     for (int base = 0; base < n_total; base += 32) {
         if (__all_sync(0xffffffffu, done)) break;
-        const int id = id1;
-        const float4 cr = cr1;
-        id1 = id2;
-        cr1 = (id1 >= 0) ? __ldg(cull4 + id1) : kEmpty;
-        id2 = (base + 64 + lane < n_total) ? (int)__ldg(plist + base + 64 + lane) : -1;
-
-        bool ov = (id >= 0) && !(cr.z < bx0 || cr.x > bx1 || cr.w < by0 || cr.y > by1);
-        if (ov) {  // second stage: the conic itself against the block (corner overlaps of the rectangle)
-            const float4* q = cullq + (size_t)id * 3;
-            ov = !block_outside(__ldg(q), __ldg(q + 1), __ldg(q + 2).x, bcx, bcy, bhx, bhy);
+        const uint32_t ent = ent_next;
+        const bool have = base + lane < n_total;
+        ent_next = (base + 32 + lane < n_total) ? __ldg(plist + base + 32 + lane) : 0u;
+        int id;
+        bool ov;
+        if (packed) {
+            id = (int)(ent & kIdMask);
+            ov = have && ((ent >> (kIdBits + warp)) & 1u);
+        } else {
+            id = (int)ent;
+            ov = have;
+            if (ov) {
+                const float4 cr = __ldg(cull4 + id);
+                ov = !(cr.z < bx0 || cr.x > bx1 || cr.w < by0 || cr.y > by1);
+            }
+            if (ov) {  // second stage: the conic itself against the block (corner overlaps of the rectangle)
+                const float4* q = cullq + (size_t)id * 3;
+                ov = !block_outside(__ldg(q), __ldg(q + 1), __ldg(q + 2).x, bcx, bcy, bhx, bhy);
+            }
         }
         const unsigned m = __ballot_sync(0xffffffffu, ov);
         if (m == 0) continue;
@@ -234,12 +243,11 @@ static int launch_one(const IsrForwardArgs& a, cudaStream_t stream) {
     char* im = static_cast<char*>(a.image);
     const char* b = static_cast<const char*>(a.binning);
     const int num_tiles = ((a.W + TILE - 1) / TILE) * ((a.H + TILE - 1) / TILE);
-    // occupancy variant: 32 warps/SM (64 registers) or 24 warps/SM (80 registers, no spills); ISR_FWD_MINBLOCKS
-    // (4 or 3 CTAs of 8 warps) and ISR_FWD_WARPS (warps per CTA) override
-    static const int env_mb = [] { const char* e = getenv("ISR_FWD_MINBLOCKS"); return e ? atoi(e) : 0; }();
-    static const int env_w = [] { const char* e = getenv("ISR_FWD_WARPS"); return e ? atoi(e) : 0; }();
-    const int mb = env_mb ? env_mb : (FP < 16 ? 4 : 3);  // measured at cfg3 (F=16): 24 warps/SM, no spills, is 6% faster
-    const int warps = (env_w == 8 || env_w == 2) ? env_w : 2;
+    // Occupancy variant = register budget: 32 warps/SM (64 registers), 28 (72) or 24 (80); the default is the largest
+    // that compiles without spills for this F (measured at cfg3, F=16: 28 beats 24 by 5% and 32 by 6%).
+    // ISR_FWD_WARPS_PER_SM overrides (24 / 28 / 32).
+    static const int env_wps = [] { const char* e = getenv("ISR_FWD_WARPS_PER_SM"); return e ? atoi(e) : 0; }();
+    const int wps = env_wps ? env_wps : (FP <= 8 ? 32 : (FP <= 24 ? 28 : 24));
     auto launch = [&](auto kern, int w) -> int {
         const size_t smem = (size_t)w * FwdSmem<FP>::per_warp;
         ISR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -248,12 +256,14 @@ static int launch_one(const IsrForwardArgs& a, cudaStream_t stream) {
             a.W, a.H, a.F, reinterpret_cast<const float4*>(g + gl.splat), reinterpret_cast<const float4*>(g + gl.cull),
             reinterpret_cast<const float4*>(g + gl.cullq), reinterpret_cast<const float4*>(g + gl.rgb), a.extra_attrs, a.background,
             reinterpret_cast<float*>(im + il.final_T), reinterpret_cast<uint32_t*>(im + il.n_contrib), a.out_color,
-            a.out_others, a.out_extra, reinterpret_cast<int2*>(a.pairs), a.pair_capacity, a.pair_count);
+            a.out_others, a.out_extra, reinterpret_cast<int2*>(a.pairs), a.pair_capacity, a.pair_count,
+            entries_packed(a.P) ? 1 : 0);
         ISR_CUDA_TRY(cudaGetLastError());
         return ISR_OK;
     };
-    if (warps == 8) return (mb >= 4) ? launch(blend_fwd_kernel<FP, kPairs, 32, 8>, 8) : launch(blend_fwd_kernel<FP, kPairs, 24, 8>, 8);
-    return (mb >= 4) ? launch(blend_fwd_kernel<FP, kPairs, 32, 2>, 2) : launch(blend_fwd_kernel<FP, kPairs, 24, 2>, 2);
+    if (wps >= 32) return launch(blend_fwd_kernel<FP, kPairs, 32, 2>, 2);
+    if (wps >= 28) return launch(blend_fwd_kernel<FP, kPairs, 28, 2>, 2);
+    return launch(blend_fwd_kernel<FP, kPairs, 24, 2>, 2);
 }
 
 template <bool kPairs>

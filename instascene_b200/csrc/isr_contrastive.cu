@@ -16,19 +16,20 @@
 
 namespace isr {
 
-// Workspace: f^ [N,F], 1/(|f|+eps) [N], counts [K], u [K,F], phi [K], coefT [K,N] (softmax coefficients, CLUSTER-major
-// so that both the per-cluster reductions and the per-sample reads are coalesced), dU [K,F].
+// Workspace.  `zeroed` (cluster sums [K,F], counts [K], spreads [K], dU [K,F]) is cleared once per forward.
 struct ContrastWs {
-    size_t fhat, inv_norm, counts, u, phi, coef, dU, total;
+    size_t fhat, inv_norm, g, zeroed, sums, counts, spread, dU, zeroed_bytes, total;
     ContrastWs(int N, int F, int K) {
         size_t o = 0;
         fhat = o;     o = align_up(o + (size_t)N * F * 4, 256);
         inv_norm = o; o = align_up(o + (size_t)N * 4, 256);
-        counts = o;   o = align_up(o + (size_t)K * 4, 256);
-        u = o;        o = align_up(o + (size_t)K * F * 4, 256);
-        phi = o;      o = align_up(o + (size_t)K * 4, 256);
-        coef = o;     o = align_up(o + (size_t)N * K * 4, 256);
+        g = o;        o = align_up(o + (size_t)N * F * 4, 256);   // sum_k coef_ik u_k (backward, without the dU term)
+        zeroed = o;
+        sums = o;     o = align_up(o + (size_t)K * F * 4, 16);
+        counts = o;   o = align_up(o + (size_t)K * 4, 16);
+        spread = o;   o = align_up(o + (size_t)K * 4, 16);
         dU = o;       o = align_up(o + (size_t)K * F * 4, 256);
+        zeroed_bytes = o - zeroed;
         total = o;
     }
 };
@@ -42,183 +43,250 @@ __global__ void gather_pixels_kernel(int F, int64_t HW, const float* __restrict_
     out[i] = (pix >= 0 && pix < HW) ? map[(size_t)ch * HW + pix] : 0.0f;
 }
 
-// 1. per sample: f^ = f / (|f| + 1e-9)
-__global__ void contrast_normalise_kernel(int N, int F, const float* __restrict__ feat, float* __restrict__ fhat,
-                                          float* __restrict__ inv_norm) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    float ss = 0.0f;
-    for (int c = 0; c < F; c++) { const float v = feat[(size_t)i * F + c]; ss = fmaf(v, v, ss); }
-    const float inv = 1.0f / (sqrtf(ss) + 1e-9f);
-    inv_norm[i] = inv;
-    for (int c = 0; c < F; c++) fhat[(size_t)i * F + c] = feat[(size_t)i * F + c] * inv;
-}
+// The loss is evaluated in four grid-wide phases (each needs a reduction over ALL samples of the previous one), every
+// phase one kernel of ceil(N/256) blocks x 256 threads, one sample per thread:
+//   stats   f^ = f/(|f|+1e-9); per-cluster sums and counts
+//   spread  u_k = mean (or predefined prototype); per-cluster sum of |f^ - u_k|
+//   loss    phi_k; logits, loss, softmax coefficients coef_ik = (p_ik - [k == y_i]) / phi_k (never stored: a block keeps
+//           64 clusters x 256 samples of them in shared memory), g_i = sum_k coef_ik u_k, dU_k = sum_i coef_ik f^_i
+//   dfeat   (backward) dL/df_i = grad_scale / (|f_i| + eps) * (g_i + [means] dU[y_i] / n_{y_i})
+// Per-cluster block reductions are "owner computes": the block's samples and labels sit in shared memory and a thread
+// sums the members of the (cluster, channel) entries it owns -- no shared-memory float atomics (CAS loops on this
+// target); one global red per entry per block.
+constexpr int kCB = 256;   // samples per block
+constexpr int kKC = 64;    // clusters per coefficient chunk
 
-// sum over the whole block (up to 1024 threads); s_red must hold 32 floats
+// sum over the block (kCB threads); s_red must hold kCB/32 floats
 __device__ __forceinline__ float block_sum(float v, float* s_red) {
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
     __syncthreads();
     float t = 0.0f;
-    const int nw = (blockDim.x + 31) >> 5;
-    for (int w = 0; w < nw; w++) t += s_red[w];
+    for (int w = 0; w < kCB / 32; w++) t += s_red[w];
     return t;
 }
 
-// 2. one block per cluster k: count, centre u_k (mean of members or predefined prototype), temperature phi_k.
-//    No atomics, deterministic; the label vector (N ints) is re-read by every block from L2.
-__global__ void __launch_bounds__(1024)
-contrast_cluster_kernel(int N, int F, int K, const float* __restrict__ fhat, const int* __restrict__ labels,
-                        const float* __restrict__ predef_u, float temp_lambda, int* __restrict__ counts,
-                        float* __restrict__ u, float* __restrict__ phi) {
-    __shared__ float s_red[32];
-    __shared__ float s_u[ISR_MAX_EXTRA_DIMS];
-    const int k = blockIdx.x;
-    float cnt = 0.0f, acc[ISR_MAX_EXTRA_DIMS];
-    for (int c = 0; c < F; c++) acc[c] = 0.0f;
-    for (int i = threadIdx.x; i < N; i += blockDim.x)
-        if (__ldg(labels + i) == k) {
-            cnt += 1.0f;
-            if (predef_u == nullptr)
-                for (int c = 0; c < F; c++) acc[c] += fhat[(size_t)i * F + c];
+// block partial of  out[k][c] += sum_{i in block, label_i == k} w_i * sf[i][c]   for k in [k0, k0+nk)
+// (w == nullptr: w_i = 1).  sw is indexed [k - k0][i] when per-cluster weights are given (kPerCluster).
+template <bool kPerCluster>
+__device__ __forceinline__ void owner_accumulate(int F, int FS, int k0, int nk, const float* __restrict__ sf,
+                                                 const int* __restrict__ sl, const float* __restrict__ sw,
+                                                 float* __restrict__ out) {
+    if ((F & 3) == 0) {
+        const int F4 = F >> 2;
+        for (int e = threadIdx.x; e < nk * F4; e += kCB) {
+            const int kk = e / F4, c4 = e - kk * F4, k = k0 + kk;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < kCB; i++) {
+                float w;
+                if (kPerCluster) { w = sw[kk * kCB + i]; if (w == 0.0f) continue; }
+                else { if (sl[i] != k) continue; w = 1.0f; }
+                const float4 f = *reinterpret_cast<const float4*>(sf + i * FS + 4 * c4);
+                acc.x = fmaf(w, f.x, acc.x); acc.y = fmaf(w, f.y, acc.y); acc.z = fmaf(w, f.z, acc.z); acc.w = fmaf(w, f.w, acc.w);
+            }
+            float* o = out + (size_t)k * F + 4 * c4;
+            if (acc.x != 0.0f) atomicAdd(o + 0, acc.x);
+            if (acc.y != 0.0f) atomicAdd(o + 1, acc.y);
+            if (acc.z != 0.0f) atomicAdd(o + 2, acc.z);
+            if (acc.w != 0.0f) atomicAdd(o + 3, acc.w);
         }
-    const float n = block_sum(cnt, s_red);
-    for (int c = 0; c < F; c++) {
-        float m;
-        if (predef_u != nullptr) m = predef_u[(size_t)k * F + c];
-        else { const float t = block_sum(acc[c], s_red); m = n > 0.0f ? t / n : 0.0f; }
-        if (threadIdx.x == 0) { s_u[c] = m; u[(size_t)k * F + c] = m; }
-    }
-    __syncthreads();
-    float spread = 0.0f;
-    for (int i = threadIdx.x; i < N; i += blockDim.x)
-        if (__ldg(labels + i) == k) {
-            float ss = 0.0f;
-            for (int c = 0; c < F; c++) { const float d = fhat[(size_t)i * F + c] - s_u[c]; ss = fmaf(d, d, ss); }
-            spread += sqrtf(ss);
+    } else {
+        for (int e = threadIdx.x; e < nk * F; e += kCB) {
+            const int kk = e / F, c = e - kk * F, k = k0 + kk;
+            float acc = 0.0f;
+            for (int i = 0; i < kCB; i++) {
+                float w;
+                if (kPerCluster) { w = sw[kk * kCB + i]; if (w == 0.0f) continue; }
+                else { if (sl[i] != k) continue; w = 1.0f; }
+                acc = fmaf(w, sf[i * FS + c], acc);
+            }
+            if (acc != 0.0f) atomicAdd(out + (size_t)k * F + c, acc);
         }
-    const float tot = block_sum(spread, s_red);
-    if (threadIdx.x == 0) {
-        counts[k] = (int)n;
-        phi[k] = n > 0.0f ? fminf(fmaxf(10.0f * (tot / (n * logf(n + temp_lambda))), 0.5f), 1.0f) : 1.0f;
     }
 }
 
-// 3. loss + softmax coefficients coefT[k][i] = (p_ik - [k == y_i]) / phi_k (0 for absent clusters / ignored samples).
-//    Four lanes per sample, each covering a quarter of the clusters; u and phi staged in shared memory.
-__global__ void __launch_bounds__(256)
-contrast_loss_kernel(int N, int F, int K, const float* __restrict__ fhat, const int* __restrict__ labels,
-                     const float* __restrict__ u, const float* __restrict__ phi, const int* __restrict__ counts,
-                     float* __restrict__ coefT, float* __restrict__ loss) {
-    extern __shared__ float s_u[];  // [K][F] then phi[K] (0 marks an absent cluster)
-    float* s_phi = s_u + (size_t)K * F;
-    for (int i = threadIdx.x; i < K * F; i += blockDim.x) s_u[i] = u[i];
-    for (int k = threadIdx.x; k < K; k += blockDim.x) s_phi[k] = counts[k] > 0 ? phi[k] : 0.0f;
+// shared-memory row stride of the block's sample matrix (16-byte aligned rows, odd multiple of 4 words: the owner
+// loops read one row at a time, so there is nothing to de-conflict beyond alignment)
+__host__ __device__ inline int sample_stride(int F) { return (F + 3) & ~3; }
+
+// phase 1   (FP: F padded to 4/8/16/24/32 so that the per-sample vectors stay in registers)
+template <int FP>
+__global__ void __launch_bounds__(kCB)
+contrast_stats_kernel(int N, int F, int K, const float* __restrict__ feat, const int* __restrict__ labels, bool want_sums,
+                      float* __restrict__ fhat, float* __restrict__ inv_norm, float* __restrict__ sums,
+                      float* __restrict__ counts, float* __restrict__ loss) {
+    extern __shared__ __align__(16) float smem[];
+    const int FS = sample_stride(F);
+    float* sf = smem;                                        // [kCB][FS]
+    int* sl = reinterpret_cast<int*>(smem + kCB * FS);       // [kCB]
+    const int i = blockIdx.x * kCB + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *loss = 0.0f;   // accumulated by phase 3
+    int y = -1;
+    if (i < N) {
+        y = labels[i];
+        if (y < 0 || y >= K) y = -1;
+        float v[FP], ss = 0.0f;
+#pragma unroll
+        for (int c = 0; c < FP; c++) { v[c] = c < F ? feat[(size_t)i * F + c] : 0.0f; ss = fmaf(v[c], v[c], ss); }
+        const float inv = 1.0f / (sqrtf(ss) + 1e-9f);
+        inv_norm[i] = inv;
+#pragma unroll
+        for (int c = 0; c < FP; c++)
+            if (c < F) { const float h = v[c] * inv; fhat[(size_t)i * F + c] = h; sf[threadIdx.x * FS + c] = h; }
+    }
+    sl[threadIdx.x] = y;
     __syncthreads();
-    const int q = threadIdx.x & 3;                          // quarter of the clusters
-    const int i = blockIdx.x * 64 + (threadIdx.x >> 2);     // sample
-    const int kq = (K + 3) / 4, k0 = q * kq, k1 = min(K, k0 + kq);
-    float li = 0.0f;
-    const bool in_range = i < N;
-    const int y = in_range ? labels[i] : -1;
-    const bool valid = in_range && y >= 0 && y < K;
-    float f[ISR_MAX_EXTRA_DIMS];
-    if (in_range) for (int c = 0; c < F; c++) f[c] = fhat[(size_t)i * F + c];
+    for (int k = threadIdx.x; k < K; k += kCB) {
+        int n = 0;
+        for (int j = 0; j < kCB; j++) n += (sl[j] == k);
+        if (n) atomicAdd(counts + k, (float)n);
+    }
+    if (want_sums) owner_accumulate<false>(F, FS, 0, K, sf, sl, nullptr, sums);
+}
+
+// u_k into shared memory: predefined prototype or mean of the members (0 for an absent cluster)
+__device__ __forceinline__ void load_centres(int F, int K, const float* __restrict__ predef_u,
+                                             const float* __restrict__ sums, const float* __restrict__ counts,
+                                             float* __restrict__ su) {
+    for (int e = threadIdx.x; e < K * F; e += kCB) {
+        const int k = e / F;
+        const float n = counts[k];
+        su[e] = predef_u ? predef_u[e] : (n > 0.0f ? sums[e] / n : 0.0f);
+    }
+}
+
+// phase 2
+__global__ void __launch_bounds__(kCB)
+contrast_spread_kernel(int N, int F, int K, const float* __restrict__ fhat, const int* __restrict__ labels,
+                       const float* __restrict__ predef_u, const float* __restrict__ sums,
+                       const float* __restrict__ counts, float* __restrict__ spread) {
+    extern __shared__ __align__(16) float smem[];
+    float* su = smem;                                   // [K][F]
+    float* sd = smem + (size_t)K * F;                   // [kCB]
+    int* sl = reinterpret_cast<int*>(sd + kCB);         // [kCB]
+    load_centres(F, K, predef_u, sums, counts, su);
+    __syncthreads();
+    const int i = blockIdx.x * kCB + threadIdx.x;
+    int y = -1;
+    float d = 0.0f;
+    if (i < N) {
+        y = labels[i];
+        if (y < 0 || y >= K) y = -1;
+        if (y >= 0) {
+            float ss = 0.0f;
+            for (int c = 0; c < F; c++) { const float t = fhat[(size_t)i * F + c] - su[(size_t)y * F + c]; ss = fmaf(t, t, ss); }
+            d = sqrtf(ss);
+        }
+    }
+    sd[threadIdx.x] = d;
+    sl[threadIdx.x] = y;
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += kCB) {
+        float s = 0.0f;
+        for (int j = 0; j < kCB; j++) if (sl[j] == k) s += sd[j];
+        if (s != 0.0f) atomicAdd(spread + k, s);
+    }
+}
+
+// phase 3
+template <int FP>
+__global__ void __launch_bounds__(kCB)
+contrast_loss_kernel(int N, int F, int K, const float* __restrict__ fhat, const int* __restrict__ labels,
+                     const float* __restrict__ predef_u, const float* __restrict__ sums,
+                     const float* __restrict__ counts, const float* __restrict__ spread, float temp_lambda,
+                     float* __restrict__ g_out, float* __restrict__ dU, float* __restrict__ loss) {
+    extern __shared__ __align__(16) float smem[];
+    const int FS = sample_stride(F);
+    float* su = smem;                                   // [K][F]
+    float* sphi = su + (size_t)K * F;                   // [K]  1/phi_k, 0 for an absent cluster
+    float* sf = sphi + ((K + 3) & ~3);                  // [kCB][FS]
+    float* sw = sf + kCB * FS;                          // [kKC][kCB] coefficient chunk
+    __shared__ float s_red[kCB / 32];
+    const bool means = predef_u == nullptr;
+    load_centres(F, K, predef_u, sums, counts, su);
+    for (int k = threadIdx.x; k < K; k += kCB) {
+        const float n = counts[k];
+        sphi[k] = n > 0.0f ? 1.0f / fminf(fmaxf(10.0f * (spread[k] / (n * logf(n + temp_lambda))), 0.5f), 1.0f) : 0.0f;
+    }
+    const int i = blockIdx.x * kCB + threadIdx.x;
+    int y = -1;
+    float f[FP];
+#pragma unroll
+    for (int c = 0; c < FP; c++) f[c] = 0.0f;
+    if (i < N) {
+        y = labels[i];
+        if (y < 0 || y >= K) y = -1;
+#pragma unroll
+        for (int c = 0; c < FP; c++)
+            if (c < F) { f[c] = fhat[(size_t)i * F + c]; sf[threadIdx.x * FS + c] = f[c]; }
+    }
+    __syncthreads();
+    const bool valid = y >= 0;
+    auto logit_exp = [&](int k) {  // exp(f . u_k / phi_k), 0 for an absent cluster
+        const float ip = sphi[k];
+        if (ip == 0.0f) return 0.0f;
+        float d0 = 0.0f, d1 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < FP; c += 2) {
+            if (c < F) d0 = fmaf(f[c], su[(size_t)k * F + c], d0);
+            if (c + 1 < F) d1 = fmaf(f[c + 1], su[(size_t)k * F + c + 1], d1);
+        }
+        return expf((d0 + d1) * ip);
+    };
     float sum = 0.0f, dy = 0.0f;
     if (valid)
-        for (int k = k0; k < k1; k++) {
-            const float ph = s_phi[k];
-            float e = 0.0f;
-            if (ph != 0.0f) {
-                float dot = 0.0f;
-                for (int c = 0; c < F; c++) dot = fmaf(f[c], s_u[(size_t)k * F + c], dot);
-                e = expf(dot / ph);
-                sum += e;
-                if (k == y) dy = e;
-            }
-            coefT[(size_t)k * N + i] = e;
-        }
-    // combine the four quarters (lanes 4j..4j+3 of a warp belong to one sample)
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1); sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    dy += __shfl_xor_sync(0xffffffffu, dy, 1);   dy += __shfl_xor_sync(0xffffffffu, dy, 2);
-    if (in_range) {
-        const float denom = sum + 1e-9f;
-        if (valid && q == 0) li = -logf(dy / denom);
-        for (int k = k0; k < k1; k++) {
-            const float ph = s_phi[k];
-            float cf = 0.0f;
-            if (valid && ph != 0.0f) cf = (coefT[(size_t)k * N + i] / denom - (k == y ? 1.0f : 0.0f)) / ph;
-            coefT[(size_t)k * N + i] = cf;
-        }
-    }
-    __shared__ float s_red[8];
-    for (int off = 16; off > 0; off >>= 1) li += __shfl_xor_sync(0xffffffffu, li, off);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = li;
-    __syncthreads();
-    if (threadIdx.x < 8) {
-        float v = s_red[threadIdx.x];
-        for (int off = 4; off > 0; off >>= 1) v += __shfl_xor_sync(0xffu, v, off);
-        if (threadIdx.x == 0) atomicAdd(loss, v);
-    }
-}
-
-// 4. dU[k][c] = sum_i coefT[k][i] * f^[i][c]: split over slabs of 128 samples; a thread owns the entries e = k*F + c with
-//    e = tid (mod 256): its coefficient reads run along the contiguous sample axis of coefT (16-byte loads, shared by
-//    the F threads of a cluster), its feature reads are coalesced across c.  One atomic per entry per slab.
-__global__ void __launch_bounds__(256)
-contrast_dU_kernel(int N, int F, int K, const float* __restrict__ coefT, const float* __restrict__ fhat,
-                   float* __restrict__ dU) {
-    constexpr int SLAB = 128;
-    const int i0 = blockIdx.x * SLAB, i1 = min(N, i0 + SLAB);
-    const int KF = K * F;
-    const bool vec = ((N & 3) == 0) && (i1 - i0 == SLAB);
-    for (int e = threadIdx.x; e < KF; e += 256) {
-        const int k = e / F, cch = e - k * F;
-        const float* cr = coefT + (size_t)k * N;
-        float acc = 0.0f;
-        if (vec) {
-            for (int i = i0; i < i1; i += 4) {
-                const float4 cf = __ldg(reinterpret_cast<const float4*>(cr + i));
-                acc = fmaf(cf.x, __ldg(fhat + (size_t)i * F + cch), acc);
-                acc = fmaf(cf.y, __ldg(fhat + (size_t)(i + 1) * F + cch), acc);
-                acc = fmaf(cf.z, __ldg(fhat + (size_t)(i + 2) * F + cch), acc);
-                acc = fmaf(cf.w, __ldg(fhat + (size_t)(i + 3) * F + cch), acc);
-            }
-        } else {
-            for (int i = i0; i < i1; i++) acc = fmaf(__ldg(cr + i), __ldg(fhat + (size_t)i * F + cch), acc);
-        }
-        if (acc != 0.0f) atomicAdd(dU + e, acc);
-    }
-}
-
-// 5. dL/df_i = grad_scale / (|f_i| + eps) * ( sum_k coefT[k][i] u_k  +  [means] dU[y_i] / n_{y_i} )
-__global__ void __launch_bounds__(256)
-contrast_dfeat_kernel(int N, int F, int K, const float* __restrict__ coefT, const int* __restrict__ labels,
-                      const float* __restrict__ u, const float* __restrict__ dU, const int* __restrict__ counts,
-                      const float* __restrict__ inv_norm, bool means, const float* __restrict__ grad_scale,
-                      float* __restrict__ dfeat) {
-    extern __shared__ float s_u[];  // [K][F]
-    for (int i = threadIdx.x; i < K * F; i += blockDim.x) s_u[i] = u[i];
-    __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const int y = labels[i];
-    float g[ISR_MAX_EXTRA_DIMS];
-    for (int c = 0; c < F; c++) g[c] = 0.0f;
-    if (y >= 0 && y < K) {
         for (int k = 0; k < K; k++) {
-            const float cf = __ldg(coefT + (size_t)k * N + i);
-            if (cf != 0.0f)
-                for (int c = 0; c < F; c++) g[c] = fmaf(cf, s_u[(size_t)k * F + c], g[c]);
+            const float e = logit_exp(k);
+            sum += e;
+            if (k == y) dy = e;
+        }
+    const float denom = sum + 1e-9f;
+    const float li = block_sum(valid ? -logf(dy / denom) : 0.0f, s_red);
+    if (threadIdx.x == 0 && li != 0.0f) atomicAdd(loss, li);
+    const float inv_denom = 1.0f / denom;
+    float g[FP];
+#pragma unroll
+    for (int c = 0; c < FP; c++) g[c] = 0.0f;
+    for (int k0 = 0; k0 < K; k0 += kKC) {
+        const int nk = min(kKC, K - k0);
+        for (int kk = 0; kk < nk; kk++) {
+            const int k = k0 + kk;
+            float cf = 0.0f;
+            if (valid && sphi[k] != 0.0f) {
+                cf = (logit_exp(k) * inv_denom - (k == y ? 1.0f : 0.0f)) * sphi[k];
+#pragma unroll
+                for (int c = 0; c < FP; c++)
+                    if (c < F) g[c] = fmaf(cf, su[(size_t)k * F + c], g[c]);
+            }
+            if (means) sw[kk * kCB + threadIdx.x] = cf;
         }
         if (means) {
-            const float inv_n = 1.0f / (float)counts[y];
-            for (int c = 0; c < F; c++) g[c] = fmaf(dU[(size_t)y * F + c], inv_n, g[c]);
+            __syncthreads();
+            owner_accumulate<true>(F, FS, k0, nk, sf, nullptr, sw, dU);
+            __syncthreads();
         }
     }
-    const float sc = (grad_scale ? *grad_scale : 1.0f) * inv_norm[i];
-    for (int c = 0; c < F; c++) dfeat[(size_t)i * F + c] = g[c] * sc;
+    if (i < N) {
+#pragma unroll
+        for (int c = 0; c < FP; c++)
+            if (c < F) g_out[(size_t)i * F + c] = g[c];
+    }
+}
+
+// phase 4 (backward)
+__global__ void __launch_bounds__(256)
+contrast_dfeat_kernel(int N, int F, int K, const float* __restrict__ g, const int* __restrict__ labels,
+                      const float* __restrict__ dU, const float* __restrict__ counts,
+                      const float* __restrict__ inv_norm, bool means, const float* __restrict__ grad_scale,
+                      float* __restrict__ dfeat) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N * F) return;
+    const int i = e / F, c = e - i * F;
+    const int y = labels[i];
+    float v = g[e];
+    if (means && y >= 0 && y < K) v = fmaf(dU[(size_t)y * F + c], 1.0f / counts[y], v);
+    dfeat[e] = v * (grad_scale ? *grad_scale : 1.0f) * inv_norm[i];
 }
 
 // ---- fused row normalisation (one thread per row, F <= 32 values in registers) ---------------------------------
@@ -390,20 +458,37 @@ int launch_contrastive_fwd(int N, int F, int K, const float* features, const int
                            float temp_lambda, void* ws, float* loss, cudaStream_t stream) {
     ContrastWs L(N, F, K);
     char* w = static_cast<char*>(ws);
-    ISR_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), stream));
-    if (N <= 0 || K <= 0) return ISR_OK;
+    if (N <= 0 || K <= 0) {
+        ISR_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), stream));
+        return ISR_OK;
+    }
     float* fhat = reinterpret_cast<float*>(w + L.fhat);
-    int* counts = reinterpret_cast<int*>(w + L.counts);
-    float* u = reinterpret_cast<float*>(w + L.u);
-    float* phi = reinterpret_cast<float*>(w + L.phi);
-    contrast_normalise_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, F, features, fhat, reinterpret_cast<float*>(w + L.inv_norm));
-    contrast_cluster_kernel<<<K, 1024, 0, stream>>>(N, F, K, fhat, labels, predef_u, temp_lambda, counts, u, phi);
-    const size_t smem = ((size_t)K * F + K) * sizeof(float);
-    ISR_CUDA_TRY(cudaFuncSetAttribute(contrast_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    contrast_loss_kernel<<<(N + 63) / 64, 256, smem, stream>>>(N, F, K, fhat, labels, u, phi, counts,
-                                                               reinterpret_cast<float*>(w + L.coef), loss);
-    ISR_CUDA_TRY(cudaGetLastError());
-    return ISR_OK;
+    float* inv_norm = reinterpret_cast<float*>(w + L.inv_norm);
+    float* sums = reinterpret_cast<float*>(w + L.sums);
+    float* counts = reinterpret_cast<float*>(w + L.counts);
+    float* spread = reinterpret_cast<float*>(w + L.spread);
+    ISR_CUDA_TRY(cudaMemsetAsync(w + L.zeroed, 0, L.zeroed_bytes, stream));
+    const int blocks = (N + kCB - 1) / kCB, FS = sample_stride(F);
+    const size_t smem1 = ((size_t)kCB * FS + kCB) * 4;
+    const size_t smem2 = ((size_t)K * F + 2 * kCB) * 4;
+    const size_t smem3 = ((size_t)K * F + ((K + 3) & ~3) + (size_t)kCB * FS + (size_t)kKC * kCB) * 4;
+    auto run = [&](auto stats_k, auto loss_k) -> int {
+        ISR_CUDA_TRY(cudaFuncSetAttribute(stats_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        ISR_CUDA_TRY(cudaFuncSetAttribute(contrast_spread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        ISR_CUDA_TRY(cudaFuncSetAttribute(loss_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        stats_k<<<blocks, kCB, smem1, stream>>>(N, F, K, features, labels, predef_u == nullptr, fhat, inv_norm, sums, counts,
+                                                loss);
+        contrast_spread_kernel<<<blocks, kCB, smem2, stream>>>(N, F, K, fhat, labels, predef_u, sums, counts, spread);
+        loss_k<<<blocks, kCB, smem3, stream>>>(N, F, K, fhat, labels, predef_u, sums, counts, spread, temp_lambda,
+                                               reinterpret_cast<float*>(w + L.g), reinterpret_cast<float*>(w + L.dU), loss);
+        ISR_CUDA_TRY(cudaGetLastError());
+        return ISR_OK;
+    };
+    if (F <= 4) return run(contrast_stats_kernel<4>, contrast_loss_kernel<4>);
+    if (F <= 8) return run(contrast_stats_kernel<8>, contrast_loss_kernel<8>);
+    if (F <= 16) return run(contrast_stats_kernel<16>, contrast_loss_kernel<16>);
+    if (F <= 24) return run(contrast_stats_kernel<24>, contrast_loss_kernel<24>);
+    return run(contrast_stats_kernel<32>, contrast_loss_kernel<32>);
 }
 
 int launch_contrastive_bwd(int N, int F, int K, const int* labels, const float* predef_u, const void* ws,
@@ -411,19 +496,11 @@ int launch_contrastive_bwd(int N, int F, int K, const int* labels, const float* 
     if (N <= 0) return ISR_OK;
     ContrastWs L(N, F, K);
     const char* w = static_cast<const char*>(ws);
-    const bool means = predef_u == nullptr;
-    float* dU = reinterpret_cast<float*>(const_cast<char*>(w) + L.dU);
-    if (means && K > 0) {
-        ISR_CUDA_TRY(cudaMemsetAsync(dU, 0, (size_t)K * F * sizeof(float), stream));
-        contrast_dU_kernel<<<(N + 127) / 128, 256, 0, stream>>>(N, F, K, reinterpret_cast<const float*>(w + L.coef),
-                                                                reinterpret_cast<const float*>(w + L.fhat), dU);
-    }
-    const size_t smem = (size_t)(K > 0 ? K : 1) * F * sizeof(float);
-    ISR_CUDA_TRY(cudaFuncSetAttribute(contrast_dfeat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    contrast_dfeat_kernel<<<(N + 255) / 256, 256, smem, stream>>>(
-        N, F, K, reinterpret_cast<const float*>(w + L.coef), labels, reinterpret_cast<const float*>(w + L.u), dU,
-        reinterpret_cast<const int*>(w + L.counts), reinterpret_cast<const float*>(w + L.inv_norm), means, grad_scale,
-        dfeat);
+    const int total = N * F;
+    contrast_dfeat_kernel<<<(total + 255) / 256, 256, 0, stream>>>(
+        N, F, K, reinterpret_cast<const float*>(w + L.g), labels, reinterpret_cast<const float*>(w + L.dU),
+        reinterpret_cast<const float*>(w + L.counts), reinterpret_cast<const float*>(w + L.inv_norm),
+        predef_u == nullptr, grad_scale, dfeat);
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }

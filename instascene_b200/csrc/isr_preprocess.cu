@@ -301,10 +301,16 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
         if (ntiles <= 64) {
             int mnx, mny, mxx, mxy;
             get_rect(cx, cy, ri, gx, gy, mnx, mny, mxx, mxy);
-            int t = 0;
-            for (int ty = mny; ty < mxy; ty++)
-                for (int tx = mnx; tx < mxx; tx++, t++)
-                    if (rect_may_touch(tx * TILE, ty * TILE, TILE, TILE, W, H, cr, q0, q1, r2)) tmask |= 1ull << t;
+            // only the tiles overlapping the cull rectangle can pass (a superset is harmless, hence the slack)
+            const int w = mxx - mnx;
+            const int tx_lo = max(mnx, __float2int_ru((cr.x - 15.0f) * 0.0625f - 1e-3f));
+            const int tx_hi = min(mxx - 1, __float2int_rd(cr.z * 0.0625f + 1e-3f));
+            const int ty_lo = max(mny, __float2int_ru((cr.y - 15.0f) * 0.0625f - 1e-3f));
+            const int ty_hi = min(mxy - 1, __float2int_rd(cr.w * 0.0625f + 1e-3f));
+            for (int ty = ty_lo; ty <= ty_hi; ty++)
+                for (int tx = tx_lo; tx <= tx_hi; tx++)
+                    if (rect_may_touch(tx * TILE, ty * TILE, TILE, TILE, W, H, cr, q0, q1, r2))
+                        tmask |= 1ull << ((ty - mny) * w + (tx - mnx));
             tcount = (uint32_t)__popcll(tmask);
         } else {
             tmask = ~0ull;

@@ -1,0 +1,11 @@
+#!/usr/bin/env bash
+cd /root/repo
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | grep -v "Warning\|warnings.warn\|^$" | tail -12 > gpurun_out/pytest_gpu.log; grep -E "passed|failed|Error|error|assert" gpurun_out/pytest_gpu.log | head -10
+for mb in 3 7 4; do
+ISR_FWD_MINBLOCKS=$mb timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-ref-cuda 2> gpurun_out/b1.err > gpurun_out/bench_cfg3_mb$mb.json; tail -2 gpurun_out/b1.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_cfg3_mb$mb.json')); r=d['roofline']; print('cfg3 mb=$mb', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'blend_ms', r['kernel_ms'], 'R', r['R'], 'R_emitted', r['R_emitted'])"
+done
+timeout 600 python bench.py --workload cfg2 --steps 20 --warmup 3 --no-cpu-baseline --no-ref-cuda 2> gpurun_out/b2.err > gpurun_out/bench_cfg2_n1.json; tail -2 gpurun_out/b2.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_cfg2_n1.json')); r=d['roofline']; print('cfg2', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'blend_ms', r['kernel_ms'])"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 260 --csv --log-file gpurun_out/launches_cfg3.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-ref-cuda > gpurun_out/ncu_b.log 2>&1

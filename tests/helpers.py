@@ -86,7 +86,9 @@ def cuda_forward(inp, want_pairs=True, device="cuda:0"):
                ranges=view(im, off(_lib.IMG_RANGES), np.uint32, 2 * tiles).reshape(tiles, 2))
     # the CUDA path emits only the tiles a Gaussian's footprint can reach: the list is shorter than num_rendered
     n_inst = int(out["tiles_emitted"].sum())
-    out["point_list"] = view(b, off(_lib.BIN_POINT_LIST), np.uint32, n_inst) if n_inst else np.zeros(0, np.uint32)
+    raw = view(b, off(_lib.BIN_POINT_LIST), np.uint32, n_inst) if n_inst else np.zeros(0, np.uint32)
+    # entries carry 8 per-block footprint bits above the 24-bit Gaussian id (P < 2^24)
+    out["point_list"], out["block_bits"] = raw & np.uint32(0xFFFFFF), raw >> np.uint32(24)
     if want_pairs:
         n = int(pidx.item()) + 1
         out["pairs"] = pairs[:n].cpu().numpy()
@@ -124,6 +126,18 @@ def check_tile_lists(c, o, W, H):
         lut = np.concatenate([[0], idx + 1]).astype(np.int64)  # CUDA position (1-based, 0 = none) -> oracle position
         mapped[:, y0:y0 + 16, x0:x0 + 16] = lut[nb]
     assert np.array_equal(mapped, o["n_contrib"]), "last/median contributor (mapped to the reference's list positions)"
+    # (4) per-block footprint bits: every (Gaussian, pixel) pair that contributed with weight >= 0.1 (the pair list)
+    #     must have the bit of the pixel's 8x4 block set in that Gaussian's entry of the pixel's tile
+    if "pairs" in c and len(c["pairs"]) and c["block_bits"].any():  # (all zero: plain-entry fallback, no bits)
+        bits = c["block_bits"].astype(np.int64)
+        entry = {}
+        for t in range(tiles_x * tiles_y):
+            for j in range(cr[t, 0], cr[t, 1]):
+                entry[(t, int(cl[j]))] = int(bits[j])
+        for gid, pix in np.asarray(c["pairs"], np.int64).reshape(-1, 2)[:20000]:
+            y, x = divmod(int(pix), W)
+            t, blk = (y // 16) * tiles_x + x // 16, ((y % 16) // 4) * 2 + (x % 16) // 8
+            assert (entry[(t, int(gid))] >> blk) & 1, "contributing pair outside the entry's block bits"
 
 
 def cuda_backward(inp, fwd, dcolor, dothers, dextra, grad_mask=15, sparse=None, flags=1):

@@ -562,3 +562,18 @@ def test_sampled_loss_with_trainable_geometry_uses_dense_backward():
         assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 1e-4, k
     assert grads["sampled_frozen"]["get_xyz"] is None
     assert rel_err(grads["sampled_frozen"]["_seg_feature"].cpu().numpy(), grads["dense"]["_seg_feature"].cpu().numpy()) < 1e-4
+
+
+def test_plain_entry_fallback_path():
+    """Scenes with >= 2^24 Gaussians cannot carry the per-block footprint bits in the list entries; the blend kernels
+    then test the footprint arithmetically.  ISR_PLAIN_ENTRIES=1 forces that path: forward parity + dense/sparse
+    backward tests must pass unchanged (run in a subprocess: the switch is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, ISR_PLAIN_ENTRIES="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_parity_gpu.py"), "-q", "-x", "-m", "gpu", "-k",
+                        "test_forward_bit_exact or test_backward_dense or test_backward_sparse_equals_dense or test_empty"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
