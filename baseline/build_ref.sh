@@ -25,8 +25,9 @@ if ! ls "$OUT"/simple_knn/_C*.so >/dev/null 2>&1; then
   touch "$OUT/simple_knn/__init__.py"
   find "$TMP/knn/build" -name "_C*.so" -exec cp {} "$OUT/simple_knn/" \;
 fi
-# the reference's Python glue on the hot path (render(), contrastive_loss and what they import)
-for d in gaussian_renderer utils scene arguments; do
+# the reference's Python glue on the hot path (render(), contrastive_loss and what they import) and the tracker
+# extraction that consumes the pair list (spatial_track/modules/init_tracker.py, golden generation only)
+for d in gaussian_renderer utils scene arguments spatial_track; do
   rm -rf "$OUT/$d"; cp -r "$REF/$d" "$OUT/$d"
 done
 rm -rf "$TMP"

@@ -31,6 +31,9 @@
  *   isr_gather_pixels                          <- train_semantic.py:124-129 (boolean-mask gather + index)
  *   isr_aux_maps_forward / _backward           <- gaussian_renderer/__init__.py:127-156 + utils/point_utils.py:10-40
  *   isr_rownorm_forward / _backward            <- scene/gaussian_model.py:121-125 + gaussian_renderer/__init__.py:60-62
+ *   isr_photometric_forward / _backward        <- l1_loss + ssim utils/loss_utils.py:18-19,39-83 as combined in
+ *                                                 train.py:76-77
+ *   isr_tracker_mark / isr_tracker_fill        <- get_segmap_gaussians spatial_track/modules/init_tracker.py:16-47
  *   isr_knn_mean_dist2                         <- SimpleKNN::knn submodules/simple-knn/simple_knn.cu:186-222
  *                                                 (distCUDA2, submodules/simple-knn/spatial.cu:15-25)
  */
@@ -243,6 +246,38 @@ int isr_aux_maps_backward(int W, int H, const float* allmap, const float* normal
 /* ---- simple-knn ------------------------------------------------------------------------------------- */
 size_t isr_knn_workspace_bytes(int P);
 int isr_knn_mean_dist2(int P, const float* points, float* mean_dist2, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- photometric loss of the RGB training step ------------------------------------------------ */
+/* loss = (1 - lambda_dssim) * mean|image - gt| + lambda_dssim * (1 - SSIM(image, gt))  (train.py:76-77) with SSIM as
+ * utils/loss_utils.py:39-83 (11x11 Gaussian window, sigma 1.5, zero padding, per channel, mean over C*H*W).
+ * image, gt: [C,H,W] fp32.  forward writes out3 = {loss, L1 mean, SSIM mean} (device floats) and the derivative maps
+ * backward needs into ws; backward writes dL_dimage[C,H,W] = *grad_scale (device float, NULL = 1) * d loss / d image. */
+size_t isr_photometric_workspace_bytes(int C, int H, int W);
+int isr_photometric_forward(int C, int H, int W, const float* image, const float* gt, float lambda_dssim, void* ws,
+                            size_t ws_bytes, float* out3, void* stream);
+int isr_photometric_backward(int C, int H, int W, const float* image, const float* gt, float lambda_dssim, const void* ws,
+                             const float* grad_scale, float* dL_dimage, void* stream);
+
+/* Densification statistics (train.py:139-142 + GaussianModel.add_densification_stats, scene/gaussian_model.py:602-605),
+ * in place, for every Gaussian with radii > 0: max_radii2D = max(max_radii2D, radii); xyz_gradient_accum +=
+ * |dL_dmeans2D[i, 0:3]|; denom += 1.   radii int32 [P], dL_dmeans2D fp32 [P,3], the three accumulators fp32 [P]. */
+int isr_densify_stats(int P, const int* radii, const float* dL_dmeans2D, float* max_radii2D, float* xyz_gradient_accum,
+                      float* denom, void* stream);
+
+/* ---- Gaussian-tracker extraction --------------------------------------------------------- */
+/* Device-side replacement of get_segmap_gaussians (spatial_track/modules/init_tracker.py:16-47): from the
+ * (gaussian id, pixel id) pair list of one view and the view's segmentation map, the set of distinct Gaussians per
+ * mask and of the whole frame -- without moving the pair list to the host.
+ * seg_rows[HW] int32: per pixel the DENSE row of its mask, 0 = background / ignored, 1..K-1 = masks (the host mirror
+ * maps the sorted distinct mask ids != 0 to rows 1..).  Row 0 of the result is the frame set.
+ * isr_tracker_mark: builds one P-bit set per row in `ws` and writes counts[K] (device int32): distinct Gaussians per
+ * row.  isr_tracker_fill: for every row with row_offsets[row] >= 0 (device int64[K]) writes the row's Gaussian ids in
+ * ASCENDING order to out_ids[row_offsets[row] ...]; rows with a negative offset are skipped (the reference drops
+ * masks with fewer than 50 Gaussians, init_tracker.py:41-42 -- that test runs on the host on K integers). */
+size_t isr_tracker_workspace_bytes(int P, int K);
+int isr_tracker_mark(const int* pairs, int64_t n_pairs, const int* seg_rows, int64_t HW, int P, int K, void* ws,
+                     size_t ws_bytes, int* counts, void* stream);
+int isr_tracker_fill(int P, int K, const void* ws, const int64_t* row_offsets, int* out_ids, void* stream);
 
 #ifdef __cplusplus
 }

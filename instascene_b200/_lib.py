@@ -59,6 +59,9 @@ EXPORTED_SYMBOLS = [
     "isr_forward_geometry", "isr_forward_render", "isr_backward", "isr_backward_extra_sparse", "isr_mark_visible",
     "isr_gather_pixels", "isr_contrastive_workspace_bytes", "isr_contrastive_forward", "isr_contrastive_backward",
     "isr_rownorm_forward", "isr_rownorm_backward", "isr_aux_maps_forward", "isr_aux_maps_backward", "isr_adam_step", "isr_knn_workspace_bytes", "isr_knn_mean_dist2",
+    "isr_tracker_workspace_bytes", "isr_tracker_mark", "isr_tracker_fill",
+    "isr_photometric_workspace_bytes", "isr_photometric_forward", "isr_photometric_backward",
+    "isr_densify_stats",
 ]
 
 _lib = None
@@ -109,6 +112,15 @@ def lib() -> C.CDLL:
     L.isr_knn_workspace_bytes.restype = C.c_size_t
     L.isr_knn_workspace_bytes.argtypes = [C.c_int]
     L.isr_knn_mean_dist2.argtypes = [C.c_int, _fp, _fp, _vp, C.c_size_t, C.c_void_p]
+    L.isr_tracker_workspace_bytes.restype = C.c_size_t
+    L.isr_tracker_workspace_bytes.argtypes = [C.c_int, C.c_int]
+    L.isr_tracker_mark.argtypes = [_ip, C.c_int64, _ip, C.c_int64, C.c_int, C.c_int, _vp, C.c_size_t, _ip, C.c_void_p]
+    L.isr_tracker_fill.argtypes = [C.c_int, C.c_int, _vp, _ip, _ip, C.c_void_p]
+    L.isr_photometric_workspace_bytes.restype = C.c_size_t
+    L.isr_photometric_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.isr_photometric_forward.argtypes = [C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_float, _vp, C.c_size_t, _fp, C.c_void_p]
+    L.isr_photometric_backward.argtypes = [C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_float, _vp, _fp, _fp, C.c_void_p]
+    L.isr_densify_stats.argtypes = [C.c_int, _ip, _fp, _fp, _fp, _fp, C.c_void_p]
     _lib = L
     return L
 

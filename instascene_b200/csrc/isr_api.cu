@@ -35,6 +35,17 @@ int launch_adam(size_t n, float* p, const float* g, float* m, float* v, float lr
                 int step, cudaStream_t stream);
 size_t knn_ws_bytes(int P);
 int launch_knn(int P, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t photometric_ws_bytes(int C, int H, int W);
+int launch_photometric_fwd(int C, int H, int W, const float* img, const float* gt, float lambda, void* ws, float* out,
+                           cudaStream_t stream);
+int launch_photometric_bwd(int C, int H, int W, const float* img, const float* gt, float lambda, const void* ws,
+                           const float* grad_scale, float* dimg, cudaStream_t stream);
+int launch_densify_stats(int P, const int* radii, const float* grad2d, float* max_radii2D, float* grad_accum, float* denom,
+                         cudaStream_t stream);
+size_t tracker_ws_bytes(int P, int K);
+int launch_tracker_mark(const int* pairs, int64_t n_pairs, const int* seg_rows, int64_t HW, int P, int K, void* ws,
+                        int* counts, cudaStream_t stream);
+int launch_tracker_fill(int P, int K, const void* ws, const int64_t* row_offsets, int* out_ids, cudaStream_t stream);
 }  // namespace isr
 
 using namespace isr;
@@ -270,6 +281,51 @@ int isr_knn_mean_dist2(int P, const float* points, float* mean_dist2, void* ws, 
     if (!points || !mean_dist2 || !ws) return ISR_ERR_INVALID_ARG;
     if (ws_bytes < knn_ws_bytes(P)) return ISR_ERR_WORKSPACE;
     return launch_knn(P, points, mean_dist2, ws, ws_bytes, static_cast<cudaStream_t>(stream_));
+}
+
+size_t isr_photometric_workspace_bytes(int C, int H, int W) {
+    return (C <= 0 || H <= 0 || W <= 0) ? 0 : photometric_ws_bytes(C, H, W);
+}
+
+int isr_photometric_forward(int C, int H, int W, const float* image, const float* gt, float lambda_dssim, void* ws,
+                            size_t ws_bytes, float* out3, void* stream_) {
+    if (C <= 0 || H <= 0 || W <= 0 || C > 65535) return ISR_ERR_INVALID_ARG;
+    if (!image || !gt || !ws || !out3) return ISR_ERR_INVALID_ARG;
+    if (ws_bytes < photometric_ws_bytes(C, H, W)) return ISR_ERR_WORKSPACE;
+    return launch_photometric_fwd(C, H, W, image, gt, lambda_dssim, ws, out3, static_cast<cudaStream_t>(stream_));
+}
+
+int isr_photometric_backward(int C, int H, int W, const float* image, const float* gt, float lambda_dssim, const void* ws,
+                             const float* grad_scale, float* dL_dimage, void* stream_) {
+    if (C <= 0 || H <= 0 || W <= 0 || C > 65535) return ISR_ERR_INVALID_ARG;
+    if (!image || !gt || !ws || !dL_dimage) return ISR_ERR_INVALID_ARG;
+    return launch_photometric_bwd(C, H, W, image, gt, lambda_dssim, ws, grad_scale, dL_dimage,
+                                  static_cast<cudaStream_t>(stream_));
+}
+
+int isr_densify_stats(int P, const int* radii, const float* dL_dmeans2D, float* max_radii2D, float* xyz_gradient_accum,
+                      float* denom, void* stream_) {
+    if (P < 0) return ISR_ERR_INVALID_ARG;
+    if (P == 0) return ISR_OK;
+    if (!radii || !dL_dmeans2D || !max_radii2D || !xyz_gradient_accum || !denom) return ISR_ERR_INVALID_ARG;
+    return launch_densify_stats(P, radii, dL_dmeans2D, max_radii2D, xyz_gradient_accum, denom, static_cast<cudaStream_t>(stream_));
+}
+
+size_t isr_tracker_workspace_bytes(int P, int K) { return (P < 0 || K < 0) ? 0 : tracker_ws_bytes(P, K) + 256; }
+
+int isr_tracker_mark(const int* pairs, int64_t n_pairs, const int* seg_rows, int64_t HW, int P, int K, void* ws,
+                     size_t ws_bytes, int* counts, void* stream_) {
+    if (P < 0 || K < 1 || n_pairs < 0 || HW < 0) return ISR_ERR_INVALID_ARG;
+    if (!ws || !counts || (n_pairs > 0 && (!pairs || !seg_rows))) return ISR_ERR_INVALID_ARG;
+    if (ws_bytes < tracker_ws_bytes(P, K)) return ISR_ERR_WORKSPACE;
+    return launch_tracker_mark(pairs, n_pairs, seg_rows, HW, P, K, ws, counts, static_cast<cudaStream_t>(stream_));
+}
+
+int isr_tracker_fill(int P, int K, const void* ws, const int64_t* row_offsets, int* out_ids, void* stream_) {
+    if (P < 0 || K < 1) return ISR_ERR_INVALID_ARG;
+    if (!ws || !row_offsets) return ISR_ERR_INVALID_ARG;
+    if (P == 0) return ISR_OK;
+    return launch_tracker_fill(P, K, ws, row_offsets, out_ids, static_cast<cudaStream_t>(stream_));
 }
 
 }  // extern "C"

@@ -174,3 +174,18 @@ def rel_err(a, b):
 def pair_set(pairs):
     p = np.asarray(pairs, np.int64).reshape(-1, 2)
     return set((p[:, 0] << 32 | p[:, 1]).tolist())
+
+
+def tracker_label_map(W, H, seed):
+    """Masks of very different sizes so that the 50-Gaussian threshold keeps some and drops others; ids are not
+    contiguous (the reference sorts `torch.unique`)."""
+    rng = np.random.default_rng(seed)
+    lab = np.zeros((H, W), np.int16)
+    lab[: H // 2, : W // 2] = 3
+    lab[: H // 2, W // 2:] = 7
+    lab[H // 2:, : W // 3] = 12
+    lab[H // 2:, W // 3: W // 3 + 3] = 40       # 3-pixel-wide sliver: few Gaussians
+    lab[H - 4:, W - 4:] = 41                    # 4x4 corner
+    lab[H // 2 + 5: H // 2 + 25, W // 2: W // 2 + 30] = 300
+    lab[rng.random((H, W)) < 0.1] = 0
+    return lab
