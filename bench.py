@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the hot path (BASELINE.json: views/sec fwd+bwd @1080p, N Gaussians x feat_dim).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-cuda] [--workload cfg3|cfg2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg5]
 
 Workloads (synthetic, seeded -- SURVEY.md §8d):
   cfg3 (default, BASELINE.json configs[2], the one the north-star target is quoted on):
@@ -10,6 +10,8 @@ Workloads (synthetic, seeded -- SURVEY.md §8d):
         dL/d_seg_feature + fused Adam step.   Views shard over ranks (weak scaling: one view per rank per step).
   cfg2 (BASELINE.json configs[1]): 500k Gaussians, F=0, 1080p, RGB+depth+normal forward + backward of ALL
         gradients with seeded random cotangents.
+  cfg5 (BASELINE.json configs[4]): 5M Gaussians, F=32, 1600x1200, the --gram_feat_3d step (two single-view terms, fixed
+        class prototypes, 3D term).  The reference CUDA leg is unavailable there (its rasterizer stops at F=24).
 One JSON line on stdout (rank 0).  See the task contract for the keys.
 """
 from __future__ import annotations
@@ -56,11 +58,18 @@ WORKLOADS = {
                  desc="cfg3: 2M Gaussians x 16-dim features @1920x1080, render + ProtoNCE(32768 px) + backward + Adam"),
     "cfg2": dict(P=500_000, F=0, W=1920, H=1080, seed=1002, n_views=200, samples=0, labels=0,
                  desc="cfg2: 500k Gaussians @1920x1080, RGB+depth+normal forward + backward of all gradients"),
+    # BASELINE.json configs[4]: the --gram_feat_3d step of train_semantic.py:102-205 -- two label maps per view (cluster
+    # means / fixed Gram-Schmidt class prototypes) + the 3D term over visible labelled Gaussians
+    "cfg5": dict(P=5_000_000, F=32, W=1600, H=1200, seed=1005, n_views=200, samples=32768, labels=64,
+                 desc="cfg5: 5M Gaussians x 32-dim features @1600x1200, --gram_feat_3d step: render + 2 single-view "
+                      "ProtoNCE terms (32768 px each) + 3D ProtoNCE (32768 Gaussians) + backward + Adam"),
 }
-KERNELS_PER_STEP = {"cfg3": 17, "cfg2": 11}
+# our own kernels per step (DESIGN.md "launch list"); cfg5 = cfg3's 17 + gather/contrast x2 more terms (1+4, 4) +
+# rownorm fwd/bwd of the sampled 3D rows
+KERNELS_PER_STEP = {"cfg3": 17, "cfg2": 11, "cfg5": 28}
 # dram__bytes_read.sum + dram__bytes_write.sum of blend_fwd_kernel per launch, from the committed `ncu --set full`
-# capture profiles/r1_ncu_blend_fwd_v3.txt (cfg3); no capture of that kernel exists for cfg2
-NCU_TRAFFIC_BYTES = {"cfg3": 244.8e6 + 264.0e6, "cfg2": None}  # our own kernels per step (see DESIGN.md "launch list")
+# capture profiles/r1_ncu_blend_fwd_v4.txt (cfg3); no capture of that kernel exists for cfg2 / cfg5
+NCU_TRAFFIC_BYTES = {"cfg3": 138.5e6 + 255.8e6, "cfg2": None, "cfg5": None}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -178,9 +187,12 @@ def run_ours(args):
         h = dict(wvt=torch.from_numpy(c.world_view_transform).pin_memory(),
                  fpt=torch.from_numpy(c.full_proj_transform).pin_memory(),
                  center=torch.from_numpy(c.camera_center).pin_memory())
-        if args.workload == "cfg3":
+        if args.workload in ("cfg3", "cfg5"):
             lab = synth.label_map(W, H, wl["seed"] + 2 + v)
             h["labels"] = torch.from_numpy(lab.reshape(-1).astype(np.int16)).pin_memory()  # the view's segmap
+            if args.workload == "cfg5":  # the view's sorted_segmap (globally consistent ids): a second labelling
+                lab2 = synth.label_map(W, H, wl["seed"] + 5000 + v, grid=6)
+                h["labels2"] = torch.from_numpy(lab2.reshape(-1).astype(np.int16)).pin_memory()
         else:
             rng = np.random.default_rng(wl["seed"] + 1 + v)
             h["dcolor"] = torch.from_numpy(rng.standard_normal((3, H, W)).astype(np.float32)).pin_memory()
@@ -190,8 +202,14 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     opt = None
-    if args.workload == "cfg3":
+    sem_opt, class_feat, labels3d = None, None, None
+    if args.workload in ("cfg3", "cfg5"):
+        from instascene_b200 import semantic_step as sstep
+        sem_opt = sstep.SemanticOpt(sample_batchsize=wl["samples"])
         opt = isr.FusedAdam([pc._seg_feature], lr=0.025, eps=1e-15)  # scene/gaussian_model.py:217-249
+    if args.workload == "cfg5":
+        class_feat = t(synth.gram_schmidt_prototypes(wl["labels"], F, wl["seed"] + 7))   # gaussian_model.py:158-176
+        labels3d = t(synth.morton_labels(scene.xyz, wl["labels"]))
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
@@ -206,11 +224,14 @@ def run_ours(args):
 
     def step(v, data):
         cam = _Cam(cams[v], data["wvt"], data["fpt"], data["center"])
-        if args.workload == "cfg3":
+        if args.workload in ("cfg3", "cfg5"):
             pkg = isr.render(cam, pc, _Pipe, bg)
-            pix, labels = isr.sample_labelled_pixels(data["labels"], wl["samples"], generator=gen)
-            feats = isr.sample_pixels(pkg["seg_feature"], pix)
-            loss = isr.contrastive_loss(feats, labels, num_labels=wl["labels"]) * (1e-6 * 0.5)
+            segmaps = [data["labels"]] if class_feat is None else [data["labels"], data["labels2"]]
+            loss = sstep.single_view_loss(pkg["seg_feature"], segmaps, class_feat, sem_opt, generator=gen,
+                                          num_labels=wl["labels"])
+            if class_feat is not None:
+                loss = loss + sstep.contrastive_3d_loss(pc._seg_feature, labels3d, pkg["radii"], class_feat, sem_opt,
+                                                        generator=gen)
             loss.backward()
             if world > 1:
                 # gradient all-reduce + Adam on a side stream; the next render() launches its geometry phase first and
@@ -285,7 +306,7 @@ def run_ours(args):
             "config": {"workload": wl["desc"], "gaussians": P, "feat_dim": F, "image": [W, H],
                        "views_per_step_per_gpu": 1, "parallelism": f"dp{world} (views sharded, grad all-reduce)",
                        "l2": "inputs larger than L2 (Gaussian state %.0f MB >> 126 MB), distinct view every step" % (P * (232 + 4 * F) / 1e6),
-                       "optimizer": "Adam(lr=0.025, eps=1e-15) on _seg_feature (isr.FusedAdam)" if args.workload == "cfg3" else "none"},
+                       "optimizer": "Adam(lr=0.025, eps=1e-15) on _seg_feature (isr.FusedAdam)" if opt is not None else "none"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
@@ -445,21 +466,35 @@ def ref_cuda_leg(args, wl, pc, cams, devdata, my_views, dev, n=4):
     except Exception as ex:  # noqa: BLE001
         return {"unavailable": repr(ex)[:200]}
     F, W, H = wl["F"], wl["W"], wl["H"]
+    if F > 24:
+        return {"unavailable": "the reference rasterizer is compiled for at most 24 feature dims (auxiliary.h:20)"}
     bg = torch.zeros(3, device=dev)
     gen = torch.Generator(device=dev)
     gen.manual_seed(99)
+    ref_class_feat = ref_labels3d = None
 
     def step(v):
         d = devdata[v]
         cam = _Cam(cams[v], d["wvt"], d["fpt"], d["center"])
         pkg = rrender(cam, pc, _Pipe, bg)
-        if args.workload == "cfg3":
-            segmap = d["labels"].reshape(H, W)
-            mask = segmap > 0                                     # train_semantic.py:118-129
-            valid_feat = pkg["seg_feature"][:, mask]
-            valid_lab = segmap[mask]
-            idx = torch.randint(0, len(valid_lab), size=(wl["samples"],), device=dev, generator=gen)
-            loss = rloss(valid_feat[:, idx].T, valid_lab[idx].long()) * (1e-6 * 0.5)
+        if args.workload in ("cfg3", "cfg5"):
+            loss = 0
+            maps = [d["labels"]] if args.workload == "cfg3" else [d["labels"], d["labels2"]]
+            for k, lab in enumerate(maps):                        # train_semantic.py:108-143
+                segmap = lab.reshape(H, W)
+                mask = segmap > 0
+                valid_feat = pkg["seg_feature"][:, mask]
+                valid_lab = segmap[mask]
+                idx = torch.randint(0, len(valid_lab), size=(wl["samples"],), device=dev, generator=gen)
+                loss = loss + rloss(valid_feat[:, idx].T, valid_lab[idx].long(),
+                                    predef_u_list=ref_class_feat if k == 1 else None) * (1e-6 * (1.0 if k == 1 else 0.5))
+            if args.workload == "cfg5":                           # train_semantic.py:175-197
+                vis = pkg["visibility_filter"]
+                vfeat, vlab = pc.get_seg_feature[vis], ref_labels3d[vis]
+                m3 = vlab > 0
+                vfeat, vlab = vfeat[m3], vlab[m3]
+                idx = torch.randint(0, len(vlab), size=(wl["samples"],), device=dev, generator=gen)
+                loss = loss + rloss(vfeat[idx], vlab[idx], predef_u_list=ref_class_feat) * 2.5e-6
             loss.backward()
             pc._seg_feature.grad = None
         else:
@@ -493,10 +528,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
+    ap.add_argument("--gaussians", type=int, default=0, help="override the workload's Gaussian count (smoke runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.gaussians > 0:
+        WORKLOADS[args.workload] = dict(WORKLOADS[args.workload], P=args.gaussians,
+                                        desc=WORKLOADS[args.workload]["desc"] + f" [--gaussians {args.gaussians}]")
     _quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)

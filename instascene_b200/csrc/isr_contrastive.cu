@@ -56,31 +56,32 @@ __global__ void gather_pixels_kernel(int F, int64_t HW, const float* __restrict_
 constexpr int kCB = 256;   // samples per block
 constexpr int kKC = 64;    // clusters per coefficient chunk
 
-// sum over the block (kCB threads); s_red must hold kCB/32 floats
+// sum over the block (kBlock threads); s_red must hold kBlock/32 floats
+template <int kBlock = kCB>
 __device__ __forceinline__ float block_sum(float v, float* s_red) {
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
     __syncthreads();
     float t = 0.0f;
-    for (int w = 0; w < kCB / 32; w++) t += s_red[w];
+    for (int w = 0; w < kBlock / 32; w++) t += s_red[w];
     return t;
 }
 
 // block partial of  out[k][c] += sum_{i in block, label_i == k} w_i * sf[i][c]   for k in [k0, k0+nk)
 // (w == nullptr: w_i = 1).  sw is indexed [k - k0][i] when per-cluster weights are given (kPerCluster).
-template <bool kPerCluster>
+template <bool kPerCluster, int kBlock = kCB>
 __device__ __forceinline__ void owner_accumulate(int F, int FS, int k0, int nk, const float* __restrict__ sf,
                                                  const int* __restrict__ sl, const float* __restrict__ sw,
                                                  float* __restrict__ out) {
     if ((F & 3) == 0) {
         const int F4 = F >> 2;
-        for (int e = threadIdx.x; e < nk * F4; e += kCB) {
+        for (int e = threadIdx.x; e < nk * F4; e += kBlock) {
             const int kk = e / F4, c4 = e - kk * F4, k = k0 + kk;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int i = 0; i < kCB; i++) {
+            for (int i = 0; i < kBlock; i++) {
                 float w;
-                if (kPerCluster) { w = sw[kk * kCB + i]; if (w == 0.0f) continue; }
+                if (kPerCluster) { w = sw[kk * kBlock + i]; if (w == 0.0f) continue; }
                 else { if (sl[i] != k) continue; w = 1.0f; }
                 const float4 f = *reinterpret_cast<const float4*>(sf + i * FS + 4 * c4);
                 acc.x = fmaf(w, f.x, acc.x); acc.y = fmaf(w, f.y, acc.y); acc.z = fmaf(w, f.z, acc.z); acc.w = fmaf(w, f.w, acc.w);
@@ -92,12 +93,12 @@ __device__ __forceinline__ void owner_accumulate(int F, int FS, int k0, int nk, 
             if (acc.w != 0.0f) atomicAdd(o + 3, acc.w);
         }
     } else {
-        for (int e = threadIdx.x; e < nk * F; e += kCB) {
+        for (int e = threadIdx.x; e < nk * F; e += kBlock) {
             const int kk = e / F, c = e - kk * F, k = k0 + kk;
             float acc = 0.0f;
-            for (int i = 0; i < kCB; i++) {
+            for (int i = 0; i < kBlock; i++) {
                 float w;
-                if (kPerCluster) { w = sw[kk * kCB + i]; if (w == 0.0f) continue; }
+                if (kPerCluster) { w = sw[kk * kBlock + i]; if (w == 0.0f) continue; }
                 else { if (sl[i] != k) continue; w = 1.0f; }
                 acc = fmaf(w, sf[i * FS + c], acc);
             }
@@ -189,82 +190,270 @@ contrast_spread_kernel(int N, int F, int K, const float* __restrict__ fhat, cons
     }
 }
 
-// phase 3
-template <int FP>
-__global__ void __launch_bounds__(kCB)
-contrast_loss_kernel(int N, int F, int K, const float* __restrict__ fhat, const int* __restrict__ labels,
-                     const float* __restrict__ predef_u, const float* __restrict__ sums,
-                     const float* __restrict__ counts, const float* __restrict__ spread, float temp_lambda,
-                     float* __restrict__ g_out, float* __restrict__ dU, float* __restrict__ loss) {
-    extern __shared__ __align__(16) float smem[];
-    const int FS = sample_stride(F);
-    float* su = smem;                                   // [K][F]
-    float* sphi = su + (size_t)K * F;                   // [K]  1/phi_k, 0 for an absent cluster
-    float* sf = sphi + ((K + 3) & ~3);                  // [kCB][FS]
-    float* sw = sf + kCB * FS;                          // [kKC][kCB] coefficient chunk
-    __shared__ float s_red[kCB / 32];
+// phase 3 -- the [N,F] x [F,K] similarity matrix on the 5th-generation tensor cores (tcgen05, accumulators in TMEM).
+//
+// One CTA = 128 samples = the M = 128 rows of a UMMA tile; the K cluster centres (pre-scaled by 1/phi_k) are the N
+// columns, the feature dim F is the contraction.  Operands are staged in shared memory in the canonical K-major
+// no-swizzle layout (8-row x 16-byte core matrices; a "panel" = the same 4 features of all rows, 16 bytes per row).
+// fp32 fidelity: each operand is split x = hi + lo with hi = the 19 leading bits (exactly a TF32 number), and
+// hi*hi + lo*hi + hi*lo is accumulated in fp32 in TMEM (3xTF32: the dropped lo*lo and the 11-bit read of lo are
+// ~2^-22 relative).  One elected thread issues the 3*F/8 tcgen05.mma (kind::tf32, M128 x N<=256 x K8) per column
+// chunk and commits them to an mbarrier; every thread then reads ITS sample's row of logits straight from TMEM
+// (tcgen05.ld 32x32b: lane = row) -- pass 0 for the softmax denominator and the loss, pass 1 for the coefficients
+// coef_ik = (p_ik - [k == y_i]) / phi_k, from which g_i = sum_k coef_ik u_k and dU_k = sum_i coef_ik f^_i are formed
+// as before.  With more than 256 clusters the columns are processed in chunks of 256 and pass 1 re-issues the MMAs.
+constexpr int kLB = 128;  // samples per CTA of the tensor-core loss kernel
+
+namespace tc {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+// start address, leading (K-direction) and stride (row-group) byte offsets in 16-byte units, version 1 (sm_100).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
+__device__ __forceinline__ uint32_t instr_desc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void commit(uint32_t mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}\n"
+        :: "r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t tmem, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(cols) : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane (lane = 32 * (warp % 4) + lane id)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+}  // namespace tc
+
+struct ContrastTcSmem {  // dynamic shared-memory carve-up of contrast_loss_tc_kernel (byte offsets)
+    int Kpad, NC, tmem_cols;
+    size_t su, sphi, sf, sw, apan, bpan, total;
+    __host__ __device__ ContrastTcSmem(int F, int FP, int K) {
+        Kpad = (K + 31) & ~31;
+        NC = Kpad < 256 ? Kpad : 256;
+        tmem_cols = 32;
+        while (tmem_cols < NC) tmem_cols <<= 1;
+        const int FS = (F + 3) & ~3;
+        size_t o = 0;
+        su = o;   o += (size_t)K * F * 4;
+        o = (o + 15) & ~(size_t)15;
+        sphi = o; o += (size_t)Kpad * 4;
+        sf = o;   o += (size_t)kLB * FS * 4;
+        sw = o;   o += (size_t)kKC * kLB * 4;
+        o = (o + 127) & ~(size_t)127;
+        apan = o; o += (size_t)2 * (FP / 4) * kLB * 16;    // [hi|lo][FP/4 panels][128 rows] x 16 B
+        bpan = o; o += (size_t)2 * (FP / 4) * Kpad * 16;   // [hi|lo][FP/4 panels][Kpad rows] x 16 B
+        total = o;
+    }
+};
+
+template <int FP>  // F padded to a multiple of 8 (one tcgen05.mma contracts 8 TF32 values)
+__global__ void __launch_bounds__(kLB)
+contrast_loss_tc_kernel(int N, int F, int K, const float* __restrict__ fhat, const int* __restrict__ labels,
+                        const float* __restrict__ predef_u, const float* __restrict__ sums,
+                        const float* __restrict__ counts, const float* __restrict__ spread, float temp_lambda,
+                        float* __restrict__ g_out, float* __restrict__ dU, float* __restrict__ loss) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_red[kLB / 32];
+    const ContrastTcSmem L(F, FP, K);
+    const int FS = sample_stride(F), Kpad = L.Kpad;
+    float* su = reinterpret_cast<float*>(smem_raw + L.su);      // [K][F]   centres (for g)
+    float* sphi = reinterpret_cast<float*>(smem_raw + L.sphi);  // [Kpad]   1/phi_k, 0 for an absent / padding cluster
+    float* sf = reinterpret_cast<float*>(smem_raw + L.sf);      // [128][FS] this CTA's samples (for dU)
+    float* sw = reinterpret_cast<float*>(smem_raw + L.sw);      // [kKC][128] coefficient chunk (for dU)
+    float4* apan = reinterpret_cast<float4*>(smem_raw + L.apan);
+    float4* bpan = reinterpret_cast<float4*>(smem_raw + L.bpan);
+    constexpr int NP = FP / 4;  // 16-byte K panels
+    const int tid = threadIdx.x, warp = tid >> 5;
     const bool means = predef_u == nullptr;
-    load_centres(F, K, predef_u, sums, counts, su);
-    for (int k = threadIdx.x; k < K; k += kCB) {
+
+    for (int e = tid; e < K * F; e += kLB) {
+        const int k = e / F;
         const float n = counts[k];
-        sphi[k] = n > 0.0f ? 1.0f / fminf(fmaxf(10.0f * (spread[k] / (n * logf(n + temp_lambda))), 0.5f), 1.0f) : 0.0f;
+        su[e] = predef_u ? predef_u[e] : (n > 0.0f ? sums[e] / n : 0.0f);
     }
-    const int i = blockIdx.x * kCB + threadIdx.x;
+    for (int k = tid; k < Kpad; k += kLB) {
+        float ip = 0.0f;
+        if (k < K) {
+            const float n = counts[k];
+            if (n > 0.0f) ip = 1.0f / fminf(fmaxf(10.0f * (spread[k] / (n * logf(n + temp_lambda))), 0.5f), 1.0f);
+        }
+        sphi[k] = ip;
+    }
+    const int i = blockIdx.x * kLB + tid;
     int y = -1;
-    float f[FP];
+    {   // A operand: this thread's sample row, split hi / lo, one float4 per panel
+        float f[FP];
 #pragma unroll
-    for (int c = 0; c < FP; c++) f[c] = 0.0f;
-    if (i < N) {
-        y = labels[i];
-        if (y < 0 || y >= K) y = -1;
+        for (int c = 0; c < FP; c++) f[c] = 0.0f;
+        if (i < N) {
+            y = labels[i];
+            if (y < 0 || y >= K) y = -1;
 #pragma unroll
-        for (int c = 0; c < FP; c++)
-            if (c < F) { f[c] = fhat[(size_t)i * F + c]; sf[threadIdx.x * FS + c] = f[c]; }
+            for (int c = 0; c < FP; c++)
+                if (c < F) { f[c] = fhat[(size_t)i * F + c]; sf[tid * FS + c] = f[c]; }
+        } else {
+            for (int c = 0; c < F; c++) sf[tid * FS + c] = 0.0f;
+        }
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            const float4 h = make_float4(tc::tf32_hi(f[4 * p]), tc::tf32_hi(f[4 * p + 1]), tc::tf32_hi(f[4 * p + 2]), tc::tf32_hi(f[4 * p + 3]));
+            apan[p * kLB + tid] = h;
+            apan[(NP + p) * kLB + tid] = make_float4(f[4 * p] - h.x, f[4 * p + 1] - h.y, f[4 * p + 2] - h.z, f[4 * p + 3] - h.w);
+        }
     }
-    __syncthreads();
-    const bool valid = y >= 0;
-    auto logit_exp = [&](int k) {  // exp(f . u_k / phi_k), 0 for an absent cluster
-        const float ip = sphi[k];
-        if (ip == 0.0f) return 0.0f;
-        float d0 = 0.0f, d1 = 0.0f;
+    __syncthreads();  // su, sphi complete
+    // B operand: centres scaled by 1/phi (so the MMA yields the logits), zero rows for absent / padding clusters
+    for (int e = tid; e < NP * Kpad; e += kLB) {
+        const int p = e / Kpad, n = e - p * Kpad;
+        float v[4];
 #pragma unroll
-        for (int c = 0; c < FP; c += 2) {
-            if (c < F) d0 = fmaf(f[c], su[(size_t)k * F + c], d0);
-            if (c + 1 < F) d1 = fmaf(f[c + 1], su[(size_t)k * F + c + 1], d1);
+        for (int j = 0; j < 4; j++) {
+            const int c = 4 * p + j;
+            v[j] = (n < K && c < F) ? su[(size_t)n * F + c] * sphi[n] : 0.0f;
         }
-        return expf((d0 + d1) * ip);
-    };
-    float sum = 0.0f, dy = 0.0f;
-    if (valid)
-        for (int k = 0; k < K; k++) {
-            const float e = logit_exp(k);
-            sum += e;
-            if (k == y) dy = e;
-        }
-    const float denom = sum + 1e-9f;
-    const float li = block_sum(valid ? -logf(dy / denom) : 0.0f, s_red);
-    if (threadIdx.x == 0 && li != 0.0f) atomicAdd(loss, li);
-    const float inv_denom = 1.0f / denom;
+        const float4 h = make_float4(tc::tf32_hi(v[0]), tc::tf32_hi(v[1]), tc::tf32_hi(v[2]), tc::tf32_hi(v[3]));
+        bpan[p * Kpad + n] = h;
+        bpan[(NP + p) * Kpad + n] = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
+    }
+    const uint32_t mbar = tc::smem_u32(&s_mbar);
+    if (tid == 0) {
+        tc::mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tc::tmem_alloc(tc::smem_u32(&s_tmem), (uint32_t)L.tmem_cols);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // operand panels -> visible to the tensor-core (async) proxy
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t a_base = tc::smem_u32(apan), b_base = tc::smem_u32(bpan);
+    const int nch = (Kpad + L.NC - 1) / L.NC;
+    uint32_t uses = 0;
+
+    const bool valid = y >= 0;
+    float sum = 0.0f, dy = 0.0f, inv_denom = 0.0f;
     float g[FP];
 #pragma unroll
     for (int c = 0; c < FP; c++) g[c] = 0.0f;
-    for (int k0 = 0; k0 < K; k0 += kKC) {
-        const int nk = min(kKC, K - k0);
-        for (int kk = 0; kk < nk; kk++) {
-            const int k = k0 + kk;
-            float cf = 0.0f;
-            if (valid && sphi[k] != 0.0f) {
-                cf = (logit_exp(k) * inv_denom - (k == y ? 1.0f : 0.0f)) * sphi[k];
+
+    for (int pass = 0; pass < 2; pass++) {
+        for (int ch = 0; ch < nch; ch++) {
+            const int n0 = ch * L.NC, ncols = min(L.NC, Kpad - n0);
+            if (pass == 0 || nch > 1) {
+                if (tid == 0) {
+                    const uint32_t idesc = tc::instr_desc_tf32(kLB, ncols);
+                    uint32_t acc = 0;
 #pragma unroll
-                for (int c = 0; c < FP; c++)
-                    if (c < F) g[c] = fmaf(cf, su[(size_t)k * F + c], g[c]);
+                    for (int ks = 0; ks < FP / 8; ks++) {
+#pragma unroll
+                        for (int t = 0; t < 3; t++) {  // hi*hi, lo*hi, hi*lo
+                            const int pa = (t == 1 ? NP : 0) + 2 * ks, pb = (t == 2 ? NP : 0) + 2 * ks;
+                            const uint64_t da = tc::smem_desc(a_base + (uint32_t)pa * kLB * 16, kLB * 16, 128);
+                            const uint64_t db = tc::smem_desc(b_base + (uint32_t)(pb * Kpad + n0) * 16, (uint32_t)Kpad * 16, 128);
+                            tc::mma_tf32(tmem, da, db, idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                    tc::commit(mbar);
+                }
+                tc::mbar_wait(mbar, uses & 1u);
+                uses++;
+                tc::fence_after();
             }
-            if (means) sw[kk * kCB + threadIdx.x] = cf;
+            // this thread's row: lane 32*warp + lane id, columns [0, ncols)
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                float lg[32];
+                tc::tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, lg);
+                if (pass == 0) {
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const int k = n0 + c0 + j;
+                            if (sphi[k] != 0.0f) {
+                                const float e = expf(lg[j]);
+                                sum += e;
+                                if (k == y) dy = e;
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const int k = n0 + c0 + j;
+                        const float ip = sphi[k];
+                        float cf = 0.0f;
+                        if (valid && ip != 0.0f) {
+                            cf = (expf(lg[j]) * inv_denom - (k == y ? 1.0f : 0.0f)) * ip;
+#pragma unroll
+                            for (int c = 0; c < FP; c++)
+                                if (c < F) g[c] = fmaf(cf, su[(size_t)k * F + c], g[c]);
+                        }
+                        if (means) sw[((c0 + j) & (kKC - 1)) * kLB + tid] = cf;
+                    }
+                    if (means && (((c0 + 32) & (kKC - 1)) == 0 || c0 + 32 >= ncols)) {  // a kKC-cluster chunk of coefficients is complete
+                        const int k0 = n0 + ((c0 + 32 - 1) & ~(kKC - 1));
+                        const int nk = min(n0 + c0 + 32, K) - k0;
+                        __syncthreads();
+                        if (nk > 0) owner_accumulate<true, kLB>(F, FS, k0, nk, sf, nullptr, sw, dU);
+                        __syncthreads();
+                    }
+                }
+            }
+            if (pass == 0 || nch > 1) {  // TMEM is overwritten by the next chunk's MMAs
+                tc::fence_before();
+                __syncthreads();
+                tc::fence_after();
+            }
         }
-        if (means) {
-            __syncthreads();
-            owner_accumulate<true>(F, FS, k0, nk, sf, nullptr, sw, dU);
-            __syncthreads();
+        if (pass == 0) {
+            const float denom = sum + 1e-9f;
+            const float li = block_sum<kLB>(valid ? -logf(dy / denom) : 0.0f, s_red);
+            if (tid == 0 && li != 0.0f) atomicAdd(loss, li);
+            inv_denom = 1.0f / denom;
         }
     }
     if (i < N) {
@@ -272,6 +461,9 @@ contrast_loss_kernel(int N, int F, int K, const float* __restrict__ fhat, const 
         for (int c = 0; c < FP; c++)
             if (c < F) g_out[(size_t)i * F + c] = g[c];
     }
+    tc::fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)L.tmem_cols);
 }
 
 // phase 4 (backward)
@@ -471,24 +663,27 @@ int launch_contrastive_fwd(int N, int F, int K, const float* features, const int
     const int blocks = (N + kCB - 1) / kCB, FS = sample_stride(F);
     const size_t smem1 = ((size_t)kCB * FS + kCB) * 4;
     const size_t smem2 = ((size_t)K * F + 2 * kCB) * 4;
-    const size_t smem3 = ((size_t)K * F + ((K + 3) & ~3) + (size_t)kCB * FS + (size_t)kKC * kCB) * 4;
-    auto run = [&](auto stats_k, auto loss_k) -> int {
+    auto run = [&](auto stats_k, auto loss_k, int FPT) -> int {
+        const ContrastTcSmem S(F, FPT, K);
+        const size_t smem3 = S.total;
+        if (smem3 > 200 * 1024) return ISR_ERR_UNSUPPORTED;  // K * F too large for one CTA's operand panels
         ISR_CUDA_TRY(cudaFuncSetAttribute(stats_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
         ISR_CUDA_TRY(cudaFuncSetAttribute(contrast_spread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         ISR_CUDA_TRY(cudaFuncSetAttribute(loss_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
         stats_k<<<blocks, kCB, smem1, stream>>>(N, F, K, features, labels, predef_u == nullptr, fhat, inv_norm, sums, counts,
                                                 loss);
         contrast_spread_kernel<<<blocks, kCB, smem2, stream>>>(N, F, K, fhat, labels, predef_u, sums, counts, spread);
-        loss_k<<<blocks, kCB, smem3, stream>>>(N, F, K, fhat, labels, predef_u, sums, counts, spread, temp_lambda,
-                                               reinterpret_cast<float*>(w + L.g), reinterpret_cast<float*>(w + L.dU), loss);
+        loss_k<<<(N + kLB - 1) / kLB, kLB, smem3, stream>>>(N, F, K, fhat, labels, predef_u, sums, counts, spread, temp_lambda,
+                                                            reinterpret_cast<float*>(w + L.g), reinterpret_cast<float*>(w + L.dU),
+                                                            loss);
         ISR_CUDA_TRY(cudaGetLastError());
         return ISR_OK;
     };
-    if (F <= 4) return run(contrast_stats_kernel<4>, contrast_loss_kernel<4>);
-    if (F <= 8) return run(contrast_stats_kernel<8>, contrast_loss_kernel<8>);
-    if (F <= 16) return run(contrast_stats_kernel<16>, contrast_loss_kernel<16>);
-    if (F <= 24) return run(contrast_stats_kernel<24>, contrast_loss_kernel<24>);
-    return run(contrast_stats_kernel<32>, contrast_loss_kernel<32>);
+    if (F <= 4) return run(contrast_stats_kernel<4>, contrast_loss_tc_kernel<8>, 8);
+    if (F <= 8) return run(contrast_stats_kernel<8>, contrast_loss_tc_kernel<8>, 8);
+    if (F <= 16) return run(contrast_stats_kernel<16>, contrast_loss_tc_kernel<16>, 16);
+    if (F <= 24) return run(contrast_stats_kernel<24>, contrast_loss_tc_kernel<24>, 24);
+    return run(contrast_stats_kernel<32>, contrast_loss_tc_kernel<32>, 32);
 }
 
 int launch_contrastive_bwd(int N, int F, int K, const int* labels, const float* predef_u, const void* ws,

@@ -577,3 +577,29 @@ def test_plain_entry_fallback_path():
                         "test_forward_bit_exact or test_backward_dense or test_backward_sparse_equals_dense or test_empty"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("N,F,K,predef", [(2048, 8, 300, True), (1000, 4, 5, False), (3000, 32, 270, False), (257, 24, 33, True)])
+def test_contrastive_loss_shapes(N, F, K, predef):
+    """Cluster counts beyond one 256-column MMA chunk, F below one 8-wide K step, ragged N (not a multiple of the
+    128-row tile), absent clusters."""
+    import torch
+    import instascene_b200 as isr
+    from instascene_b200 import synth
+    from oracle.contrastive_ref import contrastive_loss_ref
+    rng = np.random.default_rng(N + K)
+    feats = rng.standard_normal((N, F)).astype(np.float32)
+    labels = rng.integers(0, K + 1, size=N).astype(np.int64)
+    labels[labels == 2] = 3
+    proto = None
+    if predef:
+        proto = rng.standard_normal((K + 1, F)).astype(np.float32)
+        proto /= np.linalg.norm(proto, axis=1, keepdims=True)
+    f64 = torch.tensor(feats, dtype=torch.float64, requires_grad=True)
+    want = contrastive_loss_ref(f64, torch.tensor(labels), None if proto is None else torch.tensor(proto, dtype=torch.float64))
+    want.backward()
+    fc = torch.tensor(feats, device="cuda", requires_grad=True)
+    got = isr.contrastive_loss(fc, torch.tensor(labels, device="cuda"), None if proto is None else torch.tensor(proto, device="cuda"))
+    got.backward()
+    assert abs(float(got) - float(want)) / abs(float(want)) < 1e-4
+    assert rel_err(fc.grad.cpu().numpy(), f64.grad.numpy()) < 1e-4

@@ -1,0 +1,128 @@
+"""SURVEY.md §8 row f-2 / BASELINE.json configs[4]: one --gram_feat_3d iteration of the semantic training loop
+(train_semantic.py:102-205) through instascene_b200.semantic_step -- two single-view ProtoNCE terms on the same render
+(cluster means, weight 0.5 / fixed class prototypes, weight 1), the 3D term over visible labelled Gaussians, backward
+to the raw seg-feature parameter -- against the CPU oracle rasterizer composed with the restated loss in torch-CPU
+float64.  F = 32 (beyond the reference's 24).  Tolerance 2e-4 norm-wise on the parameter gradient, 1e-4 on the loss."""
+import numpy as np
+import pytest
+
+from helpers import oracle_backward, oracle_forward, rel_err, scene_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene_objects(inp, W, H, dev):
+    import torch
+    sc, cam = inp["scene"], inp["cam"]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    class PC:
+        active_sh_degree, max_sh_degree = 3, 3
+        get_xyz, get_opacity = t(sc.xyz), t(sc.opacities()).reshape(-1, 1)
+        get_scaling, get_rotation, get_features = t(sc.scales()), t(sc.rotations()), t(sc.shs())
+        _seg_feature = t(sc.seg_feature_raw).requires_grad_(True)
+
+        @property
+        def get_seg_feature(self):
+            return self._seg_feature / (torch.norm(self._seg_feature, p=2, dim=1, keepdim=True) + 1e-6)
+
+    class Cam:
+        FoVx, FoVy, image_width, image_height = cam.FoVx, cam.FoVy, W, H
+        world_view_transform, full_proj_transform, camera_center = t(cam.world_view_transform), t(cam.full_proj_transform), t(cam.camera_center)
+        znear, zfar = 0.01, 100.0
+
+    class Pipe:
+        compute_cov3D_python, convert_SHs_python, depth_ratio = False, False, 1.0
+
+    return PC(), Cam(), Pipe(), t
+
+
+def test_gram_feat_3d_step_matches_oracle(oracle, monkeypatch):
+    import torch
+    import instascene_b200 as isr
+    from instascene_b200 import semantic_step as sstep, synth
+    from oracle.contrastive_ref import contrastive_loss_ref
+    P, F, W, H, seed, n = 5000, 32, 128, 80, 71, 4096
+    inp = scene_inputs(P, F, W, H, seed)
+    pc, cam, pipe, t = _scene_objects(inp, W, H, "cuda:0")
+    sc = inp["scene"]
+    lab_a = synth.label_map(W, H, seed + 2)              # view.segmap        (8x8 grid, ids 1..64)
+    lab_b = synth.label_map(W, H, seed + 3, grid=6)      # view.sorted_segmap (6x6 grid, ids 1..36)
+    class_feat = synth.gram_schmidt_prototypes(40, F, seed + 4)
+    labels3d = synth.morton_labels(sc.xyz, 36)
+    opt = sstep.SemanticOpt(sample_batchsize=n)
+
+    pkg = isr.render(cam, pc, pipe, t(inp["bg"]))
+    radii = pkg["radii"].cpu().numpy()
+    # fixed samples, shared with the oracle: the three draws of the step, in call order
+    rng = np.random.default_rng(seed + 5)
+    va, vb = np.flatnonzero(lab_a.reshape(-1) > 0), np.flatnonzero(lab_b.reshape(-1) > 0)
+    v3 = np.flatnonzero((radii > 0) & (labels3d > 0))
+    draws = [va[rng.integers(0, va.size, n)], vb[rng.integers(0, vb.size, n)], v3[rng.integers(0, v3.size, n)]]
+    queue = list(draws)
+
+    def fixed_sampler(labels_flat, count, generator=None):
+        ids = torch.from_numpy(queue.pop(0)).to(labels_flat.device)
+        assert count == n and bool((labels_flat[ids] > 0).all())
+        return ids, labels_flat[ids]
+
+    monkeypatch.setattr(sstep, "sample_labelled_pixels", fixed_sampler)
+    cf = t(class_feat)
+    loss = sstep.single_view_loss(pkg["seg_feature"], [t(lab_a.reshape(-1)), t(lab_b.reshape(-1))], cf, opt)
+    loss = loss + sstep.contrastive_3d_loss(pc._seg_feature, t(labels3d), pkg["radii"], cf, opt)
+    loss.backward()
+    assert not queue
+    got = pc._seg_feature.grad.cpu().numpy()
+
+    # ---- oracle ------------------------------------------------------------------------------------------------
+    with torch.no_grad():
+        segn = isr.normalize_rows(pc._seg_feature.detach(), 1e-6, 1e-9, stages=2)
+    inp["extra_attrs"] = segn.cpu().numpy()
+    o = oracle_forward(oracle, inp)
+    assert np.array_equal(pkg["seg_feature"].detach().cpu().numpy().view(np.uint32), o["extra"].view(np.uint32))
+    emap = torch.tensor(o["extra"], dtype=torch.float64, requires_grad=True)
+    raw = torch.tensor(sc.seg_feature_raw, dtype=torch.float64, requires_grad=True)
+    cf64 = torch.tensor(class_feat, dtype=torch.float64)
+    fa = emap.reshape(F, -1)[:, torch.tensor(draws[0])].t()
+    fb = emap.reshape(F, -1)[:, torch.tensor(draws[1])].t()
+    la = torch.tensor(lab_a.reshape(-1)[draws[0]].astype(np.int64))
+    lb = torch.tensor(lab_b.reshape(-1)[draws[1]].astype(np.int64))
+    l_ref = contrastive_loss_ref(fa, la) * (1e-6 * 0.5) + contrastive_loss_ref(fb, lb, cf64) * (1e-6 * 1.0)   # :133-143
+    act = raw / (torch.norm(raw, p=2, dim=1, keepdim=True) + 1e-6)                     # get_seg_feature
+    l3 = contrastive_loss_ref(act[torch.tensor(draws[2])], torch.tensor(labels3d[draws[2]]), cf64) * 2.5e-6     # :191-194
+    (l_ref + l3).backward()
+    assert abs(float(loss) - float(l_ref + l3)) / abs(float(l_ref + l3)) < 1e-4
+    og = oracle_backward(oracle, inp, o, np.zeros((3, H, W), np.float32), np.zeros((7, H, W), np.float32),
+                         emap.grad.numpy().astype(np.float32))
+    raw2 = torch.tensor(sc.seg_feature_raw, dtype=torch.float64, requires_grad=True)
+    a = raw2 / (torch.norm(raw2, p=2, dim=1, keepdim=True) + 1e-6)
+    a = a / (a.norm(dim=-1, keepdim=True) + 1e-9)
+    a.backward(torch.tensor(og["dL_dextra"], dtype=torch.float64))
+    want = raw.grad.numpy() + raw2.grad.numpy()
+    assert rel_err(got, want) < 2e-4
+
+
+def test_multiview_loss_equals_stacked_reference_sampling(monkeypatch):
+    """multiview_loss (train_semantic.py:146-173) gathers per view instead of stacking [V,F,H,W]; same value as the
+    reference's stacked formulation for the same draw."""
+    import torch
+    from instascene_b200 import semantic_step as sstep, synth
+    from oracle.contrastive_ref import contrastive_loss_ref
+    V, F, W, H, n = 3, 8, 40, 24, 2048
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    maps = [torch.randn((F, H, W), device="cuda", generator=gen, requires_grad=True) for _ in range(V)]
+    labs = [torch.from_numpy(synth.label_map(W, H, 90 + v, grid=3)).cuda().reshape(-1) for v in range(V)]
+    flat = torch.cat(labs)
+    valid = torch.nonzero(flat > 0).reshape(-1)
+    draw = valid[torch.randint(0, valid.numel(), (n,), device="cuda", generator=gen)]
+    monkeypatch.setattr(sstep, "sample_labelled_pixels", lambda lf, c, generator=None: (draw, lf[draw]))
+    cf = torch.from_numpy(synth.gram_schmidt_prototypes(12, F, 5)).cuda()
+    loss = sstep.multiview_loss(maps, labs, cf, sstep.SemanticOpt(sample_batchsize=n))
+    loss.backward()
+    stacked = torch.stack([m.detach().double().cpu() for m in maps], 0).requires_grad_(True)   # [V,F,H,W]
+    feats = stacked.permute(1, 0, 2, 3).reshape(F, -1)[:, draw.cpu()].t()                       # :163-167
+    want = contrastive_loss_ref(feats, flat[draw].cpu().long(), cf.double().cpu()) * 1e-6
+    want.backward()
+    assert abs(float(loss) - float(want)) / abs(float(want)) < 1e-4
+    got = torch.stack([m.grad for m in maps], 0).cpu().numpy()
+    assert rel_err(got, stacked.grad.numpy()) < 1e-4
