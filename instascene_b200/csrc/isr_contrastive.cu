@@ -402,6 +402,7 @@ contrast_loss_tc_kernel(int N, int F, int K, const float* __restrict__ fhat, con
                 }
                 tc::mbar_wait(mbar, uses & 1u);
                 uses++;
+                __syncwarp();  // lane 0 issued the MMAs: reconverge before the .aligned TMEM loads
                 tc::fence_after();
             }
             // this thread's row: lane 32*warp + lane id, columns [0, ncols)
