@@ -66,7 +66,7 @@ WORKLOADS = {
 }
 # our own kernels per step (DESIGN.md "launch list"); cfg5 = cfg3's 17 + gather/contrast x2 more terms (1+4, 4) +
 # rownorm fwd/bwd of the sampled 3D rows
-KERNELS_PER_STEP = {"cfg3": 17, "cfg2": 11, "cfg5": 28}
+KERNELS_PER_STEP = {"cfg3": 17, "cfg2": 12, "cfg5": 28}
 # dram__bytes_read.sum + dram__bytes_write.sum of blend_fwd_kernel per launch, from the committed `ncu --set full`
 # capture profiles/r1_ncu_blend_fwd_v4.txt (cfg3); no capture of that kernel exists for cfg2 / cfg5
 NCU_TRAFFIC_BYTES = {"cfg3": 138.5e6 + 255.8e6, "cfg2": None, "cfg5": None}
@@ -182,10 +182,17 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------------------------------
 def build_workload(name: str, n_views_needed: int):
-    from instascene_b200 import synth
+    """Seeded synthetic scene + the ring of views.  The views travel through a synthetic COLMAP model on disk
+    (cameras.bin / images.bin, BASELINE.json configs[3] "200 synthetic COLMAP views") and are read back the way the
+    reference derives its cameras from those files (scene/colmap_loader.py:180-241, scene/dataset_readers.py:68-101)."""
+    import tempfile
+    from instascene_b200 import io as isr_io, synth
     w = WORKLOADS[name]
     scene = synth.synth_scene(w["P"], F=w["F"], seed=w["seed"])
-    cams = synth.ring_cameras(w["n_views"], w["W"], w["H"])
+    with tempfile.TemporaryDirectory(prefix="isr_colmap_") as d:
+        isr_io.write_synthetic_colmap(os.path.join(d, "sparse", "0"), synth.ring_cameras(w["n_views"], w["W"], w["H"]))
+        cams = isr_io.load_colmap_cameras(os.path.join(d, "sparse", "0"))
+    assert len(cams) == w["n_views"]
     return w, scene, cams
 
 
@@ -379,7 +386,8 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "gaussians": P, "feat_dim": F, "image": [W, H],
-                       "views_per_step_per_gpu": 1, "preheat_steps_untimed": preheat, "parallelism": f"dp{world} (views sharded, grad all-reduce)",
+                       "views_per_step_per_gpu": 1, "views": f"{len(cams)} synthetic COLMAP views (cameras.bin/images.bin round trip)",
+                       "preheat_steps_untimed": preheat, "parallelism": f"dp{world} (views sharded, grad all-reduce)",
                        "l2": "inputs larger than L2 (Gaussian state %.0f MB >> 126 MB), distinct view every step" % (P * (232 + 4 * F) / 1e6),
                        "optimizer": "Adam(lr=0.025, eps=1e-15) on _seg_feature (isr.FusedAdam)" if opt is not None else "none"},
             "clocks": clocks,

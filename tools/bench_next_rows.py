@@ -49,9 +49,24 @@ def main():
 
     chw = img.numel()
     t_o, t_r = ev_time(ours), ev_time(ref)
-    alg = chw * 4 * (2 + 3) + chw * 4 * (3 + 2 + 1)
-    out["photometric_1080p"] = {"ours_ms": t_o, "torch_formula_ms": t_r, "speedup": t_r / t_o, "algorithmic_bytes": alg,
-                                "achieved_GBs": alg / t_o / 1e6, "hbm_peak_GBs": peaks.get("hbm_gbs")}
+    # the two kernels alone, through the C ABI (no autograd / Python between launches)
+    from instascene_b200 import _lib
+    L = _lib.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    ws_bytes = L.isr_photometric_workspace_bytes(3, 1080, 1920)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    out3 = torch.empty(3, device="cuda")
+    dimg = torch.empty_like(img)
+    fwd = lambda: _lib.check(L.isr_photometric_forward(3, 1080, 1920, img.data_ptr(), gt.data_ptr(), 0.2, ws.data_ptr(), ws_bytes,
+                                                       out3.data_ptr(), stream), "fwd")
+    bwd = lambda: _lib.check(L.isr_photometric_backward(3, 1080, 1920, img.data_ptr(), gt.data_ptr(), 0.2, ws.data_ptr(), None,
+                                                        dimg.data_ptr(), stream), "bwd")
+    t_f, t_b = ev_time(fwd, n=50), ev_time(bwd, n=50)
+    alg_f, alg_b = chw * 4 * (2 + 3), chw * 4 * (3 + 2 + 1)
+    out["photometric_1080p"] = {"autograd_fwd_bwd_ms": t_o, "torch_formula_ms": t_r, "speedup": t_r / t_o,
+                                "fwd_kernel_ms": t_f, "bwd_kernel_ms": t_b, "fwd_GBs": alg_f / t_f / 1e6,
+                                "bwd_GBs": alg_b / t_b / 1e6, "algorithmic_bytes_fwd": alg_f, "algorithmic_bytes_bwd": alg_b,
+                                "hbm_peak_GBs": peaks.get("hbm_gbs")}
     # tracker on a cfg3-sized pair list
     P, W, H = 2_000_000, 1920, 1080
     scene = synth.synth_scene(P, F=0, seed=1003)
