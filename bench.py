@@ -292,10 +292,20 @@ def run_ours(args):
             setattr(pc, name, p)
             geo_params.append(p)
 
-    def step(v, data):
+    # Semantic-feature training optimises `_seg_feature` only (train_semantic.py), so the geometry phase of the NEXT
+    # view (projection, depth sort, instance count -- none of it reads the features) can be started on a side stream
+    # while the loss / backward / optimizer tail of the current view runs: isr.prefetch_geometry.  Not valid for cfg2
+    # (RGB training moves the geometry every step).  ISR_BENCH_PREFETCH=0 disables it.
+    use_prefetch = args.workload in ("cfg3", "cfg5") and os.environ.get("ISR_BENCH_PREFETCH", "1") != "0"
+    prefetched = {}
+
+    def step(v, data, nxt=None):
         cam = _Cam(cams[v], data["wvt"], data["fpt"], data["center"])
         if args.workload in ("cfg3", "cfg5"):
-            pkg = isr.render(cam, pc, _Pipe, bg)
+            pkg = isr.render(cam, pc, _Pipe, bg, prefetched=prefetched.pop(v, None))
+            if use_prefetch and nxt is not None:
+                vn, dn = nxt
+                prefetched[vn] = isr.prefetch_geometry(_Cam(cams[vn], dn["wvt"], dn["fpt"], dn["center"]), pc, _Pipe, bg)
             segmaps = [data["labels"]] if class_feat is None else [data["labels"], data["labels2"]]
             loss = sstep.single_view_loss(pkg["seg_feature"], segmaps, class_feat, sem_opt, generator=gen,
                                           num_labels=wl["labels"])
@@ -341,15 +351,27 @@ def run_ours(args):
         h2d = d2h = 0
         e0.record()
         last = None
+        view_of = lambda s: my_views[s % len(my_views)] if wrap else my_views[s]
+        cam_keys = ("wvt", "fpt", "center")
+        upload = lambda v, keys: {k: host[v][k].to(dev, non_blocking=True) for k in keys}
+        cam_next = None  # e2e: the next view's camera matrices are uploaded one step ahead (they feed the prefetch)
+        prefetched.clear()
         for s in range(first, first + n_steps):
-            v = my_views[s % len(my_views)] if wrap else my_views[s]
+            v = view_of(s)
+            nxt = None
             if e2e:
-                data = {k: x.to(dev, non_blocking=True) for k, x in host[v].items()}
+                data = cam_next if cam_next is not None else upload(v, cam_keys)
+                data.update(upload(v, [k for k in host[v] if k not in cam_keys]))
                 if s == first:
                     h2d = sum(x.numel() * x.element_size() for x in host[v].values())
+                if s + 1 < first + n_steps:
+                    cam_next = upload(view_of(s + 1), cam_keys)
+                    nxt = (view_of(s + 1), cam_next)
             else:
                 data = devdata[v]
-            loss = step(v, data)
+                if s + 1 < first + n_steps:
+                    nxt = (view_of(s + 1), devdata[view_of(s + 1)])
+            loss = step(v, data, nxt)
             if e2e:
                 last = float(loss.detach().to("cpu", non_blocking=False))  # device -> host read of the step's result
                 d2h = 4
@@ -387,7 +409,9 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "gaussians": P, "feat_dim": F, "image": [W, H],
                        "views_per_step_per_gpu": 1, "views": f"{len(cams)} synthetic COLMAP views (cameras.bin/images.bin round trip)",
-                       "preheat_steps_untimed": preheat, "parallelism": f"dp{world} (views sharded, grad all-reduce)",
+                       "preheat_steps_untimed": preheat,
+                       "geometry_prefetch": "next view's projection + depth sort overlap the current step's loss/backward/Adam "
+                                            "(isr.prefetch_geometry)" if use_prefetch else "off", "parallelism": f"dp{world} (views sharded, grad all-reduce)",
                        "l2": "inputs larger than L2 (Gaussian state %.0f MB >> 126 MB), distinct view every step" % (P * (232 + 4 * F) / 1e6),
                        "optimizer": "Adam(lr=0.025, eps=1e-15) on _seg_feature (isr.FusedAdam)" if opt is not None else "none"},
             "clocks": clocks,

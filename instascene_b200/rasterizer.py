@@ -69,12 +69,12 @@ def _require_cuda_lib():
 class _ForwardState:
     """Everything between the two phases of the forward (isr_forward_geometry -> isr_forward_render)."""
     __slots__ = ("args", "keep", "P", "H", "W", "dev", "want_pairs", "out_color", "out_others", "radii", "geom", "img",
-                 "pairs", "pair_count", "nr_host")
+                 "pairs", "pair_count", "nr_host", "ready_event")
 
 
 def launch_geometry(background, means3D, colors, opacity, scales, rotations, scale_modifier, transMat_precomp, viewmatrix,
                     projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
-                    want_pairs: bool = True) -> Optional[_ForwardState]:
+                    want_pairs: bool = True, pinned_counts: Optional[torch.Tensor] = None) -> Optional[_ForwardState]:
     """Phase A of the forward: K1 projection + depth order + offsets, enqueued asynchronously on the current stream.
     Nothing here depends on extra_attrs (the semantic features), so a caller may start it before the features of the
     step are final (e.g. while the previous step's gradient all-reduce / optimizer step runs on another stream)."""
@@ -99,6 +99,7 @@ def launch_geometry(background, means3D, colors, opacity, scales, rotations, sca
     sh = _f32c(sh, "sh") if sh.numel() else sh
     M = int(sh.shape[1]) if sh.numel() else 0
     st = _ForwardState()
+    st.ready_event = None  # set when phase A was launched on another stream (renderer.prefetch_geometry)
     st.P, st.H, st.W, st.dev, st.want_pairs = P, H, W, dev, want_pairs
     st.out_color = torch.empty((3, H, W), **f32)
     st.out_others = torch.empty((7, H, W), **f32)
@@ -109,7 +110,7 @@ def launch_geometry(background, means3D, colors, opacity, scales, rotations, sca
     pair_cap = 9 * H * W if want_pairs else 0
     st.pairs = torch.empty((pair_cap, 2), dtype=torch.int32, device=dev)
     st.pair_count = torch.zeros(1, dtype=torch.int32, device=dev)
-    st.nr_host = _pinned_i64(dev)
+    st.nr_host = pinned_counts if pinned_counts is not None else _pinned_i64(dev)
     a = _lib.IsrForwardArgs()
     a.P, a.sh_degree, a.sh_coeffs, a.F, a.W, a.H = P, int(degree), M, 0, W, H
     a.flags = 0 if want_pairs else _lib.FLAG_NO_PAIRS
@@ -138,7 +139,13 @@ def finish_render(st: _ForwardState, extra_attrs, F: int, debug: bool = False, r
         a.F, a.extra_attrs, a.out_extra = F, extra_attrs.data_ptr(), out_extra.data_ptr()
     else:
         out_extra = torch.empty(0, dtype=torch.float32, device=dev)
-    torch.cuda.current_stream().synchronize()  # the reference blocks on a cudaMemcpy here (rasterizer_impl.cu:287)
+    if st.ready_event is not None:
+        # phase A ran on another stream (usually a whole step earlier): order this stream behind it and wait on the host
+        # for THAT event only -- nothing queued on the current stream is waited for
+        torch.cuda.current_stream().wait_event(st.ready_event)
+        st.ready_event.synchronize()
+    else:
+        torch.cuda.current_stream().synchronize()  # the reference blocks on a cudaMemcpy here (rasterizer_impl.cu:287)
     # [0]: what the reference reports as num_rendered (all tiles of every rectangle); [1]: instances actually binned
     num_rendered, n_inst = int(st.nr_host[0]), int(st.nr_host[1])
     bin_bytes = L.isr_binning_bytes(st.P, n_inst, st.W, st.H)

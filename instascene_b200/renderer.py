@@ -213,9 +213,8 @@ def _precomputed_transmats(camera, pc, scaling_modifier, device):
     return (splat2world[:, [0, 1, 3]] @ world2pix[:, [0, 1, 3]]).permute(0, 2, 1).reshape(-1, 9)
 
 
-def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
-           norm_seg_feat=True, want_pairs: bool = True):
-    """Rasterise `pc` from `viewpoint_camera`.  `bg_color` must live on the GPU."""
+def _raster_inputs(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, override_color, want_pairs):
+    """Settings tuple + geometry / appearance arguments of one view, as render() assembles them (reference :36-100)."""
     xyz = pc.get_xyz
     settings_cls = _SettingsDeferPairs if want_pairs else _SettingsNoPairs
     settings = settings_cls(
@@ -224,7 +223,6 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
         scale_modifier=scaling_modifier, viewmatrix=viewpoint_camera.world_view_transform,
         projmatrix=viewpoint_camera.full_proj_transform, sh_degree=pc.active_sh_degree,
         campos=viewpoint_camera.camera_center, prefiltered=False, debug=False)
-
     geometry = {}
     if pipe.compute_cov3D_python:
         geometry["cov3D_precomp"] = _precomputed_transmats(viewpoint_camera, pc, scaling_modifier, xyz.device)
@@ -232,11 +230,85 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
         geometry["scales"], geometry["rotations"] = pc.get_scaling, pc.get_rotation
     pipe.convert_SHs_python = False  # the reference mutates the caller's object in the same way (Q10)
     appearance = {"shs": pc.get_features} if override_color is None else {"colors_precomp": override_color}
+    return settings, xyz, pc.get_opacity, geometry, appearance
+
+
+def _launch_phase_a(settings, xyz, opacity, geometry, appearance, viewpoint_camera, pc, bg_color, scaling_modifier, want_pairs,
+                    pinned_counts=None):
+    none = torch.empty(0, dtype=torch.float32, device=xyz.device)
+    return launch_geometry(
+        bg_color, xyz, appearance.get("colors_precomp", none), opacity, geometry.get("scales", none),
+        geometry.get("rotations", none), scaling_modifier, geometry.get("cov3D_precomp", none),
+        viewpoint_camera.world_view_transform, viewpoint_camera.full_proj_transform, settings.tanfovx,
+        settings.tanfovy, settings.image_height, settings.image_width, appearance.get("shs", none),
+        pc.active_sh_degree, viewpoint_camera.camera_center, want_pairs=want_pairs, pinned_counts=pinned_counts)
+
+
+class PrefetchedGeometry:
+    """Phase A (projection, depth order, offsets, instance count) of a FUTURE view, already running on a side stream."""
+    __slots__ = ("state", "key")
+
+    def __init__(self, state, key):
+        self.state, self.key = state, key
+
+
+def _prefetch_key(viewpoint_camera, pc, scaling_modifier, want_pairs):
+    return (viewpoint_camera.world_view_transform.data_ptr(), viewpoint_camera.full_proj_transform.data_ptr(),
+            int(viewpoint_camera.image_height), int(viewpoint_camera.image_width), pc.get_xyz.data_ptr(),
+            float(scaling_modifier), bool(want_pairs))
+
+
+_prefetch_streams = {}
+_prefetch_pinned = {}  # device index -> [ring of pinned int64[2] count buffers, next slot]: up to 4 views in flight
+
+
+def _next_pinned_counts(dev_index):
+    ring = _prefetch_pinned.get(dev_index)
+    if ring is None:
+        ring = _prefetch_pinned[dev_index] = [[torch.zeros(2, dtype=torch.int64).pin_memory() for _ in range(4)], 0]
+    buf = ring[0][ring[1] % 4]
+    ring[1] += 1
+    return buf
+
+
+def prefetch_geometry(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
+                      want_pairs: bool = True, stream=None) -> PrefetchedGeometry:
+    """Starts phase A of render() for a view that will be rendered LATER (typically the next training view, drawn one
+    iteration ahead) on a side stream, so that it overlaps the latency-bound loss / backward / optimizer tail of the
+    current iteration and the host never waits for the instance count in the middle of the next forward.  Valid
+    whenever nothing phase A reads changes in between: positions, scales, rotations, opacities, SH -- i.e. in the
+    semantic-feature training loop (train_semantic.py optimises `_seg_feature` only), NOT in RGB training.  Pass the
+    handle to `render(..., prefetched=handle)` with the same camera object; results are identical to an inline render.
+    The side stream first waits for everything already queued on the current stream (so every buffer it may recycle is
+    no longer in use), then runs K1 + the depth sort."""
+    dev = pc.get_xyz.device
+    main = torch.cuda.current_stream()
+    side = stream if stream is not None else _prefetch_streams.get(dev.index)
+    if side is None:
+        side = _prefetch_streams[dev.index] = torch.cuda.Stream(device=dev)
+    with torch.no_grad():
+        settings, xyz, opacity, geometry, appearance = _raster_inputs(viewpoint_camera, pc, pipe, bg_color, scaling_modifier,
+                                                                      override_color, want_pairs)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            st = _launch_phase_a(settings, xyz, opacity, geometry, appearance, viewpoint_camera, pc, bg_color,
+                                 scaling_modifier, want_pairs, pinned_counts=_next_pinned_counts(dev.index))
+            if st is not None:
+                st.ready_event = torch.cuda.Event()
+                st.ready_event.record(side)
+    return PrefetchedGeometry(st, _prefetch_key(viewpoint_camera, pc, scaling_modifier, want_pairs))
+
+
+def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
+           norm_seg_feat=True, want_pairs: bool = True, prefetched: "PrefetchedGeometry | None" = None):
+    """Rasterise `pc` from `viewpoint_camera`.  `bg_color` must live on the GPU.  `prefetched`: handle of
+    `prefetch_geometry` for this very view (ignored if it was made for different inputs)."""
+    settings, xyz, opacity, geometry, appearance = _raster_inputs(viewpoint_camera, pc, pipe, bg_color, scaling_modifier,
+                                                                  override_color, want_pairs)
 
     # Phase A (projection, depth order, offsets) does not read the semantic features: launch it first so that it can
     # overlap whatever still produces them (pc._isr_param_ready_event: e.g. the previous step's gradient all-reduce +
     # optimizer step running on another stream).  Same kernels, same order of results.
-    opacity = pc.get_opacity
     # Dummy leaf that receives the densification proxy dL/dmean2D (reference :29-33).  The reference makes it require
     # grad unconditionally; here only when some geometry/appearance input does (the proxy is read by densification,
     # which optimises those).  With frozen geometry -- train_semantic.py -- that keeps the backward on the
@@ -244,14 +316,12 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
     geom_trainable = torch.is_grad_enabled() and any(
         t.requires_grad for t in (xyz, opacity, *geometry.values(), *appearance.values()))
     screen_pts = torch.zeros_like(xyz, requires_grad=bool(geom_trainable))
-    none = torch.empty(0, dtype=torch.float32, device=xyz.device)
-    if getattr(pipe, "geometry_first", _GEOMETRY_FIRST):
-        settings._geom_state = launch_geometry(
-            bg_color, xyz, appearance.get("colors_precomp", none), opacity, geometry.get("scales", none),
-            geometry.get("rotations", none), scaling_modifier, geometry.get("cov3D_precomp", none),
-            viewpoint_camera.world_view_transform, viewpoint_camera.full_proj_transform, settings.tanfovx,
-            settings.tanfovy, settings.image_height, settings.image_width, appearance.get("shs", none),
-            pc.active_sh_degree, viewpoint_camera.camera_center, want_pairs=want_pairs)
+    if (prefetched is not None and prefetched.state is not None and not geom_trainable
+            and prefetched.key == _prefetch_key(viewpoint_camera, pc, scaling_modifier, want_pairs)):
+        settings._geom_state = prefetched.state
+    elif getattr(pipe, "geometry_first", _GEOMETRY_FIRST):
+        settings._geom_state = _launch_phase_a(settings, xyz, opacity, geometry, appearance, viewpoint_camera, pc, bg_color,
+                                               scaling_modifier, want_pairs)
     ready = getattr(pc, "_isr_param_ready_event", None)
     if ready is not None:
         torch.cuda.current_stream().wait_event(ready)

@@ -126,3 +126,44 @@ def test_multiview_loss_equals_stacked_reference_sampling(monkeypatch):
     assert abs(float(loss) - float(want)) / abs(float(want)) < 1e-4
     got = torch.stack([m.grad for m in maps], 0).cpu().numpy()
     assert rel_err(got, stacked.grad.numpy()) < 1e-4
+
+
+def test_prefetched_geometry_render_is_bitwise_the_inline_render():
+    """isr.prefetch_geometry starts phase A of a later view on a side stream; render(prefetched=...) must return exactly
+    what an inline render returns (outputs, pair list, gradient of the features), also when several views are in
+    flight, and must ignore a handle made for a different camera."""
+    import torch
+    import instascene_b200 as isr
+    from instascene_b200 import synth
+    P, F, W, H, seed = 6000, 16, 160, 96, 81
+    inp = scene_inputs(P, F, W, H, seed)
+    pc, cam0, pipe, t = _scene_objects(inp, W, H, "cuda:0")
+    cams = []
+    for c in synth.ring_cameras(4, W, H):
+        class Cam:
+            FoVx, FoVy, image_width, image_height = c.FoVx, c.FoVy, W, H
+            world_view_transform, full_proj_transform, camera_center = t(c.world_view_transform), t(c.full_proj_transform), t(c.camera_center)
+            znear, zfar = 0.01, 100.0
+        cams.append(Cam())
+    bg = t(inp["bg"])
+
+    def run(cam, handle=None):
+        pc._seg_feature.grad = None
+        pkg = isr.render(cam, pc, pipe, bg, prefetched=handle)
+        (pkg["seg_feature"] * pkg["seg_feature"]).sum().backward()
+        pairs = pkg["gau_related_pixels"]
+        return (pkg["render"].detach().clone(), pkg["seg_feature"].detach().clone(), pkg["radii"].clone(),
+                pairs[torch.argsort(pairs[:, 0].long() * (W * H) + pairs[:, 1].long())].clone(), pc._seg_feature.grad.clone())
+
+    want = [run(c) for c in cams]
+    handles = [isr.prefetch_geometry(c, pc, pipe, bg) for c in cams[:3]]       # three views in flight
+    got = [run(cams[1], handles[1]), run(cams[0], handles[0]), run(cams[2], handles[2])]
+    for g, w in zip(got, [want[1], want[0], want[2]]):
+        for a, b in zip(g[:4], w[:4]):
+            assert torch.equal(a, b)
+        assert rel_err(g[4].cpu().numpy(), w[4].cpu().numpy()) < 1e-5        # float atomics: summation order differs run to run
+    stale = isr.prefetch_geometry(cams[0], pc, pipe, bg)
+    g = run(cams[3], stale)                                                    # wrong view: handle ignored
+    for a, b in zip(g[:4], want[3][:4]):
+        assert torch.equal(a, b)
+    torch.cuda.synchronize()
