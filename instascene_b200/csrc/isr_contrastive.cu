@@ -667,7 +667,9 @@ int launch_contrastive_fwd(int N, int F, int K, const float* features, const int
     auto run = [&](auto stats_k, auto loss_k, int FPT) -> int {
         const ContrastTcSmem S(F, FPT, K);
         const size_t smem3 = S.total;
-        if (smem3 > 200 * 1024) return ISR_ERR_UNSUPPORTED;  // K * F too large for one CTA's operand panels
+        // centres + operand panels of ALL K clusters live in one CTA's shared memory (227 KB opt-in on sm_100, a few bytes
+        // of it static): K <= ~890 at F = 16, ~385 at F = 32
+        if (smem3 > 226 * 1024) return ISR_ERR_UNSUPPORTED;
         ISR_CUDA_TRY(cudaFuncSetAttribute(stats_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
         ISR_CUDA_TRY(cudaFuncSetAttribute(contrast_spread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         ISR_CUDA_TRY(cudaFuncSetAttribute(loss_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
