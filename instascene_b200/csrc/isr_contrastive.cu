@@ -8,8 +8,8 @@
 //   u_k   = predef_u[k]  or  mean_{i in k} f^_i   (gradient flows through mean)  (:44-45, :54-58)
 //   phi_k = clip(10 * sum_{i in k} |f^_i - u_k| / (n_k log(n_k + lambda)), .5, 1)  detached   (:60-66)
 //   loss  = - sum_i log( exp(f^_i.u_{y_i}/phi_{y_i}) / (sum_k exp(f^_i.u_k/phi_k) + 1e-9) )       (:68-71)
-// The [N,F]x[F,K] logits contraction is ~70 MFLOP at N=32768,K=64,F=16: it is evaluated in exact fp32 FFMA
-// (u_k staged in shared memory), one sample per thread.
+// The [N,F]x[F,K] logits contraction (~70 MFLOP at N=32768,K=64,F=16) is the one GEMM-shaped piece of the path: it runs
+// on the tensor cores (tcgen05.mma kind::tf32 with a 3xTF32 split, fp32 accumulation in TMEM), see phase 3 below.
 #include <cmath>
 
 #include "isr_common.cuh"
@@ -44,11 +44,11 @@ __global__ void gather_pixels_kernel(int F, int64_t HW, const float* __restrict_
 }
 
 // The loss is evaluated in four grid-wide phases (each needs a reduction over ALL samples of the previous one), every
-// phase one kernel of ceil(N/256) blocks x 256 threads, one sample per thread:
+// phase one kernel, one sample per thread (256-thread blocks; the tensor-core loss kernel: 128 = the rows of a UMMA tile):
 //   stats   f^ = f/(|f|+1e-9); per-cluster sums and counts
 //   spread  u_k = mean (or predefined prototype); per-cluster sum of |f^ - u_k|
-//   loss    phi_k; logits, loss, softmax coefficients coef_ik = (p_ik - [k == y_i]) / phi_k (never stored: a block keeps
-//           64 clusters x 256 samples of them in shared memory), g_i = sum_k coef_ik u_k, dU_k = sum_i coef_ik f^_i
+//   loss    phi_k; logits (tcgen05), loss, softmax coefficients coef_ik = (p_ik - [k == y_i]) / phi_k (never stored: a block
+//           keeps 64 clusters x 128 samples of them in shared memory), g_i = sum_k coef_ik u_k, dU_k = sum_i coef_ik f^_i
 //   dfeat   (backward) dL/df_i = grad_scale / (|f_i| + eps) * (g_i + [means] dU[y_i] / n_{y_i})
 // Per-cluster block reductions are "owner computes": the block's samples and labels sit in shared memory and a thread
 // sums the members of the (cluster, channel) entries it owns -- no shared-memory float atomics (CAS loops on this
