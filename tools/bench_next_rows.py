@@ -32,7 +32,6 @@ def main():
     from instascene_b200 import synth
     from instascene_b200.tracker import segmap_gaussians
     from test_losses import _torch_reference
-    from oracle.tracker_ref import segmap_gaussians_ref
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     out = {}
     gen = torch.Generator(device="cuda").manual_seed(1)
