@@ -229,3 +229,26 @@ def test_gloo_world2_gradient_allreduce(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_cfg1_plumbing_config_on_the_cpu_port(oracle):
+    """BASELINE.json configs[0]: 50k random Gaussians, one 512x512 camera, RGB-only forward on the CPU restatement
+    (the reference has no CPU path; this is the plumbing config that needs no GPU).  Size-independent properties."""
+    from helpers import oracle_forward, scene_inputs
+    P, W, H = 50_000, 512, 512
+    inp = scene_inputs(P, 0, W, H, 1001, view=0, n_views=8)
+    o = oracle_forward(oracle, inp, want_pairs=False)
+    vis = o["radii"] > 0
+    assert 0.3 * P < vis.sum() <= P and o["num_rendered"] == int(o["tiles_touched"].sum()) > P
+    assert o["color"].shape == (3, H, W) and np.isfinite(o["color"]).all() and np.isfinite(o["others"]).all()
+    r = o["ranges"].astype(np.int64)
+    assert r.shape[0] == (W // 16) * (H // 16) and int((r[:, 1] - r[:, 0]).sum()) == o["num_rendered"]
+    keys = o["keys"]
+    assert np.all(keys[1:] >= keys[:-1])                                        # (tile, depth) sortedness
+    T = o["final_T"][0]
+    assert np.all(T >= 1e-4 - 1e-9) and np.all(T <= 1.0) and np.allclose(o["others"][1], 1.0 - T, atol=1e-6)
+    # colour = blended colour + T * background: with a black background the image is bounded by alpha * max colour
+    inp_black = dict(inp, bg=np.zeros(3, np.float32))
+    ob = oracle_forward(oracle, inp_black, want_pairs=False)
+    assert np.allclose(o["color"] - ob["color"], T[None] * inp["bg"][:, None, None], atol=1e-6)   # linear in the background
+    assert np.array_equal(o["n_contrib"], ob["n_contrib"]) and np.array_equal(o["others"], ob["others"])
