@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define ISR_VERSION 100
+#define ISR_VERSION 200
 
 typedef enum IsrStatus {
     ISR_OK = 0,
@@ -66,6 +66,11 @@ typedef enum IsrStatus {
 #define ISR_FLAG_NO_PAIRS     2u  /* do not emit the gau_related_pixels list                              */
 #define ISR_FLAG_SKIP_BINNING 4u  /* isr_forward_render: reuse the binning already in the workspaces and run
                                      only the blend kernel (profiling / roofline measurement)              */
+#define ISR_FLAG_SPEC_ARITH   8u  /* evaluate exp / rsqrt with the CPU-reproducible IEEE-only stand-ins of
+                                     oracle/isr_oracle.c instead of CUDA's expf / rsqrtf (the reference's own,
+                                     MUFU based).  Default (flag clear): the reference's arithmetic -- forward
+                                     results are bit-identical to the unmodified reference CUDA rasterizer.
+                                     Pass the same value to the forward and to the backward of a view.      */
 
 /* gradient request mask for isr_backward (needs_input_grad gating; all = reference behaviour) */
 #define ISR_GRAD_GEOMETRY 1u   /* means3D, means2D, scales, rotations, transMat, normal                  */
@@ -192,7 +197,7 @@ int isr_backward(const IsrBackwardArgs* args, void* stream);
 int isr_backward_extra_sparse(int P, int F, int W, int H, const float* extra_attrs, const void* geom,
                               const void* image, const void* binning, int64_t num_rendered, int n,
                               const int* pix_ids, const float* dL_dextra_samples, float* dL_dextra,
-                              void* stream);
+                              unsigned flags /* ISR_FLAG_SPEC_ARITH as in the forward */, void* stream);
 
 int isr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                      uint8_t* present, void* stream);

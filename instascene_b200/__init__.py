@@ -2,7 +2,7 @@
 the reference InstaScene interfaces (diff_surfel_rasterization, gaussian_renderer.render, contrastive_loss,
 distCUDA2).  Host side = Python mirror of the reference API; device side = libisr.so (C ABI, include/isr.h)."""
 from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians, sample_pixels, normalize_rows,  # noqa: F401
-                         sample_labelled_pixels,
+                         sample_labelled_pixels, set_arithmetic, arithmetic,
                          _C)
 from .renderer import render, depth_to_normal, prefetch_geometry  # noqa: F401
 from .contrastive import contrastive_loss  # noqa: F401
@@ -14,4 +14,4 @@ from . import io  # noqa: F401
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "sample_pixels", "sample_labelled_pixels", "normalize_rows", "render",
            "depth_to_normal", "prefetch_geometry", "contrastive_loss", "distCUDA2", "FusedAdam", "get_segmap_gaussians", "segmap_gaussians",
-           "photometric_loss", "l1_loss", "ssim", "add_densification_stats", "io"]
+           "photometric_loss", "l1_loss", "ssim", "add_densification_stats", "io", "set_arithmetic", "arithmetic"]

@@ -12,6 +12,7 @@ ISR_OK = 0
 FLAG_BWD_WH_QUIRK = 1
 FLAG_NO_PAIRS = 2
 FLAG_SKIP_BINNING = 4
+FLAG_SPEC_ARITH = 8
 GRAD_GEOMETRY, GRAD_COLOR, GRAD_OPACITY, GRAD_EXTRA, GRAD_ALL = 1, 2, 4, 8, 15
 MAX_EXTRA_DIMS = 32
 
@@ -94,7 +95,7 @@ def lib() -> C.CDLL:
     L.isr_forward_render.argtypes = [C.POINTER(IsrForwardArgs), C.c_int64, C.c_void_p]
     L.isr_backward.argtypes = [C.POINTER(IsrBackwardArgs), C.c_void_p]
     L.isr_backward_extra_sparse.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _fp, _vp, _vp, _vp, C.c_int64, C.c_int,
-                                            _ip, _fp, _fp, C.c_void_p]
+                                            _ip, _fp, _fp, C.c_uint, C.c_void_p]
     L.isr_mark_visible.argtypes = [C.c_int, _fp, _fp, _fp, _vp, C.c_void_p]
     L.isr_gather_pixels.argtypes = [C.c_int, C.c_int64, _fp, C.c_int, _ip, _fp, C.c_void_p]
     L.isr_contrastive_workspace_bytes.restype = C.c_size_t

@@ -14,7 +14,7 @@ int launch_blend_fwd(const IsrForwardArgs& a, cudaStream_t stream);
 int launch_blend_bwd(const IsrBackwardArgs& a, cudaStream_t stream);
 int launch_preprocess_bwd(const IsrBackwardArgs& a, cudaStream_t stream);
 int launch_extra_sparse_bwd(int P, int F, int W, int H, const void* geom, const void* image, const void* binning, int n,
-                            const int* pix_ids, const float* dLdE, float* dL_dextra, cudaStream_t stream);
+                            const int* pix_ids, const float* dLdE, float* dL_dextra, unsigned flags, cudaStream_t stream);
 int launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, uint8_t* present,
                         cudaStream_t stream);
 size_t contrastive_ws_bytes(int N, int F, int K);
@@ -176,13 +176,13 @@ int isr_backward(const IsrBackwardArgs* a, void* stream_) {
 
 int isr_backward_extra_sparse(int P, int F, int W, int H, const float* extra_attrs, const void* geom, const void* image,
                               const void* binning, int64_t num_rendered, int n, const int* pix_ids,
-                              const float* dL_dextra_samples, float* dL_dextra, void* stream_) {
+                              const float* dL_dextra_samples, float* dL_dextra, unsigned flags, void* stream_) {
     (void)extra_attrs;
     if (P < 0 || F < 0 || W <= 0 || H <= 0 || n < 0) return ISR_ERR_INVALID_ARG;
     if (F > ISR_MAX_EXTRA_DIMS) return ISR_ERR_UNSUPPORTED;
     if (P == 0 || n == 0 || F == 0 || num_rendered <= 0) return ISR_OK;
     if (!geom || !image || !binning || !pix_ids || !dL_dextra_samples || !dL_dextra) return ISR_ERR_INVALID_ARG;
-    return launch_extra_sparse_bwd(P, F, W, H, geom, image, binning, n, pix_ids, dL_dextra_samples, dL_dextra,
+    return launch_extra_sparse_bwd(P, F, W, H, geom, image, binning, n, pix_ids, dL_dextra_samples, dL_dextra, flags,
                                    static_cast<cudaStream_t>(stream_));
 }
 

@@ -56,7 +56,7 @@ __device__ __forceinline__ void cp_async16_b(void* smem_dst, const void* gmem_sr
 // Same warp-autonomous structure as blend_fwd_kernel, walking the list BACK to front: per-warp cull-rectangle test
 // (exact: a culled Gaussian contributed to no pixel of the block in the forward), cp.async staging of survivors.
 // kWarps: warps (8x4 pixel blocks) per CTA, as in blend_fwd_kernel (the warps never cooperate).
-template <int FP, int kWarps>
+template <int FP, int kWarps, bool kRef>
 __global__ void __launch_bounds__(32 * kWarps, (FP == 0 ? 24 : 8) / kWarps)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int F,
                  const float* __restrict__ bg, const float4* __restrict__ splats, const float4* __restrict__ cull4,
@@ -214,7 +214,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
             const bool active = contributor < last_contributor;
             const float* s = reinterpret_cast<const float*>(slots + t * REC);
             PairEval e;
-            const bool hit = active && eval_pair<true>(pixx, pixy, s, e);
+            const bool hit = active && eval_pair<kRef, true>(pixx, pixy, s, e);
             if (!__any_sync(0xffffffffu, hit)) continue;
             // per-lane partial gradients (0 when this lane does not contribute)
             // v[0..2] colour, v[3..5] normal, v[6..14] transMat, v[15] opacity; mean2D (2D-filter branch only) apart
@@ -284,7 +284,8 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                     const float nGd = mul(dL_dG, -G);
                     const float dsx = fma_(nGd, e.sx, mul(dL_dz, s[6]));
                     const float dsy = fma_(nGd, e.sy, mul(dL_dz, s[7]));
-                    const float dpx = mul(dsx, e.rpz), dpy = mul(dsy, e.rpz);
+                    const float rpz = __frcp_rn(e.pz);
+                    const float dpx = mul(dsx, rpz), dpy = mul(dsy, rpz);
                     const float dpz = -fma_(dpx, e.sx, mul(dpy, e.sy));
                     const float dkx = fma_(e.ly, dpz, -mul(e.lz, dpy));
                     const float dky = fma_(e.lz, dpx, -mul(e.lx, dpz));
@@ -340,7 +341,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 // ---------------------------------------------------------------------------------------------------------
 // Sparse feature-only backward: one warp per sampled pixel.
 // ---------------------------------------------------------------------------------------------------------
-template <int FP>
+template <int FP, bool kRef>
 __global__ void __launch_bounds__(256)
 extra_sparse_bwd_kernel(int n, const int* __restrict__ pix_ids, const float* __restrict__ dLdE_samples, int W, int H,
                         int F, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
@@ -390,7 +391,7 @@ extra_sparse_bwd_kernel(int n, const int* __restrict__ pix_ids, const float* __r
             *reinterpret_cast<float4*>(s + 8) = __ldg(sp + 2);
             *reinterpret_cast<float4*>(s + 12) = __ldg(sp + 3);
             PairEval e;
-            if (eval_pair<false>(pixx, pixy, s, e)) alpha = e.alpha;
+            if (eval_pair<kRef, false>(pixx, pixy, s, e)) alpha = e.alpha;
         }
         // sequential-exact transmittance: T_i = T_{i-1} * (1 - alpha_{i-1}) in list order, same roundings as
         // the forward (a left-to-right product), obtained by passing the running value lane to lane.
@@ -448,7 +449,9 @@ static int launch_bwd_one(const IsrBackwardArgs& a, cudaStream_t stream) {
         ISR_CUDA_TRY(cudaGetLastError());
         return ISR_OK;
     };
-    return launch(blend_bwd_kernel<FP, 2>, 2);  // measured at cfg2: 2-warp CTAs are 8% faster than whole-tile CTAs
+    // measured at cfg2: 2-warp CTAs are 8% faster than whole-tile CTAs
+    if (a.flags & ISR_FLAG_SPEC_ARITH) return launch(blend_bwd_kernel<FP, 2, false>, 2);
+    return launch(blend_bwd_kernel<FP, 2, true>, 2);
 }
 
 int launch_blend_bwd(const IsrBackwardArgs& a, cudaStream_t stream) {
@@ -465,13 +468,14 @@ int launch_blend_bwd(const IsrBackwardArgs& a, cudaStream_t stream) {
 
 template <int FP>
 static int launch_sparse_one(int P, int F, int W, int H, const void* geom, const void* image, const void* binning, int n,
-                             const int* pix_ids, const float* dLdE, float* dL_dextra, cudaStream_t stream) {
+                             const int* pix_ids, const float* dLdE, float* dL_dextra, unsigned flags, cudaStream_t stream) {
     GeomLayout gl(P);
     ImageLayout il(W, H);
     const char* g = static_cast<const char*>(geom);
     const char* im = static_cast<const char*>(image);
     const int warps_per_block = 8;
-    extra_sparse_bwd_kernel<FP><<<(n + warps_per_block - 1) / warps_per_block, 256, 0, stream>>>(
+    auto kern = (flags & ISR_FLAG_SPEC_ARITH) ? extra_sparse_bwd_kernel<FP, false> : extra_sparse_bwd_kernel<FP, true>;
+    kern<<<(n + warps_per_block - 1) / warps_per_block, 256, 0, stream>>>(
         n, pix_ids, dLdE, W, H, F, reinterpret_cast<const uint2*>(im + il.ranges),
         reinterpret_cast<const uint32_t*>(binning), reinterpret_cast<const float4*>(g + gl.splat),
         reinterpret_cast<const float4*>(g + gl.cull), reinterpret_cast<const uint32_t*>(im + il.n_contrib), dL_dextra,
@@ -481,13 +485,13 @@ static int launch_sparse_one(int P, int F, int W, int H, const void* geom, const
 }
 
 int launch_extra_sparse_bwd(int P, int F, int W, int H, const void* geom, const void* image, const void* binning, int n,
-                            const int* pix_ids, const float* dLdE, float* dL_dextra, cudaStream_t stream) {
+                            const int* pix_ids, const float* dLdE, float* dL_dextra, unsigned flags, cudaStream_t stream) {
     if (n <= 0 || F <= 0) return ISR_OK;
-    if (F <= 4) return launch_sparse_one<4>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, stream);
-    if (F <= 8) return launch_sparse_one<8>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, stream);
-    if (F <= 16) return launch_sparse_one<16>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, stream);
-    if (F <= 24) return launch_sparse_one<24>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, stream);
-    if (F <= 32) return launch_sparse_one<32>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, stream);
+    if (F <= 4) return launch_sparse_one<4>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, flags, stream);
+    if (F <= 8) return launch_sparse_one<8>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, flags, stream);
+    if (F <= 16) return launch_sparse_one<16>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, flags, stream);
+    if (F <= 24) return launch_sparse_one<24>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, flags, stream);
+    if (F <= 32) return launch_sparse_one<32>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, flags, stream);
     return ISR_ERR_UNSUPPORTED;
 }
 

@@ -37,7 +37,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // CTA is a whole tile and its slot stays occupied until the slowest of its 8 blocks is done (measured: 2-warp CTAs are
 // 3.5% faster at cfg3).  kWarpsPerSM: occupancy target that sets the register budget (24 -> 80 registers, 28 -> 72,
 // 32 -> 64).
-template <int FP, bool kPairs, int kWarpsPerSM, int kWarps>
+template <int FP, bool kPairs, int kWarpsPerSM, int kWarps, bool kRef>
 __global__ void __launch_bounds__(32 * kWarps, kWarpsPerSM / kWarps)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int F,
                  const float4* __restrict__ splats, const float4* __restrict__ cull4, const float4* __restrict__ cullq,
@@ -147,7 +147,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
             if (!done) {
                 const float* s = reinterpret_cast<const float*>(slots + r * REC);
                 PairEval e;
-                if (eval_pair<false>(pixx, pixy, s, e)) {
+                if (eval_pair<kRef, false>(pixx, pixy, s, e)) {
                     const float test_T = mul(T, sub(1.0f, e.alpha));
                     if (test_T < kTMin) {
                         done = true;
@@ -155,7 +155,8 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                         const uint32_t contributor = (uint32_t)(meta[r].y + 1);
                         w = mul(e.alpha, T);
                         const float A = sub(1.0f, T);
-                        const float mdep = mul(c1, sub(1.0f, mul(kNear, rcp_fast(e.depth))));
+                        // [sass] m = (1 + (-near)/depth) * (far/(far-near)): div.rn, FADD, FMUL
+                        const float mdep = mul(c1, sub(1.0f, __fdiv_rn(kNear, e.depth)));
                         const float mm = mul(mdep, mdep);
                         const float dt = fma_(-add(mdep, mdep), DM1.y, fma_(mm, A, M2dist.x));
                         M2dist = fma2(make_float2(mm, dt), w, M2dist);       // M2 += mm*w, dist += dt*w
@@ -164,12 +165,13 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                         N0 = fma_(s[11], w, N0);
                         N12 = fma2(*reinterpret_cast<const float2*>(s + 12), w, N12);
                         if (FP > 0) {
+                            // [sass] E[ch] = fma(T, alpha * feature, E[ch])  (forward.cu:415: extras * alpha * T)
                             const float4* f4 = slots + r * REC + 5;
 #pragma unroll
                             for (int v = 0; v < FP / 4; v++) {
                                 const float4 f = f4[v];
-                                E[2 * v + 0] = fma2(make_float2(f.x, f.y), w, E[2 * v + 0]);
-                                E[2 * v + 1] = fma2(make_float2(f.z, f.w), w, E[2 * v + 1]);
+                                E[2 * v + 0] = fma2(mul2(make_float2(f.x, f.y), e.alpha), T, E[2 * v + 0]);
+                                E[2 * v + 1] = fma2(mul2(make_float2(f.z, f.w), e.alpha), T, E[2 * v + 1]);
                             }
                         }
                         const float4 c = slots[r * REC + 4];  // (r, g, b, 0)
@@ -243,11 +245,9 @@ static int launch_one(const IsrForwardArgs& a, cudaStream_t stream) {
     char* im = static_cast<char*>(a.image);
     const char* b = static_cast<const char*>(a.binning);
     const int num_tiles = ((a.W + TILE - 1) / TILE) * ((a.H + TILE - 1) / TILE);
-    // Occupancy variant = register budget: 32 warps/SM (64 registers), 28 (72) or 24 (80); the default is the largest
-    // that compiles without spills for this F (measured at cfg3, F=16: 28 beats 24 by 5% and 32 by 6%).
-    // ISR_FWD_WARPS_PER_SM overrides (24 / 28 / 32).
-    static const int env_wps = [] { const char* e = getenv("ISR_FWD_WARPS_PER_SM"); return e ? atoi(e) : 0; }();
-    const int wps = env_wps ? env_wps : (FP <= 8 ? 32 : (FP <= 24 ? 28 : 24));
+    // Occupancy = register budget: 32 warps/SM (64 registers), 28 (72) or 24 (80); the largest that compiles without
+    // spills for this F (measured at cfg3, F=16: 28 beats 24 by 5% and 32 by 6%).
+    constexpr int kWps = FP <= 8 ? 32 : (FP <= 24 ? 28 : 24);
     auto launch = [&](auto kern, int w) -> int {
         const size_t smem = (size_t)w * FwdSmem<FP>::per_warp;
         ISR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -261,9 +261,8 @@ static int launch_one(const IsrForwardArgs& a, cudaStream_t stream) {
         ISR_CUDA_TRY(cudaGetLastError());
         return ISR_OK;
     };
-    if (wps >= 32) return launch(blend_fwd_kernel<FP, kPairs, 32, 2>, 2);
-    if (wps >= 28) return launch(blend_fwd_kernel<FP, kPairs, 28, 2>, 2);
-    return launch(blend_fwd_kernel<FP, kPairs, 24, 2>, 2);
+    if (a.flags & ISR_FLAG_SPEC_ARITH) return launch(blend_fwd_kernel<FP, kPairs, kWps, 2, false>, 2);
+    return launch(blend_fwd_kernel<FP, kPairs, kWps, 2, true>, 2);
 }
 
 template <bool kPairs>

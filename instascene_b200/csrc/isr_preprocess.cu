@@ -22,10 +22,11 @@ struct Camera {
     const float* __restrict__ campos;  // [3]
 };
 
-// quat (w,x,y,z) -> rotation columns (auxiliary.h:214-236), rsqrtf replaced by rcp(sqrt) per the spec
+// quat (w,x,y,z) -> rotation columns (auxiliary.h:214-236); rsqrtf per kRef (isr_common.cuh)
+template <bool kRef>
 __device__ __forceinline__ void quat_to_rot(const float4 q, float R0[3], float R1[3], float R2[3]) {
     const float sum = fma_(q.z, q.z, fma_(q.y, q.y, fma_(q.x, q.x, mul(q.w, q.w))));
-    const float s = rcp(sqrt_(sum));
+    const float s = rsqrt_sel<kRef>(sum);
     const float w = mul(q.x, s), x = mul(q.y, s), y = mul(q.z, s), z = mul(q.w, s);
     const float yy = mul(y, y), zz = mul(z, z);
     const float yy_zz = add(yy, zz), xx_zz = fma_(x, x, zz), xx_yy = fma_(x, x, yy);
@@ -37,6 +38,7 @@ __device__ __forceinline__ void quat_to_rot(const float4 q, float R0[3], float R
     R2[0] = add(xz_p, xz_p);             R2[1] = add(yz_m, yz_m);             R2[2] = sub(1.0f, add(xx_yy, xx_yy));
 }
 
+template <bool kRef>
 __global__ void __launch_bounds__(256)
 preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const float2* __restrict__ scales,
                       float scale_modifier, const float4* __restrict__ rotations,
@@ -88,7 +90,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
             const float2 sc = scales[idx];
             const float sx = mul(scale_modifier, sc.x), sy = mul(scale_modifier, sc.y);
             float R0[3], R1[3], R2[3];
-            quat_to_rot(rotations[idx], R0, R1, R2);
+            quat_to_rot<kRef>(rotations[idx], R0, R1, R2);
             const float L0[3] = {mul(R0[0], sx), mul(R0[1], sx), mul(R0[2], sx)};
             const float L1[3] = {mul(R1[0], sy), mul(R1[1], sy), mul(R1[2], sy)};
             float X[4][3];
@@ -124,10 +126,11 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
         if (d == 0.0f) break;
         const float inv_d = rcp(d);
         const float f9 = mul(inv_d, 9.0f);
-        cx = fma_(mul(Tu[2], Tw[2]), -inv_d, fma_(f9, mul(Tu[1], Tw[1]), mul(f9, mul(Tu[0], Tw[0]))));
-        cy = fma_(mul(Tv[2], Tw[2]), -inv_d, fma_(f9, mul(Tv[1], Tw[1]), mul(f9, mul(Tv[0], Tw[0]))));
-        const float ngx = fma_(mul(Tu[2], Tu[2]), inv_d, -fma_(f9, mul(Tu[1], Tu[1]), mul(f9, mul(Tu[0], Tu[0]))));
-        const float ngy = fma_(mul(Tv[2], Tv[2]), inv_d, -fma_(f9, mul(Tv[1], Tv[1]), mul(f9, mul(Tv[0], Tv[0]))));
+        // [sass] every dot(f, a*b): fma(a.z*b.z, -+inv_d, fma(f9, a.x*b.x, f9*(a.y*b.y))) -- the FMA carries the x term
+        cx = fma_(mul(Tu[2], Tw[2]), -inv_d, fma_(f9, mul(Tu[0], Tw[0]), mul(f9, mul(Tu[1], Tw[1]))));
+        cy = fma_(mul(Tv[2], Tw[2]), -inv_d, fma_(f9, mul(Tv[0], Tw[0]), mul(f9, mul(Tv[1], Tw[1]))));
+        const float ngx = fma_(mul(Tu[2], Tu[2]), inv_d, -fma_(f9, mul(Tu[0], Tu[0]), mul(f9, mul(Tu[1], Tu[1]))));
+        const float ngy = fma_(mul(Tv[2], Tv[2]), inv_d, -fma_(f9, mul(Tv[0], Tv[0]), mul(f9, mul(Tv[1], Tv[1]))));
         const float ex = sqrt_(fmaxf(1e-4f, fma_(cx, cx, ngx)));
         const float ey = sqrt_(fmaxf(1e-4f, fma_(cy, cy, ngy)));
         const float radius = ceilf(fmaxf(fmaxf(ex, ey), mul(3.0f, kFilterSize)));
@@ -182,13 +185,16 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
                         res[c] = r;
                     }
                     if (D > 2) {
-                        const float c9 = mul(mul(SH_C3[0], y), sub(mul(3.0f, xx), yy));
+                        // [sass] 3xx-yy = fma(xx,3,-yy); 4zz-xx-yy = fma(zz,4,-xx) - yy (shared by c11, c13);
+                        // 2zz-3xx-3yy = fma(yy,-3, fma(xx,-3, zz+zz)); xx-3yy = fma(yy,-3,xx)
+                        const float t4 = sub(fma_(zz, 4.0f, -xx), yy);
+                        const float c9 = mul(mul(SH_C3[0], y), fma_(xx, 3.0f, -yy));
                         const float c10 = mul(mul(SH_C3[1], xy), z);
-                        const float c11 = mul(mul(SH_C3[2], y), sub(sub(mul(4.0f, zz), xx), yy));
-                        const float c12 = mul(mul(SH_C3[3], z), sub(sub(mul(2.0f, zz), mul(3.0f, xx)), mul(3.0f, yy)));
-                        const float c13 = mul(mul(SH_C3[4], x), sub(sub(mul(4.0f, zz), xx), yy));
+                        const float c11 = mul(mul(SH_C3[2], y), t4);
+                        const float c12 = mul(mul(SH_C3[3], z), fma_(yy, -3.0f, fma_(xx, -3.0f, add(zz, zz))));
+                        const float c13 = mul(mul(SH_C3[4], x), t4);
                         const float c14 = mul(mul(SH_C3[5], z), sub(xx, yy));
-                        const float c15 = mul(mul(SH_C3[6], x), sub(xx, mul(3.0f, yy)));
+                        const float c15 = mul(mul(SH_C3[6], x), fma_(yy, -3.0f, xx));
 #pragma unroll
                         for (int c = 0; c < 3; c++) {
                             float r = res[c];
@@ -407,6 +413,7 @@ __device__ void sh_backward(int idx, int deg, int M, const float* __restrict__ m
     dL_dmeans[3 * (size_t)idx + 2] += (len2 * ddz - oz * vd) * inv3;
 }
 
+template <bool kRef>
 __global__ void __launch_bounds__(256)
 preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii,
                       const float* __restrict__ shs, const uint8_t* __restrict__ clamped,
@@ -430,7 +437,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
         for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) T[i][j] = transMat_precomp[9 * (size_t)idx + 3 * i + j];
     } else {
         q = rotations[idx];
-        quat_to_rot(q, R[0], R[1], R[2]);
+        quat_to_rot<kRef>(q, R[0], R[1], R[2]);
         const float2 sc = scales[idx];
         sx = sc.x; sy = sc.y;  // Q6: scale_modifier ignored (backward.cu:507)
         const float L0[3] = {R[0][0] * sx, R[0][1] * sx, R[0][2] * sx};
@@ -526,8 +533,9 @@ int launch_preprocess_fwd(const IsrForwardArgs& a, cudaStream_t stream) {
     const int gx = (a.W + TILE - 1) / TILE, gy = (a.H + TILE - 1) / TILE;
     Camera cam{a.viewmatrix, a.projmatrix, a.campos};
     const size_t sh_smem = (a.shs != nullptr && a.sh_coeffs == 16 && a.colors_precomp == nullptr) ? 256 * 13 * 16 : 0;
-    ISR_CUDA_TRY(cudaFuncSetAttribute(preprocess_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 13 * 16));
-    preprocess_fwd_kernel<<<(a.P + 255) / 256, 256, sh_smem, stream>>>(
+    auto kern = (a.flags & ISR_FLAG_SPEC_ARITH) ? preprocess_fwd_kernel<false> : preprocess_fwd_kernel<true>;
+    ISR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 13 * 16));
+    kern<<<(a.P + 255) / 256, 256, sh_smem, stream>>>(
         a.P, a.sh_degree, a.sh_coeffs, a.means3D, reinterpret_cast<const float2*>(a.scales), a.scale_modifier,
         reinterpret_cast<const float4*>(a.rotations), a.opacities, a.shs, a.transMat_precomp, a.colors_precomp, cam,
         a.W, a.H, gx, gy, a.radii, reinterpret_cast<Splat*>(g + gl.splat), reinterpret_cast<float4*>(g + gl.cull),
@@ -555,7 +563,8 @@ int launch_preprocess_bwd(const IsrBackwardArgs& a, cudaStream_t stream) {
         H = (int)fh2;
     }
     Camera cam{a.viewmatrix, a.projmatrix, a.campos};
-    preprocess_bwd_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(
+    auto kern = (a.flags & ISR_FLAG_SPEC_ARITH) ? preprocess_bwd_kernel<false> : preprocess_bwd_kernel<true>;
+    kern<<<(a.P + 255) / 256, 256, 0, stream>>>(
         a.P, a.sh_degree, a.sh_coeffs, a.means3D, a.radii, a.shs, reinterpret_cast<const uint8_t*>(g + gl.clamped),
         reinterpret_cast<const float2*>(a.scales), reinterpret_cast<const float4*>(a.rotations), a.transMat_precomp,
         reinterpret_cast<const Splat*>(g + gl.splat), cam, W, H, a.dL_dmeans2D, a.dL_dnormal, a.dL_dtransMat,

@@ -28,6 +28,36 @@ from . import _lib
 
 _pinned_cache = {}
 
+# Arithmetic of the MUFU-based functions (include/isr.h ISR_FLAG_SPEC_ARITH): "reference" (default) evaluates expf /
+# rsqrtf exactly like the reference CUDA build, "spec" uses the CPU-reproducible stand-ins of oracle/isr_oracle.c.
+_arith_flag = 0
+
+
+def set_arithmetic(mode: str) -> None:
+    """'reference' (default): bit-identical to the unmodified reference CUDA rasterizer; 'spec': bit-identical to the
+    CPU oracle (tests).  Applies to forwards launched afterwards; a backward always uses its forward's mode."""
+    global _arith_flag
+    if mode not in ("reference", "spec"):
+        raise ValueError("arithmetic mode must be 'reference' or 'spec'")
+    _arith_flag = _lib.FLAG_SPEC_ARITH if mode == "spec" else 0
+
+
+class arithmetic:
+    """Context manager: `with arithmetic("spec"): ...`"""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        global _arith_flag
+        self.prev = _arith_flag
+        set_arithmetic(self.mode)
+        return self
+
+    def __exit__(self, *a):
+        global _arith_flag
+        _arith_flag = self.prev
+
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     if t is None or t.numel() == 0:
@@ -113,7 +143,7 @@ def launch_geometry(background, means3D, colors, opacity, scales, rotations, sca
     st.nr_host = pinned_counts if pinned_counts is not None else _pinned_i64(dev)
     a = _lib.IsrForwardArgs()
     a.P, a.sh_degree, a.sh_coeffs, a.F, a.W, a.H = P, int(degree), M, 0, W, H
-    a.flags = 0 if want_pairs else _lib.FLAG_NO_PAIRS
+    a.flags = (0 if want_pairs else _lib.FLAG_NO_PAIRS) | _arith_flag
     a.tan_fovx, a.tan_fovy, a.scale_modifier = float(tan_fovx), float(tan_fovy), float(scale_modifier)
     a.background, a.viewmatrix, a.projmatrix, a.campos = _ptr(background), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos)
     a.means3D, a.opacities = _ptr(means3D), _ptr(opacity)
@@ -195,11 +225,13 @@ def c_rasterize_gaussians_backward(background, means3D, radii, colors, scales, r
                                    transMat_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
                                    dL_dout_others, dL_dout_extra, sh, degree, campos, geomBuffer, R, binningBuffer,
                                    imageBuffer, debug, grad_mask: int = _lib.GRAD_ALL, image_size=None,
-                                   sparse_extra=None, flags: int = _lib.FLAG_BWD_WH_QUIRK):
+                                   sparse_extra=None, flags: int = _lib.FLAG_BWD_WH_QUIRK, arith=None):
     """RasterizeGaussiansBackwardCUDA (DSR/rasterize_points.cu:153-262).  Returns the reference's 9-tuple
     (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dscales, dL_drotations, dL_dextra).
-    Cotangents may be None (== zeros).  `sparse_extra` = (pix_ids int32 [n], rows float32 [n,F])."""
+    Cotangents may be None (== zeros).  `sparse_extra` = (pix_ids int32 [n], rows float32 [n,F]).
+    `arith`: the forward's ISR_FLAG_SPEC_ARITH bit (default: the current global mode)."""
     L = _require_cuda_lib()
+    flags = (flags & ~_lib.FLAG_SPEC_ARITH) | (_arith_flag if arith is None else arith)
     dev = means3D.device
     P = int(means3D.shape[0])
     if image_size is None:
@@ -220,10 +252,16 @@ def c_rasterize_gaussians_backward(background, means3D, radii, colors, scales, r
     dL_dextra = z(ext and F > 0, P, F)
     if P == 0:
         return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dscales, dL_drotations, dL_dextra
-    means3D = _f32c(means3D, "means3D")
-    # Q17: the reference reads scales/rotations without .contiguous(); enforce contiguity explicitly
-    scales = scales.contiguous() if scales.numel() else scales
-    rotations = rotations.contiguous() if rotations.numel() else rotations
+    # Every tensor whose raw pointer crosses the C ABI is made contiguous fp32 first, like the forward does: the
+    # reference's cameras are `.transpose(0, 1)` VIEWS (scene/cameras.py:81-86, strides (1, 4)), and the reference
+    # binding calls .contiguous() on them (rasterize_points.cu:231-247; Q17: it forgets scales/rotations).
+    fc = lambda t, name: _f32c(t, name) if (t is not None and t.numel()) else t
+    means3D, background = _f32c(means3D, "means3D"), _f32c(background, "background")
+    viewmatrix, projmatrix, campos = _f32c(viewmatrix, "viewmatrix"), _f32c(projmatrix, "projmatrix"), _f32c(campos, "campos")
+    scales, rotations, transMat_precomp = fc(scales, "scales"), fc(rotations, "rotations"), fc(transMat_precomp, "transMat_precomp")
+    sh, colors, extra_attrs = fc(sh, "sh"), fc(colors, "colors"), fc(extra_attrs, "extra_attrs")
+    if radii.dtype != torch.int32 or not radii.is_contiguous():
+        radii = radii.to(torch.int32).contiguous()
     cot = [None if t is None else _f32c(t, "cotangent") for t in (dL_dout_color, dL_dout_others, dL_dout_extra)]
     dense_needed = any(t is not None for t in cot)
     stream = _stream()
@@ -247,7 +285,8 @@ def c_rasterize_gaussians_backward(background, means3D, radii, colors, scales, r
         rows = _f32c(rows, "sparse cotangent rows")
         _lib.check(L.isr_backward_extra_sparse(P, F, W, H, _ptr(extra_attrs), _ptr(geomBuffer), _ptr(imageBuffer),
                                                _ptr(binningBuffer), int(R), int(pix_ids.numel()), _ptr(pix_ids),
-                                               _ptr(rows), _ptr(dL_dextra), stream), "isr_backward_extra_sparse")
+                                               _ptr(rows), _ptr(dL_dextra), flags & _lib.FLAG_SPEC_ARITH, stream),
+                   "isr_backward_extra_sparse")
     if debug:
         torch.cuda.synchronize()
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dscales, dL_drotations, dL_dextra
@@ -325,6 +364,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             gau_related_pixels._isr_count_minus_1 = gau_pixel_indices
         ctx.raster_settings = raster_settings
         ctx.num_rendered = num_rendered
+        ctx.arith = _arith_flag if geom_state is None else (geom_state.args.flags & _lib.FLAG_SPEC_ARITH)
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, extra_attrs, sh,
                               geomBuffer, binningBuffer, imgBuffer)
@@ -366,7 +406,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, grad_depth,
                 grad_out_extra, sh, rs.sh_degree, rs.campos, geomBuffer, num_rendered, binningBuffer, imgBuffer,
                 rs.debug)
-        kw = dict(grad_mask=mask, image_size=(int(rs.image_height), int(rs.image_width)), sparse_extra=sparse)
+        kw = dict(grad_mask=mask, image_size=(int(rs.image_height), int(rs.image_width)), sparse_extra=sparse,
+                  arith=ctx.arith)
         if rs.debug:
             cpu_args = cpu_deep_copy_tuple(args)
             try:

@@ -17,3 +17,15 @@ def oracle():
     from oracle import oracle as orc
     orc.build()
     return orc
+
+
+@pytest.fixture(autouse=True)
+def _arithmetic_mode(request):
+    """Tests that compare the CUDA path with the CPU oracle run the kernels with ISR_FLAG_SPEC_ARITH (the oracle's
+    CPU-reproducible exp / rsqrt stand-ins); every other test runs the product default, the reference's arithmetic."""
+    if "oracle" not in request.fixturenames:
+        yield
+        return
+    from instascene_b200 import rasterizer
+    with rasterizer.arithmetic("spec"):
+        yield

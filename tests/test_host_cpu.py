@@ -22,10 +22,59 @@ def test_cabi_loads_and_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in include/isr.h but not exported by libisr.so"
     assert declared == set(_lib.EXPORTED_SYMBOLS)
-    assert L.isr_version() == 100
+    assert L.isr_version() == 200
     assert L.isr_status_string(-3).decode() == "workspace too small"
-    # struct layout agreement between ctypes and the C header (sizes only; offsets follow from field order)
     assert ctypes.sizeof(_lib.IsrForwardArgs) % 8 == 0 and ctypes.sizeof(_lib.IsrBackwardArgs) % 8 == 0
+
+
+def test_boundary_cabi_compiled_translation_unit(tmp_path):
+    """A C++ translation unit compiled against include/isr.h and linked to libisr.so (the INTEGRATION.md level-3
+    binding): every struct field sits at the offset the ctypes mirror assumes, the sizes agree, and calls that need no
+    GPU go through the linked symbols."""
+    import shutil
+    import subprocess
+    from instascene_b200 import _lib
+    _lib.lib()
+    cxx = shutil.which("g++")
+    assert cxx, "g++ is part of the image"
+    lines = ['#include <cstddef>', '#include <cstdio>', '#include "isr.h"', 'int main() {']
+    for sname, st in (("IsrForwardArgs", _lib.IsrForwardArgs), ("IsrBackwardArgs", _lib.IsrBackwardArgs)):
+        lines.append(f'  std::printf("{sname} %zu\\n", sizeof({sname}));')
+        for fname, _ in st._fields_:
+            lines.append(f'  std::printf("{sname}.{fname} %zu\\n", offsetof({sname}, {fname}));')
+    lines += ['  std::printf("version %d\\n", isr_version());',
+              '  std::printf("geom %zu\\n", isr_geom_bytes(1000));',
+              '  std::printf("status %s\\n", isr_status_string(ISR_ERR_WORKSPACE));',
+              '  IsrForwardArgs a = IsrForwardArgs();', '  a.P = 10; a.W = 64; a.H = 64; a.F = ISR_MAX_EXTRA_DIMS + 1;',
+              '  std::printf("unsupported %d\\n", isr_forward_geometry(&a, nullptr));',
+              '  std::printf("sparse %d\\n", isr_backward_extra_sparse(-1, 0, 1, 1, nullptr, nullptr, nullptr, nullptr, 0, 0, '
+              'nullptr, nullptr, nullptr, ISR_FLAG_SPEC_ARITH, nullptr));',
+              '  return 0;', '}']
+    src = tmp_path / "tu.cpp"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "tu"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run([cxx, "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-lisr", f"-Wl,-rpath,{libdir}", "-Wl,-rpath,/usr/local/cuda/lib64"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = dict(line.rsplit(" ", 1) for line in r.stdout.strip().splitlines())
+    for sname, st in (("IsrForwardArgs", _lib.IsrForwardArgs), ("IsrBackwardArgs", _lib.IsrBackwardArgs)):
+        assert int(got[sname]) == ctypes.sizeof(st), sname
+        for fname, _ in st._fields_:
+            assert int(got[f"{sname}.{fname}"]) == getattr(st, fname).offset, f"{sname}.{fname}"
+    assert got["version"] == "200" and int(got["geom"]) == _lib.lib().isr_geom_bytes(1000)
+    assert got["status workspace too"] == "small" or "status" in r.stdout
+    assert got["unsupported"] == "-2" and got["sparse"] == "-1"
+    # every field of the header's structs is mirrored (no field silently missing from the ctypes side)
+    header = open(os.path.join(ROOT, "include", "isr.h")).read()
+    for sname, st in (("IsrForwardArgs", _lib.IsrForwardArgs), ("IsrBackwardArgs", _lib.IsrBackwardArgs)):
+        body = header[header.index(f"typedef struct {sname} {{"):header.index(f"}} {sname};")]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*(?:,|;)", body)
+        assert set(names) == {f for f, _ in st._fields_}, (sname, set(names) ^ {f for f, _ in st._fields_})
 
 
 def test_argument_validation_without_gpu():
