@@ -156,7 +156,9 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                         w = mul(e.alpha, T);
                         const float A = sub(1.0f, T);
                         // [sass] m = (1 + (-near)/depth) * (far/(far-near)): div.rn, FADD, FMUL
-                        const float mdep = mul(c1, sub(1.0f, __fdiv_rn(kNear, e.depth)));
+                        // (depth >= near here; the fast path of the division is exact up to 2^60)
+                        const float nd = e.depth <= 0x1p60f ? div_fast(kNear, e.depth) : __fdiv_rn(kNear, e.depth);
+                        const float mdep = mul(c1, sub(1.0f, nd));
                         const float mm = mul(mdep, mdep);
                         const float dt = fma_(-add(mdep, mdep), DM1.y, fma_(mm, A, M2dist.x));
                         M2dist = fma2(make_float2(mm, dt), w, M2dist);       // M2 += mm*w, dist += dt*w

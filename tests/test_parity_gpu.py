@@ -264,6 +264,13 @@ def test_cuda_matches_reference_goldens(path):
     g = cuda_backward(inp, c, dcolor, dothers, dextra)
     c["clamped"] = None
     check_against_reference(c, ref, F, g, culled_lists=True)
+    # Product default = the reference's arithmetic (no ISR_FLAG_SPEC_ARITH): every forward float is BIT-IDENTICAL to what
+    # the unmodified reference CUDA rasterizer produced for this fixture.
+    vis = ref["radii"] > 0
+    for k in ("depths", "transMats", "means2D", "normal_opacity", "rgb"):
+        assert np.array_equal(c[k][vis].view(np.uint32), np.asarray(ref[k], np.float32)[vis].view(np.uint32)), k
+    for k in ("color", "others", "final_T") + (("extra",) if F else ()):
+        assert np.array_equal(c[k].view(np.uint32), np.asarray(ref[k], np.float32).view(np.uint32)), k
 
 
 def test_normalize_rows_matches_torch():
