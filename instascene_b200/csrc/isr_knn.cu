@@ -142,11 +142,14 @@ knn_search_kernel(int P, const float* __restrict__ pts, const int* __restrict__ 
                     if (x1 != x0 && x1 <= G - 1) visit(x1, y, z);
                 }
             }
-        // every unvisited point lies outside the cube of cells [c-r, c+r]: lower bound on its distance
+        // every unvisited point lies outside the cube of cells [c-r, c+r]: lower bound on its distance.  An axis along
+        // which the cloud has no extent (planar / collinear input: every point sits in cell 0 of that axis) is covered
+        // from the first ring on -- without this the bound on that axis stays ~0 and a planar cloud scans all G rings.
         float bound = FLT_MAX;
         bool covers_all = true;
         const int lo[3] = {x0, y0, z0}, hi[3] = {x1, y1, z1};
         for (int a = 0; a < 3; a++) {
+            if (!(ordered_to_float(bbox[3 + a]) > origin[a])) continue;
             if (lo[a] > 0) { covers_all = false; bound = fminf(bound, p[a] - (origin[a] + cell[a] * (float)lo[a])); }
             if (hi[a] < G - 1) { covers_all = false; bound = fminf(bound, (origin[a] + cell[a] * (float)(hi[a] + 1)) - p[a]); }
         }

@@ -189,3 +189,17 @@ def tracker_label_map(W, H, seed):
     lab[H // 2 + 5: H // 2 + 25, W // 2: W // 2 + 30] = 300
     lab[rng.random((H, W)) < 0.1] = 0
     return lab
+
+
+def knn_fixture_points(P, seed):
+    """Point cloud of the kNN fixtures: a uniform cube, a dense cluster (1/4 of the points, 100x denser), a planar sheet
+    (z constant) and a few exact duplicates -- the cases the reference's Morton-box search and the uniform-grid search
+    could disagree on."""
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(-1.5, 1.5, size=(P, 3)).astype(np.float32)
+    q = P // 4
+    pts[:q] = (rng.standard_normal((q, 3)) * 0.01 + np.array([0.3, -0.2, 0.5])).astype(np.float32)
+    pts[q:q + P // 8, 2] = np.float32(0.25)
+    d = max(P // 100, 1)
+    pts[-d:] = pts[q + P // 8: q + P // 8 + d]
+    return np.ascontiguousarray(pts)

@@ -84,3 +84,15 @@ def test_oracle_matches_reference(oracle, path):
 
 def test_fixtures_present():
     assert len(FIXTURES) >= 4
+
+
+def test_oracle_knn_matches_reference_simple_knn(oracle):
+    """The brute-force kNN oracle is pinned by distCUDA2 of the unmodified reference simple_knn
+    (tests/golden/knn_g1.npz, tests/golden/make_knn_golden.py): bit-identical."""
+    from helpers import knn_fixture_points
+    path = os.path.join(HERE, "golden", "knn_g1.npz")
+    z = np.load(path)
+    pts = knn_fixture_points(int(z["P"]), int(z["seed"]))
+    assert np.uint32(np.bitwise_xor.reduce(pts.view(np.uint32).reshape(-1))) == z["points_crc"]
+    got = oracle.knn_mean_dist2(pts)
+    assert np.array_equal(got.view(np.uint32), z["ref_mean_dist2"].view(np.uint32))

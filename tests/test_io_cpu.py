@@ -4,9 +4,12 @@ readers (scene/colmap_loader.py) -- on the GPU box that leg is skipped."""
 import importlib.util
 import os
 import struct
+import sys
 
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 from instascene_b200 import io as isr_io
 from instascene_b200 import synth
@@ -121,3 +124,43 @@ def test_reference_colmap_reader_parses_our_files(tmp_path):
         assert np.array_equal(rex[k].qvec, oex[k].qvec) and np.array_equal(rex[k].tvec, oex[k].tvec)
         assert np.allclose(ref.qvec2rotmat(rex[k].qvec), isr_io.qvec2rotmat(oex[k].qvec), atol=1e-15)
         assert np.allclose(ref.rotmat2qvec(ref.qvec2rotmat(rex[k].qvec)), isr_io.rotmat2qvec(isr_io.qvec2rotmat(oex[k].qvec)), atol=1e-9)
+
+
+def _ply_fixture_tensors():
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_ply_golden import fixture_model_tensors
+    return fixture_model_tensors()
+
+
+def test_ply_writer_matches_reference_fixture(tmp_path):
+    """tests/golden/ply_g1*.ply were written by the reference's UNMODIFIED GaussianModel.save_ply
+    (tests/golden/make_ply_golden.py); our writer must produce the same bytes from the same tensors, and our reader must
+    return the tensors from the reference's file."""
+    import torch
+    t = _ply_fixture_tensors()
+    gold = os.path.join(ROOT, "tests", "golden")
+    isr_io.save_ply(str(tmp_path / "a.ply"), t["xyz"], t["features_dc"], t["features_rest"], t["opacity"], t["scaling"],
+                    t["rotation"], t["seg_feature"])
+    assert open(tmp_path / "a.ply", "rb").read() == open(os.path.join(gold, "ply_g1.ply"), "rb").read()
+    mask = torch.arange(t["xyz"].shape[0]) % 3 != 0
+    isr_io.save_ply(str(tmp_path / "b.ply"), t["xyz"], t["features_dc"], t["features_rest"], t["opacity"], t["scaling"],
+                    t["rotation"], None, crop_mask=mask)
+    assert open(tmp_path / "b.ply", "rb").read() == open(os.path.join(gold, "ply_g1_noseg_crop.ply"), "rb").read()
+    g = isr_io.load_ply(os.path.join(gold, "ply_g1.ply"), max_sh_degree=3, seg_feat_dim=16)
+    assert np.array_equal(g.xyz, t["xyz"].numpy()) and np.array_equal(g.seg_feature, t["seg_feature"].numpy())
+    assert np.array_equal(g.features_dc, t["features_dc"].numpy()) and np.array_equal(g.features_rest, t["features_rest"].numpy())
+    assert np.array_equal(g.opacity, t["opacity"].numpy()) and np.array_equal(g.scaling, t["scaling"].numpy())
+    assert np.array_equal(g.rotation, t["rotation"].numpy())
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "scene")), reason="baseline/_ref not installed")
+def test_reference_save_ply_live_equals_ours(tmp_path):
+    """The reference's own save_ply, run here, against our writer on fresh random tensors (not just the fixture)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_ply_golden import fixture_model_tensors, reference_model
+    for P, F, seed in ((5, 4, 1), (257, 24, 2), (1000, 32, 3)):  # (the reference's PCA preview needs >= 3 rows)
+        t = fixture_model_tensors(P, F, seed)
+        reference_model(t, True).save_ply(str(tmp_path / f"r{seed}" / "pc.ply"))
+        isr_io.save_ply(str(tmp_path / f"m{seed}.ply"), t["xyz"], t["features_dc"], t["features_rest"], t["opacity"],
+                        t["scaling"], t["rotation"], t["seg_feature"])
+        assert open(tmp_path / f"r{seed}" / "pc.ply", "rb").read() == open(tmp_path / f"m{seed}.ply", "rb").read()

@@ -148,6 +148,71 @@ def test_knn(oracle):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), P
 
 
+def test_knn_matches_reference_fixture():
+    """tests/golden/knn_g1.npz = distCUDA2 of the UNMODIFIED reference simple_knn (tests/golden/make_knn_golden.py) on a
+    cloud with a dense cluster, a planar sheet and exact duplicates: bit-identical (both are exact 3-NN searches and
+    the squared distance / mean use the reference's FMA pattern, simple_knn.cu:123-124,183)."""
+    import os
+    import torch
+    import instascene_b200 as isr
+    from helpers import knn_fixture_points
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "knn_g1.npz"))
+    pts = knn_fixture_points(int(z["P"]), int(z["seed"]))
+    assert np.uint32(np.bitwise_xor.reduce(pts.view(np.uint32).reshape(-1))) == z["points_crc"]
+    got = isr.distCUDA2(torch.from_numpy(pts).cuda()).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), z["ref_mean_dist2"].view(np.uint32))
+
+
+def test_knn_bit_identical_to_reference_simple_knn_at_1M():
+    """Live against baseline/_ref/simple_knn (the unmodified reference build) at P = 1M: uniform + clustered."""
+    import os
+    import sys
+    import torch
+    import instascene_b200 as isr
+    from helpers import knn_fixture_points
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_dir = os.path.join(root, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "simple_knn")):
+        pytest.skip("baseline/_ref/simple_knn is not installed (baseline/build_ref.sh)")
+    sys.path.insert(0, ref_dir)
+    from simple_knn._C import distCUDA2 as ref_dist
+    for P, seed in ((1_000_000, 9), (300_001, 10)):
+        pts = torch.from_numpy(knn_fixture_points(P, seed)).cuda()
+        want = ref_dist(pts)
+        got = isr.distCUDA2(pts)
+        torch.cuda.synchronize()
+        assert torch.equal(got.view(torch.int32), want.view(torch.int32)), (P, int((got != want).sum()))
+
+
+def test_knn_degenerate_clouds(oracle):
+    """Planar / collinear / all-identical clouds (a grid axis with no extent): exact result, and no O(P * cells) scan --
+    a 200k-point planar cloud must finish in well under a second."""
+    import time
+    import torch
+    import instascene_b200 as isr
+    rng = np.random.default_rng(3)
+    for kind in ("planar", "collinear", "identical"):
+        pts = rng.standard_normal((4000, 3)).astype(np.float32)
+        if kind == "planar":
+            pts[:, 1] = 0.5
+        elif kind == "collinear":
+            pts[:, 1:] = 0.0
+        else:
+            pts[:] = pts[0]
+        got = isr.distCUDA2(torch.from_numpy(pts).cuda()).cpu().numpy()
+        want = oracle.knn_mean_dist2(pts)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), kind
+    big = rng.standard_normal((200_000, 3)).astype(np.float32)
+    big[:, 2] = -1.0
+    t = torch.from_numpy(big).cuda()
+    isr.distCUDA2(t)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    out = isr.distCUDA2(t)
+    torch.cuda.synchronize()
+    assert time.time() - t0 < 1.0 and bool(torch.isfinite(out).all())
+
+
 @pytest.mark.parametrize("predef,consider_negative", [(False, False), (True, False), (False, True)])
 def test_contrastive_loss(predef, consider_negative):
     import torch
