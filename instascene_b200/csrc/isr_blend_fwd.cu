@@ -279,7 +279,12 @@ static int dispatch_F(const IsrForwardArgs& a, cudaStream_t stream) {
     return ISR_ERR_UNSUPPORTED;
 }
 
+int launch_blend_fwd2(const IsrForwardArgs& a, cudaStream_t stream);
+
 int launch_blend_fwd(const IsrForwardArgs& a, cudaStream_t stream) {
+    // experiment switch: ISR_FWD_IMPL=1 selects the one-pixel-per-lane kernel of this file, default = isr_blend_fwd2.cu
+    static const int impl = [] { const char* e = getenv("ISR_FWD_IMPL"); return e ? atoi(e) : 2; }();
+    if (impl == 2) return launch_blend_fwd2(a, stream);
     const bool want_pairs = a.pairs != nullptr && a.pair_count != nullptr && !(a.flags & ISR_FLAG_NO_PAIRS);
     return want_pairs ? dispatch_F<true>(a, stream) : dispatch_F<false>(a, stream);
 }
