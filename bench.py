@@ -64,12 +64,17 @@ WORKLOADS = {
                  desc="cfg5: 5M Gaussians x 32-dim features @1600x1200, --gram_feat_3d step: render + 2 single-view "
                       "ProtoNCE terms (32768 px each) + 3D ProtoNCE (32768 Gaussians) + backward + Adam"),
 }
-# our own kernels per step (DESIGN.md "launch list"); cfg5 = cfg3's 17 + gather/contrast x2 more terms (1+4, 4) +
-# rownorm fwd/bwd of the sampled 3D rows
-KERNELS_PER_STEP = {"cfg3": 17, "cfg2": 12, "cfg5": 28}
-# dram__bytes_read.sum + dram__bytes_write.sum of blend_fwd_kernel per launch, from the committed `ncu --set full`
-# capture profiles/r1_ncu_blend_fwd_v4.txt (cfg3); no capture of that kernel exists for cfg2 / cfg5
-NCU_TRAFFIC_BYTES = {"cfg3": 138.5e6 + 255.8e6, "cfg2": None, "cfg5": None}
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch comes from the committed `ncu --set full`
+# capture of THIS round, stamped with the kernel it was captured on (profiles/r2_traffic.json); a workload without a
+# capture reports null.
+def ncu_traffic(workload: str, kernel_name: str):
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).get(workload)
+    except Exception:
+        return None, None
+    if not rec or rec.get("kernel") != kernel_name:
+        return None, None
+    return float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"]), rec.get("source")
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -86,7 +91,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int, period_s: float = 0.004, enabled: bool = True):
+    def __init__(self, gpu_index: int, period_s: float = 0.010, enabled: bool = True):
         self.gpu, self.period_s = gpu_index, period_s
         self.enabled = enabled and os.environ.get("ISR_BENCH_NO_CLOCKS", "0") != "1"
         self.samples, self._stop, self._t, self._nvml, self._h, self._active = [], threading.Event(), None, None, None, False
@@ -123,11 +128,7 @@ class ClockSampler:
             mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
         except Exception:
             mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-        try:
-            power = n.nvmlDeviceGetPowerUsage(h) / 1e3
-        except Exception:
-            power = None
-        return sm, mask, power
+        return sm, mask, None   # (the power query is slow -- tens of ms -- and is read once after the region)
 
     def _run(self):
         while not self._stop.is_set():
@@ -161,6 +162,11 @@ class ClockSampler:
         self._active = False
         if self.enabled and self._nvml is None:
             self._smi_once()
+        elif self.enabled and self._nvml is not None:
+            try:
+                self._power_after = self._nvml.nvmlDeviceGetPowerUsage(self._h) / 1e3
+            except Exception:
+                self._power_after = None
 
     def stop(self):
         self._stop.set()
@@ -174,6 +180,8 @@ class ClockSampler:
         for s in self.samples:
             mask |= s[1]
         power = [s[2] for s in self.samples if s[2] is not None]
+        if getattr(self, "_power_after", None) is not None:
+            power.append(self._power_after)
         return {"sm_mhz": float(np.median([s[0] for s in self.samples])), "sm_max_mhz": self._max,
                 "reasons": sorted(name for bit, name in self.REASONS if mask & bit), "samples": len(self.samples),
                 "power_w_max": max(power) if power else None,
@@ -344,19 +352,30 @@ def run_ours(args):
                 p.grad = None
             return loss
 
+    import gc
+    from instascene_b200 import _lib as _isr_lib
+    launch_count = _isr_lib.lib().isr_kernel_launch_count
+
     def timed(n_steps, first, e2e, wrap=False):
+        """Times exactly n_steps steps: barrier + synchronize on both sides, one CUDA event per step boundary on the
+        launching stream; returns the max over ranks of the region time plus per-step statistics.  The cyclic GC is
+        switched off inside the region (a generation-2 collection over a heap with hundreds of live tensors is a
+        multi-millisecond host stall that a 50-ms region cannot absorb)."""
+        gc.collect()
+        gc.disable()
         idist.barrier(world)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps + 1)]
         h2d = d2h = 0
-        e0.record()
+        n_launch0 = launch_count()
+        evs[0].record()
         last = None
         view_of = lambda s: my_views[s % len(my_views)] if wrap else my_views[s]
         cam_keys = ("wvt", "fpt", "center")
         upload = lambda v, keys: {k: host[v][k].to(dev, non_blocking=True) for k in keys}
         cam_next = None  # e2e: the next view's camera matrices are uploaded one step ahead (they feed the prefetch)
         prefetched.clear()
-        for s in range(first, first + n_steps):
+        for n, s in enumerate(range(first, first + n_steps)):
             v = view_of(s)
             nxt = None
             if e2e:
@@ -375,16 +394,42 @@ def run_ours(args):
             if e2e:
                 last = float(loss.detach().to("cpu", non_blocking=False))  # device -> host read of the step's result
                 d2h = 4
+            if n + 1 < n_steps:
+                evs[n + 1].record()
         if comm is not None:  # the last step's all-reduce + optimizer step belong to the timed region
             torch.cuda.current_stream().wait_stream(comm)
-        e1.record()
+        evs[n_steps].record()
         torch.cuda.synchronize()
+        n_launch = launch_count() - n_launch0
         idist.barrier(world)
-        ms = idist.max_over_ranks(e0.elapsed_time(e1), world, dev)
-        return ms, h2d, d2h, last
+        gc.enable()
+        total = evs[0].elapsed_time(evs[n_steps])
+        per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(n_steps)] or [total]
+        ms = idist.max_over_ranks(total, world, dev)
+        stats = step_stats(per_step, total, rank, world, dev)
+        return ms, h2d, d2h, last, stats, n_launch
+
+    def step_stats(per_step, total, rank, world, dev):
+        """p50 / p90 / max of the per-step device times over all ranks, and which rank owned the slowest step."""
+        mine = torch.tensor(per_step + [total], dtype=torch.float64, device=dev)
+        if world > 1:
+            import torch.distributed as tdist
+            allr = [torch.empty_like(mine) for _ in range(world)]
+            tdist.all_gather(allr, mine)
+            allr = torch.stack(allr).cpu().numpy()
+        else:
+            allr = mine.cpu().numpy()[None, :]
+        steps_ms = allr[:, :-1]
+        worst = np.unravel_index(int(np.argmax(steps_ms)), steps_ms.shape) if steps_ms.size else (0, 0)
+        out = {"p50": float(np.percentile(steps_ms, 50)), "p90": float(np.percentile(steps_ms, 90)), "max": float(steps_ms.max()),
+               "max_rank": int(worst[0]), "max_step": int(worst[1]), "region_ms_per_rank": [float(x) for x in allr[:, -1]]}
+        if out["max"] > 3.0 * out["p50"] and rank == 0:
+            print(f"[bench] WARNING: slowest step {out['max']:.3f} ms (rank {out['max_rank']}, step {out['max_step']}) is more than "
+                  f"3x the median {out['p50']:.3f} ms -- the timed region swallowed a stall", file=sys.stderr)
+        return out
 
     cs = ClockSampler(local_rank, enabled=(rank == 0)).start()
-    ms_warm, _, _, _ = timed(args.warmup, 0, False)  # warm-up (untimed)
+    timed(args.warmup, 0, False)  # warm-up (untimed)
     # Pre-heat (untimed, not part of W or K): the process has just spent ~10 s building the synthetic scene on the CPU with
     # the GPU idle, and W = 3 steps are ~10 ms of GPU work -- not enough for a cold GPU (and, at N > 1, NCCL and the
     # caching allocator) to reach steady state: measured on a fresh 4-GPU box the first timed region ran 4.2-4.5 ms/step,
@@ -392,12 +437,12 @@ def run_ours(args):
     # rank runs the same number of collectives.
     preheat = 0
     if os.environ.get("ISR_BENCH_PREHEAT", "1") != "0":
-        ms_probe, _, _, _ = timed(10, 0, False, wrap=True)   # the W warm-up steps include first-call overheads
+        ms_probe = timed(10, 0, False, wrap=True)[0]   # the W warm-up steps include first-call overheads
         preheat = 10 + int(min(600, max(1, 1000.0 / max(ms_probe / 10.0, 0.5))))
         timed(preheat - 10, 0, False, wrap=True)
     with cs:
-        ms, _, _, _ = timed(args.steps, args.warmup, False)
-    ms_e2e, h2d, d2h, _ = timed(args.steps, args.warmup, True)
+        ms, _, _, _, stats, n_launch = timed(args.steps, args.warmup, False)
+    ms_e2e, h2d, d2h, _, stats_e2e, _ = timed(args.steps, args.warmup, True)
     cs.stop()
     clocks = cs.summary()
     views = args.steps * world
@@ -407,22 +452,28 @@ def run_ours(args):
     line = {"metric": "views/sec fwd+bwd @1080p", "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "step_ms_p50": stats["p50"], "step_ms_p90": stats["p90"], "step_ms_max": stats["max"],
+            "step_ms_max_owner": {"rank": stats["max_rank"], "step": stats["max_step"]},
             "config": {"workload": wl["desc"], "gaussians": P, "feat_dim": F, "image": [W, H],
                        "views_per_step_per_gpu": 1, "views": f"{len(cams)} synthetic COLMAP views (cameras.bin/images.bin round trip)",
                        "preheat_steps_untimed": preheat,
                        "geometry_prefetch": "next view's projection + depth sort overlap the current step's loss/backward/Adam "
                                             "(isr.prefetch_geometry)" if use_prefetch else "off", "parallelism": f"dp{world} (views sharded, grad all-reduce)",
+                       "trainable": "_seg_feature only; geometry frozen, as GaussianModel.training_setup does for semantic "
+                                    "training (scene/gaussian_model.py:226-232)" if opt is not None else "all geometry / appearance tensors",
                        "l2": "inputs larger than L2 (Gaussian state %.0f MB >> 126 MB), distinct view every step" % (P * (232 + 4 * F) / 1e6),
                        "optimizer": "Adam(lr=0.025, eps=1e-15) on _seg_feature (isr.FusedAdam)" if opt is not None else "none"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": KERNELS_PER_STEP[args.workload] * args.steps}
+                    "ms_per_step": ms_e2e / args.steps, "step_ms_p50": stats_e2e["p50"], "step_ms_max": stats_e2e["max"]},
+            # kernels of libisr.so launched by THIS rank inside the timed region (isr_kernel_launch_count; library
+            # kernels -- CUB sort/scan, torch glue, NCCL -- are not included)
+            "gpu_launches": int(n_launch)}
 
     if rank == 0:
         line["roofline"] = measure_roofline(args, wl, pc, cams, devdata, my_views, dev)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args.workload, budget_s=20.0)
+            line["cpu_baseline"] = cpu_baseline(args.workload, budget_s=25.0)
         if world == 1 and not args.no_ref_cuda:
             rc = ref_cuda_leg(args, wl, pc, cams, devdata, my_views, dev)
             if rc is not None:
@@ -471,8 +522,13 @@ def measure_roofline(args, wl, pc, cams, devdata, my_views, dev):
     ms = float(np.mean(times))
     HW = W * H
     # sorted id (4) + instance record gather (64 + 12 + 4F) per instance, outputs 4*(3+7+F) and
-    # saved per-pixel state (20) per pixel, 8 bytes per emitted pair
-    alg = R * (4 + 64 + 12 + 4 * F) + HW * 4 * (3 + 7 + F) + HW * 20 + 8 * G
+    # saved per-pixel state (20) per pixel, 8 bytes per emitted pair.  The kernel walks the footprint-culled list
+    # (R_emitted instances), so THAT count defines the bytes it has to move; the figure with the reference's instance
+    # count R (what a kernel without the culling would have to gather) is reported beside it.
+    n_inst = int(a._n_inst)
+    per_inst, per_px = 4 + 64 + 12 + 4 * F, 4 * (3 + 7 + F) + 20
+    alg = n_inst * per_inst + HW * per_px + 8 * G
+    alg_ref = R * per_inst + HW * per_px + 8 * G
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -480,82 +536,190 @@ def measure_roofline(args, wl, pc, cams, devdata, my_views, dev):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg / (ms / 1e3) / 1e9
-    return {"bound": "hbm", "kernel": "blend_fwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    kname = f"blend_fwd_kernel<F={F}>"
+    traffic, traffic_src = ncu_traffic(args.workload, kname)
+    return {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "peak_source": "measured" if peaks else "fallback",
-            "traffic": NCU_TRAFFIC_BYTES.get(args.workload),
-            "kernel_ms": ms, "algorithmic_bytes": alg, "R": R, "R_emitted": int(a._n_inst), "V": V, "pairs": G,
-            "note": "instruction-issue bound (79% of issue slots busy, DRAM 4% of peak): every pixel walks its tile list; "
-                    "algorithmic bytes count one record gather per (tile, Gaussian) instance, most of which hit L2"}
+            "traffic": traffic, "traffic_source": traffic_src,
+            "kernel_ms": ms, "algorithmic_bytes": alg, "R": R, "R_emitted": n_inst, "V": V, "pairs": G,
+            "frac_with_reference_instance_count": alg_ref / (ms / 1e3) / 1e9 / peak,
+            "note": "instruction-issue bound (~80% of issue slots busy, DRAM 3% of peak): every pixel walks its tile list; "
+                    "algorithmic bytes count one record gather per emitted (tile, Gaussian) instance, most of which hit L2"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_baseline(workload: str, budget_s: float = 20.0, steps: int = 1, warmup: int = 0):
-    """The reference has no CPU rasterizer; its algorithm restated in C (oracle/, OpenMP, all host cores) is timed on a
-    bounded sample: one view, ALL Gaussians preprocessed + binned, blend forward + dense backward on every S-th tile,
-    extrapolated to the full view."""
-    from instascene_b200 import synth
-    from oracle import oracle as orc
-    wl = WORKLOADS[workload]
-    P, F, W, H = wl["P"], wl["F"], wl["W"], wl["H"]
-    scene = synth.synth_scene(P, F=F, seed=wl["seed"])
-    cam = synth.ring_cameras(wl["n_views"], W, H)[0]
-    cores = orc.num_threads()
-    kw = dict(scales=scene.scales(), rotations=scene.rotations(), shs=scene.shs(), sh_degree=3,
-              extra_attrs=scene.seg_features())
-    base = (scene.xyz, scene.opacities(), cam.world_view_transform, cam.full_proj_transform, cam.camera_center, W, H,
-            np.zeros(3, np.float32))
-    rng = np.random.default_rng(1)
-    dcolor = rng.standard_normal((3, H, W)).astype(np.float32)
-    dothers = rng.standard_normal((7, H, W)).astype(np.float32)
-    dextra = rng.standard_normal((F, H, W)).astype(np.float32) if F else None
-    # calibration with a coarse sample
-    stride = 64
-    t0 = time.time()
-    fwd = orc.forward(*base, **kw, want_pairs=False, blend=False)
-    t_pre = time.time() - t0
-    t0 = time.time()
-    fwd = orc.forward(*base, **kw, want_pairs=False, tile_stride=stride)
-    t_cal = max(time.time() - t0 - t_pre, 1e-3)
-    est_full_fwd = t_cal * stride
-    per_step = budget_s / max(steps + warmup, 1)
-    stride = int(min(256, max(1, math.ceil(est_full_fwd * 3.0 / max(per_step - t_pre, 1.0)))))
-    results = []
-    for s in range(steps + warmup):
+class CpuWorkload:
+    """The same step as the GPU arm, on the reference's algorithm restated in C (oracle/, OpenMP on every host core; the
+    reference ships no CPU rasterizer, DSR/rasterize_points.cu:27-28), LIKE FOR LIKE:
+      cfg3 / cfg5: forward of one view (colour, 7 aux maps, F feature channels, pair list) + sampled-pixel ProtoNCE
+                   (oracle/contrastive_ref.py) + backward of dL/d(features) over exactly the sampled pixels + the double
+                   normalisation backward + Adam on [P,F] (numpy) -- only `_seg_feature` is trainable
+                   (scene/gaussian_model.py:226-232), which is also all the GPU arm differentiates;
+      cfg2:        forward + dense backward of every gradient with seeded random cotangents + K8.
+    `tile_stride` > 1 runs the per-tile blends on every S-th tile only (bounded sample; projection, binning and the
+    per-Gaussian work always cover all Gaussians)."""
+
+    def __init__(self, workload: str):
+        from instascene_b200 import synth
+        from oracle import oracle as orc
+        self.orc, self.wl, self.name = orc, WORKLOADS[workload], workload
+        wl = self.wl
+        P, F, W, H = wl["P"], wl["F"], wl["W"], wl["H"]
+        orc.set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1: ask for every core explicitly
+        self.cores = orc.num_threads()
+        self.scene = scene = synth.synth_scene(P, F=F, seed=wl["seed"])
+        self.cams = synth.ring_cameras(wl["n_views"], W, H)
+        self.raw = scene.seg_feature_raw.astype(np.float32).copy() if F else None
+        self.kw = dict(scales=scene.scales(), rotations=scene.rotations(), shs=scene.shs(), sh_degree=3)
+        self.adam = None
+        rng = np.random.default_rng(1)
+        if not F:
+            self.dcolor = rng.standard_normal((3, H, W)).astype(np.float32)
+            self.dothers = rng.standard_normal((7, H, W)).astype(np.float32)
+        self.rng = rng
+        self.synth = synth
+
+    def _features(self):
+        x = self.raw
+        n1 = np.linalg.norm(x, axis=1, keepdims=True) + 1e-6
+        y = x / n1
+        n2 = np.linalg.norm(y, axis=1, keepdims=True) + 1e-9
+        return (y / n2).astype(np.float32)
+
+    def preprocess_only(self, view=0):
+        cam, sc, wl = self.cams[view], self.scene, self.wl
+        return self.orc.forward(sc.xyz, sc.opacities(), cam.world_view_transform, cam.full_proj_transform, cam.camera_center,
+                                wl["W"], wl["H"], np.zeros(3, np.float32), **self.kw, want_pairs=False, blend=False)
+
+    def step(self, view: int, tile_stride: int = 1):
+        import torch
+        cam, sc, wl, orc = self.cams[view % len(self.cams)], self.scene, self.wl, self.orc
+        P, F, W, H = wl["P"], wl["F"], wl["W"], wl["H"]
+        base = (sc.xyz, sc.opacities(), cam.world_view_transform, cam.full_proj_transform, cam.camera_center, W, H,
+                np.zeros(3, np.float32))
+        bw_args = (sc.xyz, cam.world_view_transform, cam.full_proj_transform, cam.camera_center, W, H, np.zeros(3, np.float32),
+                   cam.tanfovx, cam.tanfovy)
+        t = {}
         t0 = time.time()
-        fwd = orc.forward(*base, **kw, want_pairs=False, tile_stride=stride)
-        t_f = time.time() - t0
-        t1 = time.time()
-        orc.backward(fwd, scene.xyz, cam.world_view_transform, cam.full_proj_transform, cam.camera_center, W, H,
-                     np.zeros(3, np.float32), cam.tanfovx, cam.tanfovy, dcolor, dothers, dextra, **kw, tile_stride=stride)
-        t_b = time.time() - t1
-        # preprocessing/binning/K8 run on all Gaussians; only the per-tile blends are sampled
-        t_view = t_pre + (t_f - t_pre) * stride + t_b * stride
-        if s >= warmup:
-            results.append(t_view)
-    t_view = float(np.mean(results))
-    return {"value": 1.0 / t_view, "unit": "views/s", "cores": cores, "kind": "port",
-            "sample": f"1 view of {wl['desc'].split(':')[0]}: all {P} Gaussians projected+sorted, blend fwd + dense bwd on "
-                      f"every {stride}-th of {((W + 15) // 16) * ((H + 15) // 16)} tiles, extrapolated x{stride}",
-            "seconds_per_view_extrapolated": t_view}
+        if not F:
+            fwd = orc.forward(*base, **self.kw, want_pairs=True, tile_stride=tile_stride)
+            t["fwd"] = time.time() - t0
+            t0 = time.time()
+            orc.backward(fwd, *bw_args, self.dcolor, self.dothers, None, **self.kw, tile_stride=tile_stride)
+            t["bwd"] = time.time() - t0
+            return t
+        feats = self._features()
+        fwd = orc.forward(*base, **self.kw, extra_attrs=feats, want_pairs=True, tile_stride=tile_stride)
+        t["fwd"] = time.time() - t0
+        t0 = time.time()
+        from oracle.contrastive_ref import contrastive_loss_ref
+        n_terms = 2 if self.name == "cfg5" else 1
+        dextra = np.zeros((F, H, W), np.float32)
+        mask = np.zeros((H, W), np.uint8)
+        for k in range(n_terms):
+            lab = self.synth.label_map(W, H, wl["seed"] + (2 if k == 0 else 5000) + view, **({} if k == 0 else {"grid": 6})).reshape(-1)
+            valid = np.flatnonzero(lab > 0)
+            pix = valid[self.rng.integers(0, len(valid), size=wl["samples"])]
+            f = torch.tensor(fwd["extra"].reshape(F, -1)[:, pix].T.astype(np.float64), requires_grad=True)
+            loss = contrastive_loss_ref(f, torch.tensor(lab[pix].astype(np.int64))) * (1e-6 * (0.5 if k == 0 else 1.0))
+            loss.backward()
+            np.add.at(dextra.reshape(F, -1).T, pix, f.grad.numpy().astype(np.float32))
+            mask.reshape(-1)[pix] = 1
+        t["loss"] = time.time() - t0
+        t0 = time.time()
+        g = orc.backward(fwd, *bw_args, np.zeros((3, H, W), np.float32), np.zeros((7, H, W), np.float32), dextra, **self.kw,
+                         extra_attrs=feats, tile_stride=tile_stride, pixel_mask=mask, preprocess=False)
+        t["bwd"] = time.time() - t0
+        t0 = time.time()
+        # backward of the two row normalisations (gaussian_model.py:124 then gaussian_renderer/__init__.py:61-62) + Adam
+        x, dy = self.raw, g["dL_dextra"]
+        n1 = np.linalg.norm(x, axis=1, keepdims=True)
+        y = x / (n1 + 1e-6)
+        n2 = np.linalg.norm(y, axis=1, keepdims=True)
+        z = y / (n2 + 1e-9)
+        dyy = dy / (n2 + 1e-9) - y * ((dy * z).sum(1, keepdims=True) / (n2 + 1e-9) / np.maximum(n2, 1e-30) * (n2 > 0))
+        dx = dyy / (n1 + 1e-6) - x * ((dyy * y).sum(1, keepdims=True) / (n1 + 1e-6) / np.maximum(n1, 1e-30) * (n1 > 0))
+        if self.adam is None:
+            self.adam = [np.zeros_like(x), np.zeros_like(x), 0]
+        m, v, n = self.adam
+        n += 1
+        m *= 0.9; m += 0.1 * dx
+        v *= 0.999; v += 0.001 * dx * dx
+        self.raw = (x - 0.025 / (1 - 0.9 ** n) * m / (np.sqrt(v) / math.sqrt(1 - 0.999 ** n) + 1e-15)).astype(np.float32)
+        self.adam[2] = n
+        t["optim"] = time.time() - t0
+        return t
+
+
+def cpu_baseline(workload: str, budget_s: float = 25.0):
+    """cpu_baseline leg of the GPU arm (rank 0, N = 1): ONE step of CpuWorkload.  The whole view when that fits the budget
+    (no extrapolation); otherwise the per-tile blends on every S-th tile, scaled by S, and the line says so."""
+    cw = CpuWorkload(workload)
+    wl = cw.wl
+    t0 = time.time()
+    cw.preprocess_only()
+    t_pre = time.time() - t0
+    # only the per-tile blends (forward minus projection/binning, backward) scale with the tile stride
+    scaled = lambda parts: max(parts["fwd"] - t_pre, 0.0) + parts["bwd"]
+    fixed = lambda parts: t_pre + parts.get("loss", 0.0) + parts.get("optim", 0.0)
+    cal = cw.step(0, tile_stride=64)
+    est_full = fixed(cal) + scaled(cal) * 64
+    stride = 1 if est_full <= budget_s * 1.6 else int(min(256, math.ceil(scaled(cal) * 64 / max(budget_s - fixed(cal), 1.0))))
+    t0 = time.time()
+    parts = cw.step(1, tile_stride=stride)
+    t_step = time.time() - t0
+    n_tiles = ((wl["W"] + 15) // 16) * ((wl["H"] + 15) // 16)
+    if stride == 1:
+        t_view, how = t_step, f"the whole view ({n_tiles} tiles), nothing extrapolated"
+    else:
+        t_view = fixed(parts) + scaled(parts) * stride
+        how = f"per-tile blends on every {stride}-th of {n_tiles} tiles, that part scaled x{stride}"
+    like = ("forward + sampled-pixel ProtoNCE + feature-only backward on the sampled pixels + Adam" if wl["F"] else
+            "forward + dense backward of all gradients")
+    return {"value": 1.0 / t_view, "unit": "views/s", "cores": cw.cores, "kind": "port",
+            "sample": f"1 step of {wl['desc'].split(':')[0]} ({like}; like for like with the GPU step): all {wl['P']} Gaussians "
+                      f"projected + sorted, {how}",
+            "seconds_per_view": t_view, "seconds_by_part": parts}
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's algorithm on the host cores (oracle port; the reference ships no CPU path)."""
+    """--impl reference: the reference's algorithm on the host cores (oracle port; the reference ships no CPU path).
+    Whole views only -- nothing is sampled or extrapolated here.  Every step is one full view of the GPU arm's workload;
+    if K steps do not fit the time budget, fewer are run and the line reports the number actually timed."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    t0 = time.time()
-    cb = cpu_baseline(args.workload, budget_s=150.0, steps=args.steps, warmup=args.warmup)
+    budget_s = float(os.environ.get("ISR_REF_BUDGET_S", 420.0))
+    t_start = time.time()
+    cw = CpuWorkload(args.workload)
+    times, parts = [], None
+    n_warm = 0
+    for s in range(args.warmup + args.steps):
+        warm = s < args.warmup
+        if warm and time.time() - t_start > 0.25 * budget_s:
+            continue                      # warm-up steps are skipped once they would eat the budget
+        if not warm and times and (time.time() - t_start) + float(np.mean(times)) > budget_s:
+            break
+        t0 = time.time()
+        parts = cw.step(s)
+        if warm:
+            n_warm += 1
+        else:
+            times.append(time.time() - t0)
+    t_view = float(np.mean(times))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    cb = {"value": 1.0 / t_view, "unit": "views/s", "cores": cw.cores, "kind": "port",
+          "sample": f"{len(times)} whole-view step(s) of {wl['desc'].split(':')[0]}, like for like with the GPU step, "
+                    f"nothing extrapolated ({n_warm} warm-up)"}
     line = {"impl": "reference", "metric": "views/sec fwd+bwd @1080p", "value": cb["value"], "unit": "views/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * cb["seconds_per_view_extrapolated"], "higher_is_better": True, "scaling": "weak",
+            "n_gpus": args.gpus, "steps": len(times), "steps_requested": args.steps, "warmup": n_warm,
+            "ms_per_step": 1e3 * t_view, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "gaussians": wl["P"], "feat_dim": wl["F"], "image": [wl["W"], wl["H"]]},
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": cb, "seconds_by_part": parts,
             "e2e": {"value": cb["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "wall_s": time.time() - t0, "world_size_env": world}
+            "wall_s": time.time() - t_start, "world_size_env": world}
     emit_line(line)
 
 

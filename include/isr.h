@@ -83,6 +83,8 @@ int isr_version(void);
 const char* isr_status_string(int status);
 int isr_last_cuda_error(void);              /* cudaError_t of the last failing CUDA call on this thread    */
 int isr_device_sm_count(void);              /* SM count of the current device, or a negative IsrStatus    */
+long long isr_kernel_launch_count(void);    /* kernels of THIS library launched by the process so far (CUB and
+                                             * memset launches are not counted)                              */
 
 /* ---- workspace sizes --------------------------------------------------------------------------------- */
 size_t isr_geom_bytes(int P);               /* per-Gaussian state saved for backward                       */

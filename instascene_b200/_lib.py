@@ -55,7 +55,7 @@ class IsrBackwardArgs(C.Structure):
 
 
 EXPORTED_SYMBOLS = [
-    "isr_version", "isr_status_string", "isr_last_cuda_error", "isr_device_sm_count",
+    "isr_version", "isr_status_string", "isr_last_cuda_error", "isr_device_sm_count", "isr_kernel_launch_count",
     "isr_geom_bytes", "isr_image_bytes", "isr_binning_bytes", "isr_field_offset",
     "isr_forward_geometry", "isr_forward_render", "isr_backward", "isr_backward_extra_sparse", "isr_mark_visible",
     "isr_gather_pixels", "isr_contrastive_workspace_bytes", "isr_contrastive_forward", "isr_contrastive_backward",
@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
             "(nvcc, sm_100a).  instascene_b200 has no CPU/PyTorch fallback.")
     L = C.CDLL(LIB_PATH)
     L.isr_status_string.restype = C.c_char_p
+    L.isr_kernel_launch_count.restype = C.c_longlong
     L.isr_geom_bytes.restype = C.c_size_t
     L.isr_geom_bytes.argtypes = [C.c_int]
     L.isr_image_bytes.restype = C.c_size_t

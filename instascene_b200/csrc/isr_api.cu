@@ -1,4 +1,5 @@
 // isr_api.cu -- the extern "C" boundary declared in include/isr.h.
+#include <atomic>
 #include <cstdio>
 
 #include "isr_common.cuh"
@@ -6,6 +7,8 @@
 namespace isr {
 static thread_local cudaError_t g_last_cuda_error = cudaSuccess;
 void set_last_cuda_error(cudaError_t e) { g_last_cuda_error = e; }
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int launch_preprocess_fwd(const IsrForwardArgs& a, cudaStream_t stream);
 int launch_depth_order_and_offsets(const IsrForwardArgs& a, cudaStream_t stream);
@@ -67,6 +70,8 @@ const char* isr_status_string(int status) {
 }
 
 int isr_last_cuda_error(void) { return (int)g_last_cuda_error; }
+
+long long isr_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int isr_device_sm_count(void) {
     int dev = 0, n = 0;

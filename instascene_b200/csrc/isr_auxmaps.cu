@@ -164,7 +164,7 @@ int launch_aux_fwd(int W, int H, const float* allmap, const float* M_host, const
                    cudaStream_t stream) {
     const dim3 grid((W + 255) / 256, H);
     aux_maps_fwd_kernel<<<grid, 256, 0, stream>>>(W, H, allmap, make_consts(M_host, K_host, depth_ratio), rend_normal,
-                                                  rend_depth, rend_median, surf_depth, surf_normal);
+                                                  rend_depth, rend_median, surf_depth, surf_normal); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }
@@ -174,7 +174,7 @@ int launch_aux_bwd(int W, int H, const float* allmap, const float* M_host, const
                    const float* g_surf_depth, const float* g_surf_normal, float* g_allmap, cudaStream_t stream) {
     const dim3 grid((W + 255) / 256, H);
     aux_maps_bwd_kernel<<<grid, 256, 0, stream>>>(W, H, allmap, make_consts(M_host, K_host, depth_ratio), g_rend_normal,
-                                                  g_rend_depth, g_rend_median, g_surf_depth, g_surf_normal, g_allmap);
+                                                  g_rend_depth, g_rend_median, g_surf_depth, g_surf_normal, g_allmap); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }

@@ -10,14 +10,26 @@
 //      emits many tiles an elongated or small splat provably never touches
 //   1. stable sort of the P Gaussians by depth bits (culled ones carry key 0xFFFFFFFF and sink to the end)
 //   2. exclusive scan of the emitted-tile counts in that depth order -> instance offsets, R_emit
-//   3. emission of (tile id, Gaussian id) in depth order for the tiles in the mask
-//   4. stable sort of the instances by tile id ONLY (13 bits at 1080p = 2 onesweep passes of 8-byte pairs)
-//   5. tile ranges from the sorted tile ids
-// Because both sorts are stable, instances of a tile end up ordered by (depth bits, Gaussian id): each tile list
-// is exactly the reference's list (ties: SURVEY.md Q2) minus entries that contribute to none of the tile's pixels
-// -- skipping those never changes a result -- while the instance-sized traffic drops by an order of magnitude.
+//   3. STABLE COUNTING PARTITION of the instances by tile, fused with their emission -- no (key, value) arrays, no
+//      sort passes over the instances, nothing sized by R on the host:
+//        a. bin_count_kernel: the depth order is cut into `chunks` runs of ~R/chunks instances; one warp per run
+//           enumerates its instances and counts them per tile in shared memory (one 32-bit counter per tile) -> a
+//           [chunks][tiles] table
+//        b. bin_colscan_kernel / bin_tilebase_kernel: exclusive scan down every tile column and across the tile
+//           totals: table[c][t] becomes the rank of chunk c's first instance in tile t, the totals become the tile
+//           ranges (identifyTileRanges for free)
+//        c. bin_scatter_kernel: the same warp re-enumerates its run in depth order and writes every list entry
+//           (Gaussian id + the 8 per-block footprint bits) straight to its final position: shared-memory cursor of
+//           the tile + rank among the lanes of the same round that hit the same tile (__match_any_sync, lane order
+//           = depth order)
+//      Instances of a tile end up ordered by (depth bits, Gaussian id): each tile list is exactly the reference's list
+//      (ties: SURVEY.md Q2) minus entries that contribute to none of the tile's pixels -- skipping those never
+//      changes a result.  The kernels read R from device memory, so phase B has no host-side dependence on it beyond
+//      the capacity of the list buffer.
+//   (fallback when the per-tile table does not fit in shared memory, > ~50k tiles: emission of (tile id, entry) pairs
+//    + CUB radix sort by tile id + tile ranges, as in round 1)
 // The reference's num_rendered (sum of tiles_touched) is still computed and reported at the boundary.
-// The radix-sort/scan primitives are CUB (CUDA toolkit), as in the reference.
+// Phase A's depth sort and offset scan use CUB (CUDA toolkit), as the reference does for its single big sort.
 #include <cub/cub.cuh>
 
 #include "isr_common.cuh"
@@ -27,6 +39,23 @@ namespace isr {
 bool entries_packed(int P) {
     static const bool plain = [] { const char* e = getenv("ISR_PLAIN_ENTRIES"); return e && e[0] == '1'; }();
     return !plain && P < (1 << kIdBits);
+}
+
+BinChunks bin_chunks(int num_tiles) {
+    static const int sm_count = [] {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;  // B200
+        return n;
+    }();
+    static const bool force_sort = [] { const char* e = getenv("ISR_BIN_SORT"); return e && e[0] == '1'; }();  // test hook
+    BinChunks bc;
+    bc.smem_bytes = align_up((size_t)(num_tiles > 0 ? num_tiles : 1) * 4, 16);
+    const size_t budget = 200 * 1024;  // per SM, leaves room for the L1 carve-out
+    int per_sm = (int)(budget / bc.smem_bytes);
+    if (per_sm > 8) per_sm = 8;
+    bc.chunks = (force_sort || per_sm < 1) ? 0 : sm_count * per_sm;
+    return bc;
 }
 
 struct TilesInDepthOrder {
@@ -41,10 +70,8 @@ size_t sort_temp_bytes_gauss(int P) {
     cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
                                     (uint32_t*)nullptr, P, 0, 32);
     cub::DeviceScan::ExclusiveSum(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr, P + 1);
-    size_t c = 0;
-    cub::DeviceReduce::Sum(nullptr, c, (const uint32_t*)nullptr, (uint32_t*)nullptr, P);
     a = a > b ? a : b;
-    return align_up((a > c ? a : c) + 256, 256);
+    return align_up(a + 256, 256);
 }
 
 size_t sort_temp_bytes_inst(int64_t R, int num_tiles) {
@@ -62,20 +89,55 @@ __global__ void iota_kernel(int n, uint32_t* __restrict__ out) {
     if (i < n) out[i] = (uint32_t)i;
 }
 
-// gathered[i] = tiles[order[i]] for i < P, gathered[P] = 0  (so that an exclusive scan over P+1 items leaves
-// R in offsets[P])
-__global__ void gather_tiles_kernel(int P, const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ order,
-                                    uint32_t* __restrict__ gathered) {
+// gathered[i] = tcount[order[i]] for i < P, gathered[P] = 0  (so that an exclusive scan over P+1 items leaves
+// R in offsets[P]).  Also accumulates, in 64 bits, the reference's num_rendered (sum of tiles_touched) and the
+// emitted-instance total (the 32-bit scan would wrap silently beyond 2^32 instances), and writes what the counting
+// partition needs per Gaussian as ONE record in depth order (so that the per-chunk warps stream it sequentially instead
+// of chasing order[i] -> per-Gaussian arrays): id, emitted tile count (bit 31: footprint of more than 64 tiles = every
+// tile of the rectangle), getRect origin, rectangle width, and the K1 footprint mask.
+__global__ void gather_tiles_kernel(int P, const uint32_t* __restrict__ tcount, const uint32_t* __restrict__ order,
+                                    const uint32_t* __restrict__ tiles_touched, const int* __restrict__ radii,
+                                    const Splat* __restrict__ splats, const unsigned long long* __restrict__ tile_mask,
+                                    int gx, int gy, uint32_t* __restrict__ gathered, uint4* __restrict__ bin_rec,
+                                    unsigned long long* __restrict__ bin_mask,
+                                    unsigned long long* __restrict__ totals /*[0] sum tiles_touched, [1] sum tcount*/) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P) gathered[i] = tiles[order[i]];
-    else if (i == P) gathered[i] = 0;
+    unsigned long long a = 0ull, b = 0ull;
+    if (i < P) {
+        const uint32_t g = order[i];
+        const uint32_t c = tcount[g];
+        gathered[i] = c;
+        b = c;
+        a = tiles_touched[i];
+        uint4 rec = make_uint4(g, 0u, 0u, 1u);
+        unsigned long long mask = 0ull;
+        if (c > 0) {
+            int mnx, mny, mxx, mxy;
+            get_rect(splats[g].mx, splats[g].my, radii[g], gx, gy, mnx, mny, mxx, mxy);
+            const uint32_t big = (mxx - mnx) * (mxy - mny) > 64 ? 0x80000000u : 0u;
+            rec = make_uint4(g, c | big, (uint32_t)mnx | ((uint32_t)mny << 16), (uint32_t)(mxx - mnx));
+            mask = tile_mask[g];
+        }
+        bin_rec[i] = rec;
+        bin_mask[i] = mask;
+    } else if (i == P) {
+        gathered[i] = 0;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
+    }
+    if ((threadIdx.x & 31) == 0 && (a | b)) {
+        if (a) atomicAdd(totals + 0, a);
+        if (b) atomicAdd(totals + 1, b);
+    }
 }
 
-// out[0] = the reference's num_rendered (all tiles of every getRect rectangle), out[1] = emitted instances
-__global__ void copy_count_kernel(const uint32_t* __restrict__ offsets, int P, const uint32_t* __restrict__ tile_total,
-                                  int64_t* __restrict__ out) {
-    out[0] = (int64_t)*tile_total;
-    out[1] = (int64_t)offsets[P];
+// out[0] = the reference's num_rendered (all tiles of every getRect rectangle), out[1] = emitted instances (64-bit sums)
+__global__ void copy_count_kernel(const unsigned long long* __restrict__ totals, int64_t* __restrict__ out) {
+    out[0] = (int64_t)totals[0];
+    out[1] = (int64_t)totals[1];
 }
 
 // One list entry: Gaussian id, plus (packed entries) the per-block footprint bits of tile (tile_x, tile_y): the test
@@ -249,33 +311,289 @@ int launch_depth_order_and_offsets(const IsrForwardArgs& a, cudaStream_t stream)
     uint32_t* keys_alt = reinterpret_cast<uint32_t*>(g + gl.keys_alt);
     uint32_t* tiles = reinterpret_cast<uint32_t*>(g + gl.tiles);
     uint32_t* tcount = reinterpret_cast<uint32_t*>(g + gl.tcount);
-    uint32_t* tile_total = reinterpret_cast<uint32_t*>(g + gl.counters);
+    unsigned long long* totals = reinterpret_cast<unsigned long long*>(g + gl.counters);  // [0], [1]; see GeomLayout
     uint32_t* offsets = reinterpret_cast<uint32_t*>(g + gl.offsets);
     void* temp = g + gl.sort_temp;
     size_t temp_bytes = gl.sort_temp_bytes;
-    if (a.num_rendered_host != nullptr)  // only the boundary's num_rendered needs the reference's count
-        ISR_CUDA_TRY(cub::DeviceReduce::Sum(temp, temp_bytes, tiles, tile_total, P, stream));
-    temp_bytes = gl.sort_temp_bytes;
-    iota_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, order_alt);
+    ISR_CUDA_TRY(cudaMemsetAsync(totals, 0, 32, stream));  // both 64-bit totals + big_list count + overflow flag
+    iota_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, order_alt); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     // stable: equal depth bits keep ascending Gaussian id
     ISR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_alt, order_alt, order, P, 0, 32, stream));
     // keys_alt now holds sorted keys (unused afterwards) -> reuse it for the gathered tile counts
-    gather_tiles_kernel<<<(P + 1 + 255) / 256, 256, 0, stream>>>(P, tcount, order, keys_alt);
+    const int gx = (a.W + TILE - 1) / TILE, gy = (a.H + TILE - 1) / TILE;
+    gather_tiles_kernel<<<(P + 1 + 255) / 256, 256, 0, stream>>>(
+        P, tcount, order, tiles, a.radii, reinterpret_cast<const Splat*>(g + gl.splat),
+        reinterpret_cast<const unsigned long long*>(g + gl.tmask), gx, gy, keys_alt, reinterpret_cast<uint4*>(g + gl.bin_rec),
+        reinterpret_cast<unsigned long long*>(g + gl.bin_mask), totals); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     temp_bytes = gl.sort_temp_bytes;
     ISR_CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, keys_alt, offsets, P + 1, stream));
     if (a.num_rendered_host != nullptr) {
-        // both counts -> int64[2] on the host; widened on the device into the scratch first
+        // both counts -> int64[2] on the host
         int64_t* wide = reinterpret_cast<int64_t*>(temp);
-        copy_count_kernel<<<1, 1, 0, stream>>>(offsets, P, tile_total, wide);
+        copy_count_kernel<<<1, 1, 0, stream>>>(totals, wide); note_launch();
         ISR_CUDA_TRY(cudaGetLastError());
         ISR_CUDA_TRY(cudaMemcpyAsync(a.num_rendered_host, wide, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
     }
     return ISR_OK;
 }
 
-// Phase B head: emission, tile sort, ranges.
+// ---------------------------------------------------------------------------------------------------------
+// Stable counting partition by tile, fused with emission (steps 3a-3c of the header).
+// ---------------------------------------------------------------------------------------------------------
+// First index i in [0, n] with a[i] >= target (a non-decreasing, a[n] readable); all lanes cooperate: 32-ary search.
+__device__ __forceinline__ int warp_lower_bound(const uint32_t* __restrict__ a, int n, uint32_t target, int lane) {
+    int lo = 0, hi = n;  // the answer lies in [lo, hi]
+    while (hi - lo > 32) {
+        const int step = (hi - lo + 32) / 33;
+        const int p = lo + (lane + 1) * step - 1;
+        const bool ge = p < hi ? (__ldg(a + p) >= target) : true;
+        const unsigned b = __ballot_sync(0xffffffffu, ge);
+        if (b == 0u) {
+            lo += 32 * step;
+        } else {
+            const int first = __ffs(b) - 1;
+            const int p_first = lo + (first + 1) * step - 1;
+            if (p_first < hi) hi = p_first;
+            lo += first * step;
+        }
+    }
+    const int p = lo + lane;
+    const bool ge = p < hi ? (__ldg(a + p) >= target) : true;
+    return lo + __ffs(__ballot_sync(0xffffffffu, ge)) - 1;
+}
+
+struct BinArgs {
+    int P, gx, gy, W, H, num_tiles, chunks, packed;
+    const uint32_t* offsets;         // [P+1] exclusive scan of the emitted tile counts in depth order; offsets[P] = R
+    const uint4* rec;                // [P] depth order (gather_tiles_kernel)
+    const unsigned long long* mask;  // [P] depth order
+    const float4* cull4;
+    const float4* cullq;
+};
+
+// Depth-order positions [i0, i1) of chunk c: the Gaussians whose first instance lies in [c*q, (c+1)*q), q = ceil(R/chunks).
+__device__ __forceinline__ void chunk_range(const BinArgs& b, int c, int lane, int& i0, int& i1) {
+    const uint32_t R = __ldg(b.offsets + b.P);
+    const uint32_t q = max(1u, (R + (uint32_t)b.chunks - 1u) / (uint32_t)b.chunks);
+    const unsigned long long lo = (unsigned long long)c * q, hi = lo + q;
+    // Everything from the first position whose start offset equals R on has no instances (that tail holds every culled
+    // Gaussian: hundreds of thousands of positions that must not land on the last chunk's single warp).
+    if (lo >= R) {
+        i0 = i1 = b.P;
+        return;
+    }
+    i0 = warp_lower_bound(b.offsets, b.P, (uint32_t)lo, lane);
+    i1 = warp_lower_bound(b.offsets, b.P, (uint32_t)(hi < R ? hi : R), lane);
+}
+
+// Enumerates, 32 per round, the emitted (Gaussian, tile) instances of depth-order positions [i0, i1) IN ORDER: the
+// lanes take consecutive instances of 32 consecutive Gaussians -- each finds the owning Gaussian by a 5-step search over
+// the warp's running counts (shuffles) and the tile as the k-th set bit of that Gaussian's K1 footprint mask (footprints
+// of more than 64 tiles: every tile of the getRect rectangle, row-major).  The records of the NEXT 32 Gaussians are
+// loaded (coalesced, independent of anything else) before the current ones are expanded.
+//   begin(g, has_g): once per batch of 32 Gaussians, all lanes (lane l holds Gaussian l of the batch)
+//   f(has, owner_lane, g, tile_x, tile_y): once per round of 32 instances, all lanes together (it may use warp
+//   collectives); lane order within a call == instance order.
+template <class Begin, class Fn>
+__device__ __forceinline__ void for_each_instance(const BinArgs& b, int i0, int i1, int lane, Begin begin, Fn f) {
+    uint4 rec_n = make_uint4(0u, 0u, 0u, 1u);
+    unsigned long long mask_n = 0ull;
+    if (i0 + lane < i1) { rec_n = __ldg(b.rec + i0 + lane); mask_n = __ldg(b.mask + i0 + lane); }
+    for (int ib = i0; ib < i1; ib += 32) {
+        const uint4 rec = rec_n;
+        const unsigned long long mask = mask_n;
+        const bool has_g = ib + lane < i1;
+        rec_n = make_uint4(0u, 0u, 0u, 1u);
+        mask_n = 0ull;
+        if (ib + 32 + lane < i1) { rec_n = __ldg(b.rec + ib + 32 + lane); mask_n = __ldg(b.mask + ib + 32 + lane); }
+        const uint32_t g = rec.x, cnt = has_g ? (rec.y & 0x7fffffffu) : 0u, big = rec.y >> 31, rect = rec.z, w = rec.w;
+        begin(g, has_g && cnt > 0);
+        // running instance count over the warp's Gaussians (inclusive scan), c_excl = instances before this lane's
+        uint32_t c_incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, c_incl, d);
+            if (lane >= d) c_incl += v;
+        }
+        const uint32_t c_excl = c_incl - cnt;
+        const uint32_t total = __shfl_sync(0xffffffffu, c_incl, 31);
+        const uint32_t mlo = (uint32_t)mask, mhi = (uint32_t)(mask >> 32);
+        for (uint32_t jb = 0; jb < total; jb += 32) {
+            const uint32_t j = jb + lane;
+            int lo = 0;  // owner = last lane whose exclusive count is <= j (lanes with no instances share their successor's)
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const uint32_t o = __shfl_sync(0xffffffffu, c_excl, lo + step);
+                if (o <= j) lo += step;
+            }
+            const uint32_t g_o = __shfl_sync(0xffffffffu, g, lo), ce_o = __shfl_sync(0xffffffffu, c_excl, lo);
+            const uint32_t rect_o = __shfl_sync(0xffffffffu, rect, lo), w_o = __shfl_sync(0xffffffffu, w, lo);
+            const uint32_t mlo_o = __shfl_sync(0xffffffffu, mlo, lo), mhi_o = __shfl_sync(0xffffffffu, mhi, lo);
+            const uint32_t big_o = __shfl_sync(0xffffffffu, big, lo);
+            const bool has = j < total;
+            int t = 0;
+            if (has) {
+                const int k = (int)(j - ce_o);
+                if (big_o) {
+                    t = k;
+                } else {
+                    unsigned long long m = (unsigned long long)mlo_o | ((unsigned long long)mhi_o << 32);
+                    for (int q = 0; q < k; q++) m &= m - 1;  // drop the k lowest set bits
+                    t = __ffsll((long long)m) - 1;
+                }
+            }
+            // t / w without an integer division: (t + 0.5) / w is at least 0.5/w away from an integer
+            const int ty = __float2int_rd(((float)t + 0.5f) * (1.0f / (float)w_o)), tx = t - ty * (int)w_o;
+            f(has, lo, g_o, (int)(rect_o & 0xffffu) + tx, (int)(rect_o >> 16) + ty);
+        }
+    }
+}
+
+// 3a: per-(chunk, tile) instance counts.  One warp per chunk; cnt[] = one 32-bit counter per tile in shared memory.
+__global__ void __launch_bounds__(32) bin_count_kernel(const BinArgs b, uint32_t* __restrict__ table) {
+    extern __shared__ uint32_t cnt[];
+    const int lane = threadIdx.x, c = blockIdx.x;
+    for (int t = lane; t < b.num_tiles; t += 32) cnt[t] = 0u;
+    __syncwarp();
+    int i0, i1;
+    chunk_range(b, c, lane, i0, i1);
+    for_each_instance(b, i0, i1, lane, [](uint32_t, bool) {}, [&](bool has, int, uint32_t, int tile_x, int tile_y) {
+        if (has) atomicAdd(&cnt[tile_y * b.gx + tile_x], 1u);
+    });
+    __syncwarp();
+    uint32_t* row = table + (size_t)c * b.num_tiles;
+    for (int t = lane; t < b.num_tiles; t += 32) row[t] = cnt[t];
+}
+
+// 3b: exclusive scan down every tile column of the [chunks][tiles] table; totals[t] = instances of tile t.  A CTA owns
+// 32 adjacent tiles (one 128-byte line per table row) and splits the chunk axis over its 8 warps: per-warp partial sums,
+// an 8-entry scan in shared memory, then the in-place exclusive scan of each warp's segment.
+__global__ void __launch_bounds__(256) bin_colscan_kernel(int num_tiles, int chunks, uint32_t* __restrict__ table,
+                                                         uint32_t* __restrict__ totals) {
+    __shared__ uint32_t seg_sum[8][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + lane;
+    const int per = (chunks + 7) / 8, c0 = wid * per, c1 = min(chunks, c0 + per);
+    const bool ok = t < num_tiles;
+    uint32_t sum = 0;
+    if (ok)
+        for (int c = c0; c < c1; c++) sum += table[(size_t)c * num_tiles + t];
+    seg_sum[wid][lane] = sum;
+    __syncthreads();
+    uint32_t run = 0;
+    for (int w = 0; w < wid; w++) run += seg_sum[w][lane];
+    if (ok) {
+        int c = c0;
+        for (; c + 4 <= c1; c += 4) {
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = table[(size_t)(c + u) * num_tiles + t];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                table[(size_t)(c + u) * num_tiles + t] = run;
+                run += v[u];
+            }
+        }
+        for (; c < c1; c++) {
+            const uint32_t v = table[(size_t)c * num_tiles + t];
+            table[(size_t)c * num_tiles + t] = run;
+            run += v;
+        }
+        if (wid == 7) totals[t] = run;
+    }
+}
+
+// 3b': exclusive scan over the tile totals -> base[t] and the tile ranges (DSR identifyTileRanges,
+// rasterizer_impl.cu:116-138: empty tiles keep (0, 0)).  One CTA.
+__global__ void __launch_bounds__(1024) bin_tilebase_kernel(int num_tiles, const uint32_t* __restrict__ totals,
+                                                           uint32_t* __restrict__ base, uint2* __restrict__ ranges,
+                                                           int64_t capacity, uint32_t* __restrict__ overflow) {
+    __shared__ uint32_t warp_sums[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int per = (num_tiles + 1023) / 1024;
+    const int t0 = tid * per, t1 = min(num_tiles, t0 + per);
+    uint32_t mine = 0;
+    for (int t = t0; t < t1; t++) mine += totals[t];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = warp_sums[lane], wi = ws;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += v;
+        }
+        warp_sums[lane] = wi - ws;  // exclusive
+        if (lane == 31 && (int64_t)wi > capacity) *overflow = 1u;  // more instances than the list buffer holds
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[wid] + incl - mine;
+    for (int t = t0; t < t1; t++) {
+        const uint32_t n = totals[t];
+        base[t] = run;
+        ranges[t] = n ? make_uint2(run, run + n) : make_uint2(0u, 0u);
+        run += n;
+    }
+}
+
+// 3c: every list entry straight to its final position, in depth order.  The footprint data of the batch's 32
+// Gaussians (cull rectangle + conic, 64 B each) is staged in shared memory once per batch, so the per-instance work
+// touches global memory only for the final 4-byte store.
+__global__ void __launch_bounds__(32) bin_scatter_kernel(const BinArgs b, const uint32_t* __restrict__ table,
+                                                        const uint32_t* __restrict__ base, int64_t capacity,
+                                                        uint32_t* __restrict__ point_list) {
+    extern __shared__ uint32_t cursor[];
+    __shared__ float4 foot[32][4];  // per Gaussian of the batch: cull rectangle, q0, q1, (r2, -, -, -)
+    const int lane = threadIdx.x, c = blockIdx.x;
+    const uint32_t* row = table + (size_t)c * b.num_tiles;
+    for (int t = lane; t < b.num_tiles; t += 32) cursor[t] = base[t] + row[t];
+    __syncwarp();
+    int i0, i1;
+    chunk_range(b, c, lane, i0, i1);
+    const unsigned below = (1u << lane) - 1u;
+    for_each_instance(
+        b, i0, i1, lane,
+        [&](uint32_t g, bool has_g) {
+            __syncwarp();  // the previous batch's rounds are done reading foot[]
+            if (b.packed && has_g) {
+                const float4* q = b.cullq + (size_t)g * 3;
+                foot[lane][0] = __ldg(b.cull4 + g);
+                foot[lane][1] = __ldg(q);
+                foot[lane][2] = __ldg(q + 1);
+                foot[lane][3] = __ldg(q + 2);
+            }
+            __syncwarp();
+        },
+        [&](bool has, int owner, uint32_t g, int tile_x, int tile_y) {
+            const uint32_t tile = (uint32_t)(tile_y * b.gx + tile_x);
+            // lanes of this round that hit the same tile, in lane (= depth) order; idle lanes get unique keys
+            const unsigned peers = __match_any_sync(0xffffffffu, has ? tile : (0x80000000u | (uint32_t)lane));
+            const int rank = __popc(peers & below);
+            const uint32_t pos = has ? cursor[tile] + (uint32_t)rank : 0u;
+            __syncwarp();
+            if (has && rank == 0) cursor[tile] += (uint32_t)__popc(peers);
+            __syncwarp();
+            if (has && (int64_t)pos < capacity) {
+                float4 cr = make_float4(0.f, 0.f, 0.f, 0.f), q0 = cr, q1 = cr;
+                float r2 = 0.0f;
+                if (b.packed) {
+                    cr = foot[owner][0]; q0 = foot[owner][1]; q1 = foot[owner][2]; r2 = foot[owner][3].x;
+                }
+                point_list[pos] = make_entry(g, tile_x, tile_y, b.packed, cr, q0, q1, r2);
+            }
+        });
+}
+
+// Phase B head: stable partition of the instances by tile (fused with emission) + tile ranges.  `R` is the CAPACITY of
+// the list buffer (>= the emitted instance count, which the kernels read from device memory).
 int launch_binning(const IsrForwardArgs& a, int64_t R, cudaStream_t stream) {
     const int P = a.P;
     const int gx = (a.W + TILE - 1) / TILE, gy = (a.H + TILE - 1) / TILE;
@@ -287,34 +605,63 @@ int launch_binning(const IsrForwardArgs& a, int64_t R, cudaStream_t stream) {
     char* im = static_cast<char*>(a.image);
     char* b = static_cast<char*>(a.binning);
     uint2* ranges = reinterpret_cast<uint2*>(im + il.ranges);
-    ISR_CUDA_TRY(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, stream));
-    if (R <= 0 || P <= 0) return ISR_OK;
+    if (R <= 0 || P <= 0) {
+        ISR_CUDA_TRY(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, stream));
+        return ISR_OK;
+    }
     uint32_t* point_list = reinterpret_cast<uint32_t*>(b + bl.point_list);
+    const int packed = entries_packed(P) ? 1 : 0;
+    const BinChunks bc = bin_chunks(num_tiles);
+    if (bc.chunks > 0) {
+        BinArgs ba;
+        ba.P = P; ba.gx = gx; ba.gy = gy; ba.W = a.W; ba.H = a.H; ba.num_tiles = num_tiles; ba.chunks = bc.chunks; ba.packed = packed;
+        ba.offsets = reinterpret_cast<const uint32_t*>(g + gl.offsets);
+        ba.rec = reinterpret_cast<const uint4*>(g + gl.bin_rec);
+        ba.mask = reinterpret_cast<const unsigned long long*>(g + gl.bin_mask);
+        ba.cull4 = reinterpret_cast<const float4*>(g + gl.cull);
+        ba.cullq = reinterpret_cast<const float4*>(g + gl.cullq);
+        uint32_t* table = reinterpret_cast<uint32_t*>(b + bl.table);
+        uint32_t* totals = reinterpret_cast<uint32_t*>(b + bl.totals);
+        uint32_t* base = reinterpret_cast<uint32_t*>(b + bl.base);
+        uint32_t* overflow = reinterpret_cast<uint32_t*>(g + gl.counters) + 5;
+        ISR_CUDA_TRY(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc.smem_bytes));
+        ISR_CUDA_TRY(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc.smem_bytes));
+        bin_count_kernel<<<bc.chunks, 32, bc.smem_bytes, stream>>>(ba, table); note_launch();
+        ISR_CUDA_TRY(cudaGetLastError());
+        bin_colscan_kernel<<<(num_tiles + 31) / 32, 256, 0, stream>>>(num_tiles, bc.chunks, table, totals); note_launch();
+        ISR_CUDA_TRY(cudaGetLastError());
+        bin_tilebase_kernel<<<1, 1024, 0, stream>>>(num_tiles, totals, base, ranges, R, overflow); note_launch();
+        ISR_CUDA_TRY(cudaGetLastError());
+        bin_scatter_kernel<<<bc.chunks, 32, bc.smem_bytes, stream>>>(ba, table, base, R, point_list); note_launch();
+        ISR_CUDA_TRY(cudaGetLastError());
+        return ISR_OK;
+    }
+    // ---- fallback: (tile id, entry) pairs + radix sort by tile id (CUB) + tile ranges --------------------------------
+    ISR_CUDA_TRY(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, stream));
     uint32_t* point_list_alt = reinterpret_cast<uint32_t*>(b + bl.point_list_alt);
     uint32_t* tile_keys = reinterpret_cast<uint32_t*>(b + bl.tile_keys);
     uint32_t* tile_keys_alt = reinterpret_cast<uint32_t*>(b + bl.tile_keys_alt);
-    uint32_t* big_count = reinterpret_cast<uint32_t*>(g + gl.counters) + 1;
+    uint32_t* big_count = reinterpret_cast<uint32_t*>(g + gl.counters) + 4;
     uint2* big_list = reinterpret_cast<uint2*>(g + gl.big_list);
-    const int packed = entries_packed(P) ? 1 : 0;
     ISR_CUDA_TRY(cudaMemsetAsync(big_count, 0, sizeof(uint32_t), stream));
     emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
         P, reinterpret_cast<const uint32_t*>(g + gl.order), reinterpret_cast<const uint32_t*>(g + gl.offsets), a.radii,
         reinterpret_cast<const Splat*>(g + gl.splat), reinterpret_cast<const unsigned long long*>(g + gl.tmask),
         reinterpret_cast<const uint32_t*>(g + gl.tcount), reinterpret_cast<const float4*>(g + gl.cull),
         reinterpret_cast<const float4*>(g + gl.cullq), gx, gy, a.W, a.H, packed, tile_keys_alt, point_list_alt, big_count,
-        big_list);
+        big_list); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     emit_big_kernel<<<592, 256, 0, stream>>>(big_count, big_list, a.radii, reinterpret_cast<const Splat*>(g + gl.splat),
                                              reinterpret_cast<const float4*>(g + gl.cull),
                                              reinterpret_cast<const float4*>(g + gl.cullq), gx, gy, a.W, a.H, packed,
-                                             tile_keys_alt, point_list_alt);
+                                             tile_keys_alt, point_list_alt); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     int bits = 1;
     while ((1 << bits) < num_tiles) bits++;
     size_t temp_bytes = bl.temp_bytes;
     ISR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(b + bl.temp, temp_bytes, tile_keys_alt, tile_keys, point_list_alt,
                                                  point_list, (int)R, 0, bits, stream));
-    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, tile_keys, ranges);
+    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, tile_keys, ranges); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }

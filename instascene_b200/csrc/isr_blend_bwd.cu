@@ -445,7 +445,7 @@ static int launch_bwd_one(const IsrBackwardArgs& a, cudaStream_t stream) {
             a.dL_dothers, a.dL_dextra_pix, (m & ISR_GRAD_GEOMETRY) ? a.dL_dtransMat : nullptr,
             (m & ISR_GRAD_GEOMETRY) ? a.dL_dmeans2D : nullptr, (m & ISR_GRAD_GEOMETRY) ? a.dL_dnormal : nullptr,
             (m & ISR_GRAD_OPACITY) ? a.dL_dopacity : nullptr, (m & ISR_GRAD_COLOR) ? a.dL_dcolors : nullptr,
-            (m & ISR_GRAD_EXTRA) ? a.dL_dextra : nullptr, entries_packed(a.P) ? 1 : 0);
+            (m & ISR_GRAD_EXTRA) ? a.dL_dextra : nullptr, entries_packed(a.P) ? 1 : 0); note_launch();
         ISR_CUDA_TRY(cudaGetLastError());
         return ISR_OK;
     };
@@ -479,7 +479,7 @@ static int launch_sparse_one(int P, int F, int W, int H, const void* geom, const
         n, pix_ids, dLdE, W, H, F, reinterpret_cast<const uint2*>(im + il.ranges),
         reinterpret_cast<const uint32_t*>(binning), reinterpret_cast<const float4*>(g + gl.splat),
         reinterpret_cast<const float4*>(g + gl.cull), reinterpret_cast<const uint32_t*>(im + il.n_contrib), dL_dextra,
-        entries_packed(P) ? 1 : 0);
+        entries_packed(P) ? 1 : 0); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }

@@ -1,7 +1,7 @@
 // isr_blend_fwd.cu -- K6: per-tile front-to-back alpha compositing of RGB + 7 auxiliary maps + F semantic
 // feature channels + the (gaussian, pixel) pair list.   Reference: DSR/cuda_rasterizer/forward.cu:256-462.
 //
-// Mapping: one CTA (256 threads) per 16x16 tile, one thread per pixel, a warp per 8x4 pixel block.  Warps are
+// Mapping: one thread per pixel, a warp per 8x4 pixel block (8 per 16x16 tile), one warp per CTA.  Warps are
 // autonomous (see blend_fwd_kernel): per-warp culling by the per-block footprint bits carried in the list entries
 // (computed at emission from a conservative per-Gaussian footprint of K1), cp.async staging of the surviving records (splat 64 B, rgb 16 B, features 4F B) into warp-private shared
 // memory, broadcast reads in the inner loop (the reference fetches rgb and features from global per contributing
@@ -26,6 +26,28 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+// Shared-memory loads through an explicit 32-bit .shared address (kept in a register by the caller): with generic
+// pointers the compiler re-derived the shared window base (S2R SR_CgaCtaId + LEA) inside the inner loop.
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int ldsi32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 
 // Warp-autonomous blend: every warp owns an 8x4 pixel block and walks its tile's list on its own, 32 entries at a
 // time: (1) ids and cull rectangles of the NEXT chunks are prefetched into registers, (2) one lane per entry tests
@@ -33,10 +55,10 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // LDGSTS, no registers) into the warp's private shared-memory slots, (4) the survivors are blended in list order
 // with broadcast shared-memory reads.  There is no block-wide barrier: warps of a tile neither wait for each other
 // nor for the slowest pixel of the tile, and a warp stops as soon as its own 32 pixels are saturated.
-// kWarps: warps (8x4 pixel blocks) per CTA; the warps never cooperate, so a CTA is just a scheduling unit: with 8 a
-// CTA is a whole tile and its slot stays occupied until the slowest of its 8 blocks is done (measured: 2-warp CTAs are
-// 3.5% faster at cfg3).  kWarpsPerSM: occupancy target that sets the register budget (24 -> 80 registers, 28 -> 72,
-// 32 -> 64).
+// kWarps: warps (8x4 pixel blocks) per CTA; the warps never cooperate, so a CTA is just a scheduling unit.  With
+// kWarps = 1 every shared-memory address of the inner loop is `constant + r * record size` (with more warps per CTA
+// the compiler re-derived the warp's slot base from S2R/LEA/IMAD in every iteration: 14 of ~165 instructions).
+// kWarpsPerSM: occupancy target that sets the register budget (24 -> 80 registers, 28 -> 72, 32 -> 64).
 template <int FP, bool kPairs, int kWarpsPerSM, int kWarps, bool kRef>
 __global__ void __launch_bounds__(32 * kWarps, kWarpsPerSM / kWarps)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int F,
@@ -46,19 +68,25 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                  uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, float* __restrict__ out_others,
                  float* __restrict__ out_extra, int2* __restrict__ pairs, int64_t pair_cap, int* __restrict__ pair_count,
                  int packed) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) float4 smem4[];
     constexpr int REC = FwdSmem<FP>::kRecF4;
+    constexpr int kWarpF4 = (int)(FwdSmem<FP>::per_warp / 16);  // float4 units per warp
+    static_assert(FwdSmem<FP>::per_warp % 16 == 0, "per-warp shared memory must be a multiple of 16 bytes");
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    unsigned char* wbase = smem_raw + (size_t)(tid >> 5) * FwdSmem<FP>::per_warp;
-    float4* slots = reinterpret_cast<float4*>(wbase);                       // [32][REC]
-    int2* meta = reinterpret_cast<int2*>(wbase + (size_t)32 * REC * 16);    // [32] (gaussian id, list index)
-    int2* my_pairs = meta + 32;                                              // [kPairStage]
+    const int wic = kWarps == 1 ? 0 : (tid >> 5);            // warp in CTA
+    float4* const slots = smem4 + wic * kWarpF4;                            // [32][REC]
+    int2* const meta = reinterpret_cast<int2*>(slots + 32 * REC);           // [32] (gaussian id, list index)
+    int2* const my_pairs = meta + 32;                                        // [kPairStage]
+    // the same two bases as .shared addresses, pinned in registers (the empty asm keeps the compiler from
+    // re-deriving them inside the loops)
+    uint32_t slots_s = (uint32_t)__cvta_generic_to_shared(slots), meta_s = (uint32_t)__cvta_generic_to_shared(meta);
+    asm volatile("" : "+r"(slots_s), "+r"(meta_s));
 
     const int tiles_x = (W + TILE - 1) / TILE;
     constexpr int kCtasPerTile = 8 / kWarps;
     const int tile_id = blockIdx.x / kCtasPerTile;
-    const int warp = (blockIdx.x % kCtasPerTile) * kWarps + (tid >> 5);  // 8x4 block of the tile: 2 across, 4 down
+    const int warp = (blockIdx.x % kCtasPerTile) * kWarps + wic;  // 8x4 block of the tile: 2 across, 4 down
     const int tile_x = tile_id % tiles_x, tile_y = tile_id / tiles_x;
     const int wx0 = tile_x * TILE + (warp & 1) * 8;
     const int wy0 = tile_y * TILE + (warp >> 1) * 4;
@@ -75,7 +103,9 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     const uint32_t* __restrict__ plist = point_list + range.x;
     const float c1 = __fdiv_rn(kFar, __fsub_rn(kFar, kNear));
 
-    bool done = !inside;
+    // `live`: the pixel still blends (inside the image and not saturated).  Kept as a full-width integer: a bool that
+    // shares a register with other byte-sized values costs PRMT repacking in every iteration.
+    uint32_t live = inside ? 1u : 0u;
     float T = 1.0f;
     // accumulators live in register pairs so that one FFMA2 updates two of them (isr::fma2, bit-identical to two FFMAs)
     float2 C01 = make_float2(0.f, 0.f), C2x = C01, N12 = C01, DM1 = C01, M2dist = C01;  // C2x.y, see below, stays 0
@@ -91,7 +121,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     uint32_t ent_next = (lane < n_total) ? __ldg(plist + lane) : 0u;
 
     for (int base = 0; base < n_total; base += 32) {
-        if (__all_sync(0xffffffffu, done)) break;
+        if (__all_sync(0xffffffffu, live == 0u)) break;
         const uint32_t ent = ent_next;
         const bool have = base + lane < n_total;
         ent_next = (base + 32 + lane < n_total) ? __ldg(plist + base + 32 + lane) : 0u;
@@ -137,22 +167,27 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                     for (int ch = 0; ch < FP; ch++) dstf[ch] = (ch < F) ? __ldg(extras + (size_t)id * F + ch) : 0.0f;
                 }
             }
-            meta[rank] = make_int2(id, base + lane);
+            meta[rank] = make_int2(id, base + lane + 1);  // .y = the reference's 1-based `contributor` of this entry
         }
         cp_async_wait_all();
         __syncwarp();
         const int n_surv = __popc(m);
-        for (int r = 0; r < n_surv; r++) {
+        uint32_t rec_s = slots_s;  // .shared address of survivor r's record
+        for (int r = 0; r < n_surv; r++, rec_s += REC * 16) {
             float w = 0.0f;  // blend weight of this (pixel, Gaussian) pair; stays 0 if the pair does not contribute
-            if (!done) {
-                const float* s = reinterpret_cast<const float*>(slots + r * REC);
+            if (live) {
+                float s[16];
+                *reinterpret_cast<float4*>(s + 0) = lds128(rec_s);
+                *reinterpret_cast<float4*>(s + 4) = lds128(rec_s + 16);
+                *reinterpret_cast<float4*>(s + 8) = lds128(rec_s + 32);
+                *reinterpret_cast<float2*>(s + 14) = lds64(rec_s + 56);  // opacity, power_cut
                 PairEval e;
                 if (eval_pair<kRef, false>(pixx, pixy, s, e)) {
                     const float test_T = mul(T, sub(1.0f, e.alpha));
                     if (test_T < kTMin) {
-                        done = true;
+                        live = 0u;
                     } else {
-                        const uint32_t contributor = (uint32_t)(meta[r].y + 1);
+                        const uint32_t contributor = (uint32_t)ldsi32(meta_s + 8 * r + 4);
                         w = mul(e.alpha, T);
                         const float A = sub(1.0f, T);
                         // [sass] m = (1 + (-near)/depth) * (far/(far-near)): div.rn, FADD, FMUL
@@ -165,18 +200,17 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                         DM1 = fma2(make_float2(e.depth, mdep), w, DM1);      // D += depth*w, M1 += mdep*w
                         if (T > 0.5f) { median_depth = e.depth; median_contributor = contributor; }
                         N0 = fma_(s[11], w, N0);
-                        N12 = fma2(*reinterpret_cast<const float2*>(s + 12), w, N12);
+                        N12 = fma2(lds64(rec_s + 48), w, N12);
                         if (FP > 0) {
                             // [sass] E[ch] = fma(T, alpha * feature, E[ch])  (forward.cu:415: extras * alpha * T)
-                            const float4* f4 = slots + r * REC + 5;
 #pragma unroll
                             for (int v = 0; v < FP / 4; v++) {
-                                const float4 f = f4[v];
+                                const float4 f = lds128(rec_s + 80 + 16 * v);
                                 E[2 * v + 0] = fma2(mul2(make_float2(f.x, f.y), e.alpha), T, E[2 * v + 0]);
                                 E[2 * v + 1] = fma2(mul2(make_float2(f.z, f.w), e.alpha), T, E[2 * v + 1]);
                             }
                         }
-                        const float4 c = slots[r * REC + 4];  // (r, g, b, 0)
+                        const float4 c = lds128(rec_s + 64);  // (r, g, b, 0)
                         C01 = fma2(make_float2(c.x, c.y), w, C01);
                         C2x = fma2(make_float2(c.z, c.w), w, C2x);
                         T = test_T;
@@ -185,8 +219,8 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                 }
             }
             if (kPairs) {
-                const bool emit = w >= 0.1f;  // reference: (double)w > 0.1 (forward.cu:422)
-                const unsigned m_emit = __ballot_sync(0xffffffffu, emit);
+                // reference: (double)w > 0.1 (forward.cu:422)  <=>  w >= 0.1f
+                const unsigned m_emit = __ballot_sync(0xffffffffu, w >= 0.1f);
                 if (m_emit) {
                     const int n_new = __popc(m_emit);
                     if (wcount + n_new > kPairStage) {
@@ -198,7 +232,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                         __syncwarp();
                         wcount = 0;
                     }
-                    if (emit) my_pairs[wcount + __popc(m_emit & ((1u << lane) - 1u))] = make_int2(meta[r].x, (int)pix_id);
+                    if (w >= 0.1f) my_pairs[wcount + __popc(m_emit & ((1u << lane) - 1u))] = make_int2(ldsi32(meta_s + 8 * r), (int)pix_id);
                     wcount += n_new;
                     __syncwarp();
                 }
@@ -259,12 +293,14 @@ static int launch_one(const IsrForwardArgs& a, cudaStream_t stream) {
             reinterpret_cast<const float4*>(g + gl.cullq), reinterpret_cast<const float4*>(g + gl.rgb), a.extra_attrs, a.background,
             reinterpret_cast<float*>(im + il.final_T), reinterpret_cast<uint32_t*>(im + il.n_contrib), a.out_color,
             a.out_others, a.out_extra, reinterpret_cast<int2*>(a.pairs), a.pair_capacity, a.pair_count,
-            entries_packed(a.P) ? 1 : 0);
+            entries_packed(a.P) ? 1 : 0); note_launch();
         ISR_CUDA_TRY(cudaGetLastError());
         return ISR_OK;
     };
-    if (a.flags & ISR_FLAG_SPEC_ARITH) return launch(blend_fwd_kernel<FP, kPairs, kWps, 2, false>, 2);
-    return launch(blend_fwd_kernel<FP, kPairs, kWps, 2, true>, 2);
+    if (a.flags & ISR_FLAG_SPEC_ARITH) return launch(blend_fwd_kernel<FP, kPairs, kWps, 1, false>, 1);
+    static const int env_w = [] { const char* e = getenv("ISR_FWD_WARPS"); return e ? atoi(e) : 1; }();  // experiment switch
+    if (env_w == 2) return launch(blend_fwd_kernel<FP, kPairs, kWps, 2, true>, 2);
+    return launch(blend_fwd_kernel<FP, kPairs, kWps, 1, true>, 1);
 }
 
 template <bool kPairs>
@@ -279,12 +315,7 @@ static int dispatch_F(const IsrForwardArgs& a, cudaStream_t stream) {
     return ISR_ERR_UNSUPPORTED;
 }
 
-int launch_blend_fwd2(const IsrForwardArgs& a, cudaStream_t stream);
-
 int launch_blend_fwd(const IsrForwardArgs& a, cudaStream_t stream) {
-    // experiment switch: ISR_FWD_IMPL=1 selects the one-pixel-per-lane kernel of this file, default = isr_blend_fwd2.cu
-    static const int impl = [] { const char* e = getenv("ISR_FWD_IMPL"); return e ? atoi(e) : 2; }();
-    if (impl == 2) return launch_blend_fwd2(a, stream);
     const bool want_pairs = a.pairs != nullptr && a.pair_count != nullptr && !(a.flags & ISR_FLAG_NO_PAIRS);
     return want_pairs ? dispatch_F<true>(a, stream) : dispatch_F<false>(a, stream);
 }

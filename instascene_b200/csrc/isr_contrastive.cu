@@ -586,8 +586,8 @@ rownorm_bwd_kernel(int P, int F, const float* __restrict__ x, const float* __res
 template <int FP>
 static int rownorm_launch(bool fwd, int P, int F, const float* x, const float* dy, float e1, float e2, int stages,
                           float* out, cudaStream_t stream) {
-    if (fwd) rownorm_fwd_kernel<FP><<<(P + 255) / 256, 256, 0, stream>>>(P, F, x, e1, e2, stages, out);
-    else rownorm_bwd_kernel<FP><<<(P + 255) / 256, 256, 0, stream>>>(P, F, x, dy, e1, e2, stages, out);
+    if (fwd) { rownorm_fwd_kernel<FP><<<(P + 255) / 256, 256, 0, stream>>>(P, F, x, e1, e2, stages, out); note_launch(); }
+    else { rownorm_bwd_kernel<FP><<<(P + 255) / 256, 256, 0, stream>>>(P, F, x, dy, e1, e2, stages, out); note_launch(); }
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }
@@ -632,7 +632,7 @@ int launch_adam(size_t n, float* p, const float* g, float* m, float* v, float lr
     const size_t n4 = n / 4;
     adam_step_kernel<<<(unsigned)((n4 + 1 + 255) / 256), 256, 0, stream>>>(
         n4, n, reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
-        reinterpret_cast<float4*>(v), beta1, beta2, eps, (float)((double)lr / b1), (float)(1.0 / sqrt(b2)));
+        reinterpret_cast<float4*>(v), beta1, beta2, eps, (float)((double)lr / b1), (float)(1.0 / sqrt(b2))); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }
@@ -642,7 +642,7 @@ size_t contrastive_ws_bytes(int N, int F, int K) { return ContrastWs(N, F, K).to
 int launch_gather_pixels(int F, int64_t HW, const float* map, int n, const int* pix_ids, float* out, cudaStream_t stream) {
     if (n <= 0 || F <= 0) return ISR_OK;
     const int total = n * F;
-    gather_pixels_kernel<<<(total + 255) / 256, 256, 0, stream>>>(F, HW, map, n, pix_ids, out);
+    gather_pixels_kernel<<<(total + 255) / 256, 256, 0, stream>>>(F, HW, map, n, pix_ids, out); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }
@@ -674,11 +674,11 @@ int launch_contrastive_fwd(int N, int F, int K, const float* features, const int
         ISR_CUDA_TRY(cudaFuncSetAttribute(contrast_spread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         ISR_CUDA_TRY(cudaFuncSetAttribute(loss_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
         stats_k<<<blocks, kCB, smem1, stream>>>(N, F, K, features, labels, predef_u == nullptr, fhat, inv_norm, sums, counts,
-                                                loss);
-        contrast_spread_kernel<<<blocks, kCB, smem2, stream>>>(N, F, K, fhat, labels, predef_u, sums, counts, spread);
+                                                loss); note_launch();
+        contrast_spread_kernel<<<blocks, kCB, smem2, stream>>>(N, F, K, fhat, labels, predef_u, sums, counts, spread); note_launch();
         loss_k<<<(N + kLB - 1) / kLB, kLB, smem3, stream>>>(N, F, K, fhat, labels, predef_u, sums, counts, spread, temp_lambda,
                                                             reinterpret_cast<float*>(w + L.g), reinterpret_cast<float*>(w + L.dU),
-                                                            loss);
+                                                            loss); note_launch();
         ISR_CUDA_TRY(cudaGetLastError());
         return ISR_OK;
     };
@@ -698,7 +698,7 @@ int launch_contrastive_bwd(int N, int F, int K, const int* labels, const float* 
     contrast_dfeat_kernel<<<(total + 255) / 256, 256, 0, stream>>>(
         N, F, K, reinterpret_cast<const float*>(w + L.g), labels, reinterpret_cast<const float*>(w + L.dU),
         reinterpret_cast<const float*>(w + L.counts), reinterpret_cast<const float*>(w + L.inv_norm),
-        predef_u == nullptr, grad_scale, dfeat);
+        predef_u == nullptr, grad_scale, dfeat); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }

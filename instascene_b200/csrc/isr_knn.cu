@@ -173,15 +173,15 @@ int launch_knn(int P, const float* points, float* out, void* ws, size_t ws_bytes
     uint32_t* ids_alt = reinterpret_cast<uint32_t*>(w + L.ids_alt);
     uint32_t* cell_start = reinterpret_cast<uint32_t*>(w + L.cell_start);
     const int G = L.G, cells = G * G * G;
-    knn_bbox_init<<<1, 32, 0, stream>>>(bbox);
-    knn_bbox_kernel<<<148 * 4, 256, 0, stream>>>(P, points, bbox);
-    knn_keys_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, points, bbox, G, keys, ids);
+    knn_bbox_init<<<1, 32, 0, stream>>>(bbox); note_launch();
+    knn_bbox_kernel<<<148 * 4, 256, 0, stream>>>(P, points, bbox); note_launch();
+    knn_keys_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, points, bbox, G, keys, ids); note_launch();
     int bits = 1;
     while ((1 << bits) < cells) bits++;
     size_t tb = L.temp_bytes;
     ISR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w + L.temp, tb, keys, keys_alt, ids, ids_alt, P, 0, bits, stream));
-    knn_cell_start_kernel<<<(P + 1 + 255) / 256, 256, 0, stream>>>(P, cells, keys_alt, cell_start);
-    knn_search_kernel<<<(P + 127) / 128, 128, 0, stream>>>(P, points, bbox, G, ids_alt, cell_start, out);
+    knn_cell_start_kernel<<<(P + 1 + 255) / 256, 256, 0, stream>>>(P, cells, keys_alt, cell_start); note_launch();
+    knn_search_kernel<<<(P + 127) / 128, 128, 0, stream>>>(P, points, bbox, G, ids_alt, cell_start, out); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }

@@ -273,7 +273,7 @@ densify_stats_kernel(int P, const int* __restrict__ radii, const float* __restri
 
 int launch_densify_stats(int P, const int* radii, const float* grad2d, float* max_radii2D, float* grad_accum, float* denom,
                          cudaStream_t stream) {
-    densify_stats_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, radii, grad2d, max_radii2D, grad_accum, denom);
+    densify_stats_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, radii, grad2d, max_radii2D, grad_accum, denom); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }
@@ -298,9 +298,9 @@ int launch_photometric_fwd(int C, int H, int W, const float* img, const float* g
     float* partials = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up(3 * chw * 4, 256));
     const int by = photo_tile_rows();
     const dim3 grid((W + kBX - 1) / kBX, (H + by - 1) / by, C);
-    if (by == 32) photometric_fwd_kernel<32><<<grid, Tile<32>::kThreads, 0, stream>>>(C, H, W, img, gt, maps, partials);
-    else photometric_fwd_kernel<16><<<grid, Tile<16>::kThreads, 0, stream>>>(C, H, W, img, gt, maps, partials);
-    photometric_reduce_kernel<<<1, 1024, 0, stream>>>(partials, (int)(grid.x * grid.y * grid.z), 1.0f / (float)chw, lambda, out);
+    if (by == 32) { photometric_fwd_kernel<32><<<grid, Tile<32>::kThreads, 0, stream>>>(C, H, W, img, gt, maps, partials); note_launch(); }
+    else { photometric_fwd_kernel<16><<<grid, Tile<16>::kThreads, 0, stream>>>(C, H, W, img, gt, maps, partials); note_launch(); }
+    photometric_reduce_kernel<<<1, 1024, 0, stream>>>(partials, (int)(grid.x * grid.y * grid.z), 1.0f / (float)chw, lambda, out); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }
@@ -311,8 +311,8 @@ int launch_photometric_bwd(int C, int H, int W, const float* img, const float* g
     const int by = photo_tile_rows();
     const dim3 grid((W + kBX - 1) / kBX, (H + by - 1) / by, C);
     const float* maps = static_cast<const float*>(ws);
-    if (by == 32) photometric_bwd_kernel<32><<<grid, Tile<32>::kThreads, 0, stream>>>(C, H, W, img, gt, maps, grad_scale, lambda, 1.0f / (float)chw, dimg);
-    else photometric_bwd_kernel<16><<<grid, Tile<16>::kThreads, 0, stream>>>(C, H, W, img, gt, maps, grad_scale, lambda, 1.0f / (float)chw, dimg);
+    if (by == 32) { photometric_bwd_kernel<32><<<grid, Tile<32>::kThreads, 0, stream>>>(C, H, W, img, gt, maps, grad_scale, lambda, 1.0f / (float)chw, dimg); note_launch(); }
+    else { photometric_bwd_kernel<16><<<grid, Tile<16>::kThreads, 0, stream>>>(C, H, W, img, gt, maps, grad_scale, lambda, 1.0f / (float)chw, dimg); note_launch(); }
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }

@@ -542,7 +542,7 @@ int launch_preprocess_fwd(const IsrForwardArgs& a, cudaStream_t stream) {
         reinterpret_cast<float4*>(g + gl.cullq), reinterpret_cast<float4*>(g + gl.rgb),
         reinterpret_cast<float*>(g + gl.depth), reinterpret_cast<uint32_t*>(g + gl.depth_key),
         reinterpret_cast<uint32_t*>(g + gl.tiles), reinterpret_cast<uint8_t*>(g + gl.clamped),
-        reinterpret_cast<unsigned long long*>(g + gl.tmask), reinterpret_cast<uint32_t*>(g + gl.tcount));
+        reinterpret_cast<unsigned long long*>(g + gl.tmask), reinterpret_cast<uint32_t*>(g + gl.tcount)); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }
@@ -568,7 +568,7 @@ int launch_preprocess_bwd(const IsrBackwardArgs& a, cudaStream_t stream) {
         a.P, a.sh_degree, a.sh_coeffs, a.means3D, a.radii, a.shs, reinterpret_cast<const uint8_t*>(g + gl.clamped),
         reinterpret_cast<const float2*>(a.scales), reinterpret_cast<const float4*>(a.rotations), a.transMat_precomp,
         reinterpret_cast<const Splat*>(g + gl.splat), cam, W, H, a.dL_dmeans2D, a.dL_dnormal, a.dL_dtransMat,
-        a.dL_dcolors, a.dL_dsh, a.dL_dmeans3D, a.dL_dscales, a.dL_drotations);
+        a.dL_dcolors, a.dL_dsh, a.dL_dmeans3D, a.dL_dscales, a.dL_drotations); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }
@@ -577,7 +577,7 @@ int launch_mark_visible(int P, const float* means3D, const float* view, const fl
                         cudaStream_t stream) {
     if (P == 0) return ISR_OK;
     Camera cam{view, proj, nullptr};
-    mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, cam, present);
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, cam, present); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }

@@ -119,13 +119,13 @@ int launch_tracker_mark(const int* pairs, int64_t n_pairs, const int* seg_rows, 
         const int64_t want = (n_pairs + 255) / 256;
         const int blocks = (int)(want < 148 * 16 ? want : 148 * 16);  // 16 CTAs of 256 threads per SM, grid-stride
         tracker_mark_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const int2*>(pairs), n_pairs, seg_rows, HW, P, K,
-                                                        bitmap, L.words_per_row);
+                                                        bitmap, L.words_per_row); note_launch();
     }
     if (L.words_per_row > 0) {
         const size_t per_block = 256 * 8;
         int bx = (int)((L.words_per_row + per_block - 1) / per_block);
         if (bx < 1) bx = 1;
-        tracker_count_kernel<<<dim3(bx, K), 256, 0, stream>>>(bitmap, L.words_per_row, counts);
+        tracker_count_kernel<<<dim3(bx, K), 256, 0, stream>>>(bitmap, L.words_per_row, counts); note_launch();
     }
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
@@ -135,7 +135,7 @@ int launch_tracker_fill(int P, int K, const void* ws, const int64_t* row_offsets
     TrackerWs L(P, K);
     const uint32_t* bitmap = reinterpret_cast<const uint32_t*>(static_cast<const char*>(ws) + L.bitmap);
     if (L.words_per_row == 0) return ISR_OK;
-    tracker_fill_kernel<<<K, kFillThreads, 0, stream>>>(bitmap, L.words_per_row, row_offsets, out_ids);
+    tracker_fill_kernel<<<K, kFillThreads, 0, stream>>>(bitmap, L.words_per_row, row_offsets, out_ids); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }

@@ -516,7 +516,9 @@ void orc_blend_backward(int W, int H, int F, const uint32_t* ranges, const uint3
                         const float* final_T, const uint32_t* n_contrib, const float* dL_dpixels,
                         const float* dL_dothers, const float* dL_dpixel_extras, float* dL_dtransMat,
                         float* dL_dmean2D /*[P][3]*/, float* dL_dnormal3D, float* dL_dopacity,
-                        float* dL_dcolors, float* dL_dextras, int tile_stride) {
+                        float* dL_dcolors, float* dL_dextras, int tile_stride,
+                        const uint8_t* pixel_mask /* [H*W] or NULL: only pixels with a non-zero entry are walked (the
+                                                     caller guarantees every cotangent of the others is zero) */) {
     const int gx = (W + BLOCK_X - 1) / BLOCK_X, gy = (H + BLOCK_Y - 1) / BLOCK_Y;
     const size_t HW = (size_t)H * W;
     const float c1 = far_n / (far_n - near_n);
@@ -539,6 +541,7 @@ void orc_blend_backward(int W, int H, int F, const uint32_t* ranges, const uint3
                     const int pxi = tx * BLOCK_X + lx, pyi = ty * BLOCK_Y + ly;
                     if (pxi >= W || pyi >= H) continue;
                     const size_t pix_id = (size_t)W * pyi + pxi;
+                    if (pixel_mask && !pixel_mask[pix_id]) continue;
                     const float pixx = (float)pxi, pixy = (float)pyi;
                     const float T_final = final_T[pix_id];
                     float T = T_final;

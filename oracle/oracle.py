@@ -127,8 +127,10 @@ def backward(fwd: Dict[str, np.ndarray], means3D, viewmatrix, projmatrix, campos
              tan_fovx: float, tan_fovy: float, dL_dcolor, dL_dothers, dL_dextra=None,
              scales=None, rotations=None, scale_modifier: float = 1.0, shs=None, sh_degree: int = 0,
              colors_precomp=None, transMat_precomp=None, extra_attrs=None,
-             flags: int = FLAG_BWD_WH_QUIRK, tile_stride: int = 1) -> Dict[str, np.ndarray]:
-    """Full backward (K7 + K8) from the buffers returned by forward()."""
+             flags: int = FLAG_BWD_WH_QUIRK, tile_stride: int = 1, pixel_mask=None,
+             preprocess: bool = True) -> Dict[str, np.ndarray]:
+    """Full backward (K7 + K8) from the buffers returned by forward().  pixel_mask (uint8 [H,W]): walk only those pixels
+    (the cotangents must be zero elsewhere); preprocess=False stops after K7 (feature-only training needs no K8)."""
     L = lib()
     means3D = _f32(means3D)
     viewmatrix, projmatrix, campos, bg = _f32(viewmatrix), _f32(projmatrix), _f32(campos), _f32(bg)
@@ -151,7 +153,10 @@ def backward(fwd: Dict[str, np.ndarray], means3D, viewmatrix, projmatrix, campos
                          _p(extra_attrs if F else None), _p(fwd["final_T"]), _p(fwd["n_contrib"]),
                          _p(dL_dcolor), _p(dL_dothers), _p(dL_dextra if F else None), _p(g["dL_dtransMat"]),
                          _p(g["dL_dmeans2D"]), _p(g["dL_dnormal"]), _p(g["dL_dopacity"]), _p(g["dL_dcolors"]),
-                         _p(g["dL_dextra"]), C.c_int(tile_stride))
+                         _p(g["dL_dextra"]), C.c_int(tile_stride),
+                         _p(None if pixel_mask is None else np.ascontiguousarray(pixel_mask, dtype=np.uint8)))
+    if not preprocess:
+        return g
     g["dL_dmeans2D_raw"] = g["dL_dmeans2D"].copy()
     g["dL_dtransMat_raw"] = g["dL_dtransMat"].copy()
     L.orc_preprocess_backward(C.c_int(P), C.c_int(sh_degree), C.c_int(M), _p(means3D), _p(fwd["radii"]),

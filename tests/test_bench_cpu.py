@@ -35,8 +35,17 @@ def test_clock_summary_flags_throttle_reasons():
     assert s["reasons"] == ["hw_thermal_slowdown", "sw_power_cap"]
 
 
-def test_kernel_count_table_covers_every_workload():
-    assert set(bench.KERNELS_PER_STEP) == set(bench.WORKLOADS) == set(bench.NCU_TRAFFIC_BYTES)
+def test_traffic_record_is_stamped_with_its_kernel():
+    """roofline.traffic comes from profiles/r2_traffic.json and only when the record was captured on the very kernel
+    the bench times; anything else reports null (no stale constants)."""
+    t, src = bench.ncu_traffic("cfg3", "no_such_kernel")
+    assert t is None and src is None
+    rec = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+    for wl, r in rec.items():
+        assert wl in bench.WORKLOADS and {"kernel", "dram_bytes_read", "dram_bytes_write", "source"} <= set(r)
+        assert os.path.exists(os.path.join(ROOT, r["source"]))
+        t, src = bench.ncu_traffic(wl, r["kernel"])
+        assert t == r["dram_bytes_read"] + r["dram_bytes_write"] and src == r["source"]
 
 
 def test_reference_arm_is_silent_on_non_zero_ranks():
@@ -58,4 +67,16 @@ def test_reference_arm_prints_one_json_line(monkeypatch):
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "views/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["steps"] == 1 and "nothing extrapolated" in d["cpu_baseline"]["sample"]
+
+
+def test_reference_arm_uses_every_core_under_torchrun_env():
+    """torchrun exports OMP_NUM_THREADS=1; the reference arm must still use all host cores."""
+    code = ("import bench, sys; bench.WORKLOADS['cfg3'] = dict(bench.WORKLOADS['cfg3'], P=2000, W=96, H=64, samples=512);"
+            "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0']; bench.main()")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=300,
+                       env=dict(os.environ, RANK="0", WORLD_SIZE="2", OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+    assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]

@@ -636,6 +636,21 @@ def test_sampled_loss_with_trainable_geometry_uses_dense_backward():
     assert rel_err(grads["sampled_frozen"]["_seg_feature"].cpu().numpy(), grads["dense"]["_seg_feature"].cpu().numpy()) < 1e-4
 
 
+def test_radix_sort_binning_fallback_matches_counting_partition():
+    """The counting partition (default) and the radix-sort fallback (more tiles than fit the shared-memory table;
+    forced here with ISR_BIN_SORT=1, read once per process) must produce the same lists: run the bit-exact forward test
+    of one case in a fresh interpreter with the fallback forced."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ISR_BIN_SORT="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(root, "tests", "test_parity_gpu.py"),
+                        "-k", "test_forward_bit_exact or test_backward_sparse_equals_dense"], env=env, cwd=root,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_plain_entry_fallback_path():
     """Scenes with >= 2^24 Gaussians cannot carry the per-block footprint bits in the list entries; the blend kernels
     then test the footprint arithmetically.  ISR_PLAIN_ENTRIES=1 forces that path: forward parity + dense/sparse
