@@ -211,12 +211,12 @@ int isr_gather_pixels(int F, int64_t HW, const float* feature_map, int n, const 
 
 size_t isr_contrastive_workspace_bytes(int N, int F, int K);
 /* features [N,F], labels [N] int32 already shifted so that valid labels are 0..K-1 and invalid ones < 0;
- * predef_u [K,F] or NULL (cluster means).  Writes *loss (device float) and saves what backward needs in ws.
- * The similarity matrix runs on tcgen05 (3xTF32, fp32 accumulation in TMEM); the centres and operand panels of all K
- * clusters are staged in one CTA's shared memory, which bounds K: about 890 clusters at F = 16, 385 at F = 32
- * (K*(12F + 4) + 1.5 KB*F + 40 KB <= 226 KB); beyond that ISR_ERR_UNSUPPORTED. */
+ * predef_u [K,F] or NULL (cluster means).  min_pixnum: clusters with <= min_pixnum samples are dropped together with
+ * their samples (utils/contrastive_utils.py:33-35; the reference's default is 0).  Writes *loss (device float) and saves
+ * what backward needs in ws.  The similarity matrix runs on tcgen05 (3xTF32, fp32 accumulation in TMEM) in column
+ * chunks of 256 clusters staged through shared memory: any K. */
 int isr_contrastive_forward(int N, int F, int K, const float* features, const int* labels,
-                            const float* predef_u, float temp_lambda, void* ws, size_t ws_bytes,
+                            const float* predef_u, float temp_lambda, int min_pixnum, void* ws, size_t ws_bytes,
                             float* loss, void* stream);
 /* dL_dfeatures[N,F] = grad_scale * d loss / d features */
 int isr_contrastive_backward(int N, int F, int K, const float* features, const int* labels,

@@ -101,7 +101,7 @@ def lib() -> C.CDLL:
     L.isr_gather_pixels.argtypes = [C.c_int, C.c_int64, _fp, C.c_int, _ip, _fp, C.c_void_p]
     L.isr_contrastive_workspace_bytes.restype = C.c_size_t
     L.isr_contrastive_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
-    L.isr_contrastive_forward.argtypes = [C.c_int, C.c_int, C.c_int, _fp, _ip, _fp, C.c_float, _vp, C.c_size_t, _fp,
+    L.isr_contrastive_forward.argtypes = [C.c_int, C.c_int, C.c_int, _fp, _ip, _fp, C.c_float, C.c_int, _vp, C.c_size_t, _fp,
                                           C.c_void_p]
     L.isr_contrastive_backward.argtypes = [C.c_int, C.c_int, C.c_int, _fp, _ip, _fp, _vp, _fp, _fp, C.c_void_p]
     L.isr_rownorm_forward.argtypes = [C.c_int, C.c_int, _fp, C.c_float, C.c_float, C.c_int, _fp, C.c_void_p]

@@ -12,7 +12,7 @@ from .rasterizer import _ptr, _require_cuda_lib, _stream
 
 class _ContrastiveLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, features, labels, predef_u, K, temp_lambda):
+    def forward(ctx, features, labels, predef_u, K, temp_lambda, min_pixnum=0):
         L = _require_cuda_lib()
         feats = features.detach().float().contiguous()
         N, F = int(feats.shape[0]), int(feats.shape[1])
@@ -22,7 +22,7 @@ class _ContrastiveLoss(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feats.device)
         loss = torch.empty((), dtype=torch.float32, device=feats.device)
         _lib.check(L.isr_contrastive_forward(N, F, K, _ptr(feats), _ptr(labels), _ptr(pu), float(temp_lambda),
-                                             ws.data_ptr(), ws_bytes, loss.data_ptr(), _stream()),
+                                             int(min_pixnum), ws.data_ptr(), ws_bytes, loss.data_ptr(), _stream()),
                    "isr_contrastive_forward")
         ctx.save_for_backward(feats, labels, ws)
         ctx.pu = pu
@@ -38,7 +38,7 @@ class _ContrastiveLoss(torch.autograd.Function):
         dfeat = torch.empty_like(feats)
         _lib.check(L.isr_contrastive_backward(N, F, ctx.K, _ptr(feats), _ptr(labels), _ptr(ctx.pu), ws.data_ptr(),
                                               g.data_ptr(), dfeat.data_ptr(), _stream()), "isr_contrastive_backward")
-        return dfeat, None, None, None, None
+        return dfeat, None, None, None, None, None
 
 
 def contrastive_loss(features: torch.Tensor, masks: torch.Tensor, predef_u_list: Optional[torch.Tensor] = None,
@@ -48,10 +48,6 @@ def contrastive_loss(features: torch.Tensor, masks: torch.Tensor, predef_u_list:
 
     `num_labels` (optional) bounds the label ids (K = num_labels); when omitted it is taken from predef_u_list or
     from `masks.max()` (one host sync, as the reference's `mask_ids.max() + 1`)."""
-    if min_pixnum != 0:
-        # reference :33-35 drops clusters with <= min_pixnum samples; the fused kernel implements the default 0
-        counts = torch.bincount(masks.clamp(min=0).long())
-        masks = torch.where(counts[masks.clamp(min=0).long()] > min_pixnum, masks, torch.full_like(masks, -1 if consider_negative else 0))
     labels = masks.to(torch.int32)
     if not consider_negative:
         labels = labels - 1  # valid ids start at 0 (:39-40); label 0 (unlabelled) becomes -1 = ignored
@@ -62,4 +58,5 @@ def contrastive_loss(features: torch.Tensor, masks: torch.Tensor, predef_u_list:
     else:
         K = int(labels.max().item()) + 1
     K = max(K, 1)
-    return _ContrastiveLoss.apply(features, labels, predef_u_list, K, float(temp_lambda))
+    # (:33-35 clusters with <= min_pixnum samples are dropped inside the kernels)
+    return _ContrastiveLoss.apply(features, labels, predef_u_list, K, float(temp_lambda), int(min_pixnum))

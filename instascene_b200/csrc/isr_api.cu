@@ -23,7 +23,7 @@ int launch_mark_visible(int P, const float* means3D, const float* view, const fl
 size_t contrastive_ws_bytes(int N, int F, int K);
 int launch_gather_pixels(int F, int64_t HW, const float* map, int n, const int* pix_ids, float* out, cudaStream_t stream);
 int launch_contrastive_fwd(int N, int F, int K, const float* features, const int* labels, const float* predef_u,
-                           float temp_lambda, void* ws, float* loss, cudaStream_t stream);
+                           float temp_lambda, int min_pixnum, void* ws, float* loss, cudaStream_t stream);
 int launch_contrastive_bwd(int N, int F, int K, const int* labels, const float* predef_u, const void* ws,
                            const float* grad_scale, float* dfeat, cudaStream_t stream);
 int launch_rownorm(bool fwd, int P, int F, const float* x, const float* dy, float e1, float e2, int stages, float* out,
@@ -212,13 +212,12 @@ size_t isr_contrastive_workspace_bytes(int N, int F, int K) {
 }
 
 int isr_contrastive_forward(int N, int F, int K, const float* features, const int* labels, const float* predef_u,
-                            float temp_lambda, void* ws, size_t ws_bytes, float* loss, void* stream_) {
+                            float temp_lambda, int min_pixnum, void* ws, size_t ws_bytes, float* loss, void* stream_) {
     if (N < 0 || F <= 0 || K < 0 || !loss) return ISR_ERR_INVALID_ARG;
     if (F > ISR_MAX_EXTRA_DIMS) return ISR_ERR_UNSUPPORTED;
     if (N > 0 && (!features || !labels || !ws)) return ISR_ERR_INVALID_ARG;
     if (ws_bytes < contrastive_ws_bytes(N, F, K)) return ISR_ERR_WORKSPACE;
-    if ((size_t)K * (F + 1) * sizeof(float) > 120 * 1024) return ISR_ERR_UNSUPPORTED;  // centres live in shared memory
-    return launch_contrastive_fwd(N, F, K, features, labels, predef_u, temp_lambda, ws, loss,
+    return launch_contrastive_fwd(N, F, K, features, labels, predef_u, temp_lambda, min_pixnum, ws, loss,
                                   static_cast<cudaStream_t>(stream_));
 }
 

@@ -51,10 +51,12 @@ BinChunks bin_chunks(int num_tiles) {
     static const bool force_sort = [] { const char* e = getenv("ISR_BIN_SORT"); return e && e[0] == '1'; }();  // test hook
     BinChunks bc;
     bc.smem_bytes = align_up((size_t)(num_tiles > 0 ? num_tiles : 1) * 4, 16);
-    const size_t budget = 200 * 1024;  // per SM, leaves room for the L1 carve-out
-    int per_sm = (int)(budget / bc.smem_bytes);
+    // per SM: 227 KB opt-in; bin_scatter_kernel adds ~8.5 KB of static shared memory (batch instance list, footprints)
+    // and every resident CTA 1 KB of system reservation
+    const size_t budget = 224 * 1024;
+    int per_sm = (int)(budget / (bc.smem_bytes + 10 * 1024));
     if (per_sm > 8) per_sm = 8;
-    bc.chunks = (force_sort || per_sm < 1) ? 0 : sm_count * per_sm;
+    bc.chunks = (force_sort || per_sm < 1 || num_tiles > 65535) ? 0 : sm_count * per_sm;
     return bc;
 }
 
@@ -388,70 +390,47 @@ __device__ __forceinline__ void chunk_range(const BinArgs& b, int c, int lane, i
     i1 = warp_lower_bound(b.offsets, b.P, (uint32_t)(hi < R ? hi : R), lane);
 }
 
-// Enumerates, 32 per round, the emitted (Gaussian, tile) instances of depth-order positions [i0, i1) IN ORDER: the
-// lanes take consecutive instances of 32 consecutive Gaussians -- each finds the owning Gaussian by a 5-step search over
-// the warp's running counts (shuffles) and the tile as the k-th set bit of that Gaussian's K1 footprint mask (footprints
-// of more than 64 tiles: every tile of the getRect rectangle, row-major).  The records of the NEXT 32 Gaussians are
-// loaded (coalesced, independent of anything else) before the current ones are expanded.
-//   begin(g, has_g): once per batch of 32 Gaussians, all lanes (lane l holds Gaussian l of the batch)
-//   f(has, owner_lane, g, tile_x, tile_y): once per round of 32 instances, all lanes together (it may use warp
-//   collectives); lane order within a call == instance order.
-template <class Begin, class Fn>
-__device__ __forceinline__ void for_each_instance(const BinArgs& b, int i0, int i1, int lane, Begin begin, Fn f) {
+// One batch = 32 consecutive Gaussians of the depth order, lane l holding Gaussian l (records prefetched one batch
+// ahead: coalesced, independent of everything else).
+struct BinBatch {
+    uint32_t g, cnt, big, w;   // Gaussian id, emitted tiles (0: none / past the end), footprint > 64 tiles, rectangle width
+    int mnx, mny;              // getRect origin
+    unsigned long long mask;   // K1 footprint mask (small footprints)
+};
+
+template <class Fn>
+__device__ __forceinline__ void for_each_batch(const BinArgs& b, int i0, int i1, int lane, Fn f) {
     uint4 rec_n = make_uint4(0u, 0u, 0u, 1u);
     unsigned long long mask_n = 0ull;
     if (i0 + lane < i1) { rec_n = __ldg(b.rec + i0 + lane); mask_n = __ldg(b.mask + i0 + lane); }
     for (int ib = i0; ib < i1; ib += 32) {
         const uint4 rec = rec_n;
-        const unsigned long long mask = mask_n;
+        BinBatch bb;
+        bb.mask = mask_n;
         const bool has_g = ib + lane < i1;
         rec_n = make_uint4(0u, 0u, 0u, 1u);
         mask_n = 0ull;
         if (ib + 32 + lane < i1) { rec_n = __ldg(b.rec + ib + 32 + lane); mask_n = __ldg(b.mask + ib + 32 + lane); }
-        const uint32_t g = rec.x, cnt = has_g ? (rec.y & 0x7fffffffu) : 0u, big = rec.y >> 31, rect = rec.z, w = rec.w;
-        begin(g, has_g && cnt > 0);
-        // running instance count over the warp's Gaussians (inclusive scan), c_excl = instances before this lane's
-        uint32_t c_incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, c_incl, d);
-            if (lane >= d) c_incl += v;
-        }
-        const uint32_t c_excl = c_incl - cnt;
-        const uint32_t total = __shfl_sync(0xffffffffu, c_incl, 31);
-        const uint32_t mlo = (uint32_t)mask, mhi = (uint32_t)(mask >> 32);
-        for (uint32_t jb = 0; jb < total; jb += 32) {
-            const uint32_t j = jb + lane;
-            int lo = 0;  // owner = last lane whose exclusive count is <= j (lanes with no instances share their successor's)
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-                const uint32_t o = __shfl_sync(0xffffffffu, c_excl, lo + step);
-                if (o <= j) lo += step;
-            }
-            const uint32_t g_o = __shfl_sync(0xffffffffu, g, lo), ce_o = __shfl_sync(0xffffffffu, c_excl, lo);
-            const uint32_t rect_o = __shfl_sync(0xffffffffu, rect, lo), w_o = __shfl_sync(0xffffffffu, w, lo);
-            const uint32_t mlo_o = __shfl_sync(0xffffffffu, mlo, lo), mhi_o = __shfl_sync(0xffffffffu, mhi, lo);
-            const uint32_t big_o = __shfl_sync(0xffffffffu, big, lo);
-            const bool has = j < total;
-            int t = 0;
-            if (has) {
-                const int k = (int)(j - ce_o);
-                if (big_o) {
-                    t = k;
-                } else {
-                    unsigned long long m = (unsigned long long)mlo_o | ((unsigned long long)mhi_o << 32);
-                    for (int q = 0; q < k; q++) m &= m - 1;  // drop the k lowest set bits
-                    t = __ffsll((long long)m) - 1;
-                }
-            }
-            // t / w without an integer division: (t + 0.5) / w is at least 0.5/w away from an integer
-            const int ty = __float2int_rd(((float)t + 0.5f) * (1.0f / (float)w_o)), tx = t - ty * (int)w_o;
-            f(has, lo, g_o, (int)(rect_o & 0xffffu) + tx, (int)(rect_o >> 16) + ty);
-        }
+        bb.g = rec.x;
+        bb.cnt = has_g ? (rec.y & 0x7fffffffu) : 0u;
+        bb.big = bb.cnt ? (rec.y >> 31) : 0u;
+        bb.mnx = (int)(rec.z & 0xffffu);
+        bb.mny = (int)(rec.z >> 16);
+        bb.w = rec.w;
+        f(bb);
     }
 }
 
+// tile (row-major index t of a rectangle of width w at (mnx, mny)) -> global tile id; t / w without an integer
+// division: (t + 0.5) / w is at least 0.5/w away from an integer
+__device__ __forceinline__ uint32_t rect_tile(int t, float inv_w, int w, int mnx, int mny, int gx) {
+    const int ty = __float2int_rd(((float)t + 0.5f) * inv_w), tx = t - ty * w;
+    return (uint32_t)((mny + ty) * gx + mnx + tx);
+}
+
 // 3a: per-(chunk, tile) instance counts.  One warp per chunk; cnt[] = one 32-bit counter per tile in shared memory.
+// Counting needs no order: every lane walks the set bits of its own Gaussian's footprint mask; the rare footprints of
+// more than 64 tiles (every tile of the rectangle) are walked by the whole warp.
 __global__ void __launch_bounds__(32) bin_count_kernel(const BinArgs b, uint32_t* __restrict__ table) {
     extern __shared__ uint32_t cnt[];
     const int lane = threadIdx.x, c = blockIdx.x;
@@ -459,8 +438,25 @@ __global__ void __launch_bounds__(32) bin_count_kernel(const BinArgs b, uint32_t
     __syncwarp();
     int i0, i1;
     chunk_range(b, c, lane, i0, i1);
-    for_each_instance(b, i0, i1, lane, [](uint32_t, bool) {}, [&](bool has, int, uint32_t, int tile_x, int tile_y) {
-        if (has) atomicAdd(&cnt[tile_y * b.gx + tile_x], 1u);
+    for_each_batch(b, i0, i1, lane, [&](const BinBatch& bb) {
+        const float inv_w = 1.0f / (float)bb.w;
+        if (bb.cnt && !bb.big) {
+            unsigned long long m = bb.mask;
+            while (m) {
+                const int t = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                atomicAdd(&cnt[rect_tile(t, inv_w, (int)bb.w, bb.mnx, bb.mny, b.gx)], 1u);
+            }
+        }
+        unsigned bigs = __ballot_sync(0xffffffffu, bb.big != 0u);
+        while (bigs) {
+            const int l = __ffs(bigs) - 1;
+            bigs &= bigs - 1;
+            const int n = (int)__shfl_sync(0xffffffffu, bb.cnt, l), w = (int)__shfl_sync(0xffffffffu, bb.w, l);
+            const int mnx = __shfl_sync(0xffffffffu, bb.mnx, l), mny = __shfl_sync(0xffffffffu, bb.mny, l);
+            const float iw = 1.0f / (float)w;
+            for (int t = lane; t < n; t += 32) atomicAdd(&cnt[rect_tile(t, iw, w, mnx, mny, b.gx)], 1u);
+        }
     });
     __syncwarp();
     uint32_t* row = table + (size_t)c * b.num_tiles;
@@ -544,14 +540,22 @@ __global__ void __launch_bounds__(1024) bin_tilebase_kernel(int num_tiles, const
     }
 }
 
-// 3c: every list entry straight to its final position, in depth order.  The footprint data of the batch's 32
-// Gaussians (cull rectangle + conic, 64 B each) is staged in shared memory once per batch, so the per-instance work
-// touches global memory only for the final 4-byte store.
+// 3c: every list entry straight to its final position, in depth order.  Per batch of 32 Gaussians the lanes first
+// MATERIALISE the batch's instances in shared memory in order -- lane l writes (tile id, owner lane) of its own
+// Gaussian's tiles at its exclusive-scan offset; no per-instance owner search -- and stage the 32 footprints (cull
+// rectangle + conic, 64 B each); then rounds of 32 consecutive instances: the rank of an instance among the lanes of
+// its round that hit the same tile comes from __match_any_sync (lane order = depth order), the rest from the tile's
+// shared-memory cursor.  Global memory is touched only by the record prefetch and the final 4-byte store.
+constexpr int kBatchCap = 32 * 64;  // instances of the small footprints of one batch
+
 __global__ void __launch_bounds__(32) bin_scatter_kernel(const BinArgs b, const uint32_t* __restrict__ table,
                                                         const uint32_t* __restrict__ base, int64_t capacity,
                                                         uint32_t* __restrict__ point_list) {
     extern __shared__ uint32_t cursor[];
-    __shared__ float4 foot[32][4];  // per Gaussian of the batch: cull rectangle, q0, q1, (r2, -, -, -)
+    __shared__ float4 foot[32][4];           // per Gaussian of the batch: cull rectangle, q0, q1, (r2, -, -, -)
+    __shared__ uint16_t inst_tile[kBatchCap];  // tile id (the table path is only taken below 65536 tiles) ...
+    __shared__ uint8_t inst_owner[kBatchCap];  // ... and owner lane of the batch's instances, in instance order
+    __shared__ uint32_t gid[32];
     const int lane = threadIdx.x, c = blockIdx.x;
     const uint32_t* row = table + (size_t)c * b.num_tiles;
     for (int t = lane; t < b.num_tiles; t += 32) cursor[t] = base[t] + row[t];
@@ -559,37 +563,88 @@ __global__ void __launch_bounds__(32) bin_scatter_kernel(const BinArgs b, const 
     int i0, i1;
     chunk_range(b, c, lane, i0, i1);
     const unsigned below = (1u << lane) - 1u;
-    for_each_instance(
-        b, i0, i1, lane,
-        [&](uint32_t g, bool has_g) {
-            __syncwarp();  // the previous batch's rounds are done reading foot[]
-            if (b.packed && has_g) {
-                const float4* q = b.cullq + (size_t)g * 3;
-                foot[lane][0] = __ldg(b.cull4 + g);
-                foot[lane][1] = __ldg(q);
-                foot[lane][2] = __ldg(q + 1);
-                foot[lane][3] = __ldg(q + 2);
+    const float inv_gx = 1.0f / (float)b.gx;
+
+    // one round: lane holds (has, tile, owner lane); writes the entry of its instance
+    auto round = [&](bool has, uint32_t tile, int owner) {
+        // lanes of this round that hit the same tile, in lane (= depth) order; idle lanes get unique keys
+        const unsigned peers = __match_any_sync(0xffffffffu, has ? tile : (0x80000000u | (uint32_t)lane));
+        const int rank = __popc(peers & below);
+        const uint32_t pos = has ? cursor[tile] + (uint32_t)rank : 0u;
+        __syncwarp();
+        if (has && rank == 0) cursor[tile] += (uint32_t)__popc(peers);
+        __syncwarp();
+        if (has && (int64_t)pos < capacity) {
+            const int tile_y = __float2int_rd(((float)tile + 0.5f) * inv_gx), tile_x = (int)tile - tile_y * b.gx;
+            float4 cr = make_float4(0.f, 0.f, 0.f, 0.f), q0 = cr, q1 = cr;
+            float r2 = 0.0f;
+            if (b.packed) {
+                cr = foot[owner][0]; q0 = foot[owner][1]; q1 = foot[owner][2]; r2 = foot[owner][3].x;
             }
-            __syncwarp();
-        },
-        [&](bool has, int owner, uint32_t g, int tile_x, int tile_y) {
-            const uint32_t tile = (uint32_t)(tile_y * b.gx + tile_x);
-            // lanes of this round that hit the same tile, in lane (= depth) order; idle lanes get unique keys
-            const unsigned peers = __match_any_sync(0xffffffffu, has ? tile : (0x80000000u | (uint32_t)lane));
-            const int rank = __popc(peers & below);
-            const uint32_t pos = has ? cursor[tile] + (uint32_t)rank : 0u;
-            __syncwarp();
-            if (has && rank == 0) cursor[tile] += (uint32_t)__popc(peers);
-            __syncwarp();
-            if (has && (int64_t)pos < capacity) {
-                float4 cr = make_float4(0.f, 0.f, 0.f, 0.f), q0 = cr, q1 = cr;
-                float r2 = 0.0f;
-                if (b.packed) {
-                    cr = foot[owner][0]; q0 = foot[owner][1]; q1 = foot[owner][2]; r2 = foot[owner][3].x;
+            point_list[pos] = make_entry(gid[owner], tile_x, tile_y, b.packed, cr, q0, q1, r2);
+        }
+    };
+
+    for_each_batch(b, i0, i1, lane, [&](const BinBatch& bb) {
+        __syncwarp();  // the previous batch's rounds are done reading foot[] / inst_*[] / gid[]
+        gid[lane] = bb.g;
+        if (b.packed && bb.cnt) {
+            const float4* q = b.cullq + (size_t)bb.g * 3;
+            foot[lane][0] = __ldg(b.cull4 + bb.g);
+            foot[lane][1] = __ldg(q);
+            foot[lane][2] = __ldg(q + 1);
+            foot[lane][3] = __ldg(q + 2);
+        }
+        // Segments of lanes separated by the (rare) footprints of more than 64 tiles, processed in lane order so that the
+        // depth order is kept: [small lanes] big [small lanes] big ...
+        unsigned bigs = __ballot_sync(0xffffffffu, bb.big != 0u);
+        int cur = 0;
+        while (cur < 32) {
+            const unsigned rest = bigs & ~((1u << cur) - 1u);
+            const int nb = rest ? __ffs(rest) - 1 : 32;  // next big lane (or the end)
+            // ---- small footprints of lanes [cur, nb): materialise, then rounds
+            const uint32_t mycnt = (lane >= cur && lane < nb && !bb.big) ? bb.cnt : 0u;
+            uint32_t c_incl = mycnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, c_incl, d);
+                if (lane >= d) c_incl += v;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, c_incl, 31);
+            if (total) {
+                if (mycnt) {
+                    const float inv_w = 1.0f / (float)bb.w;
+                    uint32_t o = c_incl - mycnt;
+                    unsigned long long m = bb.mask;
+                    while (m) {
+                        const int t = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        inst_tile[o] = (uint16_t)rect_tile(t, inv_w, (int)bb.w, bb.mnx, bb.mny, b.gx);
+                        inst_owner[o++] = (uint8_t)lane;
+                    }
                 }
-                point_list[pos] = make_entry(g, tile_x, tile_y, b.packed, cr, q0, q1, r2);
+                __syncwarp();
+                for (uint32_t jb = 0; jb < total; jb += 32) {
+                    const uint32_t j = jb + lane;
+                    const bool has = j < total;
+                    round(has, has ? (uint32_t)inst_tile[j] : 0u, has ? (int)inst_owner[j] : 0);
+                }
+                __syncwarp();
             }
-        });
+            // ---- the big footprint of lane nb: every tile of its rectangle, row-major, by the whole warp
+            if (nb < 32) {
+                const int n = (int)__shfl_sync(0xffffffffu, bb.cnt, nb), w = (int)__shfl_sync(0xffffffffu, bb.w, nb);
+                const int mnx = __shfl_sync(0xffffffffu, bb.mnx, nb), mny = __shfl_sync(0xffffffffu, bb.mny, nb);
+                const float iw = 1.0f / (float)w;
+                for (int tb = 0; tb < n; tb += 32) {
+                    const int t = tb + lane;
+                    const bool has = t < n;
+                    round(has, has ? rect_tile(t, iw, w, mnx, mny, b.gx) : 0u, nb);
+                }
+            }
+            cur = nb + 1;
+        }
+    });
 }
 
 // Phase B head: stable partition of the instances by tile (fused with emission) + tile ranges.  `R` is the CAPACITY of

@@ -138,36 +138,48 @@ contrast_stats_kernel(int N, int F, int K, const float* __restrict__ feat, const
     }
     sl[threadIdx.x] = y;
     __syncthreads();
-    for (int k = threadIdx.x; k < K; k += kCB) {
-        int n = 0;
-        for (int j = 0; j < kCB; j++) n += (sl[j] == k);
-        if (n) atomicAdd(counts + k, (float)n);
+    // owner computes, label driven: the first sample of the block that carries a label owns that cluster for this block
+    // (cost independent of K): count its members and, for cluster means, sum their rows -- one global red per value
+    int* sfirst = sl + kCB;  // [kCB] 1 = first occurrence of its label in the block
+    {
+        bool first = y >= 0;
+        if (first)
+            for (int j = 0; j < (int)threadIdx.x; j++) if (sl[j] == y) { first = false; break; }
+        sfirst[threadIdx.x] = first ? 1 : 0;
+        if (first) {
+            int n = 0;
+            for (int j = threadIdx.x; j < kCB; j++) n += (sl[j] == y);
+            atomicAdd(counts + y, (float)n);
+        }
     }
-    if (want_sums) owner_accumulate<false>(F, FS, 0, K, sf, sl, nullptr, sums);
+    if (want_sums) {
+        __syncthreads();
+        // entries (owner sample, group of 4 channels) spread over the threads; members summed in ascending sample order
+        const int G = (F + 3) >> 2;
+        for (int e = threadIdx.x; e < kCB * G; e += kCB) {
+            const int j0 = e / G, cg = e - j0 * G;
+            if (!sfirst[j0]) continue;
+            const int k = sl[j0];
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = j0; j < kCB; j++) {
+                if (sl[j] != k) continue;
+#pragma unroll
+                for (int c = 0; c < 4; c++) if (4 * cg + c < F) acc[c] += sf[j * FS + 4 * cg + c];
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (4 * cg + c < F && acc[c] != 0.0f) atomicAdd(sums + (size_t)k * F + 4 * cg + c, acc[c]);
+        }
+    }
 }
 
-// u_k into shared memory: predefined prototype or mean of the members (0 for an absent cluster)
-__device__ __forceinline__ void load_centres(int F, int K, const float* __restrict__ predef_u,
-                                             const float* __restrict__ sums, const float* __restrict__ counts,
-                                             float* __restrict__ su) {
-    for (int e = threadIdx.x; e < K * F; e += kCB) {
-        const int k = e / F;
-        const float n = counts[k];
-        su[e] = predef_u ? predef_u[e] : (n > 0.0f ? sums[e] / n : 0.0f);
-    }
-}
-
-// phase 2
+// phase 2   (a sample needs only ITS cluster's centre: read from global memory, so K is not bounded by shared memory)
 __global__ void __launch_bounds__(kCB)
 contrast_spread_kernel(int N, int F, int K, const float* __restrict__ fhat, const int* __restrict__ labels,
                        const float* __restrict__ predef_u, const float* __restrict__ sums,
                        const float* __restrict__ counts, float* __restrict__ spread) {
-    extern __shared__ __align__(16) float smem[];
-    float* su = smem;                                   // [K][F]
-    float* sd = smem + (size_t)K * F;                   // [kCB]
-    int* sl = reinterpret_cast<int*>(sd + kCB);         // [kCB]
-    load_centres(F, K, predef_u, sums, counts, su);
-    __syncthreads();
+    __shared__ float sd[kCB];
+    __shared__ int sl[kCB];
     const int i = blockIdx.x * kCB + threadIdx.x;
     int y = -1;
     float d = 0.0f;
@@ -175,18 +187,29 @@ contrast_spread_kernel(int N, int F, int K, const float* __restrict__ fhat, cons
         y = labels[i];
         if (y < 0 || y >= K) y = -1;
         if (y >= 0) {
+            const float n = counts[y];
             float ss = 0.0f;
-            for (int c = 0; c < F; c++) { const float t = fhat[(size_t)i * F + c] - su[(size_t)y * F + c]; ss = fmaf(t, t, ss); }
+            for (int c = 0; c < F; c++) {
+                const float u = predef_u ? predef_u[(size_t)y * F + c] : (n > 0.0f ? sums[(size_t)y * F + c] / n : 0.0f);
+                const float t = fhat[(size_t)i * F + c] - u;
+                ss = fmaf(t, t, ss);
+            }
             d = sqrtf(ss);
         }
     }
     sd[threadIdx.x] = d;
     sl[threadIdx.x] = y;
     __syncthreads();
-    for (int k = threadIdx.x; k < K; k += kCB) {
-        float s = 0.0f;
-        for (int j = 0; j < kCB; j++) if (sl[j] == k) s += sd[j];
-        if (s != 0.0f) atomicAdd(spread + k, s);
+    // owner computes: the clusters present in this block are few; walk the block's labels once per distinct label
+    // (first occurrence owns it) instead of once per cluster id, so the cost does not grow with K
+    if (y >= 0) {
+        bool first = true;
+        for (int j = 0; j < (int)threadIdx.x; j++) if (sl[j] == y) { first = false; break; }
+        if (first) {
+            float sacc = 0.0f;
+            for (int j = threadIdx.x; j < kCB; j++) if (sl[j] == y) sacc += sd[j];
+            if (sacc != 0.0f) atomicAdd(spread + y, sacc);
+        }
     }
 }
 
@@ -267,6 +290,8 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__flo
 }  // namespace tc
 
 struct ContrastTcSmem {  // dynamic shared-memory carve-up of contrast_loss_tc_kernel (byte offsets)
+    // Everything per COLUMN CHUNK of at most 256 clusters (the N extent of one UMMA tile): the shared-memory footprint
+    // does not depend on K, chunks beyond the first are re-staged from global memory (any K is supported).
     int Kpad, NC, tmem_cols;
     size_t su, sphi, sf, sw, apan, bpan, total;
     __host__ __device__ ContrastTcSmem(int F, int FP, int K) {
@@ -276,14 +301,14 @@ struct ContrastTcSmem {  // dynamic shared-memory carve-up of contrast_loss_tc_k
         while (tmem_cols < NC) tmem_cols <<= 1;
         const int FS = (F + 3) & ~3;
         size_t o = 0;
-        su = o;   o += (size_t)K * F * 4;
+        su = o;   o += (size_t)NC * F * 4;
         o = (o + 15) & ~(size_t)15;
-        sphi = o; o += (size_t)Kpad * 4;
+        sphi = o; o += (size_t)NC * 4;
         sf = o;   o += (size_t)kLB * FS * 4;
         sw = o;   o += (size_t)kKC * kLB * 4;
         o = (o + 127) & ~(size_t)127;
         apan = o; o += (size_t)2 * (FP / 4) * kLB * 16;    // [hi|lo][FP/4 panels][128 rows] x 16 B
-        bpan = o; o += (size_t)2 * (FP / 4) * Kpad * 16;   // [hi|lo][FP/4 panels][Kpad rows] x 16 B
+        bpan = o; o += (size_t)2 * (FP / 4) * NC * 16;     // [hi|lo][FP/4 panels][NC rows] x 16 B
         total = o;
     }
 };
@@ -293,15 +318,15 @@ __global__ void __launch_bounds__(kLB)
 contrast_loss_tc_kernel(int N, int F, int K, const float* __restrict__ fhat, const int* __restrict__ labels,
                         const float* __restrict__ predef_u, const float* __restrict__ sums,
                         const float* __restrict__ counts, const float* __restrict__ spread, float temp_lambda,
-                        float* __restrict__ g_out, float* __restrict__ dU, float* __restrict__ loss) {
+                        float min_count, float* __restrict__ g_out, float* __restrict__ dU, float* __restrict__ loss) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ uint32_t s_tmem;
     __shared__ float s_red[kLB / 32];
     const ContrastTcSmem L(F, FP, K);
-    const int FS = sample_stride(F), Kpad = L.Kpad;
-    float* su = reinterpret_cast<float*>(smem_raw + L.su);      // [K][F]   centres (for g)
-    float* sphi = reinterpret_cast<float*>(smem_raw + L.sphi);  // [Kpad]   1/phi_k, 0 for an absent / padding cluster
+    const int FS = sample_stride(F), Kpad = L.Kpad, NC = L.NC;
+    float* su = reinterpret_cast<float*>(smem_raw + L.su);      // [NC][F]   centres of the current column chunk (for g)
+    float* sphi = reinterpret_cast<float*>(smem_raw + L.sphi);  // [NC]      1/phi_k, 0 for an absent / dropped / padding cluster
     float* sf = reinterpret_cast<float*>(smem_raw + L.sf);      // [128][FS] this CTA's samples (for dU)
     float* sw = reinterpret_cast<float*>(smem_raw + L.sw);      // [kKC][128] coefficient chunk (for dU)
     float4* apan = reinterpret_cast<float4*>(smem_raw + L.apan);
@@ -310,19 +335,45 @@ contrast_loss_tc_kernel(int N, int F, int K, const float* __restrict__ fhat, con
     const int tid = threadIdx.x, warp = tid >> 5;
     const bool means = predef_u == nullptr;
 
-    for (int e = tid; e < K * F; e += kLB) {
-        const int k = e / F;
-        const float n = counts[k];
-        su[e] = predef_u ? predef_u[e] : (n > 0.0f ? sums[e] / n : 0.0f);
-    }
-    for (int k = tid; k < Kpad; k += kLB) {
-        float ip = 0.0f;
-        if (k < K) {
-            const float n = counts[k];
-            if (n > 0.0f) ip = 1.0f / fminf(fmaxf(10.0f * (spread[k] / (n * logf(n + temp_lambda))), 0.5f), 1.0f);
+    // Stages column chunk [n0, n0 + NC): centres, 1/phi (0 = the cluster does not take part: absent, or not more than
+    // min_count members -- utils/contrastive_utils.py:33-35), and the B operand panels (centres scaled by 1/phi so that
+    // the MMA yields the logits; zero rows for clusters that do not take part).
+    auto stage_chunk = [&](int n0) {
+        for (int e = tid; e < NC * F; e += kLB) {
+            const int k = n0 + e / F;
+            float u = 0.0f;
+            if (k < K) {
+                const float n = counts[k];
+                u = predef_u ? predef_u[(size_t)n0 * F + e] : (n > 0.0f ? sums[(size_t)n0 * F + e] / n : 0.0f);
+            }
+            su[e] = u;
         }
-        sphi[k] = ip;
-    }
+        for (int kk = tid; kk < NC; kk += kLB) {
+            const int k = n0 + kk;
+            float ip = 0.0f;
+            if (k < K) {
+                const float n = counts[k];
+                if (n > min_count) ip = 1.0f / fminf(fmaxf(10.0f * (spread[k] / (n * logf(n + temp_lambda))), 0.5f), 1.0f);
+            }
+            sphi[kk] = ip;
+        }
+        __syncthreads();
+        for (int e = tid; e < NP * NC; e += kLB) {
+            const int p = e / NC, n = e - p * NC;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int c = 4 * p + j;
+                v[j] = (c < F) ? su[(size_t)n * F + c] * sphi[n] : 0.0f;
+            }
+            const float4 h = make_float4(tc::tf32_hi(v[0]), tc::tf32_hi(v[1]), tc::tf32_hi(v[2]), tc::tf32_hi(v[3]));
+            bpan[p * NC + n] = h;
+            bpan[(NP + p) * NC + n] = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // operand panels -> visible to the tensor-core (async) proxy
+        __syncthreads();
+    };
+
     const int i = blockIdx.x * kLB + tid;
     int y = -1;
     {   // A operand: this thread's sample row, split hi / lo, one float4 per panel
@@ -332,6 +383,7 @@ contrast_loss_tc_kernel(int N, int F, int K, const float* __restrict__ fhat, con
         if (i < N) {
             y = labels[i];
             if (y < 0 || y >= K) y = -1;
+            if (y >= 0 && !(counts[y] > min_count)) y = -1;  // its cluster was dropped
 #pragma unroll
             for (int c = 0; c < FP; c++)
                 if (c < F) { f[c] = fhat[(size_t)i * F + c]; sf[tid * FS + c] = f[c]; }
@@ -345,33 +397,19 @@ contrast_loss_tc_kernel(int N, int F, int K, const float* __restrict__ fhat, con
             apan[(NP + p) * kLB + tid] = make_float4(f[4 * p] - h.x, f[4 * p + 1] - h.y, f[4 * p + 2] - h.z, f[4 * p + 3] - h.w);
         }
     }
-    __syncthreads();  // su, sphi complete
-    // B operand: centres scaled by 1/phi (so the MMA yields the logits), zero rows for absent / padding clusters
-    for (int e = tid; e < NP * Kpad; e += kLB) {
-        const int p = e / Kpad, n = e - p * Kpad;
-        float v[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int c = 4 * p + j;
-            v[j] = (n < K && c < F) ? su[(size_t)n * F + c] * sphi[n] : 0.0f;
-        }
-        const float4 h = make_float4(tc::tf32_hi(v[0]), tc::tf32_hi(v[1]), tc::tf32_hi(v[2]), tc::tf32_hi(v[3]));
-        bpan[p * Kpad + n] = h;
-        bpan[(NP + p) * Kpad + n] = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
-    }
     const uint32_t mbar = tc::smem_u32(&s_mbar);
     if (tid == 0) {
         tc::mbar_init(mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tc::tmem_alloc(tc::smem_u32(&s_tmem), (uint32_t)L.tmem_cols);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // operand panels -> visible to the tensor-core (async) proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc::fence_before();
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem = s_tmem;
     const uint32_t a_base = tc::smem_u32(apan), b_base = tc::smem_u32(bpan);
-    const int nch = (Kpad + L.NC - 1) / L.NC;
+    const int nch = (Kpad + NC - 1) / NC;
     uint32_t uses = 0;
 
     const bool valid = y >= 0;
@@ -382,8 +420,9 @@ contrast_loss_tc_kernel(int N, int F, int K, const float* __restrict__ fhat, con
 
     for (int pass = 0; pass < 2; pass++) {
         for (int ch = 0; ch < nch; ch++) {
-            const int n0 = ch * L.NC, ncols = min(L.NC, Kpad - n0);
+            const int n0 = ch * NC, ncols = min(NC, Kpad - n0);
             if (pass == 0 || nch > 1) {
+                stage_chunk(n0);
                 if (tid == 0) {
                     const uint32_t idesc = tc::instr_desc_tf32(kLB, ncols);
                     uint32_t acc = 0;
@@ -393,7 +432,7 @@ contrast_loss_tc_kernel(int N, int F, int K, const float* __restrict__ fhat, con
                         for (int t = 0; t < 3; t++) {  // hi*hi, lo*hi, hi*lo
                             const int pa = (t == 1 ? NP : 0) + 2 * ks, pb = (t == 2 ? NP : 0) + 2 * ks;
                             const uint64_t da = tc::smem_desc(a_base + (uint32_t)pa * kLB * 16, kLB * 16, 128);
-                            const uint64_t db = tc::smem_desc(b_base + (uint32_t)(pb * Kpad + n0) * 16, (uint32_t)Kpad * 16, 128);
+                            const uint64_t db = tc::smem_desc(b_base + (uint32_t)(pb * NC) * 16, (uint32_t)NC * 16, 128);
                             tc::mma_tf32(tmem, da, db, idesc, acc);
                             acc = 1;
                         }
@@ -413,25 +452,25 @@ contrast_loss_tc_kernel(int N, int F, int K, const float* __restrict__ fhat, con
                     if (valid) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
-                            const int k = n0 + c0 + j;
-                            if (sphi[k] != 0.0f) {
+                            const int kk = c0 + j;
+                            if (sphi[kk] != 0.0f) {
                                 const float e = expf(lg[j]);
                                 sum += e;
-                                if (k == y) dy = e;
+                                if (n0 + kk == y) dy = e;
                             }
                         }
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
-                        const int k = n0 + c0 + j;
-                        const float ip = sphi[k];
+                        const int kk = c0 + j;
+                        const float ip = sphi[kk];
                         float cf = 0.0f;
                         if (valid && ip != 0.0f) {
-                            cf = (expf(lg[j]) * inv_denom - (k == y ? 1.0f : 0.0f)) * ip;
+                            cf = (expf(lg[j]) * inv_denom - (n0 + kk == y ? 1.0f : 0.0f)) * ip;
 #pragma unroll
                             for (int c = 0; c < FP; c++)
-                                if (c < F) g[c] = fmaf(cf, su[(size_t)k * F + c], g[c]);
+                                if (c < F) g[c] = fmaf(cf, su[(size_t)kk * F + c], g[c]);
                         }
                         if (means) sw[((c0 + j) & (kKC - 1)) * kLB + tid] = cf;
                     }
@@ -444,7 +483,7 @@ contrast_loss_tc_kernel(int N, int F, int K, const float* __restrict__ fhat, con
                     }
                 }
             }
-            if (pass == 0 || nch > 1) {  // TMEM is overwritten by the next chunk's MMAs
+            if (pass == 0 || nch > 1) {  // TMEM and the chunk's shared-memory panels are overwritten by the next chunk
                 tc::fence_before();
                 __syncthreads();
                 tc::fence_after();
@@ -648,7 +687,7 @@ int launch_gather_pixels(int F, int64_t HW, const float* map, int n, const int* 
 }
 
 int launch_contrastive_fwd(int N, int F, int K, const float* features, const int* labels, const float* predef_u,
-                           float temp_lambda, void* ws, float* loss, cudaStream_t stream) {
+                           float temp_lambda, int min_pixnum, void* ws, float* loss, cudaStream_t stream) {
     ContrastWs L(N, F, K);
     char* w = static_cast<char*>(ws);
     if (N <= 0 || K <= 0) {
@@ -662,21 +701,18 @@ int launch_contrastive_fwd(int N, int F, int K, const float* features, const int
     float* spread = reinterpret_cast<float*>(w + L.spread);
     ISR_CUDA_TRY(cudaMemsetAsync(w + L.zeroed, 0, L.zeroed_bytes, stream));
     const int blocks = (N + kCB - 1) / kCB, FS = sample_stride(F);
-    const size_t smem1 = ((size_t)kCB * FS + kCB) * 4;
-    const size_t smem2 = ((size_t)K * F + 2 * kCB) * 4;
+    const size_t smem1 = ((size_t)kCB * FS + 2 * kCB) * 4;
     auto run = [&](auto stats_k, auto loss_k, int FPT) -> int {
         const ContrastTcSmem S(F, FPT, K);
         const size_t smem3 = S.total;
-        // centres + operand panels of ALL K clusters live in one CTA's shared memory (227 KB opt-in on sm_100, a few bytes
-        // of it static): K <= ~890 at F = 16, ~385 at F = 32
-        if (smem3 > 226 * 1024) return ISR_ERR_UNSUPPORTED;
+        if (smem3 > 226 * 1024) return ISR_ERR_UNSUPPORTED;  // (177 KB at F = 32: cannot happen for F <= 32)
         ISR_CUDA_TRY(cudaFuncSetAttribute(stats_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        ISR_CUDA_TRY(cudaFuncSetAttribute(contrast_spread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         ISR_CUDA_TRY(cudaFuncSetAttribute(loss_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
         stats_k<<<blocks, kCB, smem1, stream>>>(N, F, K, features, labels, predef_u == nullptr, fhat, inv_norm, sums, counts,
                                                 loss); note_launch();
-        contrast_spread_kernel<<<blocks, kCB, smem2, stream>>>(N, F, K, fhat, labels, predef_u, sums, counts, spread); note_launch();
+        contrast_spread_kernel<<<blocks, kCB, 0, stream>>>(N, F, K, fhat, labels, predef_u, sums, counts, spread); note_launch();
         loss_k<<<(N + kLB - 1) / kLB, kLB, smem3, stream>>>(N, F, K, fhat, labels, predef_u, sums, counts, spread, temp_lambda,
+                                                            (float)(min_pixnum > 0 ? min_pixnum : 0),
                                                             reinterpret_cast<float*>(w + L.g), reinterpret_cast<float*>(w + L.dU),
                                                             loss); note_launch();
         ISR_CUDA_TRY(cudaGetLastError());

@@ -238,6 +238,39 @@ def test_contrastive_loss(predef, consider_negative):
     assert rel_err(fc.grad.cpu().numpy() * 2.0, f64.grad.numpy()) < 1e-4
 
 
+@pytest.mark.parametrize("predef", [False, True])
+def test_contrastive_loss_min_pixnum(predef):
+    """utils/contrastive_utils.py:33-35: clusters with <= min_pixnum samples are dropped together with their samples --
+    inside the kernels (no bincount / where prefilter on the host)."""
+    import torch
+    import instascene_b200 as isr
+    from oracle.contrastive_ref import contrastive_loss_ref
+    rng = np.random.default_rng(77)
+    N, F, K = 4000, 16, 40
+    feats = rng.standard_normal((N, F)).astype(np.float32)
+    # very uneven cluster sizes: some below, some above the threshold
+    p = rng.random(K + 1) ** 4
+    labels = rng.choice(K + 1, size=N, p=p / p.sum()).astype(np.int64)
+    counts = np.bincount(labels, minlength=K + 1)
+    thr = int(np.sort(counts[1:])[K // 2])
+    assert (counts[1:] <= thr).any() and (counts[1:] > thr).any()
+    proto = None
+    if predef:
+        proto = rng.standard_normal((K + 1, F)).astype(np.float32)
+        proto /= np.linalg.norm(proto, axis=1, keepdims=True)
+    for mp in (thr, 1, 0):
+        f64 = torch.tensor(feats, dtype=torch.float64, requires_grad=True)
+        want = contrastive_loss_ref(f64, torch.tensor(labels), None if proto is None else torch.tensor(proto, dtype=torch.float64),
+                                    min_pixnum=mp)
+        want.backward()
+        fc = torch.tensor(feats, device="cuda", requires_grad=True)
+        got = isr.contrastive_loss(fc, torch.tensor(labels, device="cuda"), None if proto is None else torch.tensor(proto, device="cuda"),
+                                   min_pixnum=mp)
+        got.backward()
+        assert abs(float(got) - float(want)) / abs(float(want)) < 1e-4, mp
+        assert rel_err(fc.grad.cpu().numpy(), f64.grad.numpy()) < 1e-4, mp
+
+
 def test_autograd_render_sample_loss(oracle):
     """render() -> sample_pixels -> contrastive_loss -> backward: gradient w.r.t. the raw seg feature parameter
     through the sparse path equals the oracle's dense backward composed with torch autograd on the CPU."""
@@ -666,7 +699,10 @@ def test_plain_entry_fallback_path():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("N,F,K,predef", [(2048, 8, 300, True), (1000, 4, 5, False), (3000, 32, 270, False), (257, 24, 33, True)])
+@pytest.mark.parametrize("N,F,K,predef", [(2048, 8, 300, True), (1000, 4, 5, False), (3000, 32, 270, False), (257, 24, 33, True),
+                                          # beyond round 1's shared-memory bound (K <= ~890 at F = 16, ~385 at F = 32): the
+                                          # reference has no limit on the number of clusters
+                                          (20000, 16, 2000, False), (9000, 32, 1100, True), (5000, 16, 5000, False)])
 def test_contrastive_loss_shapes(N, F, K, predef):
     """Cluster counts beyond one 256-column MMA chunk, F below one 8-wide K step, ragged N (not a multiple of the
     128-row tile), absent clusters."""
