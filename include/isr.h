@@ -29,6 +29,7 @@
  *                                                 DSR/cuda_rasterizer/rasterizer_impl.h:29-72
  *   isr_contrastive_forward / _backward        <- utils/contrastive_utils.py:18-73 (contrastive_loss)
  *   isr_gather_pixels                          <- train_semantic.py:124-129 (boolean-mask gather + index)
+ *   isr_sample_labelled                        <- train_semantic.py:118-126 (valid-pixel mask + randint)
  *   isr_aux_maps_forward / _backward           <- gaussian_renderer/__init__.py:127-156 + utils/point_utils.py:10-40
  *   isr_rownorm_forward / _backward            <- scene/gaussian_model.py:121-125 + gaussian_renderer/__init__.py:60-62
  *   isr_photometric_forward / _backward        <- l1_loss + ssim utils/loss_utils.py:18-19,39-83 as combined in
@@ -209,6 +210,15 @@ int isr_mark_visible(int P, const float* means3D, const float* viewmatrix, const
 int isr_gather_pixels(int F, int64_t HW, const float* feature_map, int n, const int* pix_ids, float* out,
                       void* stream);
 
+/* n pixel ids drawn uniformly WITH replacement among the pixels whose label is > 0 (train_semantic.py:118-129 without
+ * the boolean-mask gather of the feature map): sample i takes the labelled pixel of rank min(int(u[i] * n_valid),
+ * n_valid - 1) in pixel order, u[i] in [0, 1) supplied by the caller (its random generator).  labels: [HW] signed
+ * integers of label_bytes (1, 2, 4 or 8) bytes.  Writes pix_out[n] (int64) and labels_out[n] (int32, the label of each
+ * drawn pixel).  No host synchronisation. */
+size_t isr_sampler_workspace_bytes(int64_t HW);
+int isr_sample_labelled(const void* labels, int label_bytes, int64_t HW, int n, const float* u, void* ws,
+                        size_t ws_bytes, int64_t* pix_out, int* labels_out, void* stream);
+
 size_t isr_contrastive_workspace_bytes(int N, int F, int K);
 /* features [N,F], labels [N] int32 already shifted so that valid labels are 0..K-1 and invalid ones < 0;
  * predef_u [K,F] or NULL (cluster means).  min_pixnum: clusters with <= min_pixnum samples are dropped together with
@@ -234,10 +244,19 @@ int isr_rownorm_backward(int P, int F, const float* x, const float* dy, float ep
 /* ---- optimizer step of the trainable tensor ------------------------------------------------------------------- */
 /* One fused pass of torch.optim.Adam's update (no weight decay / amsgrad / maximize) over n fp32 elements:
  * exp_avg = b1*exp_avg + (1-b1)*g; exp_avg_sq = b2*exp_avg_sq + (1-b2)*g*g;
- * param -= lr/(1-b1^step) * exp_avg / (sqrt(exp_avg_sq)/sqrt(1-b2^step) + eps).   `step` is the 1-based step count.
+ * param -= lr/(1-b1^step) * exp_avg / (sqrt(exp_avg_sq)/sqrt(1-b2^step) + eps).   `step` is the 1-based step count; with
+ * step_dev != NULL the count is read from that DEVICE int32 instead (the caller increments it on the stream), so that a
+ * captured CUDA graph replays with the right bias correction.
  * (scene/gaussian_model.py:217-249 trains _seg_feature with Adam(lr=0.025, eps=1e-15)) */
 int isr_adam_step(size_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
-                  float beta2, float eps, int step, void* stream);
+                  float beta2, float eps, int step, const int* step_dev, void* stream);
+/* The same update for a [P,F] parameter whose gradient arrives as dy = dL/d(normalised rows) of isr_rownorm_forward
+ * (same eps1, eps2, stages): the chain rule of isr_rownorm_backward is applied on the fly and the chained gradient is
+ * never materialised (param, dy, exp_avg, exp_avg_sq are each read once).  grad_extra [P,F]: an ordinary gradient of the
+ * parameter from its other uses, added after the chain rule, or NULL. */
+int isr_adam_rownorm_step(int P, int F, float* param, const float* dy, const float* grad_extra, float* exp_avg,
+                          float* exp_avg_sq, float eps1, float eps2, int stages, float lr, float beta1, float beta2, float eps,
+                          int step, const int* step_dev, void* stream);
 
 /* ---- derived maps of render() ------------------------------------------------------------------------------- */
 /* Fused post-processing of allmap[7,H,W] (gaussian_renderer/__init__.py:127-156, utils/point_utils.py:10-40):

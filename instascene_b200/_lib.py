@@ -58,8 +58,8 @@ EXPORTED_SYMBOLS = [
     "isr_version", "isr_status_string", "isr_last_cuda_error", "isr_device_sm_count", "isr_kernel_launch_count",
     "isr_geom_bytes", "isr_image_bytes", "isr_binning_bytes", "isr_field_offset",
     "isr_forward_geometry", "isr_forward_render", "isr_backward", "isr_backward_extra_sparse", "isr_mark_visible",
-    "isr_gather_pixels", "isr_contrastive_workspace_bytes", "isr_contrastive_forward", "isr_contrastive_backward",
-    "isr_rownorm_forward", "isr_rownorm_backward", "isr_aux_maps_forward", "isr_aux_maps_backward", "isr_adam_step", "isr_knn_workspace_bytes", "isr_knn_mean_dist2",
+    "isr_gather_pixels", "isr_sampler_workspace_bytes", "isr_sample_labelled", "isr_contrastive_workspace_bytes", "isr_contrastive_forward", "isr_contrastive_backward",
+    "isr_rownorm_forward", "isr_rownorm_backward", "isr_aux_maps_forward", "isr_aux_maps_backward", "isr_adam_step", "isr_adam_rownorm_step", "isr_knn_workspace_bytes", "isr_knn_mean_dist2",
     "isr_tracker_workspace_bytes", "isr_tracker_mark", "isr_tracker_fill",
     "isr_photometric_workspace_bytes", "isr_photometric_forward", "isr_photometric_backward",
     "isr_densify_stats",
@@ -99,6 +99,9 @@ def lib() -> C.CDLL:
                                             _ip, _fp, _fp, C.c_uint, C.c_void_p]
     L.isr_mark_visible.argtypes = [C.c_int, _fp, _fp, _fp, _vp, C.c_void_p]
     L.isr_gather_pixels.argtypes = [C.c_int, C.c_int64, _fp, C.c_int, _ip, _fp, C.c_void_p]
+    L.isr_sampler_workspace_bytes.restype = C.c_size_t
+    L.isr_sampler_workspace_bytes.argtypes = [C.c_int64]
+    L.isr_sample_labelled.argtypes = [_vp, C.c_int, C.c_int64, C.c_int, _fp, _vp, C.c_size_t, _ip, _ip, C.c_void_p]
     L.isr_contrastive_workspace_bytes.restype = C.c_size_t
     L.isr_contrastive_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     L.isr_contrastive_forward.argtypes = [C.c_int, C.c_int, C.c_int, _fp, _ip, _fp, C.c_float, C.c_int, _vp, C.c_size_t, _fp,
@@ -110,7 +113,9 @@ def lib() -> C.CDLL:
                                        _fp, _fp, C.c_void_p]
     L.isr_aux_maps_backward.argtypes = [C.c_int, C.c_int, _fp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, _fp, _fp, _fp,
                                         _fp, _fp, _fp, C.c_void_p]
-    L.isr_adam_step.argtypes = [C.c_size_t, _fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p]
+    L.isr_adam_step.argtypes = [C.c_size_t, _fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _ip, C.c_void_p]
+    L.isr_adam_rownorm_step.argtypes = [C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_int, C.c_float,
+                                        C.c_float, C.c_float, C.c_float, C.c_int, _ip, C.c_void_p]
     L.isr_knn_workspace_bytes.restype = C.c_size_t
     L.isr_knn_workspace_bytes.argtypes = [C.c_int]
     L.isr_knn_mean_dist2.argtypes = [C.c_int, _fp, _fp, _vp, C.c_size_t, C.c_void_p]

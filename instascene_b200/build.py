@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libisr.so")
 OBJ = os.path.join(HERE, "_obj")
 SOURCES = ["isr_api.cu", "isr_preprocess.cu", "isr_binning.cu", "isr_blend_fwd.cu", "isr_blend_bwd.cu",
-           "isr_contrastive.cu", "isr_knn.cu", "isr_auxmaps.cu", "isr_tracker.cu", "isr_photometric.cu"]
+           "isr_contrastive.cu", "isr_sampler.cu", "isr_knn.cu", "isr_auxmaps.cu", "isr_tracker.cu", "isr_photometric.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

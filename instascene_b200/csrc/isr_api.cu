@@ -35,7 +35,13 @@ int launch_aux_bwd(int W, int H, const float* allmap, const float* M_host, const
                    const float* g_rend_normal, const float* g_rend_depth, const float* g_rend_median,
                    const float* g_surf_depth, const float* g_surf_normal, float* g_allmap, cudaStream_t stream);
 int launch_adam(size_t n, float* p, const float* g, float* m, float* v, float lr, float beta1, float beta2, float eps,
-                int step, cudaStream_t stream);
+                int step, const int* step_dev, cudaStream_t stream);
+int launch_adam_rownorm(int P, int F, float* x, const float* dy, const float* g_extra, float* m, float* v, float e1, float e2,
+                        int stages, float lr, float beta1, float beta2, float eps, int step, const int* step_dev,
+                        cudaStream_t stream);
+size_t sampler_ws_bytes(int64_t HW);
+int launch_sampler(const void* labels, int label_bytes, int64_t HW, int n, const float* u, void* ws, int64_t* pix_out,
+                   int* lab_out, cudaStream_t stream);
 size_t knn_ws_bytes(int P);
 int launch_knn(int P, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t photometric_ws_bytes(int C, int H, int W);
@@ -206,6 +212,17 @@ int isr_gather_pixels(int F, int64_t HW, const float* feature_map, int n, const 
     return launch_gather_pixels(F, HW, feature_map, n, pix_ids, out, static_cast<cudaStream_t>(stream_));
 }
 
+size_t isr_sampler_workspace_bytes(int64_t HW) { return HW < 0 ? 0 : sampler_ws_bytes(HW); }
+
+int isr_sample_labelled(const void* labels, int label_bytes, int64_t HW, int n, const float* u, void* ws, size_t ws_bytes,
+                        int64_t* pix_out, int* labels_out, void* stream_) {
+    if (HW < 0 || n < 0) return ISR_ERR_INVALID_ARG;
+    if (n == 0) return ISR_OK;
+    if (!labels || !u || !ws || !pix_out || !labels_out || HW == 0) return ISR_ERR_INVALID_ARG;
+    if (ws_bytes < sampler_ws_bytes(HW)) return ISR_ERR_WORKSPACE;
+    return launch_sampler(labels, label_bytes, HW, n, u, ws, pix_out, labels_out, static_cast<cudaStream_t>(stream_));
+}
+
 size_t isr_contrastive_workspace_bytes(int N, int F, int K) {
     if (N < 0 || F < 0 || K < 0) return 0;
     return contrastive_ws_bytes(N, F, K) + 256;
@@ -269,12 +286,27 @@ int isr_aux_maps_backward(int W, int H, const float* allmap, const float* normal
 }
 
 int isr_adam_step(size_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
-                  float beta2, float eps, int step, void* stream_) {
-    if (step < 1) return ISR_ERR_INVALID_ARG;
+                  float beta2, float eps, int step, const int* step_dev, void* stream_) {
+    if (step < 1 && step_dev == nullptr) return ISR_ERR_INVALID_ARG;
     if (n == 0) return ISR_OK;
     if (!param || !grad || !exp_avg || !exp_avg_sq) return ISR_ERR_INVALID_ARG;
     if (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) return ISR_ERR_INVALID_ARG;
-    return launch_adam(n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, static_cast<cudaStream_t>(stream_));
+    return launch_adam(n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, step_dev,
+                       static_cast<cudaStream_t>(stream_));
+}
+
+int isr_adam_rownorm_step(int P, int F, float* param, const float* dy, const float* grad_extra, float* exp_avg,
+                          float* exp_avg_sq, float eps1, float eps2, int stages, float lr, float beta1, float beta2, float eps,
+                          int step, const int* step_dev, void* stream_) {
+    if (P < 0 || F < 0 || stages < 1 || stages > 2) return ISR_ERR_INVALID_ARG;
+    if (step < 1 && step_dev == nullptr) return ISR_ERR_INVALID_ARG;
+    if (F > ISR_MAX_EXTRA_DIMS) return ISR_ERR_UNSUPPORTED;
+    if (P == 0 || F == 0) return ISR_OK;
+    if (!param || !dy || !exp_avg || !exp_avg_sq) return ISR_ERR_INVALID_ARG;
+    if ((F & 3) == 0 && (((uintptr_t)param | (uintptr_t)dy | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq | (uintptr_t)grad_extra) & 15))
+        return ISR_ERR_INVALID_ARG;
+    return launch_adam_rownorm(P, F, param, dy, grad_extra, exp_avg, exp_avg_sq, eps1, eps2, stages, lr, beta1, beta2, eps, step,
+                               step_dev, static_cast<cudaStream_t>(stream_));
 }
 
 size_t isr_knn_workspace_bytes(int P) { return P < 0 ? 0 : knn_ws_bytes(P) + 256; }

@@ -51,11 +51,12 @@ BinChunks bin_chunks(int num_tiles) {
     static const bool force_sort = [] { const char* e = getenv("ISR_BIN_SORT"); return e && e[0] == '1'; }();  // test hook
     BinChunks bc;
     bc.smem_bytes = align_up((size_t)(num_tiles > 0 ? num_tiles : 1) * 4, 16);
-    // per SM: 227 KB opt-in; bin_scatter_kernel adds ~8.5 KB of static shared memory (batch instance list, footprints)
-    // and every resident CTA 1 KB of system reservation
-    const size_t budget = 224 * 1024;
-    int per_sm = (int)(budget / (bc.smem_bytes + 10 * 1024));
-    if (per_sm > 8) per_sm = 8;
+    // per SM: 227 KB opt-in; a chunk = one CTA of 8 warps: the tile table + 8 per-warp segment buffers (bin_scatter_kernel)
+    // + 1 KB of system reservation per resident CTA
+    bc.smem_bytes += 8 * 512 * 8;
+    const size_t budget = 226 * 1024;
+    int per_sm = (int)(budget / (bc.smem_bytes + 1024));
+    if (per_sm > 4) per_sm = 4;
     bc.chunks = (force_sort || per_sm < 1 || num_tiles > 65535) ? 0 : sm_count * per_sm;
     return bc;
 }
@@ -390,35 +391,29 @@ __device__ __forceinline__ void chunk_range(const BinArgs& b, int c, int lane, i
     i1 = warp_lower_bound(b.offsets, b.P, (uint32_t)(hi < R ? hi : R), lane);
 }
 
-// One batch = 32 consecutive Gaussians of the depth order, lane l holding Gaussian l (records prefetched one batch
-// ahead: coalesced, independent of everything else).
+// One batch = 32 consecutive Gaussians of the depth order, lane l holding Gaussian l.  A chunk is processed by a CTA of
+// kBinWarps warps: "super-batch" s = batches [kBinWarps*s, kBinWarps*(s+1)), warp w takes batch kBinWarps*s + w.
+constexpr int kBinWarps = 8;
+
 struct BinBatch {
     uint32_t g, cnt, big, w;   // Gaussian id, emitted tiles (0: none / past the end), footprint > 64 tiles, rectangle width
     int mnx, mny;              // getRect origin
     unsigned long long mask;   // K1 footprint mask (small footprints)
 };
 
-template <class Fn>
-__device__ __forceinline__ void for_each_batch(const BinArgs& b, int i0, int i1, int lane, Fn f) {
-    uint4 rec_n = make_uint4(0u, 0u, 0u, 1u);
-    unsigned long long mask_n = 0ull;
-    if (i0 + lane < i1) { rec_n = __ldg(b.rec + i0 + lane); mask_n = __ldg(b.mask + i0 + lane); }
-    for (int ib = i0; ib < i1; ib += 32) {
-        const uint4 rec = rec_n;
-        BinBatch bb;
-        bb.mask = mask_n;
-        const bool has_g = ib + lane < i1;
-        rec_n = make_uint4(0u, 0u, 0u, 1u);
-        mask_n = 0ull;
-        if (ib + 32 + lane < i1) { rec_n = __ldg(b.rec + ib + 32 + lane); mask_n = __ldg(b.mask + ib + 32 + lane); }
-        bb.g = rec.x;
-        bb.cnt = has_g ? (rec.y & 0x7fffffffu) : 0u;
-        bb.big = bb.cnt ? (rec.y >> 31) : 0u;
-        bb.mnx = (int)(rec.z & 0xffffu);
-        bb.mny = (int)(rec.z >> 16);
-        bb.w = rec.w;
-        f(bb);
-    }
+__device__ __forceinline__ BinBatch load_batch(const BinArgs& b, int ib, int i1, int lane) {
+    BinBatch bb;
+    uint4 rec = make_uint4(0u, 0u, 0u, 1u);
+    bb.mask = 0ull;
+    const bool has_g = ib + lane < i1;
+    if (has_g) { rec = __ldg(b.rec + ib + lane); bb.mask = __ldg(b.mask + ib + lane); }
+    bb.g = rec.x;
+    bb.cnt = has_g ? (rec.y & 0x7fffffffu) : 0u;
+    bb.big = bb.cnt ? (rec.y >> 31) : 0u;
+    bb.mnx = (int)(rec.z & 0xffffu);
+    bb.mny = (int)(rec.z >> 16);
+    bb.w = rec.w;
+    return bb;
 }
 
 // tile (row-major index t of a rectangle of width w at (mnx, mny)) -> global tile id; t / w without an integer
@@ -428,17 +423,18 @@ __device__ __forceinline__ uint32_t rect_tile(int t, float inv_w, int w, int mnx
     return (uint32_t)((mny + ty) * gx + mnx + tx);
 }
 
-// 3a: per-(chunk, tile) instance counts.  One warp per chunk; cnt[] = one 32-bit counter per tile in shared memory.
-// Counting needs no order: every lane walks the set bits of its own Gaussian's footprint mask; the rare footprints of
-// more than 64 tiles (every tile of the rectangle) are walked by the whole warp.
-__global__ void __launch_bounds__(32) bin_count_kernel(const BinArgs b, uint32_t* __restrict__ table) {
+// 3a: per-(chunk, tile) instance counts.  One CTA per chunk; cnt[] = one 32-bit counter per tile in shared memory,
+// shared by the CTA's warps (counting needs no order).  Every lane walks the set bits of its own Gaussian's footprint
+// mask; the rare footprints of more than 64 tiles (every tile of the rectangle) are walked by the whole warp.
+__global__ void __launch_bounds__(32 * kBinWarps) bin_count_kernel(const BinArgs b, uint32_t* __restrict__ table) {
     extern __shared__ uint32_t cnt[];
-    const int lane = threadIdx.x, c = blockIdx.x;
-    for (int t = lane; t < b.num_tiles; t += 32) cnt[t] = 0u;
-    __syncwarp();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.x;
+    for (int t = threadIdx.x; t < b.num_tiles; t += blockDim.x) cnt[t] = 0u;
+    __syncthreads();
     int i0, i1;
     chunk_range(b, c, lane, i0, i1);
-    for_each_batch(b, i0, i1, lane, [&](const BinBatch& bb) {
+    for (int ib = i0 + warp * 32; ib < i1; ib += 32 * kBinWarps) {
+        const BinBatch bb = load_batch(b, ib, i1, lane);
         const float inv_w = 1.0f / (float)bb.w;
         if (bb.cnt && !bb.big) {
             unsigned long long m = bb.mask;
@@ -457,10 +453,10 @@ __global__ void __launch_bounds__(32) bin_count_kernel(const BinArgs b, uint32_t
             const float iw = 1.0f / (float)w;
             for (int t = lane; t < n; t += 32) atomicAdd(&cnt[rect_tile(t, iw, w, mnx, mny, b.gx)], 1u);
         }
-    });
-    __syncwarp();
+    }
+    __syncthreads();
     uint32_t* row = table + (size_t)c * b.num_tiles;
-    for (int t = lane; t < b.num_tiles; t += 32) row[t] = cnt[t];
+    for (int t = threadIdx.x; t < b.num_tiles; t += blockDim.x) row[t] = cnt[t];
 }
 
 // 3b: exclusive scan down every tile column of the [chunks][tiles] table; totals[t] = instances of tile t.  A CTA owns
@@ -540,111 +536,146 @@ __global__ void __launch_bounds__(1024) bin_tilebase_kernel(int num_tiles, const
     }
 }
 
-// 3c: every list entry straight to its final position, in depth order.  Per batch of 32 Gaussians the lanes first
-// MATERIALISE the batch's instances in shared memory in order -- lane l writes (tile id, owner lane) of its own
-// Gaussian's tiles at its exclusive-scan offset; no per-instance owner search -- and stage the 32 footprints (cull
-// rectangle + conic, 64 B each); then rounds of 32 consecutive instances: the rank of an instance among the lanes of
-// its round that hit the same tile comes from __match_any_sync (lane order = depth order), the rest from the tile's
-// shared-memory cursor.  Global memory is touched only by the record prefetch and the final 4-byte store.
-constexpr int kBatchCap = 32 * 64;  // instances of the small footprints of one batch
+// 3c: every list entry straight to its final position, in depth order.  One CTA (kBinWarps warps) per chunk with ONE
+// table of per-tile cursors in shared memory.  Per super-batch:
+//   parallel part (all warps at once): a warp materialises its batch's instances in shared memory IN ORDER -- lane l
+//     writes (tile id, owner lane) of its own Gaussian's tiles at its exclusive-scan offset, no per-instance owner search --
+//     and computes every instance's list entry (Gaussian id + the 8 per-block footprint bits, 32 instances per round);
+//   ordered part (one warp at a time, in batch = depth order): position = the tile's cursor + the rank among the lanes of
+//     the same round that hit the same tile (__match_any_sync; lane order = instance order), one 4-byte store per
+//     instance.  ~15 instructions per 32 instances are serialised; everything else runs at full occupancy.
+// A batch whose small footprints hold more than kSegCap instances is cut into segments of consecutive lanes; footprints
+// of more than 64 tiles are walked arithmetically by the whole warp.  Both continue inside the warp's ordered turn (rare).
+constexpr int kSegCap = 512;                    // instances per segment (8 lanes x 64 tiles always fit)
+constexpr int kSegBytes = kSegCap * (4 + 2 + 2);  // entry u32 + tile u16 + owner u8 (padded to u16)
 
-__global__ void __launch_bounds__(32) bin_scatter_kernel(const BinArgs b, const uint32_t* __restrict__ table,
-                                                        const uint32_t* __restrict__ base, int64_t capacity,
-                                                        uint32_t* __restrict__ point_list) {
-    extern __shared__ uint32_t cursor[];
-    __shared__ float4 foot[32][4];           // per Gaussian of the batch: cull rectangle, q0, q1, (r2, -, -, -)
-    __shared__ uint16_t inst_tile[kBatchCap];  // tile id (the table path is only taken below 65536 tiles) ...
-    __shared__ uint8_t inst_owner[kBatchCap];  // ... and owner lane of the batch's instances, in instance order
-    __shared__ uint32_t gid[32];
-    const int lane = threadIdx.x, c = blockIdx.x;
+__global__ void __launch_bounds__(32 * kBinWarps) bin_scatter_kernel(const BinArgs b, const uint32_t* __restrict__ table,
+                                                                    const uint32_t* __restrict__ base, int64_t capacity,
+                                                                    uint32_t* __restrict__ point_list) {
+    extern __shared__ __align__(16) unsigned char bin_smem[];
+    uint32_t* cursor = reinterpret_cast<uint32_t*>(bin_smem);  // [num_tiles]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.x;
+    unsigned char* seg = bin_smem + align_up((size_t)b.num_tiles * 4, 16) + (size_t)warp * kSegBytes;
+    uint32_t* seg_entry = reinterpret_cast<uint32_t*>(seg);                          // [kSegCap]
+    uint16_t* seg_tile = reinterpret_cast<uint16_t*>(seg + kSegCap * 4);             // [kSegCap]
+    uint16_t* seg_owner = reinterpret_cast<uint16_t*>(seg + kSegCap * 6);            // [kSegCap]
     const uint32_t* row = table + (size_t)c * b.num_tiles;
-    for (int t = lane; t < b.num_tiles; t += 32) cursor[t] = base[t] + row[t];
-    __syncwarp();
+    for (int t = threadIdx.x; t < b.num_tiles; t += blockDim.x) cursor[t] = base[t] + row[t];
+    __syncthreads();
     int i0, i1;
     chunk_range(b, c, lane, i0, i1);
     const unsigned below = (1u << lane) - 1u;
     const float inv_gx = 1.0f / (float)b.gx;
 
-    // one round: lane holds (has, tile, owner lane); writes the entry of its instance
-    auto round = [&](bool has, uint32_t tile, int owner) {
-        // lanes of this round that hit the same tile, in lane (= depth) order; idle lanes get unique keys
+    auto entry_of = [&](uint32_t g, uint32_t tile) -> uint32_t {
+        const int tile_y = __float2int_rd(((float)tile + 0.5f) * inv_gx), tile_x = (int)tile - tile_y * b.gx;
+        float4 cr = make_float4(0.f, 0.f, 0.f, 0.f), q0 = cr, q1 = cr;
+        float r2 = 0.0f;
+        if (b.packed) {
+            cr = __ldg(b.cull4 + g);
+            const float4* q = b.cullq + (size_t)g * 3;
+            q0 = __ldg(q); q1 = __ldg(q + 1); r2 = __ldg(q + 2).x;
+        }
+        return make_entry(g, tile_x, tile_y, b.packed, cr, q0, q1, r2);
+    };
+    // ordered: 32 instances (has, tile, entry) of this warp's turn -> final positions
+    auto commit_round = [&](bool has, uint32_t tile, uint32_t entry) {
         const unsigned peers = __match_any_sync(0xffffffffu, has ? tile : (0x80000000u | (uint32_t)lane));
         const int rank = __popc(peers & below);
         const uint32_t pos = has ? cursor[tile] + (uint32_t)rank : 0u;
         __syncwarp();
         if (has && rank == 0) cursor[tile] += (uint32_t)__popc(peers);
         __syncwarp();
-        if (has && (int64_t)pos < capacity) {
-            const int tile_y = __float2int_rd(((float)tile + 0.5f) * inv_gx), tile_x = (int)tile - tile_y * b.gx;
-            float4 cr = make_float4(0.f, 0.f, 0.f, 0.f), q0 = cr, q1 = cr;
-            float r2 = 0.0f;
-            if (b.packed) {
-                cr = foot[owner][0]; q0 = foot[owner][1]; q1 = foot[owner][2]; r2 = foot[owner][3].x;
-            }
-            point_list[pos] = make_entry(gid[owner], tile_x, tile_y, b.packed, cr, q0, q1, r2);
-        }
+        if (has && (int64_t)pos < capacity) point_list[pos] = entry;
     };
-
-    for_each_batch(b, i0, i1, lane, [&](const BinBatch& bb) {
-        __syncwarp();  // the previous batch's rounds are done reading foot[] / inst_*[] / gid[]
-        gid[lane] = bb.g;
-        if (b.packed && bb.cnt) {
-            const float4* q = b.cullq + (size_t)bb.g * 3;
-            foot[lane][0] = __ldg(b.cull4 + bb.g);
-            foot[lane][1] = __ldg(q);
-            foot[lane][2] = __ldg(q + 1);
-            foot[lane][3] = __ldg(q + 2);
-        }
-        // Segments of lanes separated by the (rare) footprints of more than 64 tiles, processed in lane order so that the
-        // depth order is kept: [small lanes] big [small lanes] big ...
-        unsigned bigs = __ballot_sync(0xffffffffu, bb.big != 0u);
-        int cur = 0;
-        while (cur < 32) {
-            const unsigned rest = bigs & ~((1u << cur) - 1u);
-            const int nb = rest ? __ffs(rest) - 1 : 32;  // next big lane (or the end)
-            // ---- small footprints of lanes [cur, nb): materialise, then rounds
-            const uint32_t mycnt = (lane >= cur && lane < nb && !bb.big) ? bb.cnt : 0u;
-            uint32_t c_incl = mycnt;
+    const int n_batches = (i1 - i0 + 31) / 32;
+    const int n_super = (n_batches + kBinWarps - 1) / kBinWarps;
+    for (int sb = 0; sb < n_super; sb++) {
+        const int ib = i0 + (sb * kBinWarps + warp) * 32;
+        const BinBatch bb = load_batch(b, ib < i1 ? ib : i1, i1, lane);  // (past the end: every count is 0)
+        // inclusive scan of the small-footprint counts: offsets of every lane's instances within the batch
+        const uint32_t small_cnt = bb.big ? 0u : bb.cnt;
+        uint32_t c_incl = small_cnt;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, c_incl, d);
-                if (lane >= d) c_incl += v;
-            }
-            const uint32_t total = __shfl_sync(0xffffffffu, c_incl, 31);
-            if (total) {
-                if (mycnt) {
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, c_incl, d);
+            if (lane >= d) c_incl += v;
+        }
+        const uint32_t c_excl = c_incl - small_cnt;
+        const unsigned bigs = __ballot_sync(0xffffffffu, bb.big != 0u);
+
+        // Segment [cur, end): consecutive lanes up to the next big footprint whose small instances fit the buffer.
+        // seg_base = instances of the lanes before `cur`.  Returns end; *n = instances materialised (entries computed).
+        auto next_segment = [&](int cur, uint32_t& n) -> int {
+            const uint32_t seg_base = __shfl_sync(0xffffffffu, c_excl, cur < 32 ? cur : 31);
+            const unsigned rest = bigs & ~((1u << cur) - 1u);
+            int end = rest ? __ffs(rest) - 1 : 32;
+            const unsigned over = __ballot_sync(0xffffffffu, lane >= cur && (c_incl - seg_base) > (uint32_t)kSegCap);
+            if (over) end = min(end, __ffs(over) - 1);
+            const uint32_t seg_end = end > 0 ? __shfl_sync(0xffffffffu, c_incl, end - 1) : 0u;
+            n = end > cur ? seg_end - seg_base : 0u;
+            if (n) {
+                if (lane >= cur && lane < end && small_cnt) {
                     const float inv_w = 1.0f / (float)bb.w;
-                    uint32_t o = c_incl - mycnt;
+                    uint32_t o = c_excl - seg_base;
                     unsigned long long m = bb.mask;
                     while (m) {
                         const int t = __ffsll((long long)m) - 1;
                         m &= m - 1;
-                        inst_tile[o] = (uint16_t)rect_tile(t, inv_w, (int)bb.w, bb.mnx, bb.mny, b.gx);
-                        inst_owner[o++] = (uint8_t)lane;
+                        seg_tile[o] = (uint16_t)rect_tile(t, inv_w, (int)bb.w, bb.mnx, bb.mny, b.gx);
+                        seg_owner[o++] = (uint16_t)lane;
                     }
                 }
                 __syncwarp();
-                for (uint32_t jb = 0; jb < total; jb += 32) {
+                for (uint32_t jb = 0; jb < n; jb += 32) {
                     const uint32_t j = jb + lane;
-                    const bool has = j < total;
-                    round(has, has ? (uint32_t)inst_tile[j] : 0u, has ? (int)inst_owner[j] : 0);
+                    const bool has = j < n;
+                    const int owner = has ? (int)seg_owner[j] : 0;
+                    const uint32_t g = __shfl_sync(0xffffffffu, bb.g, owner);
+                    if (has) seg_entry[j] = entry_of(g, (uint32_t)seg_tile[j]);
                 }
                 __syncwarp();
             }
-            // ---- the big footprint of lane nb: every tile of its rectangle, row-major, by the whole warp
-            if (nb < 32) {
-                const int n = (int)__shfl_sync(0xffffffffu, bb.cnt, nb), w = (int)__shfl_sync(0xffffffffu, bb.w, nb);
-                const int mnx = __shfl_sync(0xffffffffu, bb.mnx, nb), mny = __shfl_sync(0xffffffffu, bb.mny, nb);
-                const float iw = 1.0f / (float)w;
-                for (int tb = 0; tb < n; tb += 32) {
-                    const int t = tb + lane;
-                    const bool has = t < n;
-                    round(has, has ? rect_tile(t, iw, w, mnx, mny, b.gx) : 0u, nb);
+            return end;
+        };
+        auto commit_segment = [&](uint32_t n) {
+            for (uint32_t jb = 0; jb < n; jb += 32) {
+                const uint32_t j = jb + lane;
+                const bool has = j < n;
+                commit_round(has, has ? (uint32_t)seg_tile[j] : 0u, has ? seg_entry[j] : 0u);
+            }
+        };
+
+        // ---- parallel part: the first segment of this warp's batch
+        uint32_t n_first = 0;
+        int cur = next_segment(0, n_first);
+        // ---- ordered part
+        for (int turn = 0; turn < kBinWarps; turn++) {
+            if (warp == turn) {
+                commit_segment(n_first);
+                while (cur < 32) {
+                    if ((bigs >> cur) & 1u) {  // a footprint of more than 64 tiles: every tile of its rectangle, row-major
+                        const int n = (int)__shfl_sync(0xffffffffu, bb.cnt, cur), w = (int)__shfl_sync(0xffffffffu, bb.w, cur);
+                        const int mnx = __shfl_sync(0xffffffffu, bb.mnx, cur), mny = __shfl_sync(0xffffffffu, bb.mny, cur);
+                        const uint32_t g = __shfl_sync(0xffffffffu, bb.g, cur);
+                        const float iw = 1.0f / (float)w;
+                        for (int tb = 0; tb < n; tb += 32) {
+                            const int t = tb + lane;
+                            const bool has = t < n;
+                            const uint32_t tile = has ? rect_tile(t, iw, w, mnx, mny, b.gx) : 0u;
+                            commit_round(has, tile, has ? entry_of(g, tile) : 0u);
+                        }
+                        cur++;
+                    } else {
+                        uint32_t n = 0;
+                        cur = next_segment(cur, n);
+                        commit_segment(n);
+                    }
                 }
             }
-            cur = nb + 1;
+            __syncthreads();
         }
-    });
+    }
 }
 
 // Phase B head: stable partition of the instances by tile (fused with emission) + tile ranges.  `R` is the CAPACITY of
@@ -681,13 +712,13 @@ int launch_binning(const IsrForwardArgs& a, int64_t R, cudaStream_t stream) {
         uint32_t* overflow = reinterpret_cast<uint32_t*>(g + gl.counters) + 5;
         ISR_CUDA_TRY(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc.smem_bytes));
         ISR_CUDA_TRY(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc.smem_bytes));
-        bin_count_kernel<<<bc.chunks, 32, bc.smem_bytes, stream>>>(ba, table); note_launch();
+        bin_count_kernel<<<bc.chunks, 32 * kBinWarps, bc.smem_bytes, stream>>>(ba, table); note_launch();
         ISR_CUDA_TRY(cudaGetLastError());
         bin_colscan_kernel<<<(num_tiles + 31) / 32, 256, 0, stream>>>(num_tiles, bc.chunks, table, totals); note_launch();
         ISR_CUDA_TRY(cudaGetLastError());
         bin_tilebase_kernel<<<1, 1024, 0, stream>>>(num_tiles, totals, base, ranges, R, overflow); note_launch();
         ISR_CUDA_TRY(cudaGetLastError());
-        bin_scatter_kernel<<<bc.chunks, 32, bc.smem_bytes, stream>>>(ba, table, base, R, point_list); note_launch();
+        bin_scatter_kernel<<<bc.chunks, 32 * kBinWarps, bc.smem_bytes, stream>>>(ba, table, base, R, point_list); note_launch();
         ISR_CUDA_TRY(cudaGetLastError());
         return ISR_OK;
     }

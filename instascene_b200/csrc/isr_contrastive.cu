@@ -643,9 +643,28 @@ int launch_rownorm(bool fwd, int P, int F, const float* x, const float* dy, floa
 }
 
 // ---- fused Adam step (one pass over param / grad / exp_avg / exp_avg_sq; torch.optim.Adam semantics, no amsgrad) ----
+// Bias corrections: from the host step count, or -- step_dev != nullptr -- from a DEVICE step counter, so that a captured
+// CUDA graph replays with the right correction (one thread per block evaluates the two pow() in double, as the host does).
+struct AdamCoef { float step_size, inv_sqrt_bias2; };
+__device__ __forceinline__ AdamCoef adam_coef(float lr, float beta1, float beta2, float step_size_host, float isb2_host,
+                                              const int* __restrict__ step_dev) {
+    __shared__ AdamCoef s_coef;
+    if (step_dev == nullptr) return AdamCoef{step_size_host, isb2_host};
+    if (threadIdx.x == 0) {
+        const double st = (double)max(1, *step_dev);
+        s_coef.step_size = (float)((double)lr / (1.0 - pow((double)beta1, st)));
+        s_coef.inv_sqrt_bias2 = (float)(1.0 / sqrt(1.0 - pow((double)beta2, st)));
+    }
+    __syncthreads();
+    return s_coef;
+}
+
 __global__ void __launch_bounds__(256)
 adam_step_kernel(size_t n4, size_t n, float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
-                 float4* __restrict__ v, float beta1, float beta2, float eps, float step_size, float inv_sqrt_bias2) {
+                 float4* __restrict__ v, float lr, float beta1, float beta2, float eps, float step_size_host, float isb2_host,
+                 const int* __restrict__ step_dev) {
+    const AdamCoef co = adam_coef(lr, beta1, beta2, step_size_host, isb2_host, step_dev);
+    const float step_size = co.step_size, inv_sqrt_bias2 = co.inv_sqrt_bias2;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     auto upd = [&](float& pp, float gg, float& mm, float& vv) {
         mm = beta1 * mm + (1.0f - beta1) * gg;
@@ -664,16 +683,119 @@ adam_step_kernel(size_t n4, size_t n, float4* __restrict__ p, const float4* __re
     }
 }
 
+// Adam on a [P,F] parameter whose gradient arrives as dL/d(normalised rows): the backward of the one / two row
+// normalisations (rownorm_bwd_kernel) is applied on the fly, so x, dy, exp_avg and exp_avg_sq are each read once and the
+// chained gradient is never written (rownorm_bwd + adam_step: 3 + 7 passes over [P,F]; here 7).  g_extra: an ordinary
+// gradient of the same parameter from other uses (added after the chain rule), or nullptr.
+template <int FP>
+__global__ void __launch_bounds__(256)
+adam_rownorm_kernel(int P, int F, float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ g_extra,
+                    float* __restrict__ m, float* __restrict__ v, float e1, float e2, int stages, float lr, float beta1,
+                    float beta2, float eps, float step_size_host, float isb2_host, const int* __restrict__ step_dev) {
+    const AdamCoef co = adam_coef(lr, beta1, beta2, step_size_host, isb2_host, step_dev);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float xv[FP], d[FP];
+    const bool vec = (F & 3) == 0;
+    auto load = [&](const float* src, float* dst) {
+#pragma unroll
+        for (int c = 0; c < FP; c += 4) {
+            if (vec && c < F) {
+                const float4 t = *reinterpret_cast<const float4*>(src + (size_t)i * F + c);
+                dst[c] = t.x; dst[c + 1] = t.y; dst[c + 2] = t.z; dst[c + 3] = t.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) dst[c + k] = (c + k < F) ? src[(size_t)i * F + c + k] : 0.0f;
+            }
+        }
+    };
+    auto store = [&](float* dst, const float* src) {
+#pragma unroll
+        for (int c = 0; c < FP; c += 4) {
+            if (vec && c < F) {
+                *reinterpret_cast<float4*>(dst + (size_t)i * F + c) = make_float4(src[c], src[c + 1], src[c + 2], src[c + 3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (c + k < F) dst[(size_t)i * F + c + k] = src[c + k];
+            }
+        }
+    };
+    load(x, xv);
+    load(dy, d);
+    // chain rule of the normalisations, innermost last (same arithmetic as rownorm_bwd_kernel)
+    if (stages > 1) {
+        float y[FP], ss = 0.0f;
+#pragma unroll
+        for (int c = 0; c < FP; c++) ss = fmaf(xv[c], xv[c], ss);
+        const float inv = 1.0f / (sqrtf(ss) + e1);
+#pragma unroll
+        for (int c = 0; c < FP; c++) y[c] = xv[c] * inv;
+        rownorm_vjp<FP>(y, d, e2);
+    }
+    rownorm_vjp<FP>(xv, d, e1);
+    if (g_extra != nullptr) {
+        float ge[FP];
+        load(g_extra, ge);
+#pragma unroll
+        for (int c = 0; c < FP; c++) d[c] += ge[c];
+    }
+    float mv[FP], vv[FP];
+    load(m, mv);
+    load(v, vv);
+#pragma unroll
+    for (int c = 0; c < FP; c++) {
+        mv[c] = beta1 * mv[c] + (1.0f - beta1) * d[c];
+        vv[c] = beta2 * vv[c] + (1.0f - beta2) * d[c] * d[c];
+        xv[c] -= co.step_size * mv[c] / (sqrtf(vv[c]) * co.inv_sqrt_bias2 + eps);
+    }
+    store(x, xv);
+    store(m, mv);
+    store(v, vv);
+}
+
+static void adam_host_coef(float lr, float beta1, float beta2, int step, float& step_size, float& isb2) {
+    const int st = step > 0 ? step : 1;
+    const double b1 = 1.0 - pow((double)beta1, (double)st), b2 = 1.0 - pow((double)beta2, (double)st);
+    step_size = (float)((double)lr / b1);
+    isb2 = (float)(1.0 / sqrt(b2));
+}
+
 int launch_adam(size_t n, float* p, const float* g, float* m, float* v, float lr, float beta1, float beta2, float eps,
-                int step, cudaStream_t stream) {
+                int step, const int* step_dev, cudaStream_t stream) {
     if (n == 0) return ISR_OK;
-    const double b1 = 1.0 - pow((double)beta1, (double)step), b2 = 1.0 - pow((double)beta2, (double)step);
+    float step_size, isb2;
+    adam_host_coef(lr, beta1, beta2, step, step_size, isb2);
     const size_t n4 = n / 4;
     adam_step_kernel<<<(unsigned)((n4 + 1 + 255) / 256), 256, 0, stream>>>(
         n4, n, reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
-        reinterpret_cast<float4*>(v), beta1, beta2, eps, (float)((double)lr / b1), (float)(1.0 / sqrt(b2))); note_launch();
+        reinterpret_cast<float4*>(v), lr, beta1, beta2, eps, step_size, isb2, step_dev); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
+}
+
+template <int FP>
+static int adam_rownorm_launch(int P, int F, float* x, const float* dy, const float* g_extra, float* m, float* v, float e1,
+                               float e2, int stages, float lr, float beta1, float beta2, float eps, int step,
+                               const int* step_dev, cudaStream_t stream) {
+    float step_size, isb2;
+    adam_host_coef(lr, beta1, beta2, step, step_size, isb2);
+    adam_rownorm_kernel<FP><<<(P + 255) / 256, 256, 0, stream>>>(P, F, x, dy, g_extra, m, v, e1, e2, stages, lr, beta1, beta2,
+                                                                 eps, step_size, isb2, step_dev); note_launch();
+    ISR_CUDA_TRY(cudaGetLastError());
+    return ISR_OK;
+}
+
+int launch_adam_rownorm(int P, int F, float* x, const float* dy, const float* g_extra, float* m, float* v, float e1, float e2,
+                        int stages, float lr, float beta1, float beta2, float eps, int step, const int* step_dev,
+                        cudaStream_t stream) {
+    if (P <= 0 || F <= 0) return ISR_OK;
+#define ISR_AR(FPV) return adam_rownorm_launch<FPV>(P, F, x, dy, g_extra, m, v, e1, e2, stages, lr, beta1, beta2, eps, step, step_dev, stream)
+    if (F <= 4) ISR_AR(4);
+    if (F <= 8) ISR_AR(8);
+    if (F <= 16) ISR_AR(16);
+    if (F <= 24) ISR_AR(24);
+    ISR_AR(32);
+#undef ISR_AR
 }
 
 size_t contrastive_ws_bytes(int N, int F, int K) { return ContrastWs(N, F, K).total; }

@@ -506,10 +506,13 @@ class _SamplePixels(torch.autograd.Function):
 
 
 class _RowNorm(torch.autograd.Function):
-    """y = x / (|x| + eps1) [then y / (|y| + eps2)] over the rows of [P,F], one fused kernel each way."""
+    """y = x / (|x| + eps1) [then y / (|y| + eps2)] over the rows of [P,F], one fused kernel each way.
+    `sink` (a tensor object, normally x itself): the backward does NOT run the chain rule; it parks dL/dy on
+    `sink._isr_deferred_dy` (+ `_isr_deferred_cfg`) for an optimizer that applies it inside its update
+    (instascene_b200.FusedAdam) and returns no gradient for x."""
 
     @staticmethod
-    def forward(ctx, x, eps1, eps2, stages):
+    def forward(ctx, x, eps1, eps2, stages, sink=None):
         L = _require_cuda_lib()
         xc = _f32c(x.detach(), "x")
         P, F = int(xc.shape[0]), int(xc.shape[1])
@@ -518,6 +521,7 @@ class _RowNorm(torch.autograd.Function):
                    "isr_rownorm_forward")
         ctx.save_for_backward(xc)
         ctx.cfg = (float(eps1), float(eps2), int(stages))
+        ctx.sink = sink
         return y
 
     @staticmethod
@@ -526,17 +530,25 @@ class _RowNorm(torch.autograd.Function):
         (xc,) = ctx.saved_tensors
         e1, e2, stages = ctx.cfg
         dyc = _f32c(dy, "dy")
+        if ctx.sink is not None:
+            prev = getattr(ctx.sink, "_isr_deferred_dy", None)
+            if prev is not None and getattr(ctx.sink, "_isr_deferred_cfg", None) != ctx.cfg:
+                raise RuntimeError("deferred row-normalisation gradients with different settings on one parameter")
+            ctx.sink._isr_deferred_dy = dyc if prev is None else prev + dyc
+            ctx.sink._isr_deferred_cfg = ctx.cfg
+            return None, None, None, None, None
         dx = torch.empty_like(xc)
         _lib.check(L.isr_rownorm_backward(int(xc.shape[0]), int(xc.shape[1]), _ptr(xc), _ptr(dyc), e1, e2, stages,
                                           _ptr(dx), _stream()), "isr_rownorm_backward")
-        return dx, None, None, None
+        return dx, None, None, None, None
 
 
-def normalize_rows(x: torch.Tensor, eps1: float, eps2: float = 0.0, stages: int = 1) -> torch.Tensor:
-    """Fused `x / (x.norm(dim=-1, keepdim=True) + eps1)`, optionally applied twice (second eps = eps2)."""
+def normalize_rows(x: torch.Tensor, eps1: float, eps2: float = 0.0, stages: int = 1, defer_to=None) -> torch.Tensor:
+    """Fused `x / (x.norm(dim=-1, keepdim=True) + eps1)`, optionally applied twice (second eps = eps2).
+    defer_to: see _RowNorm (the gradient of x is left to an optimizer that fuses the chain rule)."""
     if x.numel() == 0:
         return x
-    return _RowNorm.apply(x, eps1, eps2, stages)
+    return _RowNorm.apply(x, eps1, eps2, stages, defer_to)
 
 
 def sample_pixels(extra_map: torch.Tensor, pix_ids: torch.Tensor) -> torch.Tensor:
@@ -551,8 +563,31 @@ def sample_pixels(extra_map: torch.Tensor, pix_ids: torch.Tensor) -> torch.Tenso
 def sample_labelled_pixels(labels_flat: torch.Tensor, n: int, generator=None):
     """Draw `n` pixel ids uniformly WITH replacement among the pixels whose label is > 0 -- the sampling of
     train_semantic.py:118-129 (`valid = segmap > 0; idx = randint(0, len(valid), (n,))`) without the boolean-mask
-    gather of the [F,H,W] map and without a host sync: inclusive scan of the mask + searchsorted.
-    Returns (pix_ids int64 [n], labels [n])."""
+    gather of the [F,H,W] map and without a host sync: one `torch.rand` (the caller's generator) + two kernels
+    (occupancy words + block counts, then per-sample rank selection; csrc/isr_sampler.cu).
+    Returns (pix_ids int64 [n], labels int32 [n])."""
+    L = _require_cuda_lib()
+    lab = labels_flat.reshape(-1)
+    if not lab.is_cuda:
+        raise RuntimeError("labels must be a CUDA tensor")
+    if lab.dtype not in (torch.int8, torch.int16, torch.int32, torch.int64):
+        lab = lab.to(torch.int32)
+    lab = lab.contiguous()
+    HW = int(lab.numel())
+    dev = lab.device
+    u = torch.rand(n, device=dev, generator=generator)
+    pix = torch.empty(n, dtype=torch.int64, device=dev)
+    out_lab = torch.empty(n, dtype=torch.int32, device=dev)
+    ws_bytes = L.isr_sampler_workspace_bytes(HW)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _lib.check(L.isr_sample_labelled(lab.data_ptr(), lab.element_size(), HW, int(n), _ptr(u), ws.data_ptr(), ws_bytes,
+                                     pix.data_ptr(), out_lab.data_ptr(), _stream()), "isr_sample_labelled")
+    return pix, out_lab
+
+
+def sample_labelled_pixels_torch(labels_flat: torch.Tensor, n: int, generator=None):
+    """Round 1's formulation of the same draw in torch ops (inclusive scan of the mask + searchsorted); kept as the
+    checker of the fused kernels: same `torch.rand` stream -> identical pixel ids."""
     mask = labels_flat > 0
     csum = torch.cumsum(mask, dim=0, dtype=torch.int32)
     n_valid = csum[-1]

@@ -195,7 +195,9 @@ def _seg_features_for_raster(pc, pipe, norm_seg_feat):
     (eps 1e-9, gaussian_renderer/__init__.py:60-62) -- Q9.  With the raw parameter available both are one kernel."""
     raw = getattr(pc, "_seg_feature", None)
     if norm_seg_feat and raw is not None and getattr(pipe, "fused_seg_activation", True):
-        return normalize_rows(raw, getattr(pc, "seg_feature_eps", 1e-6), 1e-9, stages=2)
+        # pipe.defer_seg_feature_grad: leave the chain rule of the two normalisations to instascene_b200.FusedAdam
+        defer = raw if (getattr(pipe, "defer_seg_feature_grad", False) and raw.requires_grad) else None
+        return normalize_rows(raw, getattr(pc, "seg_feature_eps", 1e-6), 1e-9, stages=2, defer_to=defer)
     feats = pc.get_seg_feature
     if feats is not None and norm_seg_feat:
         feats = normalize_rows(feats, 1e-9)

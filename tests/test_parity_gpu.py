@@ -439,9 +439,38 @@ def test_sample_labelled_pixels_is_uniform_over_valid():
     lab[valid] = torch.tensor([5, 6, 7, 8], dtype=torch.int16, device="cuda")
     pix, labels = isr.sample_labelled_pixels(lab, 40000, generator=g)
     assert set(pix.cpu().tolist()) == set(valid.cpu().tolist())
-    assert torch.equal(labels, lab[pix])
+    assert torch.equal(labels.long(), lab[pix].long())
     counts = torch.bincount(pix, minlength=10000)[valid].float()
     assert float((counts / 10000.0 - 1.0).abs().max()) < 0.05
+
+
+@pytest.mark.parametrize("dtype", ["int16", "int32", "int64"])
+def test_fused_sampler_equals_torch_formulation(dtype):
+    """The two-kernel sampler against round 1's torch formulation (mask, cumsum, rand, searchsorted, index) on the same
+    `torch.rand` stream: identical pixel ids and labels -- label maps with a ragged size (not a multiple of the
+    4096-pixel count block), a fully unlabelled stretch longer than a block, and a map with a single labelled pixel."""
+    import torch
+    import instascene_b200 as isr
+    from instascene_b200.rasterizer import sample_labelled_pixels_torch
+    dt = getattr(torch, dtype)
+    rng = np.random.default_rng(5)
+    H, W = 1080, 1917
+    lab = rng.integers(-1, 60, size=H * W)
+    lab[rng.random(H * W) < 0.4] = 0
+    lab[100000:140000] = 0
+    maps = [torch.tensor(lab, dtype=dt, device="cuda")]
+    single = torch.zeros(5000, dtype=dt, device="cuda")
+    single[4321] = 9
+    maps.append(single)
+    for m in maps:
+        g1, g2 = torch.Generator(device="cuda"), torch.Generator(device="cuda")
+        g1.manual_seed(11)
+        g2.manual_seed(11)
+        pix, labels = isr.sample_labelled_pixels(m, 32768, generator=g1)
+        pix_t, labels_t = sample_labelled_pixels_torch(m, 32768, generator=g2)
+        assert pix.dtype == torch.int64 and torch.equal(pix, pix_t)
+        assert torch.equal(labels.long(), labels_t.long())
+        assert bool((m[pix] > 0).all())
 
 
 def test_fused_aux_maps_match_torch_glue():
@@ -568,6 +597,35 @@ def test_fused_adam_matches_torch():
             a.grad, b.grad = g.clone(), g.clone()
             oa.step(); ob.step()
         assert float((a - b).abs().max()) < 1e-5 * float(b.abs().max())
+
+
+@pytest.mark.parametrize("F,stages", [(16, 2), (7, 2), (32, 1)])
+def test_fused_adam_with_deferred_rownorm_equals_unfused(F, stages):
+    """normalize_rows(..., defer_to=param) + FusedAdam (chain rule of the normalisation inside the Adam kernel, device
+    step counter) against the unfused path (rownorm backward kernel -> param.grad -> torch.optim.Adam), several steps,
+    including a step with an extra ordinary gradient on the same parameter."""
+    import torch
+    import instascene_b200 as isr
+    torch.manual_seed(3)
+    P = 5000
+    a = (torch.randn(P, F, device="cuda") * 2).requires_grad_(True)
+    b = a.detach().clone().requires_grad_(True)
+    oa = isr.FusedAdam([a], lr=0.025, eps=1e-15, capturable=True)
+    ob = torch.optim.Adam([b], lr=0.025, eps=1e-15)
+    for it in range(4):
+        w = torch.randn(P, F, device="cuda")
+        ya = isr.normalize_rows(a, 1e-6, 1e-9, stages=stages, defer_to=a)
+        yb = isr.normalize_rows(b, 1e-6, 1e-9, stages=stages)
+        la, lb = (ya * w).sum(), (yb * w).sum()
+        if it == 2:  # another use of the raw parameter: its ordinary gradient is added after the chain rule
+            la = la + (a[::7] ** 2).sum() * 0.01
+            lb = lb + (b[::7] ** 2).sum() * 0.01
+        la.backward(); lb.backward()
+        assert getattr(a, "_isr_deferred_dy", None) is not None and (a.grad is None) == (it != 2)
+        oa.step(); ob.step()
+        oa.zero_grad(); ob.zero_grad()
+        assert getattr(a, "_isr_deferred_dy", None) is None
+    assert float((a - b).abs().max()) < 2e-5 * float(b.abs().max())
 
 
 def test_render_geometry_first_and_param_ready_event():
