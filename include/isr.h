@@ -67,6 +67,10 @@ typedef enum IsrStatus {
 #define ISR_FLAG_NO_PAIRS     2u  /* do not emit the gau_related_pixels list                              */
 #define ISR_FLAG_SKIP_BINNING 4u  /* isr_forward_render: reuse the binning already in the workspaces and run
                                      only the blend kernel (profiling / roofline measurement)              */
+#define ISR_FLAG_SKIP_BLEND   16u  /* isr_forward_render: run only the binning (instance partition + tile ranges); the
+                                     blend follows in a later call with ISR_FLAG_SKIP_BINNING on the same workspaces
+                                     and the same R.  Binning reads no semantic features, so it can be queued ahead
+                                     (instascene_b200.prefetch_geometry)                                       */
 #define ISR_FLAG_SPEC_ARITH   8u  /* evaluate exp / rsqrt with the CPU-reproducible IEEE-only stand-ins of
                                      oracle/isr_oracle.c instead of CUDA's expf / rsqrtf (the reference's own,
                                      MUFU based).  Default (flag clear): the reference's arithmetic -- forward
@@ -159,7 +163,11 @@ typedef struct IsrForwardArgs {
  * binning workspace with isr_binning_bytes(P, R = num_rendered_host[1], W, H) and calls phase B with that R.
  * (The reference blocks on a cudaMemcpy at the same point, rasterizer_impl.cu:287.) */
 int isr_forward_geometry(const IsrForwardArgs* args, void* stream);
-/* Phase B: instance emission, stable tile sort, tile ranges, front-to-back blend. */
+/* Phase B: stable partition of the instances by tile (fused with their emission) + tile ranges, then the front-to-back
+ * blend.  R = the CAPACITY (in instances) of the binning workspace, >= num_rendered_host[1]; the kernels read the
+ * actual count from device memory, so a caller may size the workspace from a high-water mark and queue phase B without
+ * reading the count first (if it turns out too small nothing is written out of bounds; compare the count with R and
+ * repeat phase B with a larger workspace). */
 int isr_forward_render(const IsrForwardArgs* args, int64_t R, void* stream);
 
 /* ---- backward ---------------------------------------------------------------------------------------- */

@@ -13,6 +13,7 @@ FLAG_BWD_WH_QUIRK = 1
 FLAG_NO_PAIRS = 2
 FLAG_SKIP_BINNING = 4
 FLAG_SPEC_ARITH = 8
+FLAG_SKIP_BLEND = 16
 GRAD_GEOMETRY, GRAD_COLOR, GRAD_OPACITY, GRAD_EXTRA, GRAD_ALL = 1, 2, 4, 8, 15
 MAX_EXTRA_DIMS = 32
 

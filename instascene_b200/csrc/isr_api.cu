@@ -145,14 +145,17 @@ int isr_forward_render(const IsrForwardArgs* a, int64_t R, void* stream_) {
     if (st != ISR_OK) return st;
     if (R < 0 || R > 0x7fffffffLL) return ISR_ERR_INVALID_ARG;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (a->pair_count) ISR_CUDA_TRY(cudaMemsetAsync(a->pair_count, 0, sizeof(int), stream));
+    const bool do_bin = !(a->flags & ISR_FLAG_SKIP_BINNING), do_blend = !(a->flags & ISR_FLAG_SKIP_BLEND);
     if (a->P > 0 && R > 0) {
         if (!a->binning || a->binning_bytes < BinLayout(a->P, R, a->W, a->H).total) return ISR_ERR_WORKSPACE;
     }
-    if (!(a->flags & ISR_FLAG_SKIP_BINNING)) {
+    if (do_bin) {
         st = launch_binning(*a, a->P > 0 ? R : 0, stream);
         if (st != ISR_OK) return st;
     }
+    if (!do_blend) return ISR_OK;
+    if (a->F > 0 && (!a->extra_attrs || !a->out_extra)) return ISR_ERR_INVALID_ARG;
+    if (a->pair_count) ISR_CUDA_TRY(cudaMemsetAsync(a->pair_count, 0, sizeof(int), stream));
     // With no instances every tile range is (0,0): the blend kernel still runs to write background / zeros.
     return launch_blend_fwd(*a, stream);
 }

@@ -537,21 +537,24 @@ __global__ void __launch_bounds__(1024) bin_tilebase_kernel(int num_tiles, const
 }
 
 // 3c: every list entry straight to its final position, in depth order.  One CTA (kBinWarps warps) per chunk with ONE
-// table of per-tile cursors in shared memory.  Per super-batch:
-//   parallel part (all warps at once): a warp materialises its batch's instances in shared memory IN ORDER -- lane l
-//     writes (tile id, owner lane) of its own Gaussian's tiles at its exclusive-scan offset, no per-instance owner search --
-//     and computes every instance's list entry (Gaussian id + the 8 per-block footprint bits, 32 instances per round);
-//   ordered part (one warp at a time, in batch = depth order): position = the tile's cursor + the rank among the lanes of
-//     the same round that hit the same tile (__match_any_sync; lane order = instance order), one 4-byte store per
-//     instance.  ~15 instructions per 32 instances are serialised; everything else runs at full occupancy.
+// table of per-tile cursors in shared memory; batch k of the chunk belongs to warp k % kBinWarps.  Per batch a warp
+//   (parallel with the other warps) loads its 32 Gaussians' footprints (cull rectangle + conic) into registers,
+//     materialises the batch's instances in shared memory IN ORDER -- lane l writes (tile id, owner lane) of its own
+//     Gaussian's tiles at its exclusive-scan offset, no per-instance owner search -- and computes every instance's list
+//     entry (Gaussian id + the 8 per-block footprint bits; 32 instances per round, footprint by shuffle from the owner);
+//   (ordered) waits for its turn -- a named barrier per receiving warp on which the previous batch's warp arrives; no
+//     block-wide barrier, no spinning -- and commits: position = the tile's cursor + the rank among the lanes of the same round that hit the same tile
+//     (__match_any_sync; lane order = instance order), one 4-byte store per instance; then hands over and starts its
+//     next batch while the following warps commit.
+// Only ~15 instructions per 32 instances are serialised; everything else runs concurrently.
 // A batch whose small footprints hold more than kSegCap instances is cut into segments of consecutive lanes; footprints
 // of more than 64 tiles are walked arithmetically by the whole warp.  Both continue inside the warp's ordered turn (rare).
-constexpr int kSegCap = 512;                    // instances per segment (8 lanes x 64 tiles always fit)
+constexpr int kSegCap = 512;                      // instances per segment (8 lanes x 64 tiles always fit)
 constexpr int kSegBytes = kSegCap * (4 + 2 + 2);  // entry u32 + tile u16 + owner u8 (padded to u16)
 
-__global__ void __launch_bounds__(32 * kBinWarps) bin_scatter_kernel(const BinArgs b, const uint32_t* __restrict__ table,
-                                                                    const uint32_t* __restrict__ base, int64_t capacity,
-                                                                    uint32_t* __restrict__ point_list) {
+__global__ void __launch_bounds__(32 * kBinWarps, 3)
+bin_scatter_kernel(const BinArgs b, const uint32_t* __restrict__ table, const uint32_t* __restrict__ base, int64_t capacity,
+                   uint32_t* __restrict__ point_list) {
     extern __shared__ __align__(16) unsigned char bin_smem[];
     uint32_t* cursor = reinterpret_cast<uint32_t*>(bin_smem);  // [num_tiles]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.x;
@@ -567,17 +570,6 @@ __global__ void __launch_bounds__(32 * kBinWarps) bin_scatter_kernel(const BinAr
     const unsigned below = (1u << lane) - 1u;
     const float inv_gx = 1.0f / (float)b.gx;
 
-    auto entry_of = [&](uint32_t g, uint32_t tile) -> uint32_t {
-        const int tile_y = __float2int_rd(((float)tile + 0.5f) * inv_gx), tile_x = (int)tile - tile_y * b.gx;
-        float4 cr = make_float4(0.f, 0.f, 0.f, 0.f), q0 = cr, q1 = cr;
-        float r2 = 0.0f;
-        if (b.packed) {
-            cr = __ldg(b.cull4 + g);
-            const float4* q = b.cullq + (size_t)g * 3;
-            q0 = __ldg(q); q1 = __ldg(q + 1); r2 = __ldg(q + 2).x;
-        }
-        return make_entry(g, tile_x, tile_y, b.packed, cr, q0, q1, r2);
-    };
     // ordered: 32 instances (has, tile, entry) of this warp's turn -> final positions
     auto commit_round = [&](bool has, uint32_t tile, uint32_t entry) {
         const unsigned peers = __match_any_sync(0xffffffffu, has ? tile : (0x80000000u | (uint32_t)lane));
@@ -588,11 +580,32 @@ __global__ void __launch_bounds__(32 * kBinWarps) bin_scatter_kernel(const BinAr
         __syncwarp();
         if (has && (int64_t)pos < capacity) point_list[pos] = entry;
     };
+
     const int n_batches = (i1 - i0 + 31) / 32;
-    const int n_super = (n_batches + kBinWarps - 1) / kBinWarps;
-    for (int sb = 0; sb < n_super; sb++) {
-        const int ib = i0 + (sb * kBinWarps + warp) * 32;
-        const BinBatch bb = load_batch(b, ib < i1 ? ib : i1, i1, lane);  // (past the end: every count is 0)
+    for (int k = warp; k < n_batches; k += kBinWarps) {
+        const BinBatch bb = load_batch(b, i0 + k * 32, i1, lane);
+        // this lane's Gaussian: footprint data for the entries (independent loads, consumed after the build loop)
+        float4 cr = make_float4(0.f, 0.f, 0.f, 0.f), q0 = cr, q1 = cr;
+        float r2 = 0.0f;
+        if (b.packed && bb.cnt) {
+            cr = __ldg(b.cull4 + bb.g);
+            const float4* q = b.cullq + (size_t)bb.g * 3;
+            q0 = __ldg(q); q1 = __ldg(q + 1); r2 = __ldg(q + 2).x;
+        }
+        // entry of (owner lane's Gaussian, tile): the owner's footprint arrives by shuffle (all lanes call together)
+        auto entry_of = [&](int owner, uint32_t tile) -> uint32_t {
+            const uint32_t g = __shfl_sync(0xffffffffu, bb.g, owner);
+            float4 c4, a0, a1;
+            c4.x = __shfl_sync(0xffffffffu, cr.x, owner); c4.y = __shfl_sync(0xffffffffu, cr.y, owner);
+            c4.z = __shfl_sync(0xffffffffu, cr.z, owner); c4.w = __shfl_sync(0xffffffffu, cr.w, owner);
+            a0.x = __shfl_sync(0xffffffffu, q0.x, owner); a0.y = __shfl_sync(0xffffffffu, q0.y, owner);
+            a0.z = __shfl_sync(0xffffffffu, q0.z, owner); a0.w = __shfl_sync(0xffffffffu, q0.w, owner);
+            a1.x = __shfl_sync(0xffffffffu, q1.x, owner); a1.y = __shfl_sync(0xffffffffu, q1.y, owner);
+            a1.z = __shfl_sync(0xffffffffu, q1.z, owner); a1.w = __shfl_sync(0xffffffffu, q1.w, owner);
+            const float rr = __shfl_sync(0xffffffffu, r2, owner);
+            const int tile_y = __float2int_rd(((float)tile + 0.5f) * inv_gx), tile_x = (int)tile - tile_y * b.gx;
+            return make_entry(g, tile_x, tile_y, b.packed, c4, a0, a1, rr);
+        };
         // inclusive scan of the small-footprint counts: offsets of every lane's instances within the batch
         const uint32_t small_cnt = bb.big ? 0u : bb.cnt;
         uint32_t c_incl = small_cnt;
@@ -605,7 +618,7 @@ __global__ void __launch_bounds__(32 * kBinWarps) bin_scatter_kernel(const BinAr
         const unsigned bigs = __ballot_sync(0xffffffffu, bb.big != 0u);
 
         // Segment [cur, end): consecutive lanes up to the next big footprint whose small instances fit the buffer.
-        // seg_base = instances of the lanes before `cur`.  Returns end; *n = instances materialised (entries computed).
+        // Materialises the segment and computes its entries; returns end, n = instances.
         auto next_segment = [&](int cur, uint32_t& n) -> int {
             const uint32_t seg_base = __shfl_sync(0xffffffffu, c_excl, cur < 32 ? cur : 31);
             const unsigned rest = bigs & ~((1u << cur) - 1u);
@@ -630,9 +643,8 @@ __global__ void __launch_bounds__(32 * kBinWarps) bin_scatter_kernel(const BinAr
                 for (uint32_t jb = 0; jb < n; jb += 32) {
                     const uint32_t j = jb + lane;
                     const bool has = j < n;
-                    const int owner = has ? (int)seg_owner[j] : 0;
-                    const uint32_t g = __shfl_sync(0xffffffffu, bb.g, owner);
-                    if (has) seg_entry[j] = entry_of(g, (uint32_t)seg_tile[j]);
+                    const uint32_t e = entry_of(has ? (int)seg_owner[j] : 0, has ? (uint32_t)seg_tile[j] : 0u);
+                    if (has) seg_entry[j] = e;
                 }
                 __syncwarp();
             }
@@ -649,31 +661,35 @@ __global__ void __launch_bounds__(32 * kBinWarps) bin_scatter_kernel(const BinAr
         // ---- parallel part: the first segment of this warp's batch
         uint32_t n_first = 0;
         int cur = next_segment(0, n_first);
-        // ---- ordered part
-        for (int turn = 0; turn < kBinWarps; turn++) {
-            if (warp == turn) {
-                commit_segment(n_first);
-                while (cur < 32) {
-                    if ((bigs >> cur) & 1u) {  // a footprint of more than 64 tiles: every tile of its rectangle, row-major
-                        const int n = (int)__shfl_sync(0xffffffffu, bb.cnt, cur), w = (int)__shfl_sync(0xffffffffu, bb.w, cur);
-                        const int mnx = __shfl_sync(0xffffffffu, bb.mnx, cur), mny = __shfl_sync(0xffffffffu, bb.mny, cur);
-                        const uint32_t g = __shfl_sync(0xffffffffu, bb.g, cur);
-                        const float iw = 1.0f / (float)w;
-                        for (int tb = 0; tb < n; tb += 32) {
-                            const int t = tb + lane;
-                            const bool has = t < n;
-                            const uint32_t tile = has ? rect_tile(t, iw, w, mnx, mny, b.gx) : 0u;
-                            commit_round(has, tile, has ? entry_of(g, tile) : 0u);
-                        }
-                        cur++;
-                    } else {
-                        uint32_t n = 0;
-                        cur = next_segment(cur, n);
-                        commit_segment(n);
-                    }
+        // ---- ordered part: wait for ticket k
+        // Hand-over through NAMED BARRIERS, one per receiving warp (ids 1..kBinWarps, 64 threads each): the warp that
+        // committed batch k-1 arrives on the barrier of batch k's warp, which waits on it in hardware.  (A spin on a
+        // shared-memory ticket made the 7 waiting warps of every CTA flood the LSU: 10x slower, measured.)
+        if (k > 0) asm volatile("bar.sync %0, 64;" :: "r"(1 + k % kBinWarps) : "memory");
+        commit_segment(n_first);
+        while (cur < 32) {
+            if ((bigs >> cur) & 1u) {  // a footprint of more than 64 tiles: every tile of its rectangle, row-major
+                const int n = (int)__shfl_sync(0xffffffffu, bb.cnt, cur), w = (int)__shfl_sync(0xffffffffu, bb.w, cur);
+                const int mnx = __shfl_sync(0xffffffffu, bb.mnx, cur), mny = __shfl_sync(0xffffffffu, bb.mny, cur);
+                const float iw = 1.0f / (float)w;
+                for (int tb = 0; tb < n; tb += 32) {
+                    const int t = tb + lane;
+                    const bool has = t < n;
+                    const uint32_t tile = has ? rect_tile(t, iw, w, mnx, mny, b.gx) : 0u;
+                    const uint32_t e = entry_of(cur, tile);
+                    commit_round(has, tile, e);
                 }
+                cur++;
+            } else {
+                uint32_t n = 0;
+                cur = next_segment(cur, n);
+                commit_segment(n);
             }
-            __syncthreads();
+        }
+        __syncwarp();
+        if (k + 1 < n_batches) {
+            __threadfence_block();  // the cursor updates above are visible to the next warp
+            asm volatile("bar.arrive %0, 64;" :: "r"(1 + (k + 1) % kBinWarps) : "memory");
         }
     }
 }

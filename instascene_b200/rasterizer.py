@@ -78,6 +78,23 @@ def _pinned_i64(device: torch.device) -> torch.Tensor:
     return t
 
 
+# High-water mark of the emitted instance count per (P, W, H): sizes the binning workspace of views whose binning is
+# queued before their count is known on the host (prefetch_geometry).
+_instance_high_water = {}
+
+
+def note_instances(P: int, W: int, H: int, n_inst: int) -> None:
+    key = (int(P), int(W), int(H))
+    if n_inst > _instance_high_water.get(key, 0):
+        _instance_high_water[key] = int(n_inst)
+
+
+def binning_capacity_hint(P: int, W: int, H: int) -> int:
+    """0 until a view of this shape has been rendered; then 1.25x the largest instance count seen, in whole millions."""
+    hw = _instance_high_water.get((int(P), int(W), int(H)), 0)
+    return 0 if hw == 0 else ((int(hw * 1.25) + (1 << 20)) >> 20) << 20
+
+
 def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor")  # CHECK_INPUT, DSR/rasterize_points.cu:27-28
@@ -99,15 +116,19 @@ def _require_cuda_lib():
 class _ForwardState:
     """Everything between the two phases of the forward (isr_forward_geometry -> isr_forward_render)."""
     __slots__ = ("args", "keep", "P", "H", "W", "dev", "want_pairs", "out_color", "out_others", "radii", "geom", "img",
-                 "pairs", "pair_count", "nr_host", "ready_event")
+                 "pairs", "pair_count", "nr_host", "ready_event", "binning", "bin_capacity")
 
 
 def launch_geometry(background, means3D, colors, opacity, scales, rotations, scale_modifier, transMat_precomp, viewmatrix,
                     projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
-                    want_pairs: bool = True, pinned_counts: Optional[torch.Tensor] = None) -> Optional[_ForwardState]:
+                    want_pairs: bool = True, pinned_counts: Optional[torch.Tensor] = None,
+                    bin_capacity: int = 0) -> Optional[_ForwardState]:
     """Phase A of the forward: K1 projection + depth order + offsets, enqueued asynchronously on the current stream.
     Nothing here depends on extra_attrs (the semantic features), so a caller may start it before the features of the
-    step are final (e.g. while the previous step's gradient all-reduce / optimizer step runs on another stream)."""
+    step are final (e.g. while the previous step's gradient all-reduce / optimizer step runs on another stream).
+    bin_capacity > 0: the binning (instance partition + tile ranges, which read no features either) is queued right
+    behind it into a workspace of that many instances -- the kernels take the actual count from device memory;
+    finish_render repeats the binning inline in the (rare) case that the count exceeds the capacity."""
     L = _require_cuda_lib()
     if means3D.dim() != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
@@ -130,6 +151,7 @@ def launch_geometry(background, means3D, colors, opacity, scales, rotations, sca
     M = int(sh.shape[1]) if sh.numel() else 0
     st = _ForwardState()
     st.ready_event = None  # set when phase A was launched on another stream (renderer.prefetch_geometry)
+    st.binning, st.bin_capacity = None, 0
     st.P, st.H, st.W, st.dev, st.want_pairs = P, H, W, dev, want_pairs
     st.out_color = torch.empty((3, H, W), **f32)
     st.out_others = torch.empty((7, H, W), **f32)
@@ -156,6 +178,16 @@ def launch_geometry(background, means3D, colors, opacity, scales, rotations, sca
     st.args = a
     st.keep = (background, means3D, colors, opacity, scales, rotations, transMat_precomp, sh, viewmatrix, projmatrix, campos)
     _lib.check(L.isr_forward_geometry(C.byref(a), _stream()), "isr_forward_geometry")
+    if bin_capacity > 0:
+        cap = int(bin_capacity)
+        bin_bytes = L.isr_binning_bytes(P, cap, W, H)
+        st.binning = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
+        st.bin_capacity = cap
+        a.binning, a.binning_bytes = st.binning.data_ptr(), bin_bytes
+        flags = a.flags
+        a.flags = flags | _lib.FLAG_SKIP_BLEND
+        _lib.check(L.isr_forward_render(C.byref(a), cap, _stream()), "isr_forward_render(binning only)")
+        a.flags = flags
     return st
 
 
@@ -178,10 +210,18 @@ def finish_render(st: _ForwardState, extra_attrs, F: int, debug: bool = False, r
         torch.cuda.current_stream().synchronize()  # the reference blocks on a cudaMemcpy here (rasterizer_impl.cu:287)
     # [0]: what the reference reports as num_rendered (all tiles of every rectangle); [1]: instances actually binned
     num_rendered, n_inst = int(st.nr_host[0]), int(st.nr_host[1])
-    bin_bytes = L.isr_binning_bytes(st.P, n_inst, st.W, st.H)
-    binningBuffer = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
-    a.binning, a.binning_bytes = binningBuffer.data_ptr(), bin_bytes
-    _lib.check(L.isr_forward_render(C.byref(a), n_inst, _stream()), "isr_forward_render")
+    note_instances(st.P, st.W, st.H, n_inst)
+    if st.binning is not None and n_inst <= st.bin_capacity:
+        # binned ahead of time (launch_geometry(bin_capacity=...)): only the blend is left
+        binningBuffer, cap = st.binning, st.bin_capacity
+        a.flags |= _lib.FLAG_SKIP_BINNING
+    else:
+        cap = n_inst
+        bin_bytes = L.isr_binning_bytes(st.P, cap, st.W, st.H)
+        binningBuffer = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
+        a.binning, a.binning_bytes = binningBuffer.data_ptr(), bin_bytes
+    _lib.check(L.isr_forward_render(C.byref(a), cap, _stream()), "isr_forward_render")
+    a.flags &= ~_lib.FLAG_SKIP_BINNING
     if debug:
         torch.cuda.synchronize()
     res = (num_rendered, st.out_color, st.out_others, st.radii, out_extra, st.geom, binningBuffer, st.img, st.pairs,
@@ -189,6 +229,7 @@ def finish_render(st: _ForwardState, extra_attrs, F: int, debug: bool = False, r
     if return_args:  # profiling hook (bench.py roofline leg); keeps every tensor the struct points to alive
         a._keepalive = st.keep + (extra_attrs, st.pair_count, st.nr_host) + res[1:9]
         a._n_inst = n_inst
+        a._bin_capacity = cap
         return res + (a,)
     return res
 

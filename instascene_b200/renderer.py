@@ -19,8 +19,8 @@ import torch
 import ctypes as C
 
 from . import _lib
-from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, launch_geometry, normalize_rows, _ptr,
-                         _require_cuda_lib, _stream)
+from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, binning_capacity_hint, launch_geometry,
+                         normalize_rows, _ptr, _require_cuda_lib, _stream)
 
 import os
 
@@ -236,14 +236,15 @@ def _raster_inputs(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, overr
 
 
 def _launch_phase_a(settings, xyz, opacity, geometry, appearance, viewpoint_camera, pc, bg_color, scaling_modifier, want_pairs,
-                    pinned_counts=None):
+                    pinned_counts=None, bin_capacity=0):
     none = torch.empty(0, dtype=torch.float32, device=xyz.device)
     return launch_geometry(
         bg_color, xyz, appearance.get("colors_precomp", none), opacity, geometry.get("scales", none),
         geometry.get("rotations", none), scaling_modifier, geometry.get("cov3D_precomp", none),
         viewpoint_camera.world_view_transform, viewpoint_camera.full_proj_transform, settings.tanfovx,
         settings.tanfovy, settings.image_height, settings.image_width, appearance.get("shs", none),
-        pc.active_sh_degree, viewpoint_camera.camera_center, want_pairs=want_pairs, pinned_counts=pinned_counts)
+        pc.active_sh_degree, viewpoint_camera.camera_center, want_pairs=want_pairs, pinned_counts=pinned_counts,
+        bin_capacity=bin_capacity)
 
 
 class PrefetchedGeometry:
@@ -274,9 +275,9 @@ def _next_pinned_counts(dev_index):
 
 
 def prefetch_geometry(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
-                      want_pairs: bool = True, stream=None) -> PrefetchedGeometry:
-    """Starts phase A of render() for a view that will be rendered LATER (typically the next training view, drawn one
-    iteration ahead) on a side stream, so that it overlaps the latency-bound loss / backward / optimizer tail of the
+                      want_pairs: bool = True, stream=None, bin_ahead: bool = True) -> PrefetchedGeometry:
+    """Starts phase A of render() -- and, once an instance-count high-water mark exists, the binning -- for a view that
+    will be rendered LATER (typically the next training view, drawn one iteration ahead) on a side stream, so that it overlaps the latency-bound loss / backward / optimizer tail of the
     current iteration and the host never waits for the instance count in the middle of the next forward.  Valid
     whenever nothing phase A reads changes in between: positions, scales, rotations, opacities, SH -- i.e. in the
     semantic-feature training loop (train_semantic.py optimises `_seg_feature` only), NOT in RGB training.  Pass the
@@ -293,8 +294,11 @@ def prefetch_geometry(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scalin
                                                                       override_color, want_pairs)
         side.wait_stream(main)
         with torch.cuda.stream(side):
+            # the binning reads no features either: queue it behind phase A, into a workspace sized from the largest
+            # instance count seen so far for this scene / image size (render() re-bins inline if that was too small)
+            cap = binning_capacity_hint(xyz.shape[0], settings.image_width, settings.image_height) if bin_ahead else 0
             st = _launch_phase_a(settings, xyz, opacity, geometry, appearance, viewpoint_camera, pc, bg_color,
-                                 scaling_modifier, want_pairs, pinned_counts=_next_pinned_counts(dev.index))
+                                 scaling_modifier, want_pairs, pinned_counts=_next_pinned_counts(dev.index), bin_capacity=cap)
             if st is not None:
                 st.ready_event = torch.cuda.Event()
                 st.ready_event.record(side)

@@ -166,4 +166,24 @@ def test_prefetched_geometry_render_is_bitwise_the_inline_render():
     g = run(cams[3], stale)                                                    # wrong view: handle ignored
     for a, b in zip(g[:4], want[3][:4]):
         assert torch.equal(a, b)
+    # The prefetch also queues the binning, into a workspace sized from the instance-count high-water mark of earlier
+    # views (the inline renders above set it).  A workspace that turns out too small must be detected and the binning
+    # repeated inline: force a capacity of 100 instances.
+    from instascene_b200 import renderer as isr_renderer
+    assert handles[0].state.binning is not None and handles[0].state.bin_capacity > 0
+    monkey = isr_renderer.binning_capacity_hint
+    isr_renderer.binning_capacity_hint = lambda P_, W_, H_: 100
+    try:
+        small = isr.prefetch_geometry(cams[2], pc, pipe, bg)
+        assert small.state.bin_capacity == 100
+        g = run(cams[2], small)
+    finally:
+        isr_renderer.binning_capacity_hint = monkey
+    for a, b in zip(g[:4], want[2][:4]):
+        assert torch.equal(a, b)
+    no_bin = isr.prefetch_geometry(cams[1], pc, pipe, bg, bin_ahead=False)    # phase A only
+    assert no_bin.state.binning is None
+    g = run(cams[1], no_bin)
+    for a, b in zip(g[:4], want[1][:4]):
+        assert torch.equal(a, b)
     torch.cuda.synchronize()
