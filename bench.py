@@ -208,6 +208,12 @@ class _Pipe:
     compute_cov3D_python, convert_SHs_python, depth_ratio = False, False, 1.0
 
 
+class _PipeDeferred(_Pipe):
+    # the chain rule of the two seg-feature normalisations is applied inside the Adam kernel (instascene_b200.FusedAdam /
+    # dist.ShardedAdam) instead of a separate rownorm-backward pass
+    defer_seg_feature_grad = True
+
+
 def _make_pc(scene, dev):
     import torch
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -279,12 +285,17 @@ def run_ours(args):
         devdata[v] = {k: x.to(dev) for k, x in h.items()}
     torch.cuda.synchronize()
 
-    opt = None
+    opt = sharded = None
     sem_opt, class_feat, labels3d = None, None, None
+    # cfg3: the raw parameter reaches the loss only through the rasterizer's normalisation -> deferred chain rule;
+    # cfg5's 3D term also reads the parameter directly (ordinary gradient), kept on the plain path
+    pipe = _PipeDeferred if args.workload == "cfg3" else _Pipe
     if args.workload in ("cfg3", "cfg5"):
         from instascene_b200 import semantic_step as sstep
         sem_opt = sstep.SemanticOpt(sample_batchsize=wl["samples"])
         opt = isr.FusedAdam([pc._seg_feature], lr=0.025, eps=1e-15)  # scene/gaussian_model.py:217-249
+        if world > 1:  # reduce-scatter -> Adam on this rank's rows -> all-gather (moments sharded)
+            sharded = idist.ShardedAdam(pc._seg_feature, world, rank, lr=0.025, eps=1e-15, chunks=4)
     if args.workload == "cfg5":
         class_feat = t(synth.gram_schmidt_prototypes(wl["labels"], F, wl["seed"] + 7))   # gaussian_model.py:158-176
         labels3d = t(synth.morton_labels(scene.xyz, wl["labels"]))
@@ -310,10 +321,10 @@ def run_ours(args):
     def step(v, data, nxt=None):
         cam = _Cam(cams[v], data["wvt"], data["fpt"], data["center"])
         if args.workload in ("cfg3", "cfg5"):
-            pkg = isr.render(cam, pc, _Pipe, bg, prefetched=prefetched.pop(v, None))
+            pkg = isr.render(cam, pc, pipe, bg, prefetched=prefetched.pop(v, None))
             if use_prefetch and nxt is not None:
                 vn, dn = nxt
-                prefetched[vn] = isr.prefetch_geometry(_Cam(cams[vn], dn["wvt"], dn["fpt"], dn["center"]), pc, _Pipe, bg)
+                prefetched[vn] = isr.prefetch_geometry(_Cam(cams[vn], dn["wvt"], dn["fpt"], dn["center"]), pc, pipe, bg)
             segmaps = [data["labels"]] if class_feat is None else [data["labels"], data["labels2"]]
             loss = sstep.single_view_loss(pkg["seg_feature"], segmaps, class_feat, sem_opt, generator=gen,
                                           num_labels=wl["labels"])
@@ -322,16 +333,19 @@ def run_ours(args):
                                                         generator=gen)
             loss.backward()
             if world > 1:
-                # gradient all-reduce + Adam on a side stream; the next render() launches its geometry phase first and
-                # waits for this event only before it reads the features (renderer.py)
-                g = pc._seg_feature.grad
+                # gradient reduce-scatter + sharded Adam + parameter all-gather on a side stream; the next render() launches
+                # (or has prefetched) its geometry phase and binning first and waits for this event only before it reads
+                # the features (renderer.py)
+                seg = pc._seg_feature
+                deferred = isr.optim.deferred_grad(seg)
+                g, cfg = deferred if deferred is not None else (seg.grad, None)
                 comm.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(comm):
-                    idist.allreduce_grads([g], world)
-                    opt.step()
+                    sharded.step(g, cfg)
                     ev = torch.cuda.Event()
                     ev.record(comm)
-                pc._seg_feature.grad = None
+                seg.grad = None
+                seg._isr_deferred_dy = None
                 pc._isr_param_ready_event = ev
                 # keep the gradient buffer alive until the main stream has waited for `ev` (next render) instead of
                 # record_stream(): its deferred frees made the caching allocator grow for dozens of steps
@@ -458,7 +472,7 @@ def run_ours(args):
                        "views_per_step_per_gpu": 1, "views": f"{len(cams)} synthetic COLMAP views (cameras.bin/images.bin round trip)",
                        "preheat_steps_untimed": preheat,
                        "geometry_prefetch": "next view's projection + depth sort overlap the current step's loss/backward/Adam "
-                                            "(isr.prefetch_geometry)" if use_prefetch else "off", "parallelism": f"dp{world} (views sharded, grad all-reduce)",
+                                            "(isr.prefetch_geometry)" if use_prefetch else "off", "parallelism": f"dp{world} (views sharded; gradient reduce-scatter, Adam on 1/N of the rows, parameter all-gather)" if world > 1 else "dp1",
                        "trainable": "_seg_feature only; geometry frozen, as GaussianModel.training_setup does for semantic "
                                     "training (scene/gaussian_model.py:226-232)" if opt is not None else "all geometry / appearance tensors",
                        "l2": "inputs larger than L2 (Gaussian state %.0f MB >> 126 MB), distinct view every step" % (P * (232 + 4 * F) / 1e6),

@@ -10,7 +10,7 @@ from .knn import distCUDA2  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .tracker import get_segmap_gaussians, segmap_gaussians  # noqa: F401
 from .losses import photometric_loss, l1_loss, ssim, add_densification_stats  # noqa: F401
-from . import io  # noqa: F401
+from . import io, optim  # noqa: F401
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "sample_pixels", "sample_labelled_pixels", "normalize_rows", "render",
            "depth_to_normal", "prefetch_geometry", "contrastive_loss", "distCUDA2", "FusedAdam", "get_segmap_gaussians", "segmap_gaussians",

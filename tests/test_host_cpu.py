@@ -280,6 +280,50 @@ def test_gloo_world2_gradient_allreduce(tmp_path):
     assert r.stdout.count("ok") == 2
 
 
+_GLOO_SHARDED_WORKER = """
+import os, sys, torch
+sys.path.insert(0, %r)
+from instascene_b200 import dist as idist
+rank, local_rank, world = idist.init("gloo")
+assert world == 2
+torch.manual_seed(0)
+P, F = 960, 8
+
+def adam_update(p, g, m, v, step, cfg, lr=0.025, b1=0.9, b2=0.999, eps=1e-15):
+    assert cfg is None
+    m.mul_(b1).add_(g, alpha=1 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    p.sub_(lr / (1 - b1 ** step) * m / (v.sqrt() / (1 - b2 ** step) ** 0.5 + eps))
+
+p0 = torch.randn(P, F)
+param = p0.clone()
+opt = idist.ShardedAdam(param, world, rank, lr=0.025, eps=1e-15, chunks=4, update_fn=adam_update)
+assert opt.exp_avg.numel() * world == P * F          # moments are sharded
+ref = p0.clone().requires_grad_(True)
+ref_opt = torch.optim.Adam([ref], lr=0.025, eps=1e-15)
+for it in range(3):
+    grads = [torch.randn(P, F) for _ in range(world)]   # gradient of each rank's view (same list on both ranks)
+    opt.step(grads[rank].clone())
+    ref.grad = sum(grads)
+    ref_opt.step()
+    assert torch.allclose(param, ref.detach(), atol=1e-6), (it, (param - ref.detach()).abs().max())
+print("rank", rank, "ok")
+"""
+
+
+def test_gloo_world2_sharded_adam_equals_full_adam_on_summed_gradients(tmp_path):
+    """reduce-scatter -> Adam on the rank's rows -> all-gather (instascene_b200.dist.ShardedAdam, world_size 2 over gloo)
+    equals torch.optim.Adam on the sum of the ranks' gradients, for several steps, with the moments sharded."""
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_SHARDED_WORKER % ROOT)
+    port = 31500 + (os.getpid() % 2000)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
+
+
 def test_cfg1_plumbing_config_on_the_cpu_port(oracle):
     """BASELINE.json configs[0]: 50k random Gaussians, one 512x512 camera, RGB-only forward on the CPU restatement
     (the reference has no CPU path; this is the plumbing config that needs no GPU).  Size-independent properties."""
