@@ -12,16 +12,16 @@
 //   2. exclusive scan of the emitted-tile counts in that depth order -> instance offsets, R_emit
 //   3. STABLE COUNTING PARTITION of the instances by tile, fused with their emission -- no (key, value) arrays, no
 //      sort passes over the instances, nothing sized by R on the host:
-//        a. bin_count_kernel: the depth order is cut into `chunks` runs of ~R/chunks instances; one warp per run
+//        a. bin_count_kernel: the depth order is cut into `chunks` runs of ~R/chunks instances; one CTA per run
 //           enumerates its instances and counts them per tile in shared memory (one 32-bit counter per tile) -> a
 //           [chunks][tiles] table
 //        b. bin_colscan_kernel / bin_tilebase_kernel: exclusive scan down every tile column and across the tile
 //           totals: table[c][t] becomes the rank of chunk c's first instance in tile t, the totals become the tile
 //           ranges (identifyTileRanges for free)
-//        c. bin_scatter_kernel: the same warp re-enumerates its run in depth order and writes every list entry
-//           (Gaussian id + the 8 per-block footprint bits) straight to its final position: shared-memory cursor of
-//           the tile + rank among the lanes of the same round that hit the same tile (__match_any_sync, lane order
-//           = depth order)
+//        c. bin_scatter_kernel: one CTA per run re-enumerates it in depth order, 128 instances per round, and writes
+//           every list entry (Gaussian id + the 8 per-block footprint bits) straight to its final position: start of
+//           (run, tile) + shared-memory cursor of the tile + instances of the same round in earlier warps (8-bit
+//           per-warp fields of one shared-memory word per tile) + rank among the lanes of the warp
 //      Instances of a tile end up ordered by (depth bits, Gaussian id): each tile list is exactly the reference's list
 //      (ties: SURVEY.md Q2) minus entries that contribute to none of the tile's pixels -- skipping those never
 //      changes a result.  The kernels read R from device memory, so phase B has no host-side dependence on it beyond
@@ -41,7 +41,9 @@ bool entries_packed(int P) {
     return !plain && P < (1 << kIdBits);
 }
 
-BinChunks bin_chunks(int num_tiles) {
+size_t scatter_smem_bytes(int num_tiles);
+
+BinChunks bin_chunks(int num_tiles, int64_t R) {
     static const int sm_count = [] {
         int dev = 0, n = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
@@ -50,14 +52,21 @@ BinChunks bin_chunks(int num_tiles) {
     }();
     static const bool force_sort = [] { const char* e = getenv("ISR_BIN_SORT"); return e && e[0] == '1'; }();  // test hook
     BinChunks bc;
-    bc.smem_bytes = align_up((size_t)(num_tiles > 0 ? num_tiles : 1) * 4, 16);
-    // per SM: 227 KB opt-in; a chunk = one CTA of 8 warps: the tile table + 8 per-warp segment buffers (bin_scatter_kernel)
-    // + 1 KB of system reservation per resident CTA
-    bc.smem_bytes += 8 * 512 * 8;
+    const int nt = num_tiles > 0 ? num_tiles : 1;
+    bc.smem_count = align_up((size_t)nt * 4, 16);
+    bc.smem_scatter = scatter_smem_bytes(nt);
+    // per SM: 227 KB opt-in, 1 KB of system reservation per resident CTA; one chunk = one CTA of bin_scatter_kernel
     const size_t budget = 226 * 1024;
-    int per_sm = (int)(budget / (bc.smem_bytes + 1024));
+    int per_sm = (int)(budget / (bc.smem_scatter + 1024 + 1280 /* static */));
     if (per_sm > 4) per_sm = 4;
     bc.chunks = (force_sort || per_sm < 1 || num_tiles > 65535) ? 0 : sm_count * per_sm;
+    // the 16-bit per-tile cursors of bin_scatter_kernel count at most one instance per Gaussian of the chunk: a chunk
+    // must start fewer than 65536 instances
+    if (bc.chunks > 0 && R > (int64_t)bc.chunks * 60000) {
+        const int64_t mult = (R + (int64_t)bc.chunks * 60000 - 1) / ((int64_t)bc.chunks * 60000);
+        if (mult > 64) bc.chunks = 0;
+        else bc.chunks *= (int)mult;
+    }
     return bc;
 }
 
@@ -99,9 +108,9 @@ __global__ void iota_kernel(int n, uint32_t* __restrict__ out) {
 // of chasing order[i] -> per-Gaussian arrays): id, emitted tile count (bit 31: footprint of more than 64 tiles = every
 // tile of the rectangle), getRect origin, rectangle width, and the K1 footprint mask.
 __global__ void gather_tiles_kernel(int P, const uint32_t* __restrict__ tcount, const uint32_t* __restrict__ order,
-                                    const uint32_t* __restrict__ tiles_touched, const int* __restrict__ radii,
-                                    const Splat* __restrict__ splats, const unsigned long long* __restrict__ tile_mask,
-                                    int gx, int gy, uint32_t* __restrict__ gathered, uint4* __restrict__ bin_rec,
+                                    const uint32_t* __restrict__ tiles_touched, const uint2* __restrict__ tile_rect,
+                                    const unsigned long long* __restrict__ tile_mask,
+                                    uint32_t* __restrict__ gathered, uint4* __restrict__ bin_rec,
                                     unsigned long long* __restrict__ bin_mask,
                                     unsigned long long* __restrict__ totals /*[0] sum tiles_touched, [1] sum tcount*/) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -115,11 +124,9 @@ __global__ void gather_tiles_kernel(int P, const uint32_t* __restrict__ tcount, 
         uint4 rec = make_uint4(g, 0u, 0u, 1u);
         unsigned long long mask = 0ull;
         if (c > 0) {
-            int mnx, mny, mxx, mxy;
-            get_rect(splats[g].mx, splats[g].my, radii[g], gx, gy, mnx, mny, mxx, mxy);
-            const uint32_t big = (mxx - mnx) * (mxy - mny) > 64 ? 0x80000000u : 0u;
-            rec = make_uint4(g, c | big, (uint32_t)mnx | ((uint32_t)mny << 16), (uint32_t)(mxx - mnx));
-            mask = tile_mask[g];
+            const uint2 r = __ldg(tile_rect + g);
+            rec = make_uint4(g, c | (c > 64u ? 0x80000000u : 0u), r.x, r.y);
+            mask = __ldg(tile_mask + g);
         }
         bin_rec[i] = rec;
         bin_mask[i] = mask;
@@ -324,10 +331,9 @@ int launch_depth_order_and_offsets(const IsrForwardArgs& a, cudaStream_t stream)
     // stable: equal depth bits keep ascending Gaussian id
     ISR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_alt, order_alt, order, P, 0, 32, stream));
     // keys_alt now holds sorted keys (unused afterwards) -> reuse it for the gathered tile counts
-    const int gx = (a.W + TILE - 1) / TILE, gy = (a.H + TILE - 1) / TILE;
     gather_tiles_kernel<<<(P + 1 + 255) / 256, 256, 0, stream>>>(
-        P, tcount, order, tiles, a.radii, reinterpret_cast<const Splat*>(g + gl.splat),
-        reinterpret_cast<const unsigned long long*>(g + gl.tmask), gx, gy, keys_alt, reinterpret_cast<uint4*>(g + gl.bin_rec),
+        P, tcount, order, tiles, reinterpret_cast<const uint2*>(g + gl.trect),
+        reinterpret_cast<const unsigned long long*>(g + gl.tmask), keys_alt, reinterpret_cast<uint4*>(g + gl.bin_rec),
         reinterpret_cast<unsigned long long*>(g + gl.bin_mask), totals); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     temp_bytes = gl.sort_temp_bytes;
@@ -391,8 +397,8 @@ __device__ __forceinline__ void chunk_range(const BinArgs& b, int c, int lane, i
     i1 = warp_lower_bound(b.offsets, b.P, (uint32_t)(hi < R ? hi : R), lane);
 }
 
-// One batch = 32 consecutive Gaussians of the depth order, lane l holding Gaussian l.  A chunk is processed by a CTA of
-// kBinWarps warps: "super-batch" s = batches [kBinWarps*s, kBinWarps*(s+1)), warp w takes batch kBinWarps*s + w.
+// One batch = 32 consecutive Gaussians of the depth order, lane l holding Gaussian l.  bin_count_kernel walks a chunk
+// with a CTA of kBinWarps warps, warp w taking batches w, w + kBinWarps, ... (counting needs no order).
 constexpr int kBinWarps = 8;
 
 struct BinBatch {
@@ -536,161 +542,206 @@ __global__ void __launch_bounds__(1024) bin_tilebase_kernel(int num_tiles, const
     }
 }
 
-// 3c: every list entry straight to its final position, in depth order.  One CTA (kBinWarps warps) per chunk with ONE
-// table of per-tile cursors in shared memory; batch k of the chunk belongs to warp k % kBinWarps.  Per batch a warp
-//   (parallel with the other warps) loads its 32 Gaussians' footprints (cull rectangle + conic) into registers,
-//     materialises the batch's instances in shared memory IN ORDER -- lane l writes (tile id, owner lane) of its own
-//     Gaussian's tiles at its exclusive-scan offset, no per-instance owner search -- and computes every instance's list
-//     entry (Gaussian id + the 8 per-block footprint bits; 32 instances per round, footprint by shuffle from the owner);
-//   (ordered) waits for its turn -- a named barrier per receiving warp on which the previous batch's warp arrives; no
-//     block-wide barrier, no spinning -- and commits: position = the tile's cursor + the rank among the lanes of the same round that hit the same tile
-//     (__match_any_sync; lane order = instance order), one 4-byte store per instance; then hands over and starts its
-//     next batch while the following warps commit.
-// Only ~15 instructions per 32 instances are serialised; everything else runs concurrently.
-// A batch whose small footprints hold more than kSegCap instances is cut into segments of consecutive lanes; footprints
-// of more than 64 tiles are walked arithmetically by the whole warp.  Both continue inside the warp's ordered turn (rare).
-constexpr int kSegCap = 512;                      // instances per segment (8 lanes x 64 tiles always fit)
-constexpr int kSegBytes = kSegCap * (4 + 2 + 2);  // entry u32 + tile u16 + owner u8 (padded to u16)
+// 3c: every list entry straight to its final position, in depth order.  One CTA of kScatWarps warps per chunk.
+// The chunk's instances are produced IN DEPTH ORDER, kScatThreads at a time ("round": thread i holds instance
+// jb + i), and every round is ranked by the whole CTA at once -- no warp ever waits for another warp's turn:
+//   position = start of (chunk, tile)                      base[t] + table[c][t]            (global, read-only)
+//            + instances of the tile in earlier rounds     cur[t]        u16 in shared memory
+//            + ... in earlier warps of this round          cnt[t]: one byte per warp in a 32-bit word; the first lane of
+//                                                          each group of equal tiles stores the group size into its
+//                                                          warp's byte (plain store, no atomics: shared-memory atomics
+//                                                          on scattered addresses cost 2 cycles per lane and made this
+//                                                          kernel LSU-bound), the lower bytes are summed with one dp4a
+//            + ... in earlier lanes of this warp           rank among equal tiles of __match_any_sync (lane order)
+// Two block barriers per round: byte stores -> [barrier] -> read word + cursor -> [barrier] -> every group leader
+// clears its own byte (no other warp writes it), the first group of each tile advances the cursor.
+// Instances are materialised per "super-batch" of kScatThreads Gaussians (thread i owns Gaussian i of the depth order):
+// each thread walks the set bits of its own footprint mask into a staging list at its block-scan offset, footprint data
+// (cull rectangle + conic) is staged per Gaussian in shared memory and fetched by owner index when the 8 per-block bits
+// of an entry are evaluated -- 1 instance per thread, all lanes busy.  The next super-batch's records (and the footprint
+// data they point at) are prefetched into registers.  A super-batch with more than kStageCap instances is cut into
+// segments of consecutive Gaussians; footprints of more than 64 tiles are walked arithmetically by the whole CTA.
+constexpr int kScatWarps = 4;
+constexpr int kScatThreads = 32 * kScatWarps;
+constexpr int kStageCap = 2048;  // instances per segment (32 Gaussians x 64 tiles always fit)
+constexpr int kFpStride = 20;    // words per staged Gaussian: 80 B keeps float4 alignment and spreads 8 owners over all banks
 
-__global__ void __launch_bounds__(32 * kBinWarps, 3)
+size_t scatter_smem_bytes(int num_tiles) {
+    return align_up((size_t)num_tiles * 4, 16) + align_up((size_t)num_tiles * 2, 16) + (size_t)kStageCap * 4 +
+           (size_t)kScatThreads * kFpStride * 4;
+}
+
+__global__ void __launch_bounds__(kScatThreads)
 bin_scatter_kernel(const BinArgs b, const uint32_t* __restrict__ table, const uint32_t* __restrict__ base, int64_t capacity,
                    uint32_t* __restrict__ point_list) {
     extern __shared__ __align__(16) unsigned char bin_smem[];
-    uint32_t* cursor = reinterpret_cast<uint32_t*>(bin_smem);  // [num_tiles]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.x;
-    unsigned char* seg = bin_smem + align_up((size_t)b.num_tiles * 4, 16) + (size_t)warp * kSegBytes;
-    uint32_t* seg_entry = reinterpret_cast<uint32_t*>(seg);                          // [kSegCap]
-    uint16_t* seg_tile = reinterpret_cast<uint16_t*>(seg + kSegCap * 4);             // [kSegCap]
-    uint16_t* seg_owner = reinterpret_cast<uint16_t*>(seg + kSegCap * 6);            // [kSegCap]
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(bin_smem);                                                // [num_tiles]
+    uint16_t* cur = reinterpret_cast<uint16_t*>(bin_smem + align_up((size_t)b.num_tiles * 4, 16));         // [num_tiles]
+    uint32_t* stage = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(cur) + align_up((size_t)b.num_tiles * 2, 16));
+    float* fp = reinterpret_cast<float*>(stage + kStageCap);                                              // [threads][kFpStride]
+    __shared__ uint32_t s_cincl[kScatThreads];
+    __shared__ uint32_t s_warp_tot[kScatWarps];
+    __shared__ uint32_t s_bigmask[kScatWarps];
+    __shared__ int s_end;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x;
     const uint32_t* row = table + (size_t)c * b.num_tiles;
-    for (int t = threadIdx.x; t < b.num_tiles; t += blockDim.x) cursor[t] = base[t] + row[t];
-    __syncthreads();
+    for (int t = tid; t < b.num_tiles; t += kScatThreads) { cnt[t] = 0u; cur[t] = 0; }
     int i0, i1;
     chunk_range(b, c, lane, i0, i1);
+    __syncthreads();
     const unsigned below = (1u << lane) - 1u;
+    const uint32_t fshift = 8u * (uint32_t)warp, flower = (1u << fshift) - 1u;
     const float inv_gx = 1.0f / (float)b.gx;
 
-    // ordered: 32 instances (has, tile, entry) of this warp's turn -> final positions
-    auto commit_round = [&](bool has, uint32_t tile, uint32_t entry) {
+    // one round: kScatThreads instances in depth order (thread order) -> final positions.  Called by every thread.
+    uint8_t* cnt8 = reinterpret_cast<uint8_t*>(cnt) + warp;  // this warp's byte of every tile's word
+    auto rank_round = [&](bool has, uint32_t tile, uint32_t entry) {
         const unsigned peers = __match_any_sync(0xffffffffu, has ? tile : (0x80000000u | (uint32_t)lane));
-        const int rank = __popc(peers & below);
-        const uint32_t pos = has ? cursor[tile] + (uint32_t)rank : 0u;
-        __syncwarp();
-        if (has && rank == 0) cursor[tile] += (uint32_t)__popc(peers);
-        __syncwarp();
+        const uint32_t rk = (uint32_t)__popc(peers & below);
+        const bool wlead = has && rk == 0u;  // first instance of its tile in this warp
+        uint32_t start = 0u;
+        if (has) start = __ldg(base + tile) + __ldg(row + tile);
+        if (wlead) cnt8[tile * 4u] = (uint8_t)__popc(peers);
+        __syncthreads();
+        const uint32_t v = has ? cnt[tile] : 0u;
+        const uint32_t c16 = has ? (uint32_t)cur[tile] : 0u;
+        const uint32_t before = __dp4a(v & flower, 0x01010101u, 0u);  // instances of the tile in earlier warps
+        const uint32_t pos = start + c16 + before + rk;
+        __syncthreads();
+        if (wlead) {
+            cnt8[tile * 4u] = 0;  // only this warp ever writes this byte
+            if (before == 0u) cur[tile] = (uint16_t)(c16 + __dp4a(v, 0x01010101u, 0u));
+        }
         if (has && (int64_t)pos < capacity) point_list[pos] = entry;
     };
-
-    const int n_batches = (i1 - i0 + 31) / 32;
-    for (int k = warp; k < n_batches; k += kBinWarps) {
-        const BinBatch bb = load_batch(b, i0 + k * 32, i1, lane);
-        // this lane's Gaussian: footprint data for the entries (independent loads, consumed after the build loop)
-        float4 cr = make_float4(0.f, 0.f, 0.f, 0.f), q0 = cr, q1 = cr;
-        float r2 = 0.0f;
-        if (b.packed && bb.cnt) {
-            cr = __ldg(b.cull4 + bb.g);
-            const float4* q = b.cullq + (size_t)bb.g * 3;
-            q0 = __ldg(q); q1 = __ldg(q + 1); r2 = __ldg(q + 2).x;
+    auto entry_of = [&](int owner, uint32_t tile) -> uint32_t {
+        const float* f = fp + owner * kFpStride;
+        const float4 cr = *reinterpret_cast<const float4*>(f), q0 = *reinterpret_cast<const float4*>(f + 4),
+                     q1 = *reinterpret_cast<const float4*>(f + 8);
+        const int tile_y = __float2int_rd(((float)tile + 0.5f) * inv_gx), tile_x = (int)tile - tile_y * b.gx;
+        return make_entry(__float_as_uint(f[13]), tile_x, tile_y, b.packed, cr, q0, q1, f[12]);
+    };
+    struct Pre {
+        uint4 rec;
+        unsigned long long mask;
+        float4 cr, q0, q1;
+        float r2;
+    };
+    auto load_rec = [&](int ib, Pre& p) {
+        p.rec = make_uint4(0u, 0u, 0u, 1u);
+        p.mask = 0ull;
+        if (ib + tid < i1) { p.rec = __ldg(b.rec + ib + tid); p.mask = __ldg(b.mask + ib + tid); }
+    };
+    auto load_fp = [&](Pre& p) {
+        p.cr = p.q0 = p.q1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        p.r2 = 0.0f;
+        if (b.packed && (p.rec.y & 0x7fffffffu)) {
+            p.cr = __ldg(b.cull4 + p.rec.x);
+            const float4* q = b.cullq + (size_t)p.rec.x * 3;
+            p.q0 = __ldg(q); p.q1 = __ldg(q + 1); p.r2 = __ldg(q + 2).x;
         }
-        // entry of (owner lane's Gaussian, tile): the owner's footprint arrives by shuffle (all lanes call together)
-        auto entry_of = [&](int owner, uint32_t tile) -> uint32_t {
-            const uint32_t g = __shfl_sync(0xffffffffu, bb.g, owner);
-            float4 c4, a0, a1;
-            c4.x = __shfl_sync(0xffffffffu, cr.x, owner); c4.y = __shfl_sync(0xffffffffu, cr.y, owner);
-            c4.z = __shfl_sync(0xffffffffu, cr.z, owner); c4.w = __shfl_sync(0xffffffffu, cr.w, owner);
-            a0.x = __shfl_sync(0xffffffffu, q0.x, owner); a0.y = __shfl_sync(0xffffffffu, q0.y, owner);
-            a0.z = __shfl_sync(0xffffffffu, q0.z, owner); a0.w = __shfl_sync(0xffffffffu, q0.w, owner);
-            a1.x = __shfl_sync(0xffffffffu, q1.x, owner); a1.y = __shfl_sync(0xffffffffu, q1.y, owner);
-            a1.z = __shfl_sync(0xffffffffu, q1.z, owner); a1.w = __shfl_sync(0xffffffffu, q1.w, owner);
-            const float rr = __shfl_sync(0xffffffffu, r2, owner);
-            const int tile_y = __float2int_rd(((float)tile + 0.5f) * inv_gx), tile_x = (int)tile - tile_y * b.gx;
-            return make_entry(g, tile_x, tile_y, b.packed, c4, a0, a1, rr);
-        };
-        // inclusive scan of the small-footprint counts: offsets of every lane's instances within the batch
-        const uint32_t small_cnt = bb.big ? 0u : bb.cnt;
+    };
+
+    const int n_sb = (i1 - i0 + kScatThreads - 1) / kScatThreads;
+    Pre nxt, nxt2;
+    load_rec(i0, nxt);
+    load_fp(nxt);
+    load_rec(i0 + kScatThreads, nxt2);
+    for (int sb = 0; sb < n_sb; sb++) {
+        const Pre me = nxt;
+        nxt = nxt2;
+        load_fp(nxt);                                     // consumed by the next super-batch
+        load_rec(i0 + (sb + 2) * kScatThreads, nxt2);     // consumed two super-batches ahead
+        const uint32_t cnt_g = me.rec.y & 0x7fffffffu;
+        const bool big = cnt_g && (me.rec.y >> 31);
+        const uint32_t small_cnt = big ? 0u : cnt_g;
+        const int mnx = (int)(me.rec.z & 0xffffu), mny = (int)(me.rec.z >> 16), w = (int)me.rec.w;
+        {   // staged footprint record of this thread's Gaussian (read by owner index in entry_of)
+            float* f = fp + tid * kFpStride;
+            *reinterpret_cast<float4*>(f) = me.cr;
+            *reinterpret_cast<float4*>(f + 4) = me.q0;
+            *reinterpret_cast<float4*>(f + 8) = me.q1;
+            f[12] = me.r2;
+            f[13] = __uint_as_float(me.rec.x);
+            f[14] = __uint_as_float(cnt_g);
+            f[15] = __uint_as_float(me.rec.z);
+            f[16] = __uint_as_float(me.rec.w);
+        }
+        // block-wide inclusive scan of the small-footprint counts
         uint32_t c_incl = small_cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, c_incl, d);
-            if (lane >= d) c_incl += v;
+            const uint32_t u = __shfl_up_sync(0xffffffffu, c_incl, d);
+            if (lane >= d) c_incl += u;
         }
+        const unsigned bigs_w = __ballot_sync(0xffffffffu, big);
+        if (lane == 31) s_warp_tot[warp] = c_incl;
+        if (lane == 0) s_bigmask[warp] = bigs_w;
+        __syncthreads();
+        bool any_big = false;
+#pragma unroll
+        for (int u = 0; u < kScatWarps; u++) {
+            if (u < warp) c_incl += s_warp_tot[u];
+            any_big |= s_bigmask[u] != 0u;
+        }
+        s_cincl[tid] = c_incl;
+        __syncthreads();
         const uint32_t c_excl = c_incl - small_cnt;
-        const unsigned bigs = __ballot_sync(0xffffffffu, bb.big != 0u);
+        const uint32_t sb_total = s_cincl[kScatThreads - 1];
+        const bool simple = !any_big && sb_total <= (uint32_t)kStageCap;
 
-        // Segment [cur, end): consecutive lanes up to the next big footprint whose small instances fit the buffer.
-        // Materialises the segment and computes its entries; returns end, n = instances.
-        auto next_segment = [&](int cur, uint32_t& n) -> int {
-            const uint32_t seg_base = __shfl_sync(0xffffffffu, c_excl, cur < 32 ? cur : 31);
-            const unsigned rest = bigs & ~((1u << cur) - 1u);
-            int end = rest ? __ffs(rest) - 1 : 32;
-            const unsigned over = __ballot_sync(0xffffffffu, lane >= cur && (c_incl - seg_base) > (uint32_t)kSegCap);
-            if (over) end = min(end, __ffs(over) - 1);
-            const uint32_t seg_end = end > 0 ? __shfl_sync(0xffffffffu, c_incl, end - 1) : 0u;
-            n = end > cur ? seg_end - seg_base : 0u;
+        int cur_g = 0;
+        while (cur_g < kScatThreads) {  // block-uniform
+            const uint32_t seg_base = cur_g ? s_cincl[cur_g - 1] : 0u;
+            int end = kScatThreads;
+            if (!simple) {
+                // first Gaussian >= cur_g that is big or would overflow the staging list
+                if (tid == 0) s_end = kScatThreads;
+                __syncthreads();
+                if (tid >= cur_g && (big || c_incl - seg_base > (uint32_t)kStageCap)) atomicMin(&s_end, tid);
+                __syncthreads();
+                end = s_end;
+            }
+            const uint32_t n = end > cur_g ? s_cincl[end - 1] - seg_base : 0u;
             if (n) {
-                if (lane >= cur && lane < end && small_cnt) {
-                    const float inv_w = 1.0f / (float)bb.w;
+                if (tid >= cur_g && tid < end && small_cnt) {
+                    const float inv_w = 1.0f / (float)w;
                     uint32_t o = c_excl - seg_base;
-                    unsigned long long m = bb.mask;
+                    unsigned long long m = me.mask;
                     while (m) {
                         const int t = __ffsll((long long)m) - 1;
                         m &= m - 1;
-                        seg_tile[o] = (uint16_t)rect_tile(t, inv_w, (int)bb.w, bb.mnx, bb.mny, b.gx);
-                        seg_owner[o++] = (uint16_t)lane;
+                        stage[o++] = rect_tile(t, inv_w, w, mnx, mny, b.gx) | ((uint32_t)tid << 16);
                     }
                 }
-                __syncwarp();
-                for (uint32_t jb = 0; jb < n; jb += 32) {
-                    const uint32_t j = jb + lane;
+                __syncthreads();
+                for (uint32_t jb = 0; jb < n; jb += kScatThreads) {
+                    const uint32_t j = jb + (uint32_t)tid;
                     const bool has = j < n;
-                    const uint32_t e = entry_of(has ? (int)seg_owner[j] : 0, has ? (uint32_t)seg_tile[j] : 0u);
-                    if (has) seg_entry[j] = e;
+                    const uint32_t s = has ? stage[j] : 0u;
+                    const uint32_t tile = s & 0xffffu;
+                    rank_round(has, tile, has ? entry_of((int)(s >> 16), tile) : 0u);
                 }
-                __syncwarp();
             }
-            return end;
-        };
-        auto commit_segment = [&](uint32_t n) {
-            for (uint32_t jb = 0; jb < n; jb += 32) {
-                const uint32_t j = jb + lane;
-                const bool has = j < n;
-                commit_round(has, has ? (uint32_t)seg_tile[j] : 0u, has ? seg_entry[j] : 0u);
-            }
-        };
-
-        // ---- parallel part: the first segment of this warp's batch
-        uint32_t n_first = 0;
-        int cur = next_segment(0, n_first);
-        // ---- ordered part: wait for ticket k
-        // Hand-over through NAMED BARRIERS, one per receiving warp (ids 1..kBinWarps, 64 threads each): the warp that
-        // committed batch k-1 arrives on the barrier of batch k's warp, which waits on it in hardware.  (A spin on a
-        // shared-memory ticket made the 7 waiting warps of every CTA flood the LSU: 10x slower, measured.)
-        if (k > 0) asm volatile("bar.sync %0, 64;" :: "r"(1 + k % kBinWarps) : "memory");
-        commit_segment(n_first);
-        while (cur < 32) {
-            if ((bigs >> cur) & 1u) {  // a footprint of more than 64 tiles: every tile of its rectangle, row-major
-                const int n = (int)__shfl_sync(0xffffffffu, bb.cnt, cur), w = (int)__shfl_sync(0xffffffffu, bb.w, cur);
-                const int mnx = __shfl_sync(0xffffffffu, bb.mnx, cur), mny = __shfl_sync(0xffffffffu, bb.mny, cur);
-                const float iw = 1.0f / (float)w;
-                for (int tb = 0; tb < n; tb += 32) {
-                    const int t = tb + lane;
-                    const bool has = t < n;
-                    const uint32_t tile = has ? rect_tile(t, iw, w, mnx, mny, b.gx) : 0u;
-                    const uint32_t e = entry_of(cur, tile);
-                    commit_round(has, tile, e);
+            if (end < kScatThreads && ((s_bigmask[end >> 5] >> (end & 31)) & 1u)) {
+                // a footprint of more than 64 tiles: every tile of its rectangle, row-major, by the whole CTA
+                const float* f = fp + end * kFpStride;
+                const int nb = (int)__float_as_uint(f[14]), bw = (int)__float_as_uint(f[16]);
+                const uint32_t org = __float_as_uint(f[15]);
+                const int bx = (int)(org & 0xffffu), by = (int)(org >> 16);
+                const float iw = 1.0f / (float)bw;
+                for (int tb = 0; tb < nb; tb += kScatThreads) {
+                    const int t = tb + tid;
+                    const bool has = t < nb;
+                    const uint32_t tile = has ? rect_tile(t, iw, bw, bx, by, b.gx) : 0u;
+                    rank_round(has, tile, has ? entry_of(end, tile) : 0u);
                 }
-                cur++;
+                cur_g = end + 1;
             } else {
-                uint32_t n = 0;
-                cur = next_segment(cur, n);
-                commit_segment(n);
+                cur_g = end;
             }
         }
-        __syncwarp();
-        if (k + 1 < n_batches) {
-            __threadfence_block();  // the cursor updates above are visible to the next warp
-            asm volatile("bar.arrive %0, 64;" :: "r"(1 + (k + 1) % kBinWarps) : "memory");
-        }
+        __syncthreads();  // fp / stage / s_cincl are rewritten by the next super-batch
     }
 }
 
@@ -713,7 +764,7 @@ int launch_binning(const IsrForwardArgs& a, int64_t R, cudaStream_t stream) {
     }
     uint32_t* point_list = reinterpret_cast<uint32_t*>(b + bl.point_list);
     const int packed = entries_packed(P) ? 1 : 0;
-    const BinChunks bc = bin_chunks(num_tiles);
+    const BinChunks bc = bin_chunks(num_tiles, R);
     if (bc.chunks > 0) {
         BinArgs ba;
         ba.P = P; ba.gx = gx; ba.gy = gy; ba.W = a.W; ba.H = a.H; ba.num_tiles = num_tiles; ba.chunks = bc.chunks; ba.packed = packed;
@@ -726,15 +777,15 @@ int launch_binning(const IsrForwardArgs& a, int64_t R, cudaStream_t stream) {
         uint32_t* totals = reinterpret_cast<uint32_t*>(b + bl.totals);
         uint32_t* base = reinterpret_cast<uint32_t*>(b + bl.base);
         uint32_t* overflow = reinterpret_cast<uint32_t*>(g + gl.counters) + 5;
-        ISR_CUDA_TRY(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc.smem_bytes));
-        ISR_CUDA_TRY(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc.smem_bytes));
-        bin_count_kernel<<<bc.chunks, 32 * kBinWarps, bc.smem_bytes, stream>>>(ba, table); note_launch();
+        ISR_CUDA_TRY(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc.smem_count));
+        ISR_CUDA_TRY(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc.smem_scatter));
+        bin_count_kernel<<<bc.chunks, 32 * kBinWarps, bc.smem_count, stream>>>(ba, table); note_launch();
         ISR_CUDA_TRY(cudaGetLastError());
         bin_colscan_kernel<<<(num_tiles + 31) / 32, 256, 0, stream>>>(num_tiles, bc.chunks, table, totals); note_launch();
         ISR_CUDA_TRY(cudaGetLastError());
         bin_tilebase_kernel<<<1, 1024, 0, stream>>>(num_tiles, totals, base, ranges, R, overflow); note_launch();
         ISR_CUDA_TRY(cudaGetLastError());
-        bin_scatter_kernel<<<bc.chunks, 32 * kBinWarps, bc.smem_bytes, stream>>>(ba, table, base, R, point_list); note_launch();
+        bin_scatter_kernel<<<bc.chunks, kScatThreads, bc.smem_scatter, stream>>>(ba, table, base, R, point_list); note_launch();
         ISR_CUDA_TRY(cudaGetLastError());
         return ISR_OK;
     }

@@ -773,12 +773,72 @@ int launch_adam(size_t n, float* p, const float* g, float* m, float* v, float lr
     return ISR_OK;
 }
 
+// Same update for F % 4 == 0 with LPR lanes per row, one float4 per lane (LPR = 1, 2, 4, 8 for F <= 4, 8, 16, 32): every
+// load / store instruction of a warp covers whole 128-byte lines (one thread per row reads 16 of every 64..128 bytes per
+// instruction and keeps 5 F-float arrays in registers), the row sums are two shuffle-reduction steps.
+template <int LPR>
+__global__ void __launch_bounds__(256)
+adam_rownorm_vec_kernel(int P, int F, float4* __restrict__ x, const float4* __restrict__ dy, const float4* __restrict__ g_extra,
+                        float4* __restrict__ m, float4* __restrict__ v, float e1, float e2, int stages, float lr, float beta1,
+                        float beta2, float eps, float step_size_host, float isb2_host, const int* __restrict__ step_dev) {
+    const AdamCoef co = adam_coef(lr, beta1, beta2, step_size_host, isb2_host, step_dev);
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t row = t / LPR;
+    const int sub = (int)(t % LPR), f4 = F >> 2;
+    const bool on = row < (size_t)P && sub < f4;
+    const size_t idx = row * (size_t)f4 + sub;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 X = z4, D = z4, M = z4, V = z4, G = z4;
+    if (on) {
+        X = x[idx]; D = dy[idx]; M = m[idx]; V = v[idx];
+        if (g_extra != nullptr) G = g_extra[idx];
+    }
+    auto row_sum = [&](float a) {
+#pragma unroll
+        for (int o = LPR >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        return a;
+    };
+    auto dot4 = [](const float4 a, const float4 b) { return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x))); };
+    // d <- vjp of y = u / (|u| + e) at u, cotangent d  (rownorm_vjp)
+    auto vjp = [&](const float4 u, float4& d, float e) {
+        const float ss = row_sum(dot4(u, u)), ud = row_sum(dot4(u, d));
+        const float n = sqrtf(ss), ne = n + e;
+        const float a = 1.0f / ne;
+        const float b = n > 0.0f ? ud / (n * ne * ne) : 0.0f;
+        d.x = fmaf(-b, u.x, a * d.x); d.y = fmaf(-b, u.y, a * d.y); d.z = fmaf(-b, u.z, a * d.z); d.w = fmaf(-b, u.w, a * d.w);
+    };
+    if (stages > 1) {
+        const float inv = 1.0f / (sqrtf(row_sum(dot4(X, X))) + e1);
+        const float4 Y = make_float4(X.x * inv, X.y * inv, X.z * inv, X.w * inv);
+        vjp(Y, D, e2);
+    }
+    vjp(X, D, e1);
+    D.x += G.x; D.y += G.y; D.z += G.z; D.w += G.w;
+    auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+        mm = beta1 * mm + (1.0f - beta1) * gg;
+        vv = beta2 * vv + (1.0f - beta2) * gg * gg;
+        pp -= co.step_size * mm / (sqrtf(vv) * co.inv_sqrt_bias2 + eps);
+    };
+    upd(X.x, D.x, M.x, V.x); upd(X.y, D.y, M.y, V.y); upd(X.z, D.z, M.z, V.z); upd(X.w, D.w, M.w, V.w);
+    if (on) { x[idx] = X; m[idx] = M; v[idx] = V; }
+}
+
 template <int FP>
 static int adam_rownorm_launch(int P, int F, float* x, const float* dy, const float* g_extra, float* m, float* v, float e1,
                                float e2, int stages, float lr, float beta1, float beta2, float eps, int step,
                                const int* step_dev, cudaStream_t stream) {
     float step_size, isb2;
     adam_host_coef(lr, beta1, beta2, step, step_size, isb2);
+    if ((F & 3) == 0) {  // (16-byte alignment of the arrays is checked at the boundary)
+        constexpr int LPR = FP <= 4 ? 1 : (FP <= 8 ? 2 : (FP <= 16 ? 4 : 8));
+        const size_t threads = (size_t)P * LPR;
+        adam_rownorm_vec_kernel<LPR><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
+            P, F, reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(g_extra),
+            reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), e1, e2, stages, lr, beta1, beta2, eps, step_size, isb2,
+            step_dev); note_launch();
+        ISR_CUDA_TRY(cudaGetLastError());
+        return ISR_OK;
+    }
     adam_rownorm_kernel<FP><<<(P + 255) / 256, 256, 0, stream>>>(P, F, x, dy, g_extra, m, v, e1, e2, stages, lr, beta1, beta2,
                                                                  eps, step_size, isb2, step_dev); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());

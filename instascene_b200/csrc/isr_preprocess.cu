@@ -50,7 +50,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
                       float* __restrict__ depths,
                       uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ tiles_touched,
                       uint8_t* __restrict__ clamped, unsigned long long* __restrict__ tile_mask,
-                      uint32_t* __restrict__ tile_count) {
+                      uint32_t* __restrict__ tile_count, uint2* __restrict__ tile_rect) {
     // SH coefficients of the block's 256 Gaussians are one contiguous 48 KB range: stage them with fully coalesced
     // 16-byte cp.async copies into per-Gaussian slots padded to 13 x 16 B (conflict-free LDS), overlapped with the
     // projection math below.  (Per-thread strided loads of the 192-byte rows ran K1 at 48% of the HBM roofline.)
@@ -71,6 +71,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
     int radius_i = 0;
     uint32_t tiles = 0, dkey = 0xFFFFFFFFu, tcount = 0;
     unsigned long long tmask = 0ull;
+    uint2 trect = make_uint2(0u, 1u);
     uint8_t clamp_mask = 0;
     bool visible = false;
     float p0 = 0, p1 = 0, p2 = 0, pvz = 0, cx = 0, cy = 0;
@@ -304,11 +305,12 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
         // Tile footprint for the binning (isr_binning.cu): bit t of the mask = tile t (row-major) of the reference's
         // getRect rectangle may receive something from this Gaussian; the others are never emitted (skipping them
         // cannot change a result).  Rectangles of more than 64 tiles are emitted whole.
+        int mnx, mny, mxx, mxy;
+        get_rect(cx, cy, ri, gx, gy, mnx, mny, mxx, mxy);
+        const int w = mxx - mnx;
+        trect = make_uint2((uint32_t)mnx | ((uint32_t)mny << 16), (uint32_t)w);  // getRect origin, width (binning)
         if (ntiles <= 64) {
-            int mnx, mny, mxx, mxy;
-            get_rect(cx, cy, ri, gx, gy, mnx, mny, mxx, mxy);
             // only the tiles overlapping the cull rectangle can pass (a superset is harmless, hence the slack)
-            const int w = mxx - mnx;
             const int tx_lo = max(mnx, __float2int_ru((cr.x - 15.0f) * 0.0625f - 1e-3f));
             const int tx_hi = min(mxx - 1, __float2int_rd(cr.z * 0.0625f + 1e-3f));
             const int ty_lo = max(mny, __float2int_ru((cr.y - 15.0f) * 0.0625f - 1e-3f));
@@ -335,6 +337,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
     clamped[idx] = clamp_mask;
     tile_mask[idx] = tmask;
     tile_count[idx] = tcount;
+    tile_rect[idx] = trect;
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const Camera cam,
@@ -542,7 +545,8 @@ int launch_preprocess_fwd(const IsrForwardArgs& a, cudaStream_t stream) {
         reinterpret_cast<float4*>(g + gl.cullq), reinterpret_cast<float4*>(g + gl.rgb),
         reinterpret_cast<float*>(g + gl.depth), reinterpret_cast<uint32_t*>(g + gl.depth_key),
         reinterpret_cast<uint32_t*>(g + gl.tiles), reinterpret_cast<uint8_t*>(g + gl.clamped),
-        reinterpret_cast<unsigned long long*>(g + gl.tmask), reinterpret_cast<uint32_t*>(g + gl.tcount)); note_launch();
+        reinterpret_cast<unsigned long long*>(g + gl.tmask), reinterpret_cast<uint32_t*>(g + gl.tcount),
+        reinterpret_cast<uint2*>(g + gl.trect)); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }
