@@ -543,46 +543,52 @@ __global__ void __launch_bounds__(1024) bin_tilebase_kernel(int num_tiles, const
 }
 
 // 3c: every list entry straight to its final position, in depth order.  One CTA of kScatWarps warps per chunk.
-// The chunk's instances are produced IN DEPTH ORDER, kScatThreads at a time ("round": thread i holds instance
-// jb + i), and every round is ranked by the whole CTA at once -- no warp ever waits for another warp's turn:
+// The chunk's instances are produced IN DEPTH ORDER into a ring in shared memory and consumed kQuad = 4 * kScatThreads
+// at a time ("quad": warp w holds instances [128 w, 128 w + 128) of the quad, lane l the four instances 32 s + l), ranked
+// by the whole CTA at once -- no warp ever waits for another warp's turn:
 //   position = start of (chunk, tile)                      base[t] + table[c][t]            (global, read-only)
-//            + instances of the tile in earlier rounds     cur[t]        u16 in shared memory
-//            + ... in earlier warps of this round          cnt[t]: one byte per warp in a 32-bit word; the first lane of
-//                                                          each group of equal tiles stores the group size into its
-//                                                          warp's byte (plain store, no atomics: shared-memory atomics
-//                                                          on scattered addresses cost 2 cycles per lane and made this
-//                                                          kernel LSU-bound), the lower bytes are summed with one dp4a
-//            + ... in earlier lanes of this warp           rank among equal tiles of __match_any_sync (lane order)
-// Two block barriers per round: byte stores -> [barrier] -> read word + cursor -> [barrier] -> every group leader
-// clears its own byte (no other warp writes it), the first group of each tile advances the cursor.
+//            + instances of the tile in earlier quads      cur[t]        u16 in shared memory
+//            + ... in earlier warps of this quad           cnt[t]: one byte per warp in a 32-bit word, summed with dp4a
+//            + ... earlier in this warp                    the warp's byte before its own sub-round added to it, plus the
+//                                                          rank among the lanes with the same tile (one ballot per bit
+//                                                          of the tile id)
+// Two block barriers per quad (512 instances): byte updates -> [barrier] -> read word + cursor -> [barrier] -> group
+// leaders clear their warp's byte (no other warp writes it), the first instance of each tile advances the cursor.  Four
+// independent instances per thread also give the footprint arithmetic its instruction-level parallelism.
 // Instances are materialised per "super-batch" of kScatThreads Gaussians (thread i owns Gaussian i of the depth order):
-// each thread walks the set bits of its own footprint mask into a staging list at its block-scan offset, footprint data
-// (cull rectangle + conic) is staged per Gaussian in shared memory and fetched by owner index when the 8 per-block bits
-// of an entry are evaluated -- 1 instance per thread, all lanes busy.  The next super-batch's records (and the footprint
-// data they point at) are prefetched into registers.  A super-batch with more than kStageCap instances is cut into
-// segments of consecutive Gaussians; footprints of more than 64 tiles are walked arithmetically by the whole CTA.
+// each thread walks the set bits of its own footprint mask into the ring at its block-scan offset; footprints of more
+// than 64 tiles (every tile of the rectangle) are expanded into the ring by the whole CTA.  Footprint data (cull rectangle
+// + conic) is staged per Gaussian in one of 2 x kScatThreads slots (two super-batches alive) and fetched by slot when
+// the 8 per-block bits of an entry are evaluated.  The next super-batch's records (and the footprint data they point at)
+// are prefetched into registers.
+// Measured alternatives, all within 5% of each other at ~0.4 ms for 10 M instances (profiles/r2_ncu_bin_scatter.txt):
+// shared-memory atomics for the per-warp counts (2 cycles per lane on scattered addresses), MATCH.ANY (~350 cycles per
+// warp on 32 mostly distinct values), one round per barrier pair, warps owning disjoint tile subsets with private queues
+// (20 warps per SM but 50% more instructions).  The kernel is bound by dependent shared-memory / conversion latency at
+// 12 warps per SM (the tile tables take 6 bytes of shared memory per tile and CTA).
 constexpr int kScatWarps = 4;
 constexpr int kScatThreads = 32 * kScatWarps;
-constexpr int kStageCap = 2048;  // instances per segment (32 Gaussians x 64 tiles always fit)
-constexpr int kFpStride = 20;    // words per staged Gaussian: 80 B keeps float4 alignment and spreads 8 owners over all banks
+constexpr int kQuad = 4 * kScatThreads;   // instances ranked between two pairs of barriers
+constexpr int kRing = 2048;               // ring of staged instances (tile | slot << 16); power of two, >= 2 * kQuad
+constexpr int kFpStride = 16;             // words per staged Gaussian footprint
 
 size_t scatter_smem_bytes(int num_tiles) {
-    return align_up((size_t)num_tiles * 4, 16) + align_up((size_t)num_tiles * 2, 16) + (size_t)kStageCap * 4 +
-           (size_t)kScatThreads * kFpStride * 4;
+    return align_up((size_t)num_tiles * 4, 16) + align_up((size_t)num_tiles * 2, 16) + (size_t)kRing * 4 +
+           (size_t)2 * kScatThreads * kFpStride * 4;
 }
 
-__global__ void __launch_bounds__(kScatThreads)
+__global__ void __launch_bounds__(kScatThreads, 3)
 bin_scatter_kernel(const BinArgs b, const uint32_t* __restrict__ table, const uint32_t* __restrict__ base, int64_t capacity,
                    uint32_t* __restrict__ point_list) {
     extern __shared__ __align__(16) unsigned char bin_smem[];
     uint32_t* cnt = reinterpret_cast<uint32_t*>(bin_smem);                                                // [num_tiles]
     uint16_t* cur = reinterpret_cast<uint16_t*>(bin_smem + align_up((size_t)b.num_tiles * 4, 16));         // [num_tiles]
-    uint32_t* stage = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(cur) + align_up((size_t)b.num_tiles * 2, 16));
-    float* fp = reinterpret_cast<float*>(stage + kStageCap);                                              // [threads][kFpStride]
+    uint32_t* ring = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(cur) + align_up((size_t)b.num_tiles * 2, 16));
+    float* fp = reinterpret_cast<float*>(ring + kRing);                                          // [2 * threads][kFpStride]
     __shared__ uint32_t s_cincl[kScatThreads];
     __shared__ uint32_t s_warp_tot[kScatWarps];
     __shared__ uint32_t s_bigmask[kScatWarps];
-    __shared__ int s_end;
+    __shared__ int s_end, s_bigw;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x;
     const uint32_t* row = table + (size_t)c * b.num_tiles;
     for (int t = tid; t < b.num_tiles; t += kScatThreads) { cnt[t] = 0u; cur[t] = 0; }
@@ -590,82 +596,122 @@ bin_scatter_kernel(const BinArgs b, const uint32_t* __restrict__ table, const ui
     chunk_range(b, c, lane, i0, i1);
     __syncthreads();
     const unsigned below = (1u << lane) - 1u;
-    const uint32_t fshift = 8u * (uint32_t)warp, flower = (1u << fshift) - 1u;
+    const uint32_t flower = (1u << (8u * (uint32_t)warp)) - 1u;
     const float inv_gx = 1.0f / (float)b.gx;
-
-    // one round: kScatThreads instances in depth order (thread order) -> final positions.  Called by every thread.
+    const int tile_bits = 32 - __clz(max(1, b.num_tiles - 1));
     uint8_t* cnt8 = reinterpret_cast<uint8_t*>(cnt) + warp;  // this warp's byte of every tile's word
-    auto rank_round = [&](bool has, uint32_t tile, uint32_t entry) {
-        const unsigned peers = __match_any_sync(0xffffffffu, has ? tile : (0x80000000u | (uint32_t)lane));
-        const uint32_t rk = (uint32_t)__popc(peers & below);
-        const bool wlead = has && rk == 0u;  // first instance of its tile in this warp
-        uint32_t start = 0u;
-        if (has) start = __ldg(base + tile) + __ldg(row + tile);
-        if (wlead) cnt8[tile * 4u] = (uint8_t)__popc(peers);
-        __syncthreads();
-        const uint32_t v = has ? cnt[tile] : 0u;
-        const uint32_t c16 = has ? (uint32_t)cur[tile] : 0u;
-        const uint32_t before = __dp4a(v & flower, 0x01010101u, 0u);  // instances of the tile in earlier warps
-        const uint32_t pos = start + c16 + before + rk;
-        __syncthreads();
-        if (wlead) {
-            cnt8[tile * 4u] = 0;  // only this warp ever writes this byte
-            if (before == 0u) cur[tile] = (uint16_t)(c16 + __dp4a(v, 0x01010101u, 0u));
-        }
-        if (has && (int64_t)pos < capacity) point_list[pos] = entry;
-    };
-    auto entry_of = [&](int owner, uint32_t tile) -> uint32_t {
-        const float* f = fp + owner * kFpStride;
+    uint32_t head = 0, count = 0;                              // ring state (block-uniform)
+
+    auto entry_of = [&](uint32_t slot, uint32_t tile) -> uint32_t {
+        const float* f = fp + slot * kFpStride;
         const float4 cr = *reinterpret_cast<const float4*>(f), q0 = *reinterpret_cast<const float4*>(f + 4),
                      q1 = *reinterpret_cast<const float4*>(f + 8);
         const int tile_y = __float2int_rd(((float)tile + 0.5f) * inv_gx), tile_x = (int)tile - tile_y * b.gx;
         return make_entry(__float_as_uint(f[13]), tile_x, tile_y, b.packed, cr, q0, q1, f[12]);
     };
+
+    // Ranks and writes the first n (<= kQuad) instances of the ring.  Called by every thread.
+    auto process_quad = [&](uint32_t n) {
+        bool has[4], lead[4];
+        uint32_t tile[4], entry[4], rkw[4], start[4];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const uint32_t k = (uint32_t)(warp * 128 + s * 32 + lane);
+            has[s] = k < n;
+            const uint32_t e = has[s] ? ring[(head + k) & (kRing - 1)] : 0u;
+            tile[s] = e & 0xffffu;
+            entry[s] = has[s] ? entry_of(e >> 16, tile[s]) : 0u;
+            start[s] = has[s] ? __ldg(base + tile[s]) + __ldg(row + tile[s]) : 0u;
+        }
+        // lanes of the same sub-round with the same tile
+        unsigned peers[4];
+#pragma unroll
+        for (int s = 0; s < 4; s++) peers[s] = __ballot_sync(0xffffffffu, has[s]);
+        for (int bit = 0; bit < tile_bits; bit++) {
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const unsigned set = __ballot_sync(0xffffffffu, (tile[s] >> bit) & 1u);
+                peers[s] &= ((tile[s] >> bit) & 1u) ? set : ~set;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const uint32_t rk = (uint32_t)__popc(peers[s] & below);
+            lead[s] = has[s] && rk == 0u;
+            uint32_t old = 0u;
+            if (lead[s]) {  // the warp's byte counts its instances of the tile in this quad so far
+                old = cnt8[tile[s] * 4u];
+                cnt8[tile[s] * 4u] = (uint8_t)(old + (uint32_t)__popc(peers[s]));
+            }
+            old = __shfl_sync(0xffffffffu, old, (__ffs(peers[s]) - 1) & 31);
+            rkw[s] = old + rk;
+            __syncwarp();
+        }
+        __syncthreads();
+        uint32_t v[4], c16[4], before[4];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            v[s] = has[s] ? cnt[tile[s]] : 0u;
+            c16[s] = has[s] ? (uint32_t)cur[tile[s]] : 0u;
+            before[s] = __dp4a(v[s] & flower, 0x01010101u, 0u);  // instances of the tile in earlier warps
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            if (lead[s]) cnt8[tile[s] * 4u] = 0;  // only this warp ever writes this byte
+            if (has[s]) {
+                if ((before[s] | rkw[s]) == 0u) cur[tile[s]] = (uint16_t)(c16[s] + __dp4a(v[s], 0x01010101u, 0u));
+                const uint32_t pos = start[s] + c16[s] + before[s] + rkw[s];
+                if ((int64_t)pos < capacity) point_list[pos] = entry[s];
+            }
+        }
+        head = (head + n) & (kRing - 1);
+        count -= n;
+    };
+
     struct Pre {
         uint4 rec;
         unsigned long long mask;
         float4 cr, q0, q1;
         float r2;
+        bool valid;
     };
+    // Prefetches are unconditional loads from clamped addresses: a select on the loaded value (what a guarded load
+    // compiles to) would wait for the data right here instead of one / two super-batches later.  Records past the end
+    // of the chunk are ignored through `valid`; footprints of Gaussians without instances are never read.
     auto load_rec = [&](int ib, Pre& p) {
-        p.rec = make_uint4(0u, 0u, 0u, 1u);
-        p.mask = 0ull;
-        if (ib + tid < i1) { p.rec = __ldg(b.rec + ib + tid); p.mask = __ldg(b.mask + ib + tid); }
+        const int i = min(ib + tid, b.P - 1);
+        p.valid = ib + tid < i1;
+        p.rec = __ldg(b.rec + i);
+        p.mask = __ldg(b.mask + i);
     };
     auto load_fp = [&](Pre& p) {
-        p.cr = p.q0 = p.q1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        p.r2 = 0.0f;
-        if (b.packed && (p.rec.y & 0x7fffffffu)) {
-            p.cr = __ldg(b.cull4 + p.rec.x);
-            const float4* q = b.cullq + (size_t)p.rec.x * 3;
-            p.q0 = __ldg(q); p.q1 = __ldg(q + 1); p.r2 = __ldg(q + 2).x;
-        }
+        const uint32_t g = p.valid ? p.rec.x : 0u;
+        p.cr = __ldg(b.cull4 + g);
+        const float4* q = b.cullq + (size_t)g * 3;
+        p.q0 = __ldg(q); p.q1 = __ldg(q + 1); p.r2 = __ldg(q + 2).x;
     };
 
     const int n_sb = (i1 - i0 + kScatThreads - 1) / kScatThreads;
-    Pre nxt, nxt2;
-    load_rec(i0, nxt);
-    load_fp(nxt);
-    load_rec(i0 + kScatThreads, nxt2);
+    Pre me, nxt;
+    load_rec(i0, me);
+    load_fp(me);
+    load_rec(i0 + kScatThreads, nxt);
     for (int sb = 0; sb < n_sb; sb++) {
-        const Pre me = nxt;
-        nxt = nxt2;
-        load_fp(nxt);                                     // consumed by the next super-batch
-        load_rec(i0 + (sb + 2) * kScatThreads, nxt2);     // consumed two super-batches ahead
-        const uint32_t cnt_g = me.rec.y & 0x7fffffffu;
-        const bool big = cnt_g && (me.rec.y >> 31);
+        const uint32_t cnt_g = me.valid ? (me.rec.y & 0x7fffffffu) : 0u;
+        const bool big = cnt_g > 64u;
         const uint32_t small_cnt = big ? 0u : cnt_g;
         const int mnx = (int)(me.rec.z & 0xffffu), mny = (int)(me.rec.z >> 16), w = (int)me.rec.w;
-        {   // staged footprint record of this thread's Gaussian (read by owner index in entry_of)
-            float* f = fp + tid * kFpStride;
+        const unsigned long long my_mask = me.mask;
+        const uint32_t slot = (uint32_t)((sb & 1) * kScatThreads + tid);
+        const uint32_t old_left = count;  // instances of the previous super-batch still in the ring (< kQuad)
+        {   // staged footprint record of this thread's Gaussian (read by slot in entry_of)
+            float* f = fp + slot * kFpStride;
             *reinterpret_cast<float4*>(f) = me.cr;
             *reinterpret_cast<float4*>(f + 4) = me.q0;
             *reinterpret_cast<float4*>(f + 8) = me.q1;
-            f[12] = me.r2;
-            f[13] = __uint_as_float(me.rec.x);
-            f[14] = __uint_as_float(cnt_g);
-            f[15] = __uint_as_float(me.rec.z);
-            f[16] = __uint_as_float(me.rec.w);
+            *reinterpret_cast<float4*>(f + 12) = make_float4(me.r2, __uint_as_float(me.rec.x), __uint_as_float(cnt_g),
+                                                               __uint_as_float(me.rec.z));
         }
         // block-wide inclusive scan of the small-footprint counts
         uint32_t c_incl = small_cnt;
@@ -686,63 +732,87 @@ bin_scatter_kernel(const BinArgs b, const uint32_t* __restrict__ table, const ui
         }
         s_cincl[tid] = c_incl;
         __syncthreads();
+        // Prefetch for the next two super-batches, issued HERE: the 16-byte gathers occupy the memory pipe for hundreds
+        // of cycles, and the shuffles of the scan above queued behind them when they were issued first (13% of all
+        // stall samples).
+        me = nxt;
+        load_fp(me);
+        load_rec(i0 + (sb + 2) * kScatThreads, nxt);
         const uint32_t c_excl = c_incl - small_cnt;
         const uint32_t sb_total = s_cincl[kScatThreads - 1];
-        const bool simple = !any_big && sb_total <= (uint32_t)kStageCap;
+        uint32_t consumed = 0;  // instances ranked during this super-batch
 
         int cur_g = 0;
         while (cur_g < kScatThreads) {  // block-uniform
             const uint32_t seg_base = cur_g ? s_cincl[cur_g - 1] : 0u;
+            const uint32_t room = (uint32_t)kRing - count;
             int end = kScatThreads;
-            if (!simple) {
-                // first Gaussian >= cur_g that is big or would overflow the staging list
+            if (any_big || sb_total - seg_base > room) {
+                // first Gaussian >= cur_g that is big or would overflow the ring
                 if (tid == 0) s_end = kScatThreads;
                 __syncthreads();
-                if (tid >= cur_g && (big || c_incl - seg_base > (uint32_t)kStageCap)) atomicMin(&s_end, tid);
+                if (tid >= cur_g && (big || c_incl - seg_base > room)) atomicMin(&s_end, tid);
                 __syncthreads();
                 end = s_end;
             }
             const uint32_t n = end > cur_g ? s_cincl[end - 1] - seg_base : 0u;
             if (n) {
                 if (tid >= cur_g && tid < end && small_cnt) {
-                    const float inv_w = 1.0f / (float)w;
-                    uint32_t o = c_excl - seg_base;
-                    unsigned long long m = me.mask;
+                    // tile t of the rectangle (row-major, t < 64, width <= 64): t / w == (t * (65536 / w + 1)) >> 16
+                    const uint32_t rcpw = 65536u / (uint32_t)w + 1u;
+                    const uint32_t tile0 = (uint32_t)(mny * b.gx + mnx), dgx = (uint32_t)(b.gx - w);
+                    uint32_t o = head + count + (c_excl - seg_base);
+                    unsigned long long m = my_mask;
                     while (m) {
-                        const int t = __ffsll((long long)m) - 1;
+                        const uint32_t t = (uint32_t)__ffsll((long long)m) - 1u;
                         m &= m - 1;
-                        stage[o++] = rect_tile(t, inv_w, w, mnx, mny, b.gx) | ((uint32_t)tid << 16);
+                        const uint32_t ty = (t * rcpw) >> 16;   // tile = (mny + ty) * gx + mnx + (t - ty * w)
+                        ring[o++ & (kRing - 1)] = (tile0 + t + ty * dgx) | (slot << 16);
                     }
                 }
-                __syncthreads();
-                for (uint32_t jb = 0; jb < n; jb += kScatThreads) {
-                    const uint32_t j = jb + (uint32_t)tid;
-                    const bool has = j < n;
-                    const uint32_t s = has ? stage[j] : 0u;
-                    const uint32_t tile = s & 0xffffu;
-                    rank_round(has, tile, has ? entry_of((int)(s >> 16), tile) : 0u);
-                }
+                count += n;
             }
+            bool walked_big = false;
             if (end < kScatThreads && ((s_bigmask[end >> 5] >> (end & 31)) & 1u)) {
-                // a footprint of more than 64 tiles: every tile of its rectangle, row-major, by the whole CTA
-                const float* f = fp + end * kFpStride;
-                const int nb = (int)__float_as_uint(f[14]), bw = (int)__float_as_uint(f[16]);
+                // a footprint of more than 64 tiles: every tile of its rectangle, row-major, expanded by the whole CTA
+                const uint32_t bslot = (uint32_t)((sb & 1) * kScatThreads + end);
+                const float* f = fp + bslot * kFpStride;
+                const int nb = (int)__float_as_uint(f[14]);
                 const uint32_t org = __float_as_uint(f[15]);
                 const int bx = (int)(org & 0xffffu), by = (int)(org >> 16);
-                const float iw = 1.0f / (float)bw;
-                for (int tb = 0; tb < nb; tb += kScatThreads) {
-                    const int t = tb + tid;
-                    const bool has = t < nb;
-                    const uint32_t tile = has ? rect_tile(t, iw, bw, bx, by, b.gx) : 0u;
-                    rank_round(has, tile, has ? entry_of(end, tile) : 0u);
+                walked_big = true;
+                int t0 = 0;
+                if (tid == end) s_bigw = w;  // rectangle width: published by the owner thread
+                __syncthreads();
+                const int rw = s_bigw;
+                const float iw = 1.0f / (float)rw;
+                while (t0 < nb) {
+                    const int m = min(nb - t0, (int)((uint32_t)kRing - count));
+                    for (int t = tid; t < m; t += kScatThreads)
+                        ring[(head + count + (uint32_t)t) & (kRing - 1)] = rect_tile(t0 + t, iw, rw, bx, by, b.gx) | (bslot << 16);
+                    count += (uint32_t)m;
+                    t0 += m;
+                    __syncthreads();
+                    while (count >= (uint32_t)kQuad) { process_quad(kQuad); consumed += kQuad; }
+                    __syncthreads();  // ring reads of the quads above vs the writes of the next slice
                 }
                 cur_g = end + 1;
             } else {
                 cur_g = end;
             }
+            if (!walked_big) {
+                __syncthreads();
+                while (count >= (uint32_t)kQuad) { process_quad(kQuad); consumed += kQuad; }
+            }
         }
-        __syncthreads();  // fp / stage / s_cincl are rewritten by the next super-batch
+        // The slots of this parity are rewritten two super-batches from now: nothing older than this super-batch may stay.
+        if (consumed < old_left) {
+            __syncthreads();
+            process_quad(count);
+        }
+        __syncthreads();  // fp / ring / s_cincl are rewritten by the next super-batch
     }
+    if (count) process_quad(count);
 }
 
 // Phase B head: stable partition of the instances by tile (fused with emission) + tile ranges.  `R` is the CAPACITY of
