@@ -22,6 +22,10 @@
  *   isr_backward_extra_sparse                  <- same, restricted to dL/d(extra_attrs) for a list of
  *                                                 sampled pixels (the only non-zero cotangents in
  *                                                 train_semantic.py:118-141)
+ *   isr_forward_sparse_extra / isr_backward_sparse_extra_views
+ *                                              <- the same forward / backward restricted to the sampled pixels
+ *                                                 of up to 8 views in one launch (train_semantic.py:102-173:
+ *                                                 render() + mask gather + randint per term)
  *   isr_mark_visible                           <- Rasterizer::markVisible rasterizer.h:24-29,
  *                                                 rasterizer_impl.cu:141-153 (_C.mark_visible, ext.cpp:18)
  *   isr_geom_bytes / isr_image_bytes / isr_binning_bytes
@@ -209,6 +213,35 @@ int isr_backward_extra_sparse(int P, int F, int W, int H, const float* extra_att
                               const void* image, const void* binning, int64_t num_rendered, int n,
                               const int* pix_ids, const float* dL_dextra_samples, float* dL_dextra,
                               unsigned flags /* ISR_FLAG_SPEC_ARITH as in the forward */, void* stream);
+
+/* ---- sampled-pixel rendering of the semantic features (train_semantic.py:102-173) ------------------------
+ * The contrastive loop of the reference renders whole [F,H,W] feature maps (gaussian_renderer/__init__.py:101-113
+ * through forward.cu:256-462) and then keeps `sample_batchsize` pixels of them (train_semantic.py:118-129; five
+ * more full renders for the cross-view term, :146-173).  These two entry points composite ONLY the sampled
+ * pixels, for up to ISR_MAX_SPARSE_VIEWS views of the same cloud in ONE launch: a warp per sample walks the
+ * tile list of its pixel front to back with exactly the arithmetic and order of the dense blend (bit-identical
+ * features), stops at saturation, and records n_contrib / final_T of that pixel for the backward.
+ * A view must be PREPARED first: isr_forward_geometry + isr_forward_render(ISR_FLAG_SKIP_BLEND) into its own
+ * geom / image / binning workspaces (the dense blend is never run).  All views share P, W, H. */
+#define ISR_MAX_SPARSE_VIEWS 8
+typedef struct IsrSparseView {
+    const void* geom;     /* isr_geom_bytes(P), filled by isr_forward_geometry                              */
+    void* image;          /* isr_image_bytes(W,H): tile ranges are read; n_contrib / final_T of the sampled
+                             pixels are written by the forward and read by the backward                      */
+    const void* binning;  /* isr_binning_bytes(...), filled by isr_forward_render(ISR_FLAG_SKIP_BLEND)      */
+} IsrSparseView;
+
+/* out_features[n,F] = rendered extra_attrs at pixel pix_ids[i] (= W*y+x, duplicates allowed) of view
+ * view_ids[i] (NULL: every sample belongs to views_host[0]).  Samples with an id out of range give zeros. */
+int isr_forward_sparse_extra(int n_views, const IsrSparseView* views_host, int P, int F, int W, int H,
+                             const float* extra_attrs, int n, const int* pix_ids, const int* view_ids,
+                             float* out_features, unsigned flags /* ISR_FLAG_SPEC_ARITH */, void* stream);
+
+/* dL/d(extra_attrs) [P,F] (+=, zero-filled by the caller) from the cotangent rows dL_dfeatures[n,F] of the same
+ * samples; needs the n_contrib entries the forward wrote (or those of a dense isr_forward_render). */
+int isr_backward_sparse_extra_views(int n_views, const IsrSparseView* views_host, int P, int F, int W, int H, int n,
+                                    const int* pix_ids, const int* view_ids, const float* dL_dfeatures,
+                                    float* dL_dextra, unsigned flags, void* stream);
 
 int isr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                      uint8_t* present, void* stream);

@@ -4,7 +4,7 @@ distCUDA2).  Host side = Python mirror of the reference API; device side = libis
 from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians, sample_pixels, normalize_rows,  # noqa: F401
                          sample_labelled_pixels, set_arithmetic, arithmetic,
                          _C)
-from .renderer import render, depth_to_normal, prefetch_geometry  # noqa: F401
+from .renderer import render, render_sampled, depth_to_normal, prefetch_geometry  # noqa: F401
 from .contrastive import contrastive_loss  # noqa: F401
 from .knn import distCUDA2  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
@@ -13,5 +13,5 @@ from .losses import photometric_loss, l1_loss, ssim, add_densification_stats  # 
 from . import io, optim  # noqa: F401
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "sample_pixels", "sample_labelled_pixels", "normalize_rows", "render",
-           "depth_to_normal", "prefetch_geometry", "contrastive_loss", "distCUDA2", "FusedAdam", "get_segmap_gaussians", "segmap_gaussians",
+           "render_sampled", "depth_to_normal", "prefetch_geometry", "contrastive_loss", "distCUDA2", "FusedAdam", "get_segmap_gaussians", "segmap_gaussians",
            "photometric_loss", "l1_loss", "ssim", "add_densification_stats", "io", "set_arithmetic", "arithmetic"]

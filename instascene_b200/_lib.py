@@ -55,10 +55,17 @@ class IsrBackwardArgs(C.Structure):
     ]
 
 
+class IsrSparseView(C.Structure):
+    _fields_ = [("geom", _vp), ("image", _vp), ("binning", _vp)]
+
+
+MAX_SPARSE_VIEWS = 8
+
 EXPORTED_SYMBOLS = [
     "isr_version", "isr_status_string", "isr_last_cuda_error", "isr_device_sm_count", "isr_kernel_launch_count",
     "isr_geom_bytes", "isr_image_bytes", "isr_binning_bytes", "isr_field_offset",
-    "isr_forward_geometry", "isr_forward_render", "isr_backward", "isr_backward_extra_sparse", "isr_mark_visible",
+    "isr_forward_geometry", "isr_forward_render", "isr_backward", "isr_backward_extra_sparse", "isr_forward_sparse_extra",
+    "isr_backward_sparse_extra_views", "isr_mark_visible",
     "isr_gather_pixels", "isr_sampler_workspace_bytes", "isr_sample_labelled", "isr_contrastive_workspace_bytes", "isr_contrastive_forward", "isr_contrastive_backward",
     "isr_rownorm_forward", "isr_rownorm_backward", "isr_aux_maps_forward", "isr_aux_maps_backward", "isr_adam_step", "isr_adam_rownorm_step", "isr_knn_workspace_bytes", "isr_knn_mean_dist2",
     "isr_tracker_workspace_bytes", "isr_tracker_mark", "isr_tracker_fill",
@@ -98,6 +105,10 @@ def lib() -> C.CDLL:
     L.isr_backward.argtypes = [C.POINTER(IsrBackwardArgs), C.c_void_p]
     L.isr_backward_extra_sparse.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _fp, _vp, _vp, _vp, C.c_int64, C.c_int,
                                             _ip, _fp, _fp, C.c_uint, C.c_void_p]
+    L.isr_forward_sparse_extra.argtypes = [C.c_int, C.POINTER(IsrSparseView), C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int,
+                                           _ip, _ip, _fp, C.c_uint, C.c_void_p]
+    L.isr_backward_sparse_extra_views.argtypes = [C.c_int, C.POINTER(IsrSparseView), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                  _ip, _ip, _fp, _fp, C.c_uint, C.c_void_p]
     L.isr_mark_visible.argtypes = [C.c_int, _fp, _fp, _fp, _vp, C.c_void_p]
     L.isr_gather_pixels.argtypes = [C.c_int, C.c_int64, _fp, C.c_int, _ip, _fp, C.c_void_p]
     L.isr_sampler_workspace_bytes.restype = C.c_size_t

@@ -18,6 +18,10 @@ int launch_blend_bwd(const IsrBackwardArgs& a, cudaStream_t stream);
 int launch_preprocess_bwd(const IsrBackwardArgs& a, cudaStream_t stream);
 int launch_extra_sparse_bwd(int P, int F, int W, int H, const void* geom, const void* image, const void* binning, int n,
                             const int* pix_ids, const float* dLdE, float* dL_dextra, unsigned flags, cudaStream_t stream);
+int launch_sparse_bwd_views(int n_views, const IsrSparseView* views, int P, int F, int W, int H, int n, const int* pix_ids,
+                            const int* view_ids, const float* dLdE, float* dL_dextra, unsigned flags, cudaStream_t stream);
+int launch_sparse_fwd_views(int n_views, const IsrSparseView* views, int P, int F, int W, int H, const float* extras, int n,
+                            const int* pix_ids, const int* view_ids, float* out, unsigned flags, cudaStream_t stream);
 int launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, uint8_t* present,
                         cudaStream_t stream);
 size_t contrastive_ws_bytes(int N, int F, int K);
@@ -197,6 +201,44 @@ int isr_backward_extra_sparse(int P, int F, int W, int H, const float* extra_att
     if (P == 0 || n == 0 || F == 0 || num_rendered <= 0) return ISR_OK;
     if (!geom || !image || !binning || !pix_ids || !dL_dextra_samples || !dL_dextra) return ISR_ERR_INVALID_ARG;
     return launch_extra_sparse_bwd(P, F, W, H, geom, image, binning, n, pix_ids, dL_dextra_samples, dL_dextra, flags,
+                                   static_cast<cudaStream_t>(stream_));
+}
+
+static int check_sparse_views(int n_views, const IsrSparseView* views, int P, int F, int W, int H, int n) {
+    if (P < 0 || F < 0 || W <= 0 || H <= 0 || n < 0 || n_views < 0) return ISR_ERR_INVALID_ARG;
+    if (F > ISR_MAX_EXTRA_DIMS || n_views > ISR_MAX_SPARSE_VIEWS) return ISR_ERR_UNSUPPORTED;
+    if (n > 0 && P > 0 && F > 0) {
+        if (n_views < 1 || !views) return ISR_ERR_INVALID_ARG;
+        for (int i = 0; i < n_views; i++)
+            if (!views[i].geom || !views[i].image || !views[i].binning) return ISR_ERR_INVALID_ARG;
+    }
+    return ISR_OK;
+}
+
+int isr_forward_sparse_extra(int n_views, const IsrSparseView* views_host, int P, int F, int W, int H, const float* extra_attrs,
+                             int n, const int* pix_ids, const int* view_ids, float* out_features, unsigned flags,
+                             void* stream_) {
+    const int st = check_sparse_views(n_views, views_host, P, F, W, H, n);
+    if (st != ISR_OK) return st;
+    if (n == 0 || F == 0) return ISR_OK;
+    if (!pix_ids || !out_features) return ISR_ERR_INVALID_ARG;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (P == 0) {  // nothing to composite: every sample renders zeros
+        ISR_CUDA_TRY(cudaMemsetAsync(out_features, 0, sizeof(float) * (size_t)n * F, stream));
+        return ISR_OK;
+    }
+    if (!extra_attrs) return ISR_ERR_INVALID_ARG;
+    return launch_sparse_fwd_views(n_views, views_host, P, F, W, H, extra_attrs, n, pix_ids, view_ids, out_features, flags, stream);
+}
+
+int isr_backward_sparse_extra_views(int n_views, const IsrSparseView* views_host, int P, int F, int W, int H, int n,
+                                    const int* pix_ids, const int* view_ids, const float* dL_dfeatures, float* dL_dextra,
+                                    unsigned flags, void* stream_) {
+    const int st = check_sparse_views(n_views, views_host, P, F, W, H, n);
+    if (st != ISR_OK) return st;
+    if (n == 0 || F == 0 || P == 0) return ISR_OK;
+    if (!pix_ids || !dL_dfeatures || !dL_dextra) return ISR_ERR_INVALID_ARG;
+    return launch_sparse_bwd_views(n_views, views_host, P, F, W, H, n, pix_ids, view_ids, dL_dfeatures, dL_dextra, flags,
                                    static_cast<cudaStream_t>(stream_));
 }
 

@@ -339,29 +339,134 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Sparse feature-only backward: one warp per sampled pixel.
+// Sampled pixels only (a warp per sample; up to ISR_MAX_SPARSE_VIEWS prepared views in one launch).
 // ---------------------------------------------------------------------------------------------------------
+// Forward: the features of one pixel, composited front to back with the arithmetic and the order of blend_fwd_kernel
+// (forward.cu:355-437 restricted to the extra channels): bit-identical to the dense map at that pixel.  Per chunk of 32
+// list entries the lanes evaluate one entry each (alpha), the contributing lanes park their Gaussian's F features in the
+// warp's shared-memory slots, then the contributors are blended serially in list order with lane c holding channel c --
+// the transmittance chain and every accumulation keep the dense kernel's sequence of roundings.  Stops at saturation
+// and writes n_contrib (1-based index of the last contributor) and the final transmittance of the pixel.
 template <int FP, bool kRef>
 __global__ void __launch_bounds__(256)
-extra_sparse_bwd_kernel(int n, const int* __restrict__ pix_ids, const float* __restrict__ dLdE_samples, int W, int H,
-                        int F, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                        const float4* __restrict__ splats, const float4* __restrict__ cull4,
-                        const uint32_t* __restrict__ n_contrib, float* __restrict__ dL_dextras, int packed) {
+extra_sparse_fwd_kernel(const SparseViewsDev v, int n, const int* __restrict__ pix_ids, const int* __restrict__ view_ids,
+                        int W, int H, int F, const float* __restrict__ extras, float* __restrict__ out, int packed) {
+    extern __shared__ __align__(16) float s_feat[];  // [8 warps][32 entries][FP]
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    if (warp_global >= n) return;
+    float* slots = s_feat + (size_t)wic * 32 * FP;
+    const int pix = pix_ids[warp_global];
+    const int vw = view_ids ? view_ids[warp_global] : 0;
+    if (pix < 0 || pix >= W * H || vw < 0 || vw >= v.n_views) {
+        if (lane < F) out[(size_t)warp_global * F + lane] = 0.0f;
+        return;
+    }
+    const int pxi = pix % W, pyi = pix / W;
+    const int tiles_x = (W + TILE - 1) / TILE;
+    const uint2 range = v.ranges[vw][(pyi / TILE) * tiles_x + (pxi / TILE)];
+    const int n_total = (int)(range.y - range.x);
+    const float4* __restrict__ splats = v.splats[vw];
+    const float4* __restrict__ cull4 = v.cull4[vw];
+    const uint32_t* __restrict__ plist = v.point_list[vw] + range.x;
+    const float pixx = (float)pxi, pixy = (float)pyi;
+    const int blk = ((pyi % TILE) / 4) * 2 + (pxi % TILE) / 8;  // the pixel's 8x4 block of its tile
+    float T = 1.0f, E = 0.0f;  // lane c accumulates channel c (warp-uniform T)
+    uint32_t last = 0;
+    bool done = false;
+    uint32_t ent_next = (lane < n_total) ? __ldg(plist + lane) : 0u;  // entries one chunk ahead
+    for (int base = 0; base < n_total && !done; base += 32) {
+        const uint32_t ent = ent_next;
+        const bool have = base + lane < n_total;
+        ent_next = (base + 32 + lane < n_total) ? __ldg(plist + base + 32 + lane) : 0u;
+        float alpha = 0.0f;
+        int g;
+        bool cand;
+        if (packed) {  // the entry says whether the Gaussian can reach this pixel's block at all
+            g = (int)(ent & kIdMask);
+            cand = have && ((ent >> (kIdBits + blk)) & 1u);
+        } else {  // exact pre-test: the pixel lies outside the Gaussian's conservative cull rectangle
+            g = (int)ent;
+            cand = have;
+            if (cand) {
+                const float4 cr = __ldg(cull4 + g);
+                cand = !(cr.z < pixx || cr.x > pixx || cr.w < pixy || cr.y > pixy);
+            }
+        }
+        if (!__any_sync(0xffffffffu, cand)) continue;
+        if (cand) {
+            float s[16];
+            const float4* sp = splats + (size_t)g * 4;
+            *reinterpret_cast<float4*>(s + 0) = __ldg(sp + 0);
+            *reinterpret_cast<float4*>(s + 4) = __ldg(sp + 1);
+            *reinterpret_cast<float4*>(s + 8) = __ldg(sp + 2);
+            *reinterpret_cast<float4*>(s + 12) = __ldg(sp + 3);
+            PairEval e;
+            if (eval_pair<kRef, false>(pixx, pixy, s, e)) alpha = e.alpha;
+        }
+        unsigned contrib = __ballot_sync(0xffffffffu, alpha != 0.0f);
+        if (contrib == 0u) continue;
+        if (alpha != 0.0f) {  // park this Gaussian's features where every lane can read its channel
+            float* dst = slots + lane * FP;
+            if ((F & 3) == 0) {
+                const float4* src = reinterpret_cast<const float4*>(extras + (size_t)g * F);
+#pragma unroll
+                for (int q = 0; q < FP / 4; q++)
+                    if (q * 4 < F) *reinterpret_cast<float4*>(dst + 4 * q) = __ldg(src + q);
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < FP; ch++)
+                    if (ch < F) dst[ch] = __ldg(extras + (size_t)g * F + ch);
+            }
+        }
+        __syncwarp();
+        while (contrib) {  // contributing entries only, in list order
+            const int l = __ffs(contrib) - 1;
+            contrib &= contrib - 1;
+            const float a_l = __shfl_sync(0xffffffffu, alpha, l);
+            const float test_T = mul(T, sub(1.0f, a_l));
+            if (test_T < kTMin) {  // forward.cu:395-399: this entry is not blended and the pixel is finished
+                done = true;
+                break;
+            }
+            const float f = (lane < F) ? slots[l * FP + (lane < FP ? lane : 0)] : 0.0f;
+            E = fma_(mul(f, a_l), T, E);  // forward.cu:415 as compiled: fma(feature * alpha, T, E)
+            T = test_T;
+            last = (uint32_t)(base + l + 1);
+        }
+        __syncwarp();  // the slots are rewritten by the next chunk
+    }
+    if (lane < F) out[(size_t)warp_global * F + lane] = E;
+    if (lane == 0) {
+        v.n_contrib[vw][pix] = last;
+        v.final_T[vw][pix] = T;
+    }
+}
+
+// Backward of the same: dL/d(extra_attrs) from the cotangent rows of the samples.
+template <int FP, bool kRef>
+__global__ void __launch_bounds__(256)
+extra_sparse_bwd_kernel(const SparseViewsDev v, int n, const int* __restrict__ pix_ids, const int* __restrict__ view_ids,
+                        const float* __restrict__ dLdE_samples, int W, int H, int F, float* __restrict__ dL_dextras,
+                        int packed) {
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp_global >= n) return;
     const int pix = pix_ids[warp_global];
-    if (pix < 0 || pix >= W * H) return;
+    const int vw = view_ids ? view_ids[warp_global] : 0;
+    if (pix < 0 || pix >= W * H || vw < 0 || vw >= v.n_views) return;
     const int pxi = pix % W, pyi = pix / W;
     const int tiles_x = (W + TILE - 1) / TILE;
-    const uint2 range = ranges[(pyi / TILE) * tiles_x + (pxi / TILE)];
-    const int last = (int)n_contrib[pix];  // number of list entries up to and including the last contributor
+    const uint2 range = v.ranges[vw][(pyi / TILE) * tiles_x + (pxi / TILE)];
+    const float4* __restrict__ splats = v.splats[vw];
+    const float4* __restrict__ cull4 = v.cull4[vw];
+    const int last = (int)v.n_contrib[vw][pix];  // number of list entries up to and including the last contributor
     const float pixx = (float)pxi, pixy = (float)pyi;
     float dE[FP];
 #pragma unroll
     for (int ch = 0; ch < FP; ch++) dE[ch] = (ch < F) ? dLdE_samples[(size_t)warp_global * F + ch] : 0.0f;
     float T = 1.0f;  // transmittance in front of the current group of 32 (warp-uniform)
-    const uint32_t* __restrict__ plist = point_list + range.x;
+    const uint32_t* __restrict__ plist = v.point_list[vw] + range.x;
     const int blk = ((pyi % TILE) / 4) * 2 + (pxi % TILE) / 8;  // the pixel's 8x4 block of its tile
     uint32_t ent_next = (lane < last) ? __ldg(plist + lane) : 0u;  // entries one chunk ahead
     for (int base = 0; base < last; base += 32) {
@@ -466,32 +571,79 @@ int launch_blend_bwd(const IsrBackwardArgs& a, cudaStream_t stream) {
     return ISR_ERR_UNSUPPORTED;
 }
 
-template <int FP>
-static int launch_sparse_one(int P, int F, int W, int H, const void* geom, const void* image, const void* binning, int n,
-                             const int* pix_ids, const float* dLdE, float* dL_dextra, unsigned flags, cudaStream_t stream) {
+static SparseViewsDev make_views(int n_views, const IsrSparseView* views, int P, int W, int H) {
+    SparseViewsDev v{};
     GeomLayout gl(P);
     ImageLayout il(W, H);
-    const char* g = static_cast<const char*>(geom);
-    const char* im = static_cast<const char*>(image);
+    v.n_views = n_views;
+    for (int i = 0; i < n_views; i++) {
+        const char* g = static_cast<const char*>(views[i].geom);
+        char* im = static_cast<char*>(views[i].image);
+        v.ranges[i] = reinterpret_cast<const uint2*>(im + il.ranges);
+        v.point_list[i] = reinterpret_cast<const uint32_t*>(views[i].binning);  // offset 0 of the binning workspace
+        v.splats[i] = reinterpret_cast<const float4*>(g + gl.splat);
+        v.cull4[i] = reinterpret_cast<const float4*>(g + gl.cull);
+        v.n_contrib[i] = reinterpret_cast<uint32_t*>(im + il.n_contrib);
+        v.final_T[i] = reinterpret_cast<float*>(im + il.final_T);
+    }
+    return v;
+}
+
+template <int FP>
+static int launch_sparse_bwd_one(const SparseViewsDev& v, int P, int F, int W, int H, int n, const int* pix_ids,
+                                 const int* view_ids, const float* dLdE, float* dL_dextra, unsigned flags, cudaStream_t stream) {
     const int warps_per_block = 8;
     auto kern = (flags & ISR_FLAG_SPEC_ARITH) ? extra_sparse_bwd_kernel<FP, false> : extra_sparse_bwd_kernel<FP, true>;
-    kern<<<(n + warps_per_block - 1) / warps_per_block, 256, 0, stream>>>(
-        n, pix_ids, dLdE, W, H, F, reinterpret_cast<const uint2*>(im + il.ranges),
-        reinterpret_cast<const uint32_t*>(binning), reinterpret_cast<const float4*>(g + gl.splat),
-        reinterpret_cast<const float4*>(g + gl.cull), reinterpret_cast<const uint32_t*>(im + il.n_contrib), dL_dextra,
-        entries_packed(P) ? 1 : 0); note_launch();
+    kern<<<(n + warps_per_block - 1) / warps_per_block, 256, 0, stream>>>(v, n, pix_ids, view_ids, dLdE, W, H, F, dL_dextra,
+                                                                        entries_packed(P) ? 1 : 0); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }
 
+int launch_sparse_bwd_views(int n_views, const IsrSparseView* views, int P, int F, int W, int H, int n, const int* pix_ids,
+                            const int* view_ids, const float* dLdE, float* dL_dextra, unsigned flags, cudaStream_t stream) {
+    if (n <= 0 || F <= 0) return ISR_OK;
+    const SparseViewsDev v = make_views(n_views, views, P, W, H);
+#define ISR_SB(FPV) return launch_sparse_bwd_one<FPV>(v, P, F, W, H, n, pix_ids, view_ids, dLdE, dL_dextra, flags, stream)
+    if (F <= 4) ISR_SB(4);
+    if (F <= 8) ISR_SB(8);
+    if (F <= 16) ISR_SB(16);
+    if (F <= 24) ISR_SB(24);
+    if (F <= 32) ISR_SB(32);
+#undef ISR_SB
+    return ISR_ERR_UNSUPPORTED;
+}
+
 int launch_extra_sparse_bwd(int P, int F, int W, int H, const void* geom, const void* image, const void* binning, int n,
                             const int* pix_ids, const float* dLdE, float* dL_dextra, unsigned flags, cudaStream_t stream) {
+    IsrSparseView one{geom, const_cast<void*>(image), binning};
+    return launch_sparse_bwd_views(1, &one, P, F, W, H, n, pix_ids, nullptr, dLdE, dL_dextra, flags, stream);
+}
+
+template <int FP>
+static int launch_sparse_fwd_one(const SparseViewsDev& v, int P, int F, int W, int H, const float* extras, int n,
+                                 const int* pix_ids, const int* view_ids, float* out, unsigned flags, cudaStream_t stream) {
+    const int warps_per_block = 8;
+    const size_t smem = (size_t)warps_per_block * 32 * FP * sizeof(float);
+    auto kern = (flags & ISR_FLAG_SPEC_ARITH) ? extra_sparse_fwd_kernel<FP, false> : extra_sparse_fwd_kernel<FP, true>;
+    ISR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(n + warps_per_block - 1) / warps_per_block, 256, smem, stream>>>(v, n, pix_ids, view_ids, W, H, F, extras, out,
+                                                                           entries_packed(P) ? 1 : 0); note_launch();
+    ISR_CUDA_TRY(cudaGetLastError());
+    return ISR_OK;
+}
+
+int launch_sparse_fwd_views(int n_views, const IsrSparseView* views, int P, int F, int W, int H, const float* extras, int n,
+                            const int* pix_ids, const int* view_ids, float* out, unsigned flags, cudaStream_t stream) {
     if (n <= 0 || F <= 0) return ISR_OK;
-    if (F <= 4) return launch_sparse_one<4>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, flags, stream);
-    if (F <= 8) return launch_sparse_one<8>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, flags, stream);
-    if (F <= 16) return launch_sparse_one<16>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, flags, stream);
-    if (F <= 24) return launch_sparse_one<24>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, flags, stream);
-    if (F <= 32) return launch_sparse_one<32>(P, F, W, H, geom, image, binning, n, pix_ids, dLdE, dL_dextra, flags, stream);
+    const SparseViewsDev v = make_views(n_views, views, P, W, H);
+#define ISR_SF(FPV) return launch_sparse_fwd_one<FPV>(v, P, F, W, H, extras, n, pix_ids, view_ids, out, flags, stream)
+    if (F <= 4) ISR_SF(4);
+    if (F <= 8) ISR_SF(8);
+    if (F <= 16) ISR_SF(16);
+    if (F <= 24) ISR_SF(24);
+    if (F <= 32) ISR_SF(32);
+#undef ISR_SF
     return ISR_ERR_UNSUPPORTED;
 }
 

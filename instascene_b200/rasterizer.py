@@ -234,6 +234,80 @@ def finish_render(st: _ForwardState, extra_attrs, F: int, debug: bool = False, r
     return res
 
 
+def finish_binning(st: _ForwardState):
+    """Phase B without the blend: after this the view is PREPARED for the sampled-pixel kernels
+    (isr_forward_sparse_extra): tile ranges + instance lists exist, no image is composited.  Returns
+    (num_rendered, binningBuffer)."""
+    L = _require_cuda_lib()
+    a = st.args
+    if st.ready_event is not None:
+        torch.cuda.current_stream().wait_event(st.ready_event)
+        st.ready_event.synchronize()
+    else:
+        torch.cuda.current_stream().synchronize()
+    num_rendered, n_inst = int(st.nr_host[0]), int(st.nr_host[1])
+    note_instances(st.P, st.W, st.H, n_inst)
+    if st.binning is not None and n_inst <= st.bin_capacity:
+        return num_rendered, st.binning  # binned ahead of time (launch_geometry(bin_capacity=...))
+    bin_bytes = L.isr_binning_bytes(st.P, n_inst, st.W, st.H)
+    st.binning = torch.empty(bin_bytes, dtype=torch.uint8, device=st.dev)
+    st.bin_capacity = n_inst
+    a.binning, a.binning_bytes = st.binning.data_ptr(), bin_bytes
+    flags = a.flags
+    a.flags = flags | _lib.FLAG_SKIP_BLEND
+    _lib.check(L.isr_forward_render(C.byref(a), n_inst, _stream()), "isr_forward_render(binning only)")
+    a.flags = flags
+    return num_rendered, st.binning
+
+
+class _SampledFeatures(torch.autograd.Function):
+    """features[n,F] = the rendered extra_attrs at (view_ids[i], pix_ids[i]) -- only those pixels are composited
+    (isr_forward_sparse_extra), all views in one launch; backward = isr_backward_sparse_extra_views."""
+
+    @staticmethod
+    def forward(ctx, extra_attrs, states, pix_ids, view_ids):
+        L = _require_cuda_lib()
+        st0 = states[0]
+        P, H, W = st0.P, st0.H, st0.W
+        feats = _f32c(extra_attrs.detach(), "extra_attrs")
+        F = int(feats.shape[1])
+        views = (_lib.IsrSparseView * len(states))()
+        for i, st in enumerate(states):
+            if (st.P, st.H, st.W) != (P, H, W):
+                raise RuntimeError("sampled rendering needs views of one cloud at one resolution")
+            views[i].geom, views[i].image, views[i].binning = st.geom.data_ptr(), st.img.data_ptr(), st.binning.data_ptr()
+        ids32 = pix_ids.to(torch.int32).contiguous()
+        vid32 = None if view_ids is None else view_ids.to(torch.int32).contiguous()
+        n = int(ids32.numel())
+        out = torch.empty((n, F), dtype=torch.float32, device=feats.device)
+        flags = st0.args.flags & _lib.FLAG_SPEC_ARITH
+        _lib.check(L.isr_forward_sparse_extra(len(states), views, P, F, W, H, _ptr(feats), n, _ptr(ids32), _ptr(vid32), _ptr(out),
+                                              flags, _stream()), "isr_forward_sparse_extra")
+        ctx.states, ctx.views, ctx.flags = states, views, flags  # the states own the workspaces the table points to
+        ctx.dims = (P, F, W, H, n)
+        ctx.save_for_backward(ids32) if vid32 is None else ctx.save_for_backward(ids32, vid32)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        L = _require_cuda_lib()
+        saved = ctx.saved_tensors
+        ids32, vid32 = saved[0], (saved[1] if len(saved) > 1 else None)
+        P, F, W, H, n = ctx.dims
+        g = _f32c(grad_out, "cotangent")
+        dL_dextra = torch.zeros((P, F), dtype=torch.float32, device=g.device)
+        _lib.check(L.isr_backward_sparse_extra_views(len(ctx.states), ctx.views, P, F, W, H, n, _ptr(ids32), _ptr(vid32), _ptr(g),
+                                                     _ptr(dL_dextra), ctx.flags, _stream()), "isr_backward_sparse_extra_views")
+        return dL_dextra, None, None, None
+
+
+def sampled_features(extra_attrs: torch.Tensor, states, pix_ids: torch.Tensor, view_ids: Optional[torch.Tensor] = None):
+    """Rendered features [n,F] at the given pixels of PREPARED views (launch_geometry + finish_binning each)."""
+    if len(states) < 1 or len(states) > _lib.MAX_SPARSE_VIEWS:
+        raise RuntimeError(f"between 1 and {_lib.MAX_SPARSE_VIEWS} views per call")
+    return _SampledFeatures.apply(extra_attrs, tuple(states), pix_ids, view_ids)
+
+
 def c_rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, transMat_precomp,
                           extra_attrs, attr_degree, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
                           image_width, sh, degree, campos, prefiltered, debug, want_pairs: bool = True,

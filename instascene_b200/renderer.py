@@ -19,8 +19,8 @@ import torch
 import ctypes as C
 
 from . import _lib
-from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, binning_capacity_hint, launch_geometry,
-                         normalize_rows, _ptr, _require_cuda_lib, _stream)
+from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, binning_capacity_hint, finish_binning,
+                         launch_geometry, normalize_rows, sampled_features, _ptr, _require_cuda_lib, _stream)
 
 import os
 
@@ -274,6 +274,15 @@ def _next_pinned_counts(dev_index):
     return buf
 
 
+def _discard_prefetched(handle) -> None:
+    """A prefetched phase A that will not be consumed: its temporaries (opacity / scale / rotation activations, the SH
+    concatenation) were allocated on the main stream and are still being read by the side stream, so the main stream is
+    ordered behind the side stream's work before the caching allocator may hand those blocks out again."""
+    st = getattr(handle, "state", None) if handle is not None else None
+    if st is not None and st.ready_event is not None:
+        torch.cuda.current_stream().wait_event(st.ready_event)
+
+
 def prefetch_geometry(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
                       want_pairs: bool = True, stream=None, bin_ahead: bool = True) -> PrefetchedGeometry:
     """Starts phase A of render() -- and, once an instance-count high-water mark exists, the binning -- for a view that
@@ -305,6 +314,52 @@ def prefetch_geometry(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scalin
     return PrefetchedGeometry(st, _prefetch_key(viewpoint_camera, pc, scaling_modifier, want_pairs))
 
 
+def render_sampled(viewpoint_cameras, pc, pipe, bg_color: torch.Tensor, pix_ids: torch.Tensor, view_ids=None,
+                   scaling_modifier=1.0, norm_seg_feat=True, prefetched=None):
+    """The `seg_feature` output of render() at SAMPLED pixels only, for 1..8 views of the same cloud in one launch.
+
+    train_semantic.py renders the whole [F,H,W] feature map of a view (and of five more views every tenth iteration,
+    :146-173) and then keeps `sample_batchsize` labelled pixels of it (:118-129); the image, depth and normal maps are
+    never used by its losses.  Here the pixels are drawn first (`sample_labelled_pixels` on the label map) and only they
+    are composited: per view projection + binning as in render(), then ONE kernel for the samples of all views -- a warp
+    per sample walking its pixel's tile list with the arithmetic and order of the dense blend, so the rows are
+    bit-identical to `render(...)["seg_feature"].reshape(F, -1)[:, pix].T`.  The gradient reaches `pc._seg_feature`
+    through the sampled-pixel backward and the fused normalisation, exactly as with render() + sample_pixels().
+
+    pix_ids: [n] flat pixel ids (= W*y + x); view_ids: [n] index into `viewpoint_cameras` (None: a single view).
+    prefetched: optional list of `prefetch_geometry` handles (one per view, None where absent).
+    Returns {"features": [n,F], "radii": [V,P] int32, "visibility_filter": [V,P] bool}."""
+    cams = list(viewpoint_cameras) if isinstance(viewpoint_cameras, (list, tuple)) else [viewpoint_cameras]
+    states = []
+    for k, cam in enumerate(cams):
+        handle = prefetched[k] if prefetched is not None else None
+        settings, xyz, opacity, geometry, appearance = _raster_inputs(cam, pc, pipe, bg_color, scaling_modifier, None, False)
+        if any(t.requires_grad for t in (xyz, opacity, *geometry.values(), *appearance.values())) and torch.is_grad_enabled():
+            raise RuntimeError("render_sampled differentiates the semantic features only: freeze the geometry "
+                               "(GaussianModel.training_setup of semantic training) or use render()")
+        if (handle is not None and handle.state is not None
+                and handle.key == _prefetch_key(cam, pc, scaling_modifier, False)):
+            st = handle.state
+        else:
+            _discard_prefetched(handle)
+            with torch.no_grad():
+                cap = binning_capacity_hint(xyz.shape[0], settings.image_width, settings.image_height)
+                st = _launch_phase_a(settings, xyz, opacity, geometry, appearance, cam, pc, bg_color, scaling_modifier, False,
+                                     pinned_counts=_next_pinned_counts(xyz.device.index), bin_capacity=cap)
+        if st is None:
+            raise RuntimeError("render_sampled needs at least one Gaussian")
+        states.append(st)
+    ready = getattr(pc, "_isr_param_ready_event", None)
+    if ready is not None:
+        torch.cuda.current_stream().wait_event(ready)
+    with torch.no_grad():
+        for st in states:
+            finish_binning(st)
+    feats = sampled_features(_seg_features_for_raster(pc, pipe, norm_seg_feat), states, pix_ids, view_ids)
+    radii = torch.stack([st.radii for st in states])
+    return {"features": feats, "radii": radii, "visibility_filter": radii > 0}
+
+
 def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
            norm_seg_feat=True, want_pairs: bool = True, prefetched: "PrefetchedGeometry | None" = None):
     """Rasterise `pc` from `viewpoint_camera`.  `bg_color` must live on the GPU.  `prefetched`: handle of
@@ -325,7 +380,9 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
     if (prefetched is not None and prefetched.state is not None and not geom_trainable
             and prefetched.key == _prefetch_key(viewpoint_camera, pc, scaling_modifier, want_pairs)):
         settings._geom_state = prefetched.state
-    elif getattr(pipe, "geometry_first", _GEOMETRY_FIRST):
+    else:
+        _discard_prefetched(prefetched)
+    if getattr(settings, "_geom_state", None) is None and getattr(pipe, "geometry_first", _GEOMETRY_FIRST):
         settings._geom_state = _launch_phase_a(settings, xyz, opacity, geometry, appearance, viewpoint_camera, pc, bg_color,
                                                scaling_modifier, want_pairs)
     ready = getattr(pc, "_isr_param_ready_event", None)

@@ -10,8 +10,10 @@
 * the gradient reaches the raw `_seg_feature` through the sampled-pixel sparse backward of the rasterizer and, for the
   3D term, through a row gather.
 
-The multi-view term (:146-173, every 10th iteration, 5 extra renders) is the same building blocks called on a stack of
-views and is composed by the caller (`multiview_loss`)."""
+The multi-view term (:146-173, every 10th iteration, 5 extra renders): `multiview_loss` composes it from rendered maps;
+`multiview_loss_sampled` draws the pixels FIRST and composites only them -- the samples of all views in one launch
+(renderer.render_sampled), no [V,F,H,W] stack, no dense blend.  `single_view_loss_sampled` is the same for the
+per-iteration term: the losses of train_semantic.py never read anything but the sampled rows of `seg_feature`."""
 from __future__ import annotations
 
 from typing import NamedTuple, Optional, Sequence
@@ -20,6 +22,7 @@ import torch
 
 from .contrastive import contrastive_loss
 from .rasterizer import normalize_rows, sample_labelled_pixels, sample_pixels
+from .renderer import render_sampled
 
 
 class SemanticOpt(NamedTuple):  # arguments/__init__.py:103-119
@@ -84,3 +87,49 @@ def multiview_loss(seg_feature_maps: Sequence[torch.Tensor], sorted_segmaps: Seq
         feats.append(sample_pixels(fmap, pix[sel] - v * hw))
     feats = torch.cat(feats)
     return contrastive_loss(feats, labels[order], predef_u_list=class_feat, num_labels=num_labels) * opt.lambda_multiview_contras
+
+
+def multiview_loss_sampled(viewpoint_cameras, pc, pipe, bg_color, sorted_segmaps: Sequence[torch.Tensor],
+                           class_feat: Optional[torch.Tensor], opt: SemanticOpt = SemanticOpt(), generator=None,
+                           num_labels: Optional[int] = None, prefetched=None):
+    """train_semantic.py:146-173 without rendering the views: the same draw as `multiview_loss` (uniform over the union
+    of the labelled pixels of the V views, same random stream), then the sampled pixels of ALL views are composited by
+    one kernel launch.  Same value and gradient as multiview_loss([render(v)["seg_feature"] for v in views], ...)."""
+    flat = torch.cat([m.reshape(-1) for m in sorted_segmaps])
+    pix, labels = sample_labelled_pixels(flat, opt.sample_batchsize, generator=generator)
+    hw = sorted_segmaps[0].numel()
+    view = torch.div(pix, hw, rounding_mode="floor")
+    out = render_sampled(viewpoint_cameras, pc, pipe, bg_color, pix - view * hw, view, prefetched=prefetched)
+    return contrastive_loss(out["features"], labels, predef_u_list=class_feat, num_labels=num_labels) * opt.lambda_multiview_contras
+
+
+def single_view_loss_sampled(viewpoint_camera, pc, pipe, bg_color, segmaps: Sequence[torch.Tensor],
+                             class_feat: Optional[torch.Tensor], opt: SemanticOpt = SemanticOpt(), generator=None,
+                             num_labels: Optional[int] = None, prefetched=None):
+    """train_semantic.py:102-143 with the pixels drawn before the view is rendered: every label map contributes
+    `sample_batchsize` samples, all of them composited by one launch.  Same value and gradient as
+    single_view_loss(render(view)["seg_feature"], ...).  Returns (loss, radii [P]) -- radii feed the 3D term."""
+    pix_l, lab_l, neg_l = [], [], []
+    for k, gt in enumerate(segmaps):
+        gt = gt.reshape(-1)
+        negative = k == 0 and opt.consider_negative_labels
+        if negative:
+            pix = torch.randint(0, gt.numel(), (opt.sample_batchsize,), device=gt.device, generator=generator)
+            labels = gt[pix]
+        else:
+            pix, labels = sample_labelled_pixels(gt, opt.sample_batchsize, generator=generator)
+        pix_l.append(pix); lab_l.append(labels); neg_l.append(negative)
+    out = render_sampled([viewpoint_camera], pc, pipe, bg_color, torch.cat(pix_l), None,
+                         prefetched=None if prefetched is None else [prefetched])
+    feats = out["features"]
+    total, start = None, 0
+    for k in range(len(segmaps)):
+        n = int(pix_l[k].numel())
+        weight = 1.0 if k == 1 else 0.5
+        term = contrastive_loss(feats[start:start + n], lab_l[k], predef_u_list=class_feat if k == 1 else None,
+                                consider_negative=neg_l[k],
+                                num_labels=None if (k == 1 and class_feat is not None) else num_labels)
+        start += n
+        term = term * (opt.lambda_singview_contras * weight)
+        total = term if total is None else total + term
+    return total, out["radii"][0]

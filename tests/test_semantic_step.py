@@ -187,3 +187,100 @@ def test_prefetched_geometry_render_is_bitwise_the_inline_render():
     for a, b in zip(g[:4], want[1][:4]):
         assert torch.equal(a, b)
     torch.cuda.synchronize()
+
+
+def _ring_cams(t, W, H, n):
+    from instascene_b200 import synth
+    cams = []
+    for c in synth.ring_cameras(max(n, 4), W, H)[:n]:
+        class Cam:
+            FoVx, FoVy, image_width, image_height = c.FoVx, c.FoVy, W, H
+            world_view_transform, full_proj_transform, camera_center = t(c.world_view_transform), t(c.full_proj_transform), t(c.camera_center)
+            znear, zfar = 0.01, 100.0
+        cams.append(Cam())
+    return cams
+
+
+@pytest.mark.parametrize("F", [16, 7, 32])
+def test_render_sampled_is_bitwise_the_dense_render_at_the_samples(F):
+    """render_sampled composites only the sampled pixels, the samples of all views in ONE launch: the rows must be
+    bit-identical to the dense render's seg_feature map at those pixels (same arithmetic, same order), and the gradient
+    of the raw parameter must equal the one obtained through render() + sample_pixels()."""
+    import torch
+    import instascene_b200 as isr
+    P, W, H, seed, V, n = 6000, 160, 96, 83, 3, 5000
+    inp = scene_inputs(P, F, W, H, seed)
+    pc, _, pipe, t = _scene_objects(inp, W, H, "cuda:0")
+    cams = _ring_cams(t, W, H, V)
+    bg = t(inp["bg"])
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    pix = torch.randint(0, W * H, (n,), device="cuda", generator=gen)
+    view = torch.randint(0, V, (n,), device="cuda", generator=gen)
+    wgt = torch.randn((n, F), device="cuda", generator=gen)
+
+    # dense path: V renders, gather, weighted sum
+    pc._seg_feature.grad = None
+    rows, radii = torch.zeros((n, F), device="cuda"), []
+    loss = 0.0
+    for v, cam in enumerate(cams):
+        pkg = isr.render(cam, pc, pipe, bg, want_pairs=False)
+        sel = torch.nonzero(view == v).reshape(-1)
+        r = isr.sample_pixels(pkg["seg_feature"], pix[sel])
+        rows[sel] = r.detach()
+        radii.append(pkg["radii"].clone())
+        loss = loss + (r * wgt[sel]).sum()
+    loss.backward()
+    want_grad = pc._seg_feature.grad.clone()
+
+    pc._seg_feature.grad = None
+    launches0 = isr._lib.lib().isr_kernel_launch_count()
+    out = isr.render_sampled(cams, pc, pipe, bg, pix, view)
+    assert torch.equal(out["features"], rows)
+    assert torch.equal(out["radii"], torch.stack(radii))
+    (out["features"] * wgt).sum().backward()
+    assert rel_err(pc._seg_feature.grad.cpu().numpy(), want_grad.cpu().numpy()) < 1e-5   # float atomics: summation order
+    # a single view without view ids, through a prefetched handle
+    pc._seg_feature.grad = None
+    h = isr.prefetch_geometry(cams[1], pc, pipe, bg, want_pairs=False)
+    sel = torch.nonzero(view == 1).reshape(-1)
+    one = isr.render_sampled(cams[1], pc, pipe, bg, pix[sel], None, prefetched=[h])
+    assert torch.equal(one["features"], rows[sel])
+    # out-of-range samples render zeros and receive no gradient
+    bad = isr.render_sampled(cams[:2], pc, pipe, bg, torch.tensor([0, W * H, 5], device="cuda"), torch.tensor([0, 1, 7], device="cuda"))
+    assert torch.equal(bad["features"][1:], torch.zeros((2, F), device="cuda"))
+    torch.cuda.synchronize()
+    assert isr._lib.lib().isr_kernel_launch_count() > launches0
+
+
+def test_sampled_losses_equal_the_rendered_ones():
+    """multiview_loss_sampled / single_view_loss_sampled (pixels drawn first, only they are composited) against
+    multiview_loss / single_view_loss on dense renders: same random stream -> same draw -> same loss and gradient."""
+    import torch
+    import instascene_b200 as isr
+    from instascene_b200 import semantic_step as sstep, synth
+    P, F, W, H, seed, V, n = 6000, 16, 160, 96, 85, 4, 4096
+    inp = scene_inputs(P, F, W, H, seed)
+    pc, _, pipe, t = _scene_objects(inp, W, H, "cuda:0")
+    cams = _ring_cams(t, W, H, V)
+    bg = t(inp["bg"])
+    labs = [torch.from_numpy(synth.label_map(W, H, 120 + v, grid=4)).cuda().reshape(-1) for v in range(V)]
+    cf = torch.from_numpy(synth.gram_schmidt_prototypes(20, F, 7)).cuda()
+    opt = sstep.SemanticOpt(sample_batchsize=n)
+
+    def grads(fn):
+        pc._seg_feature.grad = None
+        loss = fn()
+        loss.backward()
+        return float(loss), pc._seg_feature.grad.clone().cpu().numpy()
+
+    mk = lambda: torch.Generator(device="cuda").manual_seed(11)
+    l_d, g_d = grads(lambda: sstep.multiview_loss([isr.render(c, pc, pipe, bg, want_pairs=False)["seg_feature"] for c in cams],
+                                                  labs, cf, opt, generator=mk()))
+    l_s, g_s = grads(lambda: sstep.multiview_loss_sampled(cams, pc, pipe, bg, labs, cf, opt, generator=mk()))
+    assert abs(l_d - l_s) <= 1e-5 * abs(l_d) and rel_err(g_s, g_d) < 1e-5
+
+    segmaps = [labs[0], labs[1]]
+    l_d, g_d = grads(lambda: sstep.single_view_loss(isr.render(cams[2], pc, pipe, bg, want_pairs=False)["seg_feature"], segmaps,
+                                                    cf, opt, generator=mk()))
+    l_s, g_s = grads(lambda: sstep.single_view_loss_sampled(cams[2], pc, pipe, bg, segmaps, cf, opt, generator=mk())[0])
+    assert abs(l_d - l_s) <= 1e-5 * abs(l_d) and rel_err(g_s, g_d) < 1e-5
