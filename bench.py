@@ -484,6 +484,45 @@ def run_ours(args):
             # kernels -- CUB sort/scan, torch glue, NCCL -- are not included)
             "gpu_launches": int(n_launch)}
 
+    # Supplementary (NOT the headline, which renders whole views like the reference): the same training step with the
+    # pixels drawn first and only they composited (semantic_step.single_view_loss_sampled) -- what a train_semantic.py
+    # iteration needs, since its losses read nothing but the sampled rows of seg_feature.
+    if args.workload == "cfg3" and world == 1 and os.environ.get("ISR_BENCH_SAMPLED", "1") != "0":
+        def sampled_step(v, data, nxt, handles):
+            cam = _Cam(cams[v], data["wvt"], data["fpt"], data["center"])
+            loss, _ = sstep.single_view_loss_sampled(cam, pc, pipe, bg, [data["labels"]], None, sem_opt, generator=gen,
+                                                     num_labels=wl["labels"], prefetched=handles.pop(v, None))
+            if use_prefetch and nxt is not None:
+                vn, dn = nxt
+                handles[vn] = isr.prefetch_geometry(_Cam(cams[vn], dn["wvt"], dn["fpt"], dn["center"]), pc, pipe, bg,
+                                                    want_pairs=False)
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return loss
+
+        def run_sampled(n_steps):
+            handles = {}
+            gc.collect(); gc.disable()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for s in range(n_steps):
+                v, vn = my_views[s % len(my_views)], my_views[(s + 1) % len(my_views)]
+                sampled_step(v, devdata[v], (vn, devdata[vn]) if s + 1 < n_steps else None, handles)
+            e1.record()
+            torch.cuda.synchronize()
+            gc.enable()
+            return e0.elapsed_time(e1)
+
+        run_sampled(10)
+        ms_s = run_sampled(args.steps)
+        line["sampled_step"] = {
+            "value": args.steps / (ms_s / 1e3), "unit": "training steps/s", "ms_per_step": ms_s / args.steps, "steps": args.steps,
+            "note": "supplementary, same workload and optimizer: labelled pixels are drawn before rendering and only those "
+                    "32768 pixels are composited (isr.render_sampled: projection + binning per view, one warp per sample, "
+                    "bit-identical features); the headline `value` composites the whole 1080p view like the reference"}
+
     if rank == 0:
         line["roofline"] = measure_roofline(args, wl, pc, cams, devdata, my_views, dev)
         if world == 1 and not args.no_cpu_baseline:
