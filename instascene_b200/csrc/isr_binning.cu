@@ -107,9 +107,8 @@ __global__ void iota_kernel(int n, uint32_t* __restrict__ out) {
 // partition needs per Gaussian as ONE record in depth order (so that the per-chunk warps stream it sequentially instead
 // of chasing order[i] -> per-Gaussian arrays): id, emitted tile count (bit 31: footprint of more than 64 tiles = every
 // tile of the rectangle), getRect origin, rectangle width, and the K1 footprint mask.
-__global__ void gather_tiles_kernel(int P, const uint32_t* __restrict__ tcount, const uint32_t* __restrict__ order,
-                                    const uint32_t* __restrict__ tiles_touched, const uint2* __restrict__ tile_rect,
-                                    const unsigned long long* __restrict__ tile_mask,
+__global__ void gather_tiles_kernel(int P, const uint32_t* __restrict__ order,
+                                    const uint32_t* __restrict__ tiles_touched, const uint4* __restrict__ tile_foot,
                                     uint32_t* __restrict__ gathered, uint4* __restrict__ bin_rec,
                                     unsigned long long* __restrict__ bin_mask,
                                     unsigned long long* __restrict__ totals /*[0] sum tiles_touched, [1] sum tcount*/) {
@@ -117,19 +116,13 @@ __global__ void gather_tiles_kernel(int P, const uint32_t* __restrict__ tcount, 
     unsigned long long a = 0ull, b = 0ull;
     if (i < P) {
         const uint32_t g = order[i];
-        const uint32_t c = tcount[g];
+        const uint4 f0 = __ldg(tile_foot + 2 * (size_t)g), f1 = __ldg(tile_foot + 2 * (size_t)g + 1);  // one 32-byte sector
+        const uint32_t c = f0.x & 0x7fffffffu;
         gathered[i] = c;
         b = c;
         a = tiles_touched[i];
-        uint4 rec = make_uint4(g, 0u, 0u, 1u);
-        unsigned long long mask = 0ull;
-        if (c > 0) {
-            const uint2 r = __ldg(tile_rect + g);
-            rec = make_uint4(g, c | (c > 64u ? 0x80000000u : 0u), r.x, r.y);
-            mask = __ldg(tile_mask + g);
-        }
-        bin_rec[i] = rec;
-        bin_mask[i] = mask;
+        bin_rec[i] = make_uint4(g, f0.x, f0.y, c ? f0.z : 1u);
+        bin_mask[i] = (unsigned long long)f1.x | ((unsigned long long)f1.y << 32);
     } else if (i == P) {
         gathered[i] = 0;
     }
@@ -138,9 +131,16 @@ __global__ void gather_tiles_kernel(int P, const uint32_t* __restrict__ tcount, 
         a += __shfl_xor_sync(0xffffffffu, a, off);
         b += __shfl_xor_sync(0xffffffffu, b, off);
     }
-    if ((threadIdx.x & 31) == 0 && (a | b)) {
-        if (a) atomicAdd(totals + 0, a);
-        if (b) atomicAdd(totals + 1, b);
+    // one pair of atomics per CTA (per warp they were 125 k same-address atomics: the bottleneck of this kernel)
+    __shared__ unsigned long long s_tot[2][8];
+    const int wid = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_tot[0][wid] = a; s_tot[1][wid] = b; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        unsigned long long t = 0ull;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += s_tot[threadIdx.x][w];
+        if (t) atomicAdd(totals + threadIdx.x, t);
     }
 }
 
@@ -198,7 +198,7 @@ __device__ __forceinline__ uint32_t make_entry(uint32_t g, int tile_x, int tile_
 __global__ void __launch_bounds__(256)
 emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
                       const int* __restrict__ radii, const Splat* __restrict__ splats,
-                      const unsigned long long* __restrict__ tile_mask, const uint32_t* __restrict__ tile_count,
+                      const uint4* __restrict__ tile_foot, const uint32_t* __restrict__ tile_count,
                       const float4* __restrict__ cull4, const float4* __restrict__ cullq, int gx, int gy, int W, int H,
                       int packed, uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ gauss_ids,
                       uint32_t* __restrict__ big_count, uint2* __restrict__ big_list) {
@@ -219,7 +219,8 @@ emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t*
                 cnt = 0;
             } else {
                 rect = (uint32_t)mnx | ((uint32_t)mny << 16);
-                mask = tile_mask[g];
+                const uint4 f1 = tile_foot[2 * (size_t)g + 1];
+                mask = (unsigned long long)f1.x | ((unsigned long long)f1.y << 32);
             }
         }
     }
@@ -320,7 +321,6 @@ int launch_depth_order_and_offsets(const IsrForwardArgs& a, cudaStream_t stream)
     uint32_t* keys = reinterpret_cast<uint32_t*>(g + gl.depth_key);
     uint32_t* keys_alt = reinterpret_cast<uint32_t*>(g + gl.keys_alt);
     uint32_t* tiles = reinterpret_cast<uint32_t*>(g + gl.tiles);
-    uint32_t* tcount = reinterpret_cast<uint32_t*>(g + gl.tcount);
     unsigned long long* totals = reinterpret_cast<unsigned long long*>(g + gl.counters);  // [0], [1]; see GeomLayout
     uint32_t* offsets = reinterpret_cast<uint32_t*>(g + gl.offsets);
     void* temp = g + gl.sort_temp;
@@ -332,8 +332,7 @@ int launch_depth_order_and_offsets(const IsrForwardArgs& a, cudaStream_t stream)
     ISR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_alt, order_alt, order, P, 0, 32, stream));
     // keys_alt now holds sorted keys (unused afterwards) -> reuse it for the gathered tile counts
     gather_tiles_kernel<<<(P + 1 + 255) / 256, 256, 0, stream>>>(
-        P, tcount, order, tiles, reinterpret_cast<const uint2*>(g + gl.trect),
-        reinterpret_cast<const unsigned long long*>(g + gl.tmask), keys_alt, reinterpret_cast<uint4*>(g + gl.bin_rec),
+        P, order, tiles, reinterpret_cast<const uint4*>(g + gl.tfoot), keys_alt, reinterpret_cast<uint4*>(g + gl.bin_rec),
         reinterpret_cast<unsigned long long*>(g + gl.bin_mask), totals); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     temp_bytes = gl.sort_temp_bytes;
@@ -869,7 +868,7 @@ int launch_binning(const IsrForwardArgs& a, int64_t R, cudaStream_t stream) {
     ISR_CUDA_TRY(cudaMemsetAsync(big_count, 0, sizeof(uint32_t), stream));
     emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
         P, reinterpret_cast<const uint32_t*>(g + gl.order), reinterpret_cast<const uint32_t*>(g + gl.offsets), a.radii,
-        reinterpret_cast<const Splat*>(g + gl.splat), reinterpret_cast<const unsigned long long*>(g + gl.tmask),
+        reinterpret_cast<const Splat*>(g + gl.splat), reinterpret_cast<const uint4*>(g + gl.tfoot),
         reinterpret_cast<const uint32_t*>(g + gl.tcount), reinterpret_cast<const float4*>(g + gl.cull),
         reinterpret_cast<const float4*>(g + gl.cullq), gx, gy, a.W, a.H, packed, tile_keys_alt, point_list_alt, big_count,
         big_list); note_launch();

@@ -38,7 +38,37 @@ __device__ __forceinline__ void quat_to_rot(const float4 q, float R0[3], float R
     R2[0] = add(xz_p, xz_p);             R2[1] = add(yz_m, yz_m);             R2[2] = sub(1.0f, add(xx_yy, xx_yy));
 }
 
-template <bool kRef>
+// SH staging, variant kBulk: ONE bulk-async copy (cp.async.bulk, the TMA unit's 1-D mode) of the block's 256 contiguous
+// rows (48 KB), completion counted in bytes on an mbarrier, instead of twelve 16-byte cp.async per thread.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+template <bool kRef, bool kBulk>
 __global__ void __launch_bounds__(256)
 preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const float2* __restrict__ scales,
                       float scale_modifier, const float4* __restrict__ rotations,
@@ -49,23 +79,36 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
                       float4* __restrict__ rgb4,
                       float* __restrict__ depths,
                       uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ tiles_touched,
-                      uint8_t* __restrict__ clamped, unsigned long long* __restrict__ tile_mask,
-                      uint32_t* __restrict__ tile_count, uint2* __restrict__ tile_rect) {
+                      uint8_t* __restrict__ clamped, uint4* __restrict__ tile_foot,
+                      uint32_t* __restrict__ tile_count) {
     // SH coefficients of the block's 256 Gaussians are one contiguous 48 KB range: stage them with fully coalesced
     // 16-byte cp.async copies into per-Gaussian slots padded to 13 x 16 B (conflict-free LDS), overlapped with the
     // projection math below.  (Per-thread strided loads of the 192-byte rows ran K1 at 48% of the HBM roofline.)
     extern __shared__ __align__(16) float4 s_sh[];
+    __shared__ __align__(8) uint64_t s_bar;
     const bool stage_sh = (shs != nullptr) && (M == 16) && (colors_precomp == nullptr);
     if (stage_sh) {
         const int block_base = blockIdx.x * blockDim.x;
-        const int n_chunks = min((int)blockDim.x, P - block_base) * 12;
-        const float4* src = reinterpret_cast<const float4*>(shs + (size_t)block_base * 48);
-        for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) {
-            const int row = c / 12, col = c - row * 12;
-            const unsigned d = (unsigned)__cvta_generic_to_shared(s_sh + row * 13 + col);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src + c));
+        const int n_rows = min((int)blockDim.x, P - block_base);
+        if constexpr (kBulk) {
+            if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+            __syncthreads();
+            // the block's rows are one contiguous range: ONE copy of up to 48 KB issued by one thread (UBLKCP takes uniform
+            // operands: a copy per row would be serialised lane by lane), landing unpadded (row stride 192 B)
+            if (threadIdx.x == 0) {
+                mbar_arrive_expect_tx(&s_bar, (unsigned)n_rows * 192u);
+                bulk_copy_g2s(s_sh, shs + (size_t)block_base * 48, (unsigned)n_rows * 192u, &s_bar);
+            }
+        } else {
+            const int n_chunks = n_rows * 12;
+            const float4* src = reinterpret_cast<const float4*>(shs + (size_t)block_base * 48);
+            for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) {
+                const int row = c / 12, col = c - row * 12;
+                const unsigned d = (unsigned)__cvta_generic_to_shared(s_sh + row * 13 + col);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src + c));
+            }
+            asm volatile("cp.async.commit_group;\n" ::);
         }
-        asm volatile("cp.async.commit_group;\n" ::);
     }
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     int radius_i = 0;
@@ -143,15 +186,19 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
         visible = true;
     } while (false);
     if (stage_sh) {
-        asm volatile("cp.async.wait_all;\n" ::: "memory");
-        __syncthreads();
+        if constexpr (kBulk) {
+            mbar_wait(&s_bar, 0);  // every row of the block has landed (each thread reads only its own)
+        } else {
+            asm volatile("cp.async.wait_all;\n" ::: "memory");
+            __syncthreads();
+        }
     }
     if (visible) {
         const float* Tu = T; const float* Tv = T + 3; const float* Tw = T + 6;
         float rgb[3];
         if (colors_precomp == nullptr) {
             // computeColorFromSH (forward.cu:20-71)
-            const float* sh = stage_sh ? reinterpret_cast<const float*>(s_sh + threadIdx.x * 13)
+            const float* sh = stage_sh ? reinterpret_cast<const float*>(s_sh + threadIdx.x * (kBulk ? 12 : 13))
                                        : shs + (size_t)idx * M * 3;
             const float dx = sub(p0, __ldg(cam.campos)), dy = sub(p1, __ldg(cam.campos + 1)), dz = sub(p2, __ldg(cam.campos + 2));
             const float len = sqrt_(fma_(dz, dz, fma_(dx, dx, mul(dy, dy))));
@@ -335,9 +382,9 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
     tiles_touched[idx] = tiles;
     depth_keys[idx] = dkey;
     clamped[idx] = clamp_mask;
-    tile_mask[idx] = tmask;
     tile_count[idx] = tcount;
-    tile_rect[idx] = trect;
+    tile_foot[2 * (size_t)idx] = make_uint4(tcount | (tcount > 64u ? 0x80000000u : 0u), trect.x, trect.y, 0u);
+    tile_foot[2 * (size_t)idx + 1] = make_uint4((uint32_t)tmask, (uint32_t)(tmask >> 32), 0u, 0u);
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const Camera cam,
@@ -536,7 +583,14 @@ int launch_preprocess_fwd(const IsrForwardArgs& a, cudaStream_t stream) {
     const int gx = (a.W + TILE - 1) / TILE, gy = (a.H + TILE - 1) / TILE;
     Camera cam{a.viewmatrix, a.projmatrix, a.campos};
     const size_t sh_smem = (a.shs != nullptr && a.sh_coeffs == 16 && a.colors_precomp == nullptr) ? 256 * 13 * 16 : 0;
-    auto kern = (a.flags & ISR_FLAG_SPEC_ARITH) ? preprocess_fwd_kernel<false> : preprocess_fwd_kernel<true>;
+    // ISR_K1_BULK=1: stage the SH rows with one cp.async.bulk per CTA instead of 12 cp.async per thread.  Measured
+    // (profiles/r2_k1_bulk.md): 6.8% fewer warp instructions but 203 -> 246 us -- the copy lands unpadded (4-way bank
+    // conflicts on the float4 reads) and every thread waits for the whole block's 48 KB.  Off by default.
+    static const bool bulk = [] { const char* e = getenv("ISR_K1_BULK"); return e && e[0] == '1'; }();
+    const bool aligned = ((uintptr_t)a.shs & 15) == 0;
+    auto kern = (a.flags & ISR_FLAG_SPEC_ARITH)
+                    ? (bulk && aligned ? preprocess_fwd_kernel<false, true> : preprocess_fwd_kernel<false, false>)
+                    : (bulk && aligned ? preprocess_fwd_kernel<true, true> : preprocess_fwd_kernel<true, false>);
     ISR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 13 * 16));
     kern<<<(a.P + 255) / 256, 256, sh_smem, stream>>>(
         a.P, a.sh_degree, a.sh_coeffs, a.means3D, reinterpret_cast<const float2*>(a.scales), a.scale_modifier,
@@ -545,8 +599,7 @@ int launch_preprocess_fwd(const IsrForwardArgs& a, cudaStream_t stream) {
         reinterpret_cast<float4*>(g + gl.cullq), reinterpret_cast<float4*>(g + gl.rgb),
         reinterpret_cast<float*>(g + gl.depth), reinterpret_cast<uint32_t*>(g + gl.depth_key),
         reinterpret_cast<uint32_t*>(g + gl.tiles), reinterpret_cast<uint8_t*>(g + gl.clamped),
-        reinterpret_cast<unsigned long long*>(g + gl.tmask), reinterpret_cast<uint32_t*>(g + gl.tcount),
-        reinterpret_cast<uint2*>(g + gl.trect)); note_launch();
+        reinterpret_cast<uint4*>(g + gl.tfoot), reinterpret_cast<uint32_t*>(g + gl.tcount)); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     return ISR_OK;
 }
