@@ -318,13 +318,17 @@ def run_ours(args):
     use_prefetch = args.workload in ("cfg3", "cfg5") and os.environ.get("ISR_BENCH_PREFETCH", "1") != "0"
     prefetched = {}
 
-    def step(v, data, nxt=None):
+    def prefetch(nx):
+        vn, dn = nx
+        if vn not in prefetched:
+            prefetched[vn] = isr.prefetch_geometry(_Cam(cams[vn], dn["wvt"], dn["fpt"], dn["center"]), pc, pipe, bg)
+
+    def step(v, data, nxt=None, nxt2=None):
         cam = _Cam(cams[v], data["wvt"], data["fpt"], data["center"])
         if args.workload in ("cfg3", "cfg5"):
             pkg = isr.render(cam, pc, pipe, bg, prefetched=prefetched.pop(v, None))
             if use_prefetch and nxt is not None:
-                vn, dn = nxt
-                prefetched[vn] = isr.prefetch_geometry(_Cam(cams[vn], dn["wvt"], dn["fpt"], dn["center"]), pc, pipe, bg)
+                prefetch(nxt)
             segmaps = [data["labels"]] if class_feat is None else [data["labels"], data["labels2"]]
             loss = sstep.single_view_loss(pkg["seg_feature"], segmaps, class_feat, sem_opt, generator=gen,
                                           num_labels=wl["labels"])
@@ -350,6 +354,11 @@ def run_ours(args):
                 # keep the gradient buffer alive until the main stream has waited for `ev` (next render) instead of
                 # record_stream(): its deferred frees made the caching allocator grow for dozens of steps
                 held.append(g)
+                # The next blend has to wait for the all-gathered parameter (~0.4 ms during which the main stream is
+                # idle and the next view's geometry is long finished): start the geometry + binning of the view AFTER
+                # the next one now, so that the SMs have work during the collective (prefetch depth 2 at N > 1).
+                if use_prefetch and nxt2 is not None:
+                    prefetch(nxt2)
             else:
                 opt.step()
                 opt.zero_grad(set_to_none=True)
@@ -387,24 +396,31 @@ def run_ours(args):
         view_of = lambda s: my_views[s % len(my_views)] if wrap else my_views[s]
         cam_keys = ("wvt", "fpt", "center")
         upload = lambda v, keys: {k: host[v][k].to(dev, non_blocking=True) for k in keys}
-        cam_next = None  # e2e: the next view's camera matrices are uploaded one step ahead (they feed the prefetch)
+        cam_ahead = {}  # e2e: camera matrices are uploaded up to two steps ahead (they feed the prefetch)
         prefetched.clear()
+        last_s = first + n_steps - 1
         for n, s in enumerate(range(first, first + n_steps)):
             v = view_of(s)
-            nxt = None
+            nxt = nxt2 = None
             if e2e:
-                data = cam_next if cam_next is not None else upload(v, cam_keys)
+                data = cam_ahead.pop(s, None) or upload(v, cam_keys)
                 data.update(upload(v, [k for k in host[v] if k not in cam_keys]))
                 if s == first:
                     h2d = sum(x.numel() * x.element_size() for x in host[v].values())
-                if s + 1 < first + n_steps:
-                    cam_next = upload(view_of(s + 1), cam_keys)
-                    nxt = (view_of(s + 1), cam_next)
+                for d in (1, 2):
+                    if s + d <= last_s and (s + d) not in cam_ahead:
+                        cam_ahead[s + d] = upload(view_of(s + d), cam_keys)
+                if s + 1 <= last_s:
+                    nxt = (view_of(s + 1), cam_ahead[s + 1])
+                if s + 2 <= last_s:
+                    nxt2 = (view_of(s + 2), cam_ahead[s + 2])
             else:
                 data = devdata[v]
-                if s + 1 < first + n_steps:
+                if s + 1 <= last_s:
                     nxt = (view_of(s + 1), devdata[view_of(s + 1)])
-            loss = step(v, data, nxt)
+                if s + 2 <= last_s:
+                    nxt2 = (view_of(s + 2), devdata[view_of(s + 2)])
+            loss = step(v, data, nxt, nxt2)
             if e2e:
                 last = float(loss.detach().to("cpu", non_blocking=False))  # device -> host read of the step's result
                 d2h = 4
@@ -471,8 +487,9 @@ def run_ours(args):
             "config": {"workload": wl["desc"], "gaussians": P, "feat_dim": F, "image": [W, H],
                        "views_per_step_per_gpu": 1, "views": f"{len(cams)} synthetic COLMAP views (cameras.bin/images.bin round trip)",
                        "preheat_steps_untimed": preheat,
-                       "geometry_prefetch": "next view's projection + depth sort overlap the current step's loss/backward/Adam "
-                                            "(isr.prefetch_geometry)" if use_prefetch else "off", "parallelism": f"dp{world} (views sharded; gradient reduce-scatter, Adam on 1/N of the rows, parameter all-gather)" if world > 1 else "dp1",
+                       "geometry_prefetch": ("next view's projection + depth sort + binning overlap the current step's loss/backward/Adam "
+                                             "(isr.prefetch_geometry)" + ("; at N > 1 one view further ahead, so that it runs under the "
+                                                                          "parameter all-gather" if world > 1 else "")) if use_prefetch else "off", "parallelism": f"dp{world} (views sharded; gradient reduce-scatter, Adam on 1/N of the rows, parameter all-gather)" if world > 1 else "dp1",
                        "trainable": "_seg_feature only; geometry frozen, as GaussianModel.training_setup does for semantic "
                                     "training (scene/gaussian_model.py:226-232)" if opt is not None else "all geometry / appearance tensors",
                        "l2": "inputs larger than L2 (Gaussian state %.0f MB >> 126 MB), distinct view every step" % (P * (232 + 4 * F) / 1e6),
