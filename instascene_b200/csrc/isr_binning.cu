@@ -42,23 +42,33 @@ bool entries_packed(int P) {
 }
 
 size_t scatter_smem_bytes(int num_tiles);
+size_t scatter_u_smem_bytes(int num_tiles);
 
-BinChunks bin_chunks(int num_tiles, int64_t R) {
+static int bin_sm_count() {
     static const int sm_count = [] {
         int dev = 0, n = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
             n = 148;  // B200
         return n;
     }();
+    return sm_count;
+}
+
+BinChunks bin_chunks(int num_tiles, int64_t R) {
+    const int sm_count = bin_sm_count();
+    // ISR_BIN_UNORDERED=1: unordered scatter + sort of the (run, tile) segments instead of the in-order ranking kernel
+    // (measured equal overall: 243 + 111 us against 366 us, two more kernels and 2R words of workspace; off by default)
+    static const bool ordered = [] { const char* e = getenv("ISR_BIN_UNORDERED"); return !(e && e[0] == '1'); }();
     static const bool force_sort = [] { const char* e = getenv("ISR_BIN_SORT"); return e && e[0] == '1'; }();  // test hook
     BinChunks bc;
     const int nt = num_tiles > 0 ? num_tiles : 1;
     bc.smem_count = align_up((size_t)nt * 4, 16);
-    bc.smem_scatter = scatter_smem_bytes(nt);
+    bc.unordered = !ordered;
+    bc.smem_scatter = bc.unordered ? scatter_u_smem_bytes(nt) : scatter_smem_bytes(nt);
     // per SM: 227 KB opt-in, 1 KB of system reservation per resident CTA; one chunk = one CTA of bin_scatter_kernel
     const size_t budget = 226 * 1024;
     int per_sm = (int)(budget / (bc.smem_scatter + 1024 + 1280 /* static */));
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 5) per_sm = 5;
     bc.chunks = (force_sort || per_sm < 1 || num_tiles > 65535) ? 0 : sm_count * per_sm;
     // the 16-bit per-tile cursors of bin_scatter_kernel count at most one instance per Gaussian of the chunk: a chunk
     // must start fewer than 65536 instances
@@ -110,7 +120,7 @@ __global__ void iota_kernel(int n, uint32_t* __restrict__ out) {
 __global__ void gather_tiles_kernel(int P, const uint32_t* __restrict__ order,
                                     const uint32_t* __restrict__ tiles_touched, const uint4* __restrict__ tile_foot,
                                     uint32_t* __restrict__ gathered, uint4* __restrict__ bin_rec,
-                                    unsigned long long* __restrict__ bin_mask,
+                                    unsigned long long* __restrict__ bin_mask, uint32_t* __restrict__ rank,
                                     unsigned long long* __restrict__ totals /*[0] sum tiles_touched, [1] sum tcount*/) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long a = 0ull, b = 0ull;
@@ -123,6 +133,7 @@ __global__ void gather_tiles_kernel(int P, const uint32_t* __restrict__ order,
         a = tiles_touched[i];
         bin_rec[i] = make_uint4(g, f0.x, f0.y, c ? f0.z : 1u);
         bin_mask[i] = (unsigned long long)f1.x | ((unsigned long long)f1.y << 32);
+        rank[g] = (uint32_t)i;
     } else if (i == P) {
         gathered[i] = 0;
     }
@@ -333,7 +344,7 @@ int launch_depth_order_and_offsets(const IsrForwardArgs& a, cudaStream_t stream)
     // keys_alt now holds sorted keys (unused afterwards) -> reuse it for the gathered tile counts
     gather_tiles_kernel<<<(P + 1 + 255) / 256, 256, 0, stream>>>(
         P, order, tiles, reinterpret_cast<const uint4*>(g + gl.tfoot), keys_alt, reinterpret_cast<uint4*>(g + gl.bin_rec),
-        reinterpret_cast<unsigned long long*>(g + gl.bin_mask), totals); note_launch();
+        reinterpret_cast<unsigned long long*>(g + gl.bin_mask), reinterpret_cast<uint32_t*>(g + gl.rank), totals); note_launch();
     ISR_CUDA_TRY(cudaGetLastError());
     temp_bytes = gl.sort_temp_bytes;
     ISR_CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, keys_alt, offsets, P + 1, stream));
@@ -814,6 +825,293 @@ bin_scatter_kernel(const BinArgs b, const uint32_t* __restrict__ table, const ui
     if (count) process_quad(count);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// 3c', experimental variant (ISR_BIN_UNORDERED=1): UNORDERED scatter + sort of the (run, tile) segments.
+// ---------------------------------------------------------------------------------------------------------
+// Within a run the final position of an instance is  start of (run, tile) + its slot among the run's instances of that
+// tile.  The ordered kernel above computes the slot as an in-order rank (ballots, per-warp count bytes, two barriers per
+// 512 instances, 12 warps per SM).  Here the slot is simply the old value of a shared-memory atomic on the tile's 16-bit
+// cursor -- no ranking, no count table (2 bytes of shared memory per tile: 20 warps per SM) -- so the instances of one
+// (run, tile) segment land in arbitrary order, while the segments themselves are where they belong (the table of step
+// 3b).  bin_fixup_kernel then sorts every segment of two or more entries by depth rank (rank[] = inverse of the depth
+// order, written by gather_tiles): one thread per (run, tile), typical length 2-4 (registers, sorting network); segments
+// longer than 32 entries go to bin_fixup_long_kernel (one CTA each, rank by counting through two scratch arrays).  The
+// result is the same list as the ordered kernel's, entry for entry.
+// (Flagging only the segments that can actually be out of order -- two instances of one tile between two block barriers
+//  -- was tried first: most segments were flagged at cfg3, and the flagging (two dependent global atomics per conflict)
+//  cost 25% of the kernel: profiles/r2_ncu_bin_scatter.txt.)
+constexpr int kUThreads = 128;
+constexpr int kStageCapU = 2048;          // staged instances (tile | owner thread << 16)
+
+size_t scatter_u_smem_bytes(int num_tiles) {
+    return align_up((size_t)((num_tiles + 1) / 2) * 4, 16) + (size_t)kStageCapU * 4 + (size_t)kUThreads * kFpStride * 4;
+}
+
+__global__ void __launch_bounds__(kUThreads, 5)
+bin_scatter_unordered_kernel(const BinArgs b, const uint32_t* __restrict__ table, const uint32_t* __restrict__ base,
+                             int64_t capacity, uint32_t* __restrict__ point_list) {
+    extern __shared__ __align__(16) unsigned char bin_smem[];
+    uint32_t* cur = reinterpret_cast<uint32_t*>(bin_smem);  // two 16-bit cursors per word: tile t -> word t/2, half t%2
+    uint32_t* stage = reinterpret_cast<uint32_t*>(bin_smem + align_up((size_t)((b.num_tiles + 1) / 2) * 4, 16));
+    float* fp = reinterpret_cast<float*>(stage + kStageCapU);  // [threads][kFpStride]
+    __shared__ uint32_t s_cincl[kUThreads];
+    __shared__ uint32_t s_warp_tot[kUThreads / 32];
+    __shared__ uint32_t s_bigmask[kUThreads / 32];
+    __shared__ int s_end, s_bigw;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x;
+    const uint32_t* row = table + (size_t)c * b.num_tiles;
+    for (int t = tid; t < (b.num_tiles + 1) / 2; t += kUThreads) cur[t] = 0u;
+    int i0, i1;
+    chunk_range(b, c, lane, i0, i1);
+    __syncthreads();
+    const float inv_gx = 1.0f / (float)b.gx;
+
+    auto entry_of = [&](uint32_t slot, uint32_t tile) -> uint32_t {
+        const float* f = fp + slot * kFpStride;
+        const float4 cr = *reinterpret_cast<const float4*>(f), q0 = *reinterpret_cast<const float4*>(f + 4),
+                     q1 = *reinterpret_cast<const float4*>(f + 8);
+        const int tile_y = __float2int_rd(((float)tile + 0.5f) * inv_gx), tile_x = (int)tile - tile_y * b.gx;
+        return make_entry(__float_as_uint(f[13]), tile_x, tile_y, b.packed, cr, q0, q1, f[12]);
+    };
+    // The n staged instances take their slots (any order) and are written.  Called by every thread; begins with a
+    // barrier (staging list complete); the caller puts one before the list is rewritten.
+    auto process_batch = [&](uint32_t n) {
+        __syncthreads();
+        for (uint32_t k0 = 0; k0 < n; k0 += 4 * kUThreads) {
+            uint32_t e[4], entry[4], st_base[4], st_row[4];
+            bool has[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t k = k0 + (uint32_t)(u * kUThreads + tid);
+                has[u] = k < n;
+                e[u] = has[u] ? stage[k] : 0u;
+                const uint32_t tile = e[u] & 0xffffu;
+                // start of (run, tile): two L2 hits, consumed only at the store below (after footprint bits and atomic)
+                st_base[u] = has[u] ? __ldg(base + tile) : 0u;
+                st_row[u] = has[u] ? __ldg(row + tile) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) entry[u] = has[u] ? entry_of(e[u] >> 16, e[u] & 0xffffu) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (has[u]) {
+                    const uint32_t tile = e[u] & 0xffffu, sh = (tile & 1u) * 16u;
+                    const uint32_t slot = (atomicAdd(&cur[tile >> 1], 1u << sh) >> sh) & 0xffffu;
+                    const uint32_t pos = st_base[u] + st_row[u] + slot;
+                    if ((int64_t)pos < capacity) point_list[pos] = entry[u];
+                }
+            }
+        }
+    };
+
+    struct Pre {
+        uint4 rec;
+        unsigned long long mask;
+        float4 cr, q0, q1;
+        float r2;
+        bool valid;
+    };
+    auto load_rec = [&](int ib, Pre& p) {  // unconditional loads from clamped addresses (see the ordered kernel)
+        const int i = min(ib + tid, b.P - 1);
+        p.valid = ib + tid < i1;
+        p.rec = __ldg(b.rec + i);
+        p.mask = __ldg(b.mask + i);
+    };
+    auto load_fp = [&](Pre& p) {
+        const uint32_t g = p.valid ? p.rec.x : 0u;
+        p.cr = __ldg(b.cull4 + g);
+        const float4* q = b.cullq + (size_t)g * 3;
+        p.q0 = __ldg(q); p.q1 = __ldg(q + 1); p.r2 = __ldg(q + 2).x;
+    };
+
+    const int n_sb = (i1 - i0 + kUThreads - 1) / kUThreads;
+    Pre me, nxt;
+    load_rec(i0, me);
+    load_fp(me);
+    load_rec(i0 + kUThreads, nxt);
+    for (int sb = 0; sb < n_sb; sb++) {
+        const uint32_t cnt_g = me.valid ? (me.rec.y & 0x7fffffffu) : 0u;
+        const bool big = cnt_g > 64u;
+        const uint32_t small_cnt = big ? 0u : cnt_g;
+        const int mnx = (int)(me.rec.z & 0xffffu), mny = (int)(me.rec.z >> 16), w = (int)me.rec.w;
+        const unsigned long long my_mask = me.mask;
+        {   // staged footprint record of this thread's Gaussian (read by owner index in entry_of)
+            float* f = fp + tid * kFpStride;
+            *reinterpret_cast<float4*>(f) = me.cr;
+            *reinterpret_cast<float4*>(f + 4) = me.q0;
+            *reinterpret_cast<float4*>(f + 8) = me.q1;
+            *reinterpret_cast<float4*>(f + 12) = make_float4(me.r2, __uint_as_float(me.rec.x), __uint_as_float(cnt_g),
+                                                               __uint_as_float(me.rec.z));
+        }
+        uint32_t c_incl = small_cnt;  // block-wide inclusive scan of the small-footprint counts
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, c_incl, d);
+            if (lane >= d) c_incl += u;
+        }
+        const unsigned bigs_w = __ballot_sync(0xffffffffu, big);
+        if (lane == 31) s_warp_tot[warp] = c_incl;
+        if (lane == 0) s_bigmask[warp] = bigs_w;
+        __syncthreads();
+        bool any_big = false;
+#pragma unroll
+        for (int u = 0; u < kUThreads / 32; u++) {
+            if (u < warp) c_incl += s_warp_tot[u];
+            any_big |= s_bigmask[u] != 0u;
+        }
+        s_cincl[tid] = c_incl;
+        __syncthreads();
+        me = nxt;  // prefetch for the next two super-batches (issued after the scan, see the ordered kernel)
+        load_fp(me);
+        load_rec(i0 + (sb + 2) * kUThreads, nxt);
+        const uint32_t c_excl = c_incl - small_cnt;
+        const uint32_t sb_total = s_cincl[kUThreads - 1];
+        const bool simple = !any_big && sb_total <= (uint32_t)kStageCapU;
+
+        int cur_g = 0;
+        bool first = true;
+        while (cur_g < kUThreads) {  // block-uniform
+            const uint32_t seg_base = cur_g ? s_cincl[cur_g - 1] : 0u;
+            int end = kUThreads;
+            if (!simple) {  // first Gaussian >= cur_g that is big or would overflow the staging list
+                if (tid == 0) s_end = kUThreads;
+                __syncthreads();  // (also: the previous segment's staging list has been consumed)
+                if (tid >= cur_g && (big || c_incl - seg_base > (uint32_t)kStageCapU)) atomicMin(&s_end, tid);
+                __syncthreads();
+                end = s_end;
+            } else if (!first) {
+                break;
+            }
+            first = false;
+            const uint32_t n = end > cur_g ? s_cincl[end - 1] - seg_base : 0u;
+            if (n) {
+                if (tid >= cur_g && tid < end && small_cnt) {
+                    // tile t of the rectangle (row-major, t < 64, width <= 64): t / w == (t * (65536 / w + 1)) >> 16
+                    const uint32_t rcpw = 65536u / (uint32_t)w + 1u;
+                    const uint32_t tile0 = (uint32_t)(mny * b.gx + mnx), dgx = (uint32_t)(b.gx - w);
+                    uint32_t o = c_excl - seg_base;
+                    unsigned long long m = my_mask;
+                    while (m) {
+                        const uint32_t t = (uint32_t)__ffsll((long long)m) - 1u;
+                        m &= m - 1;
+                        const uint32_t ty = (t * rcpw) >> 16;
+                        stage[o++] = (tile0 + t + ty * dgx) | ((uint32_t)tid << 16);
+                    }
+                }
+                process_batch(n);
+            }
+            if (end < kUThreads && ((s_bigmask[end >> 5] >> (end & 31)) & 1u)) {
+                // a footprint of more than 64 tiles: every tile of its rectangle, row-major, expanded by the whole CTA
+                const float* f = fp + end * kFpStride;
+                const int nb = (int)__float_as_uint(f[14]);
+                const uint32_t org = __float_as_uint(f[15]);
+                const int bx = (int)(org & 0xffffu), by = (int)(org >> 16);
+                if (tid == end) s_bigw = w;  // rectangle width: published by the owner thread
+                for (int t0 = 0; t0 < nb; t0 += kStageCapU) {
+                    __syncthreads();  // s_bigw visible; the previous staging list has been consumed
+                    const int rw = s_bigw;
+                    const float iw = 1.0f / (float)rw;
+                    const int m = min(nb - t0, kStageCapU);
+                    for (int t = tid; t < m; t += kUThreads) stage[t] = rect_tile(t0 + t, iw, rw, bx, by, b.gx) | ((uint32_t)end << 16);
+                    process_batch((uint32_t)m);
+                }
+                cur_g = end + 1;
+            } else {
+                cur_g = end;
+            }
+        }
+        __syncthreads();  // fp / staging list / s_cincl are rewritten by the next super-batch
+    }
+}
+
+// Sorts every (run, tile) segment of two or more entries by depth rank.  One thread per segment (t fastest: the table
+// rows are read coalesced); up to 4 entries in registers (all loads in flight together, 5-comparator network), up to 32
+// by insertion in local memory, longer ones are queued for bin_fixup_long_kernel.  (A warp-cooperative version -- 32
+// segments gathered into shared memory, rank by counting with every lane busy -- was measured slower: 150 vs 111 us.)
+__global__ void __launch_bounds__(256)
+bin_fixup_kernel(int num_tiles, int chunks, const uint32_t* __restrict__ table, const uint32_t* __restrict__ totals,
+                 const uint32_t* __restrict__ base, const uint32_t* __restrict__ rank, int packed, int64_t capacity,
+                 uint32_t* __restrict__ fix_counters, uint32_t* __restrict__ long_list, uint32_t long_cap,
+                 uint32_t* __restrict__ point_list) {
+    const uint32_t idm = packed ? kIdMask : 0xffffffffu;
+    const size_t n_seg = (size_t)chunks * num_tiles;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_seg; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(i / (size_t)num_tiles), t = (uint32_t)(i - (size_t)c * num_tiles);
+        const uint32_t s0 = table[i];
+        const uint32_t s1 = (int)c + 1 < chunks ? table[i + num_tiles] : totals[t];
+        const uint32_t len = s1 - s0;
+        if (len < 2u) continue;
+        const uint32_t off = base[t] + s0;
+        if ((int64_t)off + len > capacity) continue;  // (list buffer too small: the host repeats the binning)
+        uint32_t* p = point_list + off;
+        if (len <= 4u) {
+            uint32_t e[4], k[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) e[j] = (uint32_t)j < len ? p[j] : 0u;
+#pragma unroll
+            for (int j = 0; j < 4; j++) k[j] = (uint32_t)j < len ? __ldg(rank + (e[j] & idm)) : 0xffffffffu;
+            bool moved = false;
+            auto cx = [&](int a, int bb) {
+                if (k[a] > k[bb]) { const uint32_t tk = k[a], te = e[a]; k[a] = k[bb]; e[a] = e[bb]; k[bb] = tk; e[bb] = te; moved = true; }
+            };
+            cx(0, 1); cx(2, 3); cx(0, 2); cx(1, 3); cx(1, 2);
+            if (moved) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) if ((uint32_t)j < len) p[j] = e[j];
+            }
+            continue;
+        }
+        if (len > 32u) {
+            const uint32_t at = atomicAdd(fix_counters + 1, 1u);
+            if (at < long_cap) long_list[at] = (uint32_t)i;
+            continue;
+        }
+        uint32_t e[32], k[32];
+        for (uint32_t j = 0; j < len; j++) e[j] = p[j];
+        for (uint32_t j = 0; j < len; j++) k[j] = __ldg(rank + (e[j] & idm));
+        for (uint32_t j = 1; j < len; j++) {
+            const uint32_t ej = e[j], kj = k[j];
+            uint32_t q = j;
+            while (q > 0 && k[q - 1] > kj) { e[q] = e[q - 1]; k[q] = k[q - 1]; q--; }
+            e[q] = ej; k[q] = kj;
+        }
+        for (uint32_t j = 0; j < len; j++) p[j] = e[j];
+    }
+}
+
+// One CTA per long segment: position of an entry = number of entries of the segment with a smaller depth rank.
+__global__ void __launch_bounds__(256)
+bin_fixup_long_kernel(int num_tiles, int chunks, const uint32_t* __restrict__ table, const uint32_t* __restrict__ totals,
+                      const uint32_t* __restrict__ base, const uint32_t* __restrict__ rank, int packed,
+                      const uint32_t* __restrict__ long_list, uint32_t long_cap, const uint32_t* __restrict__ fix_counters,
+                      uint32_t* __restrict__ scratch_k, uint32_t* __restrict__ scratch_e, uint32_t* __restrict__ point_list) {
+    const uint32_t n_long = min(fix_counters[1], long_cap);
+    const uint32_t idm = packed ? kIdMask : 0xffffffffu;
+    for (uint32_t i = blockIdx.x; i < n_long; i += gridDim.x) {
+        const uint32_t bit = long_list[i];
+        const uint32_t c = bit / (uint32_t)num_tiles, t = bit - c * (uint32_t)num_tiles;
+        const uint32_t s0 = table[(size_t)c * num_tiles + t];
+        const uint32_t s1 = (int)c + 1 < chunks ? table[(size_t)(c + 1) * num_tiles + t] : totals[t];
+        const uint32_t len = s1 - s0, off = base[t] + s0;
+        uint32_t* p = point_list + off;
+        uint32_t* sk = scratch_k + off;
+        uint32_t* se = scratch_e + off;
+        for (uint32_t j = threadIdx.x; j < len; j += blockDim.x) {
+            const uint32_t ej = p[j];
+            se[j] = ej;
+            sk[j] = __ldg(rank + (ej & idm));
+        }
+        __syncthreads();
+        for (uint32_t j = threadIdx.x; j < len; j += blockDim.x) {
+            const uint32_t kj = sk[j];
+            uint32_t pos = 0;
+            for (uint32_t q = 0; q < len; q++) pos += sk[q] < kj ? 1u : 0u;  // ranks are distinct
+            p[pos] = se[j];
+        }
+        __syncthreads();
+    }
+}
+
 // Phase B head: stable partition of the instances by tile (fused with emission) + tile ranges.  `R` is the CAPACITY of
 // the list buffer (>= the emitted instance count, which the kernels read from device memory).
 int launch_binning(const IsrForwardArgs& a, int64_t R, cudaStream_t stream) {
@@ -854,7 +1152,25 @@ int launch_binning(const IsrForwardArgs& a, int64_t R, cudaStream_t stream) {
         ISR_CUDA_TRY(cudaGetLastError());
         bin_tilebase_kernel<<<1, 1024, 0, stream>>>(num_tiles, totals, base, ranges, R, overflow); note_launch();
         ISR_CUDA_TRY(cudaGetLastError());
-        bin_scatter_kernel<<<bc.chunks, kScatThreads, bc.smem_scatter, stream>>>(ba, table, base, R, point_list); note_launch();
+        if (!bc.unordered) {
+            bin_scatter_kernel<<<bc.chunks, kScatThreads, bc.smem_scatter, stream>>>(ba, table, base, R, point_list); note_launch();
+            ISR_CUDA_TRY(cudaGetLastError());
+            return ISR_OK;
+        }
+        uint32_t* fix_counters = reinterpret_cast<uint32_t*>(b + bl.fix_counters);
+        uint32_t* long_list = reinterpret_cast<uint32_t*>(b + bl.long_list);
+        ISR_CUDA_TRY(cudaMemsetAsync(fix_counters, 0, 256, stream));
+        ISR_CUDA_TRY(cudaFuncSetAttribute(bin_scatter_unordered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc.smem_scatter));
+        bin_scatter_unordered_kernel<<<bc.chunks, kUThreads, bc.smem_scatter, stream>>>(ba, table, base, R, point_list); note_launch();
+        ISR_CUDA_TRY(cudaGetLastError());
+        const uint32_t* rank = reinterpret_cast<const uint32_t*>(g + gl.rank);
+        bin_fixup_kernel<<<bin_sm_count() * 16, 256, 0, stream>>>(num_tiles, bc.chunks, table, totals, base, rank, packed, R,
+                                                                 fix_counters, long_list, (uint32_t)bl.long_cap, point_list); note_launch();
+        ISR_CUDA_TRY(cudaGetLastError());
+        bin_fixup_long_kernel<<<bin_sm_count(), 256, 0, stream>>>(num_tiles, bc.chunks, table, totals, base, rank, packed, long_list,
+                                                                 (uint32_t)bl.long_cap, fix_counters,
+                                                                 reinterpret_cast<uint32_t*>(b + bl.scratch_k),
+                                                                 reinterpret_cast<uint32_t*>(b + bl.scratch_e), point_list); note_launch();
         ISR_CUDA_TRY(cudaGetLastError());
         return ISR_OK;
     }

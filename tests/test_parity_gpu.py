@@ -742,6 +742,41 @@ def test_radix_sort_binning_fallback_matches_counting_partition():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+def test_unordered_scatter_with_segment_sort_matches_ordered_ranking():
+    """The binning's shipped scatter (in-order ranking) and the experimental one (unordered slots + sort of every
+    (run, tile) segment by depth rank; ISR_BIN_UNORDERED=1, read once per process) must produce the same lists: the
+    bit-exact forward tests and the crowded-tile order tests in a fresh interpreter with the experimental kernel."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ISR_BIN_UNORDERED="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(root, "tests", "test_parity_gpu.py"),
+                        "-k", "test_forward_bit_exact or test_backward_sparse_equals_dense or test_crowded"], env=env, cwd=root,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("P,W,H", [(400_000, 64, 48), (120_000, 160, 96)])
+def test_crowded_tiles_keep_depth_order(P, W, H):
+    """Hundreds of thousands of Gaussians on a dozen tiles: every (run, tile) segment of the partition holds many
+    instances (with ISR_BIN_UNORDERED=1 the long-segment sort, > 32 entries, one CTA each, is exercised).  Every tile list must be ascending in (depth bits, Gaussian id) -- the reference's order -- and the tile
+    ranges must partition the list."""
+    inp = scene_inputs(P, 0, W, H, 97)
+    c = cuda_forward(inp, want_pairs=False)
+    ranges, pl = c["ranges"].astype(np.int64), c["point_list"].astype(np.int64)
+    assert int((ranges[:, 1] - ranges[:, 0]).sum()) == len(pl) == int(c["tiles_emitted"].sum())
+    key = c["depths"].view(np.uint32).astype(np.int64) << 32
+    longest = 0
+    for t in range(len(ranges)):
+        ids = pl[ranges[t, 0]:ranges[t, 1]]
+        k = key[ids] | ids
+        assert np.all(np.diff(k) > 0), f"tile {t}: list not in (depth, id) order"
+        longest = max(longest, len(ids))
+    if W == 64:
+        assert longest > 740 * 32  # pigeonhole over at most 740 runs: some (run, tile) segment is longer than 32 entries
+
+
 def test_plain_entry_fallback_path():
     """Scenes with >= 2^24 Gaussians cannot carry the per-block footprint bits in the list entries; the blend kernels
     then test the footprint arithmetically.  ISR_PLAIN_ENTRIES=1 forces that path: forward parity + dense/sparse
