@@ -552,11 +552,20 @@ __global__ void __launch_bounds__(1024) bin_tilebase_kernel(int num_tiles, const
     }
 }
 
+// 3b'': table[c][t] += base[t]: the table then holds the ABSOLUTE list position of the first instance of (run, tile), so
+// that the scatter kernels need one global load per instance instead of two.
+__global__ void __launch_bounds__(256) bin_addbase_kernel(int num_tiles, int chunks, const uint32_t* __restrict__ base,
+                                                         uint32_t* __restrict__ table) {
+    const size_t n = (size_t)chunks * num_tiles;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        table[i] += __ldg(base + (i % (size_t)num_tiles));
+}
+
 // 3c: every list entry straight to its final position, in depth order.  One CTA of kScatWarps warps per chunk.
 // The chunk's instances are produced IN DEPTH ORDER into a ring in shared memory and consumed kQuad = 4 * kScatThreads
 // at a time ("quad": warp w holds instances [128 w, 128 w + 128) of the quad, lane l the four instances 32 s + l), ranked
 // by the whole CTA at once -- no warp ever waits for another warp's turn:
-//   position = start of (chunk, tile)                      base[t] + table[c][t]            (global, read-only)
+//   position = start of (chunk, tile)                      table[c][t] (absolute after bin_addbase)  (global, read-only)
 //            + instances of the tile in earlier quads      cur[t]        u16 in shared memory
 //            + ... in earlier warps of this quad           cnt[t]: one byte per warp in a 32-bit word, summed with dp4a
 //            + ... earlier in this warp                    the warp's byte before its own sub-round added to it, plus the
@@ -631,7 +640,7 @@ bin_scatter_kernel(const BinArgs b, const uint32_t* __restrict__ table, const ui
             const uint32_t e = has[s] ? ring[(head + k) & (kRing - 1)] : 0u;
             tile[s] = e & 0xffffu;
             entry[s] = has[s] ? entry_of(e >> 16, tile[s]) : 0u;
-            start[s] = has[s] ? __ldg(base + tile[s]) + __ldg(row + tile[s]) : 0u;
+            start[s] = has[s] ? __ldg(row + tile[s]) : 0u;  // absolute position of the first instance of (run, tile)
         }
         // lanes of the same sub-round with the same tile
         unsigned peers[4];
@@ -887,7 +896,7 @@ bin_scatter_unordered_kernel(const BinArgs b, const uint32_t* __restrict__ table
                 e[u] = has[u] ? stage[k] : 0u;
                 const uint32_t tile = e[u] & 0xffffu;
                 // start of (run, tile): two L2 hits, consumed only at the store below (after footprint bits and atomic)
-                st_base[u] = has[u] ? __ldg(base + tile) : 0u;
+                st_base[u] = 0u;
                 st_row[u] = has[u] ? __ldg(row + tile) : 0u;
             }
 #pragma unroll
@@ -1038,10 +1047,10 @@ bin_fixup_kernel(int num_tiles, int chunks, const uint32_t* __restrict__ table, 
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_seg; i += (size_t)gridDim.x * blockDim.x) {
         const uint32_t c = (uint32_t)(i / (size_t)num_tiles), t = (uint32_t)(i - (size_t)c * num_tiles);
         const uint32_t s0 = table[i];
-        const uint32_t s1 = (int)c + 1 < chunks ? table[i + num_tiles] : totals[t];
+        const uint32_t s1 = (int)c + 1 < chunks ? table[i + num_tiles] : base[t] + totals[t];  // (the table is absolute)
         const uint32_t len = s1 - s0;
         if (len < 2u) continue;
-        const uint32_t off = base[t] + s0;
+        const uint32_t off = s0;
         if ((int64_t)off + len > capacity) continue;  // (list buffer too small: the host repeats the binning)
         uint32_t* p = point_list + off;
         if (len <= 4u) {
@@ -1091,8 +1100,8 @@ bin_fixup_long_kernel(int num_tiles, int chunks, const uint32_t* __restrict__ ta
         const uint32_t bit = long_list[i];
         const uint32_t c = bit / (uint32_t)num_tiles, t = bit - c * (uint32_t)num_tiles;
         const uint32_t s0 = table[(size_t)c * num_tiles + t];
-        const uint32_t s1 = (int)c + 1 < chunks ? table[(size_t)(c + 1) * num_tiles + t] : totals[t];
-        const uint32_t len = s1 - s0, off = base[t] + s0;
+        const uint32_t s1 = (int)c + 1 < chunks ? table[(size_t)(c + 1) * num_tiles + t] : base[t] + totals[t];
+        const uint32_t len = s1 - s0, off = s0;
         uint32_t* p = point_list + off;
         uint32_t* sk = scratch_k + off;
         uint32_t* se = scratch_e + off;
@@ -1151,6 +1160,8 @@ int launch_binning(const IsrForwardArgs& a, int64_t R, cudaStream_t stream) {
         bin_colscan_kernel<<<(num_tiles + 31) / 32, 256, 0, stream>>>(num_tiles, bc.chunks, table, totals); note_launch();
         ISR_CUDA_TRY(cudaGetLastError());
         bin_tilebase_kernel<<<1, 1024, 0, stream>>>(num_tiles, totals, base, ranges, R, overflow); note_launch();
+        ISR_CUDA_TRY(cudaGetLastError());
+        bin_addbase_kernel<<<bin_sm_count() * 8, 256, 0, stream>>>(num_tiles, bc.chunks, base, table); note_launch();
         ISR_CUDA_TRY(cudaGetLastError());
         if (!bc.unordered) {
             bin_scatter_kernel<<<bc.chunks, kScatThreads, bc.smem_scatter, stream>>>(ba, table, base, R, point_list); note_launch();
