@@ -98,8 +98,9 @@ long long isr_kernel_launch_count(void);    /* kernels of THIS library launched 
 /* ---- workspace sizes --------------------------------------------------------------------------------- */
 size_t isr_geom_bytes(int P);               /* per-Gaussian state saved for backward                       */
 size_t isr_image_bytes(int W, int H);       /* per-pixel state saved for backward + per-tile ranges        */
-size_t isr_binning_bytes(int P, int64_t R, int W, int H);  /* sorted instance list + sort scratch; R = the
-                                                             * emitted instance count num_rendered_host[1]  */
+size_t isr_binning_bytes(int P, int64_t R, int W, int H);  /* instance list (per tile, depth order) + the partition's
+                                                             * count table; R = capacity in instances, >= the
+                                                             * emitted count num_rendered_host[1]              */
 
 /* Offsets (in bytes) of the fields inside the geometry / image / binning workspaces, so that tests and
  * tools can compare intermediates with the oracle.  Field ids: */
