@@ -15,18 +15,20 @@
 //        a. bin_count_kernel: the depth order is cut into `chunks` runs of ~R/chunks instances; one CTA per run
 //           enumerates its instances and counts them per tile in shared memory (one 32-bit counter per tile) -> a
 //           [chunks][tiles] table
-//        b. bin_colscan_kernel / bin_tilebase_kernel: exclusive scan down every tile column and across the tile
-//           totals: table[c][t] becomes the rank of chunk c's first instance in tile t, the totals become the tile
-//           ranges (identifyTileRanges for free)
-//        c. bin_scatter_kernel: one CTA per run re-enumerates it in depth order, 128 instances per round, and writes
-//           every list entry (Gaussian id + the 8 per-block footprint bits) straight to its final position: start of
-//           (run, tile) + shared-memory cursor of the tile + instances of the same round in earlier warps (8-bit
-//           per-warp fields of one shared-memory word per tile) + rank among the lanes of the warp
+//        b. bin_colscan_kernel / bin_tilebase_kernel / bin_addbase_kernel: exclusive scan down every tile column and
+//           across the tile totals: table[c][t] becomes the list position of chunk c's first instance in tile t, the
+//           totals become the tile ranges (identifyTileRanges for free)
+//        c. bin_scatter_kernel: one CTA per run re-enumerates it in depth order into a shared-memory ring, 512
+//           instances per round, and writes every list entry (Gaussian id + the 8 per-block footprint bits) straight
+//           to its final position: start of (run, tile) + shared-memory cursor of the tile + instances of the same
+//           round in earlier warps (one count byte per warp in a shared-memory word per tile) + rank in the warp
+//           (ISR_BIN_UNORDERED=1: unordered slots + a sort of every (run, tile) segment by depth rank instead; same
+//           lists, measured equal)
 //      Instances of a tile end up ordered by (depth bits, Gaussian id): each tile list is exactly the reference's list
 //      (ties: SURVEY.md Q2) minus entries that contribute to none of the tile's pixels -- skipping those never
 //      changes a result.  The kernels read R from device memory, so phase B has no host-side dependence on it beyond
 //      the capacity of the list buffer.
-//   (fallback when the per-tile table does not fit in shared memory, > ~50k tiles: emission of (tile id, entry) pairs
+//   (fallback when the per-tile tables do not fit in shared memory, > ~37k tiles: emission of (tile id, entry) pairs
 //    + CUB radix sort by tile id + tile ranges, as in round 1)
 // The reference's num_rendered (sum of tiles_touched) is still computed and reported at the boundary.
 // Phase A's depth sort and offset scan use CUB (CUDA toolkit), as the reference does for its single big sort.
