@@ -28,7 +28,7 @@
 //      (ties: SURVEY.md Q2) minus entries that contribute to none of the tile's pixels -- skipping those never
 //      changes a result.  The kernels read R from device memory, so phase B has no host-side dependence on it beyond
 //      the capacity of the list buffer.
-//   (fallback when the per-tile tables do not fit in shared memory, > ~37k tiles: emission of (tile id, entry) pairs
+//   (fallback when the per-tile tables do not fit in shared memory, > ~34k tiles (beyond 4K resolution): emission of (tile id, entry) pairs
 //    + CUB radix sort by tile id + tile ranges, as in round 1)
 // The reference's num_rendered (sum of tiles_touched) is still computed and reported at the boundary.
 // Phase A's depth sort and offset scan use CUB (CUDA toolkit), as the reference does for its single big sort.
